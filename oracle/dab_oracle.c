@@ -1,0 +1,451 @@
+/*
+ * dab_oracle.c -- the oracle's public API (dab_oracle.h): shared constant tables plus the Tier-C loops
+ * (frame/sync/AFC loop, FIC regroup, CIF assembly, time de-interleaver, energy dispersal, CRC) restated
+ * in plain C from the reference, on top of the Tier-A/B primitives of orc_kernels.h.  The same file is
+ * linked into liboracle.so (primitives = orc_port.c) and into _ref/libdabref.so (primitives = the
+ * reference's own classes, ref_shim/ref_provider.cpp).
+ * TEST INFRASTRUCTURE ONLY -- nothing in the product path may call this (see dab_oracle.h).
+ * All file:line citations are relative to /root/reference.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include "dab_oracle.h"
+#include "orc_kernels.h"
+
+#define INPUT_RATE 2048000              /* includes/dab-constants.h:79 */
+
+const char *orc_build_kind (void) { return k_kind (); }
+
+/* ---- mode parameters: gui.cpp:1328-1372; CIF geometry: msc-handler.cpp:61-71; FIC: fic-handler.cpp:192-230 */
+int orc_mode_params (int mode, orc_params *p) {
+	memset (p, 0, sizeof (*p));
+	switch (mode) {
+	   case 1: p -> L = 76;  p -> K = 1536; p -> T_null = 2656; p -> T_F = 196608; p -> T_s = 2552;
+	           p -> T_u = 2048; p -> carrierDiff = 1000; p -> blocksPerCIF = 18; break;
+	   case 2: p -> L = 76;  p -> K = 384;  p -> T_null = 664;  p -> T_F = 49152;  p -> T_s = 638;
+	           p -> T_u = 512;  p -> carrierDiff = 4000; p -> blocksPerCIF = 72; break;
+	   case 3: p -> L = 153; p -> K = 192;  p -> T_null = 345;  p -> T_F = 49152;  p -> T_s = 319;
+	           p -> T_u = 256;  p -> carrierDiff = 2000; p -> blocksPerCIF = 18; break;   /* sic: ref values */
+	   case 4: p -> L = 76;  p -> K = 768;  p -> T_null = 1328; p -> T_F = 98304;  p -> T_s = 1276;
+	           p -> T_u = 1024; p -> carrierDiff = 2000; p -> blocksPerCIF = 36; break;
+	   default: return -1;
+	}
+	p -> dabMode = mode;
+	p -> T_g = p -> T_s - p -> T_u;
+	p -> ficSymbols = 3;                               /* ofdm-processor.cpp:421-422 */
+	p -> ficGroups = 3 * 2 * p -> K / 2304;            /* fic-handler.cpp:211-217 */
+	p -> cifsPerFrame = (p -> L - 4) / p -> blocksPerCIF;
+	return 0;
+}
+
+int   orc_perm_table (int mode, int16_t *out) { orc_params p; if (orc_mode_params (mode, &p)) return -1; return k_perm_table (&p, out); }
+float orc_phi (int mode, int k) { return k_phi (mode, k); }
+int   orc_pcode (int n, int8_t *out) { return k_pcode (n, out); }
+int   orc_ref_table (int mode, float *out) {
+	orc_params p; if (orc_mode_params (mode, &p)) return -1;
+	k_ofdm *o = k_ofdm_new (&p, 3, 1);
+	k_get_ref_table (o, out);
+	k_ofdm_free (o);
+	return 0;
+}
+
+/* ---- UEP profiles: deconvolve.cpp:28-114 {bitRate, protLevel, L1..L4, PI1..PI4}; PI4 == -1 -> unused.
+ * Row {80,1} keeps the reference's PI2 = 7. */
+static const int16_t uep_rows [][10] = {
+	{32,5, 3,4,17,0, 5,3,2,-1},     {32,4, 3,3,18,0, 11,6,5,-1},    {32,3, 3,4,14,3, 15,9,6,8},
+	{32,2, 3,4,14,3, 22,13,8,13},   {32,1, 3,5,13,3, 24,17,12,17},
+	{48,5, 4,3,26,3, 5,4,2,3},      {48,4, 3,4,26,3, 9,6,4,6},      {48,3, 3,4,26,3, 15,10,6,9},
+	{48,2, 3,4,26,3, 24,14,8,15},   {48,1, 3,5,25,3, 24,18,13,18},
+	{64,5, 6,9,31,2, 5,3,2,3},      {64,4, 6,9,33,0, 11,6,6,-1},    {64,3, 6,12,27,3, 16,8,6,9},
+	{64,2, 6,10,29,3, 23,13,8,13},  {64,1, 6,11,28,3, 24,18,12,18},
+	{80,5, 6,10,41,3, 6,3,2,3},     {80,4, 6,10,41,3, 11,6,5,6},    {80,3, 6,11,40,3, 16,8,6,7},
+	{80,2, 6,10,41,3, 23,13,8,13},  {80,1, 6,10,41,3, 24,7,12,18},
+	{96,5, 7,9,53,3, 5,4,2,4},      {96,4, 7,10,52,3, 9,6,4,6},     {96,3, 6,12,51,3, 16,9,6,10},
+	{96,2, 6,10,53,3, 22,12,9,12},  {96,1, 6,13,50,3, 24,18,13,19},
+	{112,5, 14,17,50,3, 5,4,2,5},   {112,4, 11,21,49,3, 9,6,4,8},   {112,3, 11,23,47,3, 16,8,6,9},
+	{112,2, 11,21,49,3, 23,12,9,14},
+	{128,5, 12,19,62,3, 5,3,2,4},   {128,4, 11,21,61,3, 11,6,5,7},  {128,3, 11,22,60,3, 16,9,6,10},
+	{128,2, 11,21,61,3, 22,12,9,14}, {128,1, 11,20,62,3, 24,17,13,19},
+	{160,5, 11,19,87,3, 5,4,2,4},   {160,4, 11,23,83,3, 11,6,5,9},  {160,3, 11,24,82,3, 16,8,6,11},
+	{160,2, 11,21,85,3, 22,11,9,13}, {160,1, 11,22,84,3, 24,18,12,19},
+	{192,5, 11,20,110,3, 6,4,2,5},  {192,4, 11,22,108,3, 10,6,4,9}, {192,3, 11,24,106,3, 16,10,6,11},
+	{192,2, 11,20,110,3, 22,13,9,13}, {192,1, 11,21,109,3, 24,20,13,24},
+	{224,5, 12,22,131,3, 8,6,2,6},  {224,4, 12,26,127,3, 12,8,4,11}, {224,3, 11,20,134,3, 16,10,7,9},
+	{224,2, 11,22,132,3, 24,16,10,15}, {224,1, 11,24,130,3, 24,20,12,20},
+	{256,5, 11,24,154,3, 6,5,2,5},  {256,4, 11,24,154,3, 12,9,5,10}, {256,3, 11,27,151,3, 16,10,7,10},
+	{256,2, 11,22,156,3, 24,14,10,13}, {256,1, 11,26,152,3, 24,19,14,18},
+	{320,5, 11,26,200,3, 8,5,2,6},  {320,4, 11,25,201,3, 13,9,5,10}, {320,2, 11,26,200,3, 24,17,9,17},
+	{384,5, 11,27,247,3, 8,6,2,7},  {384,3, 11,24,250,3, 16,9,7,10}, {384,1, 12,28,245,3, 24,20,14,23},
+};
+
+int orc_uep_profile (int bitRate, int protLevel, int16_t L [4], int16_t PI [4]) {
+	for (unsigned r = 0; r < sizeof (uep_rows) / sizeof (uep_rows [0]); r ++)
+		if (uep_rows [r][0] == bitRate && uep_rows [r][1] == protLevel) {        /* deconvolve.cpp:123-133 */
+			for (int j = 0; j < 4; j ++) { L [j] = uep_rows [r][2 + j]; PI [j] = uep_rows [r][6 + j]; }
+			if (PI [3] < 0) PI [3] = 0;                                           /* :162-165, never read: L4 == 0 */
+			return 0;
+		}
+	return -1;
+}
+
+/* EEP profiles: deconvolve.cpp:249-318.  protLevel is 0100+level (A) or 0200+level (B). */
+int orc_eep_profile (int bitRate, int protLevel, int16_t L [2], int16_t PI [2]) {
+	const int lvl = protLevel & 07;
+	if (protLevel & 0100) {
+		switch (lvl) {
+		   case 1: L [0] = 6 * bitRate / 8 - 3; L [1] = 3; PI [0] = 24; PI [1] = 23; return 0;
+		   case 2: if (bitRate == 8) { L [0] = 5; L [1] = 1; PI [0] = 13; PI [1] = 12; }
+		           else { L [0] = 2 * bitRate / 8 - 3; L [1] = 4 * bitRate / 8 + 3; PI [0] = 14; PI [1] = 13; }
+		           return 0;
+		   case 3: L [0] = 6 * bitRate / 8 - 3; L [1] = 3; PI [0] = 8; PI [1] = 7; return 0;
+		   case 4: L [0] = 4 * bitRate / 8 - 3; L [1] = 2 * bitRate / 8 + 3; PI [0] = 3; PI [1] = 2; return 0;
+		}
+	} else if (protLevel & 0200) {
+		L [0] = 24 * bitRate / 32 - 3; L [1] = 3;
+		switch (lvl) {
+		   case 1: PI [0] = 10; PI [1] = 9; return 0;
+		   case 2: PI [0] = 6;  PI [1] = 5; return 0;
+		   case 3: PI [0] = 4;  PI [1] = 3; return 0;
+		   case 4: PI [0] = 2;  PI [1] = 1; return 0;
+		}
+	}
+	return -1;          /* the reference leaves L1/L2/PI uninitialised here (UB); the oracle reports it */
+}
+
+/* ---- energy-dispersal PRBS: fic-handler.cpp:100-108 (== dab-concurrent.cpp:183-190) ---- */
+void orc_prbs (uint8_t *out, int n) {
+	uint8_t sr [9];
+	memset (sr, 1, 9);
+	for (int i = 0; i < n; i ++) {
+		const uint8_t b = sr [8] ^ sr [4];
+		for (int j = 8; j > 0; j --) sr [j] = sr [j - 1];
+		sr [0] = b;
+		out [i] = b;
+	}
+}
+
+/* ---- FIB CRC: dab-constants.h:310-340, on a private copy ---- */
+int orc_check_crc (const uint8_t *src, int size) {
+	static const uint8_t poly [15] = { 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0 };
+	uint8_t b [16], in [4096];
+	if (size < 16 || size > 4096) return 0;
+	memcpy (in, src, size);
+	memset (b, 1, 16);
+	for (int i = size - 16; i < size; i ++) in [i] ^= 1;
+	for (int i = 0; i < size; i ++) {
+		if ((b [0] ^ in [i]) == 1) {
+			for (int f = 0; f < 15; f ++) b [f] = poly [f] ^ b [f + 1];
+			b [15] = 1;
+		} else {
+			memmove (&b [0], &b [1], 15);
+			b [15] = 0;
+		}
+	}
+	int sum = 0;
+	for (int i = 0; i < 16; i ++) sum += b [i];
+	return sum == 0;
+}
+
+int orc_viterbi (int frameBits, const int16_t *soft, uint8_t *out) { return k_viterbi (frameBits, soft, out); }
+
+static int prot_once (int bitRate, int uepFlag, int protLevel, const int16_t *v, int32_t size, uint8_t *out) {
+	k_prot *p = k_prot_new (bitRate, uepFlag, protLevel);
+	if (!p) return -1;
+	k_prot_deconvolve (p, v, size, out);
+	k_prot_free (p);
+	return 0;
+}
+int orc_eep_deconvolve (int bitRate, int protLevel, const int16_t *v, int32_t size, uint8_t *out) {
+	int16_t L [2], PI [2];
+	if (orc_eep_profile (bitRate, protLevel, L, PI)) return -1;
+	return prot_once (bitRate, 1, protLevel, v, size, out);
+}
+int orc_uep_deconvolve (int bitRate, int protLevel, const int16_t *v, int32_t size, uint8_t *out) {
+	int16_t L [4], PI [4];
+	if (orc_uep_profile (bitRate, protLevel, L, PI)) return -1;
+	return prot_once (bitRate, 0, protLevel, v, size, out);
+}
+
+/* ---- FIC code word: fic-handler.cpp:241-321 (without the fib_processor hand-over) ---- */
+int orc_fic_decode (const int16_t *fic, uint8_t *bits768, uint8_t *crc_ok) {
+	int16_t block [3072 + 24];
+	int8_t pi16 [32], pi15 [32];
+	uint8_t prbs [768];
+	int in = 0, local = 0;
+	k_pcode (16, pi16); k_pcode (15, pi15);
+	for (int i = 0; i < 21; i ++)                       /* :254-262 */
+		for (int k = 0; k < 128; k ++) block [local ++] = pi16 [k % 32] == 1 ? fic [in ++] : 0;
+	for (int i = 0; i < 3; i ++)                        /* :269-276 */
+		for (int k = 0; k < 128; k ++) block [local ++] = pi15 [k % 32] == 1 ? fic [in ++] : 0;
+	for (int k = 0; k < 24; k ++)                       /* :282-288, PI_X = 1100 x 6 */
+		block [local ++] = (k & 3) < 2 ? fic [in ++] : 0;
+	if (k_viterbi (768, block, bits768)) return -1;     /* :293 */
+	orc_prbs (prbs, 768);
+	for (int i = 0; i < 768; i ++) bits768 [i] ^= prbs [i];   /* :301-302 */
+	for (int i = 0; i < 3; i ++) crc_ok [i] = (uint8_t) orc_check_crc (&bits768 [256 * i], 256);  /* :310-312 */
+	return 0;
+}
+
+/* ---- time de-interleaver: dab-concurrent.cpp:41-43, 162-169 ---- */
+static const int8_t interleave_delays [16] = { 15, 7, 11, 3, 13, 5, 9, 1, 14, 6, 10, 2, 12, 4, 8, 0 };
+
+typedef struct { int fragmentSize; int16_t *hist; } deint_t;      /* hist[i][16] shift registers */
+static deint_t *deint_new (int fragmentSize) {
+	deint_t *d = (deint_t *) malloc (sizeof (deint_t));
+	d -> fragmentSize = fragmentSize;
+	d -> hist = (int16_t *) calloc ((size_t) fragmentSize * 16, sizeof (int16_t));
+	return d;
+}
+static void deint_free (deint_t *d) { free (d -> hist); free (d); }
+static void deint_step (deint_t *d, int16_t *Data) {                /* in place, like the reference */
+	for (int i = 0; i < d -> fragmentSize; i ++) {
+		int16_t *h = &d -> hist [16 * (size_t) i];
+		const int dl = interleave_delays [i & 017];
+		h [dl] = Data [i];
+		Data [i] = h [0];
+		memmove (&h [0], &h [1], dl * sizeof (int16_t));
+	}
+}
+
+void orc_time_deinterleave (const int16_t *in, int ncif, int fragmentSize, int16_t *out) {
+	deint_t *d = deint_new (fragmentSize);
+	for (int t = 0; t < ncif; t ++) {
+		memcpy (&out [(size_t) t * fragmentSize], &in [(size_t) t * fragmentSize], sizeof (int16_t) * fragmentSize);
+		deint_step (d, &out [(size_t) t * fragmentSize]);
+	}
+	deint_free (d);
+}
+
+/* ---- MSC back end: dab-concurrent.cpp:144-193 ---- */
+int orc_msc_backend (const int16_t *in, int ncif, int fragmentSize, int bitRate, int uepFlag,
+                     int protLevel, uint8_t *out) {
+	k_prot *prot = k_prot_new (bitRate, uepFlag, protLevel);
+	if (!prot) return -1;
+	deint_t *d = deint_new (fragmentSize);
+	int16_t *Data = (int16_t *) malloc (sizeof (int16_t) * fragmentSize);
+	uint8_t *prbs = (uint8_t *) malloc (24 * bitRate);
+	orc_prbs (prbs, 24 * bitRate);
+	int countforInterleaver = 0, nout = 0;
+	for (int t = 0; t < ncif; t ++) {
+		memcpy (Data, &in [(size_t) t * fragmentSize], sizeof (int16_t) * fragmentSize);   /* :161 */
+		deint_step (d, Data);                                                                /* :162-169 */
+		if (countforInterleaver <= 15) { countforInterleaver ++; continue; }                 /* :172-175 */
+		uint8_t *outV = &out [(size_t) nout * 24 * bitRate];
+		k_prot_deconvolve (prot, Data, fragmentSize, outV);                                  /* :177-180 */
+		for (int i = 0; i < 24 * bitRate; i ++) outV [i] ^= prbs [i];                        /* :183-190 */
+		nout ++;
+	}
+	free (prbs); free (Data); deint_free (d); k_prot_free (prot);
+	return nout;
+}
+
+/* ---- FIC regroup over frames: fic-handler.cpp:192-230 ---- */
+int orc_fic_frames (int mode, const int16_t *sym, int nframes, uint8_t *bits, uint8_t *crc_ok) {
+	orc_params p;
+	if (orc_mode_params (mode, &p)) return -1;
+	const int bpb = 2 * p. K;
+	int16_t ofdm_input [2304];
+	int index = 0, ngroups = 0;
+	for (int f = 0; f < nframes; f ++)
+		for (int blkno = 1; blkno < 4; blkno ++) {
+			const int16_t *data = &sym [((size_t) f * (p. L - 1) + (blkno - 1)) * bpb];
+			if (blkno == 1) index = 0;                                    /* :206-209 */
+			for (int i = 0; i < bpb; i ++) {
+				ofdm_input [index ++] = data [i];
+				if (index >= 2304) {                                      /* :213-217 */
+					orc_fic_decode (ofdm_input, &bits [(size_t) ngroups * 768], &crc_ok [(size_t) ngroups * 3]);
+					index = 0;
+					ngroups ++;
+				}
+			}
+		}
+	return ngroups;
+}
+
+/* ---- CIF assembly + sub-channel slice: msc-handler.cpp:125-193 ---- */
+int orc_msc_slice (int mode, const int16_t *sym, int nframes, int startAddr, int Length, int16_t *frag) {
+	orc_params p;
+	if (orc_mode_params (mode, &p) || mode == 3) return -1;     /* Mode III: "cannot happen" branch :70-71 */
+	const int bpb = 2 * p. K;
+	int16_t *cif = (int16_t *) calloc (55296, sizeof (int16_t));
+	int ncif = 0;
+	for (int f = 0; f < nframes; f ++)
+		for (int blkno = 4; blkno < p. L; blkno ++) {
+			const int cur = (blkno - 4) % p. blocksPerCIF;                              /* :133 */
+			memcpy (&cif [cur * bpb], &sym [((size_t) f * (p. L - 1) + (blkno - 1)) * bpb], sizeof (int16_t) * bpb);
+			if (cur < p. blocksPerCIF - 1) continue;                                    /* :181-182 */
+			memcpy (&frag [(size_t) ncif * Length * 64], &cif [startAddr * 64], sizeof (int16_t) * Length * 64);
+			ncif ++;
+		}
+	free (cif);
+	return ncif;
+}
+
+/* ---- OFDM front end ---- */
+struct orc_ofdm { orc_params p; k_ofdm *k; };
+orc_ofdm *orc_ofdm_new (int mode, int threshold, int freqSyncMethod) {
+	orc_ofdm *o = (orc_ofdm *) calloc (1, sizeof (orc_ofdm));
+	if (orc_mode_params (mode, &o -> p)) { free (o); return NULL; }
+	o -> k = k_ofdm_new (&o -> p, threshold, freqSyncMethod);
+	return o;
+}
+void orc_ofdm_free (orc_ofdm *o) { if (o) { k_ofdm_free (o -> k); free (o); } }
+int  orc_fft (float *v, int n, int inverse) { return k_fft (v, n, inverse); }
+int32_t orc_find_index (orc_ofdm *o, const float *v) { return k_find_index (o -> k, v); }
+int  orc_block0 (orc_ofdm *o, const float *v, int flag) { return k_block0 (o -> k, v, flag); }
+void orc_token (orc_ofdm *o, const float *inv, int16_t *ibits) { k_token (o -> k, inv, ibits); }
+void orc_get_phase_reference (orc_ofdm *o, float *out) { k_get_phase_reference (o -> k, out); }
+
+/* oscillator table: ofdm-processor.cpp:76-81 (double cos/sin rounded to float), built once */
+static float *osc_table;
+static const float *oscillator (void) {
+	if (!osc_table) {
+		float *t = (float *) malloc (sizeof (float) * 2 * INPUT_RATE);
+		for (int i = 0; i < INPUT_RATE; i ++) {
+			t [2 * i]     = (float) cos (2.0 * M_PI * i / INPUT_RATE);
+			t [2 * i + 1] = (float) sin (2.0 * M_PI * i / INPUT_RATE);
+		}
+		if (!__sync_bool_compare_and_swap (&osc_table, NULL, t)) free (t);
+	}
+	return osc_table;
+}
+
+/* the ofdmProcessor's sample pump (ofdm-processor.cpp:133-183, 186-240) over an in-memory u8 "rawfile"
+ * (rawfiles.cpp:113-116) */
+typedef struct {
+	const uint8_t *iq; int64_t n, pos;
+	const float *osc; int32_t localPhase; float sLevel;
+} pump_t;
+
+static inline int pump_sample (pump_t *s, int32_t phase, float *re, float *im) {
+	if (s -> pos >= s -> n) return 0;                 /* the reference blocks/throws here (:135-145) */
+	const float a = (float) (s -> iq [2 * s -> pos] - 128) / 128.0f;
+	const float b = (float) (s -> iq [2 * s -> pos + 1] - 128) / 128.0f;
+	s -> pos ++;
+	s -> localPhase -= phase;                                           /* :165 */
+	s -> localPhase = (s -> localPhase + INPUT_RATE) % INPUT_RATE;      /* :166 */
+	const float c = s -> osc [2 * s -> localPhase], d = s -> osc [2 * s -> localPhase + 1];
+	*re = a * c - b * d;                                                /* :167 */
+	*im = a * d + b * c;
+	float ar = *re < 0 ? - *re : *re, ai = *im < 0 ? - *im : *im;
+	s -> sLevel = (float) (0.00001 * (ar + ai) + (1 - 0.00001) * s -> sLevel);   /* :168 */
+	return 1;
+}
+static inline int pump_samples (pump_t *s, float *v, int n, int32_t phase) {
+	if (s -> pos + n > s -> n) return 0;
+	for (int i = 0; i < n; i ++) pump_sample (s, phase, &v [2 * i], &v [2 * i + 1]);
+	return 1;
+}
+
+int orc_ofdm_run (int mode, int threshold, int freqSyncMethod, const uint8_t *iq, int64_t nsamples,
+                  int max_frames, int16_t *sym, orc_frame_info *info) {
+	orc_params p;
+	if (orc_mode_params (mode, &p)) return -1;
+	const int T_u = p. T_u, T_s = p. T_s, T_null = p. T_null, T_F = p. T_F, K = p. K;
+	k_ofdm *dec = k_ofdm_new (&p, threshold, freqSyncMethod);
+	pump_t s = { iq, nsamples, 0, oscillator (), 0, 0 };
+	float *ofdmBuffer = (float *) malloc (sizeof (float) * 2 * 76 * T_s);
+	float *envBuffer = (float *) calloc (32768, sizeof (float));
+	const int syncBufferMask = 32768 - 1;
+	int syncBufferIndex = 0;
+	float currentStrength = 0;
+	int16_t fineCorrector = 0, previous_1 = 1000, previous_2 = 999;
+	int32_t coarseCorrector = 0, counter, startIndex, i;
+	int f2Correction = 1, nframes = 0;
+	float re, im;
+
+	s. sLevel = 0;                                                     /* :271 */
+notSynced:                                                              /* :275-293 */
+	syncBufferIndex = 0; currentStrength = 0; s. sLevel = 0;
+	for (i = 0; i < 20 * T_s; i ++)
+		if (!pump_sample (&s, 0, &re, &im)) goto done;
+	syncBufferIndex = 0; currentStrength = 0;
+	for (i = 0; i < 50; i ++) {
+		if (!pump_sample (&s, 0, &re, &im)) goto done;
+		envBuffer [syncBufferIndex] = (re < 0 ? -re : re) + (im < 0 ? -im : im);
+		currentStrength += envBuffer [syncBufferIndex];
+		syncBufferIndex ++;
+	}
+/* SyncOnNull: :298-317 */
+	counter = 0;
+	while (currentStrength / 50 > 0.40 * s. sLevel) {
+		if (!pump_sample (&s, coarseCorrector + fineCorrector, &re, &im)) goto done;
+		envBuffer [syncBufferIndex] = (re < 0 ? -re : re) + (im < 0 ? -im : im);
+		currentStrength += envBuffer [syncBufferIndex] - envBuffer [(syncBufferIndex - 50) & syncBufferMask];
+		syncBufferIndex = (syncBufferIndex + 1) & syncBufferMask;
+		counter ++;
+		if (counter > T_F) goto notSynced;
+	}
+	counter = 0;
+/* SyncOnEndNull: :322-338 (true magnitude here) */
+	while (currentStrength / 50 < 0.75 * s. sLevel) {
+		if (!pump_sample (&s, coarseCorrector + fineCorrector, &re, &im)) goto done;
+		envBuffer [syncBufferIndex] = hypotf (re, im);
+		currentStrength += envBuffer [syncBufferIndex] - envBuffer [(syncBufferIndex - 50) & syncBufferMask];
+		syncBufferIndex = (syncBufferIndex + 1) & syncBufferMask;
+		counter ++;
+		if (counter > T_null + 50) goto notSynced;
+	}
+SyncOnPhase:                                                            /* :344-381 */
+	if (nframes >= max_frames) goto done;
+	{
+		orc_frame_info fi;
+		memset (&fi, 0, sizeof (fi));
+		fi. pos = s. pos; fi. phase0 = s. localPhase;
+		if (!pump_samples (&s, ofdmBuffer, T_u, coarseCorrector + fineCorrector)) goto done;
+		startIndex = k_find_index (dec, ofdmBuffer);
+		if (startIndex < 0) goto notSynced;
+		memmove (ofdmBuffer, &ofdmBuffer [2 * startIndex], sizeof (float) * 2 * (T_u - startIndex));
+		const int ofdmBufferIndex = T_u - startIndex;
+/* OFDM_PRS: :383-406 */
+		if (!pump_samples (&s, &ofdmBuffer [2 * ofdmBufferIndex], T_u - ofdmBufferIndex,
+		                   coarseCorrector + fineCorrector)) goto done;
+		const int16_t correction = (int16_t) k_block0 (dec, ofdmBuffer, f2Correction);
+		if (f2Correction) {
+			if (correction == 0 && previous_1 == 0 && previous_2 == 0)
+				f2Correction = 0;
+			else if (correction != 100) {
+				coarseCorrector += correction * p. carrierDiff;
+				if (abs (coarseCorrector) > 35 * 1000) coarseCorrector = 0;
+				previous_2 = previous_1;
+				previous_1 = correction;
+			}
+		}
+		fi. startIndex = startIndex; fi. correction = correction;
+		fi. coarse = coarseCorrector; fi. fine = fineCorrector;
+/* OFDM_SYMBOLS: :414-442.  Symbols 1..3 go to the FIC handler, 4..L-1 to the MSC handler; here both
+ * land in sym[frame][symbol-1][2K]. */
+		float fcRe = 0, fcIm = 0;
+		int16_t *fsym = &sym [(size_t) nframes * (p. L - 1) * 2 * K];
+		for (int n = 1; n < p. L; n ++) {
+			if (!pump_samples (&s, ofdmBuffer, T_s, coarseCorrector + fineCorrector)) goto done;
+			for (i = T_u; i < T_s; i ++) {              /* :424-425: FreqCorr += x[i] * conj (x[i - T_u]) */
+				const float a = ofdmBuffer [2 * i], b = ofdmBuffer [2 * i + 1];
+				const float c = ofdmBuffer [2 * (i - T_u)], d = ofdmBuffer [2 * (i - T_u) + 1];
+				fcRe += a * c + b * d;
+				fcIm += b * c - a * d;
+			}
+			k_token (dec, ofdmBuffer, &fsym [(size_t) (n - 1) * 2 * K]);
+		}
+		/* :445-446 fineCorrector (int16) += 0.1 * arg (FreqCorr) / M_PI * (carrierDiff / 2) */
+		fineCorrector = (int16_t) ((double) fineCorrector +
+		                           0.1 * atan2f (fcIm, fcRe) / M_PI * (p. carrierDiff / 2));
+		fi. freqCorrRe = fcRe; fi. freqCorrIm = fcIm;
+		info [nframes] = fi;
+		nframes ++;
+		syncBufferIndex = 0; currentStrength = 0;
+		/* :453: skip the null symbol (the frame is complete even if the stream ends inside it) */
+		if (!pump_samples (&s, ofdmBuffer, T_null, coarseCorrector + fineCorrector)) goto done;
+		if (fineCorrector > p. carrierDiff / 2) {        /* :458-465 */
+			coarseCorrector += p. carrierDiff; fineCorrector -= p. carrierDiff;
+		} else if (fineCorrector < - p. carrierDiff / 2) {
+			coarseCorrector -= p. carrierDiff; fineCorrector += p. carrierDiff;
+		}
+	}
+	goto SyncOnPhase;
+done:
+	free (envBuffer); free (ofdmBuffer); k_ofdm_free (dec);
+	return nframes;
+}

@@ -1,0 +1,209 @@
+"""ctypes binding of the CPU oracle (oracle/dab_oracle.h).  TEST INFRASTRUCTURE ONLY.
+
+Two builds export the same API: ``oracle/_build/liboracle.so`` (plain-C restatement, kind "port") and
+``oracle/_ref/libdabref.so`` (Tier-A/B = the reference's own classes compiled unmodified, kind "reference").
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("dabMode", "L", "K", "T_null", "T_F", "T_s", "T_u", "T_g", "carrierDiff",
+                                         "ficSymbols", "ficGroups", "cifsPerFrame", "blocksPerCIF")]
+
+
+class FrameInfo(C.Structure):
+    _fields_ = [("pos", C.c_int64), ("startIndex", C.c_int32), ("coarse", C.c_int32), ("fine", C.c_int32),
+                ("phase0", C.c_int32), ("correction", C.c_int32), ("freqCorrRe", C.c_float), ("freqCorrIm", C.c_float)]
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def build(target="all"):
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, target], check=True)
+
+
+class Oracle:
+    def __init__(self, kind="port"):
+        path = os.path.join(ORACLE_DIR, "_build", "liboracle.so") if kind == "port" else \
+            os.path.join(ORACLE_DIR, "_ref", "libdabref.so")
+        if not os.path.exists(path):
+            build("port" if kind == "port" else "ref")
+        self.lib = L = C.CDLL(path)
+        L.orc_build_kind.restype = C.c_char_p
+        L.orc_phi.restype = C.c_float
+        L.orc_ofdm_new.restype = C.c_void_p
+        L.orc_ofdm_free.argtypes = [C.c_void_p]
+        L.orc_find_index.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_block0.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_token.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_get_phase_reference.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_ofdm_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+        self.kind = L.orc_build_kind().decode()
+        assert self.kind == ("port" if kind == "port" else "reference")
+
+    # ---- tables ----
+    def mode_params(self, mode):
+        p = Params()
+        if self.lib.orc_mode_params(mode, C.byref(p)) != 0:
+            raise ValueError("bad mode")
+        return p
+
+    def perm_table(self, mode):
+        out = np.zeros(self.mode_params(mode).K, np.int16)
+        assert self.lib.orc_perm_table(mode, _p(out, C.c_int16)) == 0
+        return out
+
+    def phi(self, mode, k):
+        return float(self.lib.orc_phi(mode, k))
+
+    def ref_table(self, mode):
+        out = np.zeros(2 * self.mode_params(mode).T_u, np.float32)
+        assert self.lib.orc_ref_table(mode, _p(out, C.c_float)) == 0
+        return out.view(np.complex64)
+
+    def pcode(self, n):
+        out = np.zeros(32, np.int8)
+        assert self.lib.orc_pcode(n, _p(out, C.c_int8)) == 0
+        return out
+
+    def uep_profile(self, bitRate, protLevel):
+        L = np.zeros(4, np.int16); PI = np.zeros(4, np.int16)
+        if self.lib.orc_uep_profile(bitRate, protLevel, _p(L, C.c_int16), _p(PI, C.c_int16)) != 0:
+            return None
+        return L, PI
+
+    def eep_profile(self, bitRate, protLevel):
+        L = np.zeros(2, np.int16); PI = np.zeros(2, np.int16)
+        if self.lib.orc_eep_profile(bitRate, protLevel, _p(L, C.c_int16), _p(PI, C.c_int16)) != 0:
+            return None
+        return L, PI
+
+    # ---- channel decoding ----
+    def viterbi(self, frameBits, soft):
+        soft = np.ascontiguousarray(soft, np.int16)
+        assert soft.size == 4 * (frameBits + 6)
+        out = np.zeros(frameBits, np.uint8)
+        assert self.lib.orc_viterbi(frameBits, _p(soft, C.c_int16), _p(out, C.c_uint8)) == 0
+        return out
+
+    def eep_deconvolve(self, bitRate, protLevel, v):
+        v = np.ascontiguousarray(v, np.int16)
+        out = np.zeros(24 * bitRate, np.uint8)
+        assert self.lib.orc_eep_deconvolve(bitRate, protLevel, _p(v, C.c_int16), v.size, _p(out, C.c_uint8)) == 0
+        return out
+
+    def uep_deconvolve(self, bitRate, protLevel, v):
+        v = np.ascontiguousarray(v, np.int16)
+        out = np.zeros(24 * bitRate, np.uint8)
+        assert self.lib.orc_uep_deconvolve(bitRate, protLevel, _p(v, C.c_int16), v.size, _p(out, C.c_uint8)) == 0
+        return out
+
+    def fic_decode(self, soft2304):
+        v = np.ascontiguousarray(soft2304, np.int16)
+        assert v.size == 2304
+        bits = np.zeros(768, np.uint8); crc = np.zeros(3, np.uint8)
+        assert self.lib.orc_fic_decode(_p(v, C.c_int16), _p(bits, C.c_uint8), _p(crc, C.c_uint8)) == 0
+        return bits, crc
+
+    def check_crc(self, bits):
+        b = np.ascontiguousarray(bits, np.uint8)
+        return bool(self.lib.orc_check_crc(_p(b, C.c_uint8), b.size))
+
+    def prbs(self, n):
+        out = np.zeros(n, np.uint8)
+        self.lib.orc_prbs(_p(out, C.c_uint8), n)
+        return out
+
+    def msc_backend(self, frags, bitRate, uepFlag, protLevel):
+        frags = np.ascontiguousarray(frags, np.int16)
+        ncif, fragmentSize = frags.shape
+        out = np.zeros((max(ncif - 16, 0), 24 * bitRate), np.uint8)
+        n = self.lib.orc_msc_backend(_p(frags, C.c_int16), ncif, fragmentSize, bitRate, uepFlag, protLevel,
+                                     _p(out, C.c_uint8))
+        assert n == out.shape[0], n
+        return out
+
+    def time_deinterleave(self, frags):
+        frags = np.ascontiguousarray(frags, np.int16)
+        out = np.zeros_like(frags)
+        self.lib.orc_time_deinterleave(_p(frags, C.c_int16), frags.shape[0], frags.shape[1], _p(out, C.c_int16))
+        return out
+
+    def fic_frames(self, mode, sym):
+        p = self.mode_params(mode)
+        sym = np.ascontiguousarray(sym, np.int16)
+        nframes = sym.shape[0]
+        bits = np.zeros((nframes * p.ficGroups, 768), np.uint8)
+        crc = np.zeros((nframes * p.ficGroups, 3), np.uint8)
+        n = self.lib.orc_fic_frames(mode, _p(sym, C.c_int16), nframes, _p(bits, C.c_uint8), _p(crc, C.c_uint8))
+        assert n == bits.shape[0]
+        return bits, crc
+
+    def msc_slice(self, mode, sym, startAddr, Length):
+        p = self.mode_params(mode)
+        sym = np.ascontiguousarray(sym, np.int16)
+        nframes = sym.shape[0]
+        frag = np.zeros((nframes * p.cifsPerFrame, Length * 64), np.int16)
+        n = self.lib.orc_msc_slice(mode, _p(sym, C.c_int16), nframes, startAddr, Length, _p(frag, C.c_int16))
+        assert n == frag.shape[0]
+        return frag
+
+    # ---- OFDM ----
+    def fft(self, v, inverse=False):
+        a = np.ascontiguousarray(v, np.complex64).copy()
+        assert self.lib.orc_fft(_p(a, C.c_float), a.size, int(inverse)) == 0
+        return a
+
+    def ofdm(self, mode, threshold=3, freqSyncMethod=1):
+        return _Ofdm(self, mode, threshold, freqSyncMethod)
+
+    def ofdm_run(self, mode, iq_u8, max_frames, threshold=3, freqSyncMethod=1):
+        p = self.mode_params(mode)
+        iq = np.ascontiguousarray(iq_u8, np.uint8)
+        sym = np.zeros((max_frames, p.L - 1, 2 * p.K), np.int16)
+        info = (FrameInfo * max_frames)()
+        n = self.lib.orc_ofdm_run(mode, threshold, freqSyncMethod, iq.ctypes.data, iq.size // 2, max_frames,
+                                  sym.ctypes.data, C.addressof(info))
+        return sym[:n], [info[i] for i in range(n)]
+
+
+class _Ofdm:
+    def __init__(self, orc, mode, threshold, method):
+        self.lib = orc.lib
+        self.p = orc.mode_params(mode)
+        self.h = self.lib.orc_ofdm_new(mode, threshold, method)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.orc_ofdm_free(self.h)
+            self.h = None
+
+    def find_index(self, v):
+        a = np.ascontiguousarray(v, np.complex64)
+        assert a.size == self.p.T_u
+        return int(self.lib.orc_find_index(self.h, a.ctypes.data))
+
+    def block0(self, v, flag=True):
+        a = np.ascontiguousarray(v, np.complex64)
+        assert a.size == self.p.T_u
+        return int(self.lib.orc_block0(self.h, a.ctypes.data, int(flag)))
+
+    def token(self, inv):
+        a = np.ascontiguousarray(inv, np.complex64)
+        assert a.size == self.p.T_s
+        out = np.zeros(2 * self.p.K, np.int16)
+        self.lib.orc_token(self.h, a.ctypes.data, out.ctypes.data)
+        return out
+
+    def phase_reference(self):
+        out = np.zeros(self.p.T_u, np.complex64)
+        self.lib.orc_get_phase_reference(self.h, out.ctypes.data)
+        return out
