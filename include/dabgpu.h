@@ -1,0 +1,166 @@
+/*
+ * dabgpu.h -- C ABI of the B200-native DAB baseband decode engine (libdabgpu.so).
+ *
+ * This is the drop-in boundary for the reference's decode hot path (AlbrechtL/sdr-j-dab 0.997).  The
+ * reference has no plugin/FFI mechanism: its "API" is C++ class composition (gui.cpp:160-179), so every
+ * entry point below names the reference member function it replaces (file:line relative to the reference
+ * tree).  sdr-j-dab_b200/host/dab_adapters.h wraps these calls in classes with the reference's names and
+ * signatures; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; buffers are caller owned HOST memory unless the name ends in _dev
+ *     (then they are device pointers on the handle's device and the call is asynchronous on the handle's
+ *     stream until dabgpu_sync);
+ *   - every function returns 0 on success or a negative dabgpu_status; text via dabgpu_last_error();
+ *     nothing throws across the ABI; there is NO CPU fallback: without a usable CUDA device
+ *     dabgpu_create fails with DABGPU_ERR_CUDA;
+ *   - a handle is not re-entrant (like the reference's viterbi objects, viterbi.h:48-66); several handles
+ *     may be used concurrently;
+ *   - soft bits: int16 in [-127,127], positive = bit 1, 0 = erasure (viterbi.cpp:229-235);
+ *     decoded bits: one bit per uint8 (viterbi.cpp:240-241).
+ */
+#ifndef DABGPU_H
+#define DABGPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dabgpu dabgpu_t;
+
+typedef enum {
+	DABGPU_OK          =  0,
+	DABGPU_ERR_ARG     = -1,   /* bad argument / unsupported parameter combination      */
+	DABGPU_ERR_CUDA    = -2,   /* CUDA runtime error (see dabgpu_last_error)             */
+	DABGPU_ERR_PROFILE = -3,   /* unknown UEP/EEP protection profile                     */
+	DABGPU_ERR_NOMEM   = -4,
+	DABGPU_ERR_STATE   = -5    /* call sequence error (e.g. token before block0)         */
+} dabgpu_status;
+
+typedef struct {
+	int32_t device;            /* CUDA device ordinal                                              */
+	int32_t dabMode;           /* 1..4 (DabParams.dabMode, gui.cpp:1328-1372)                      */
+	int32_t threshold;         /* phaseReference level, default 3 (gui.cpp:98-99)                  */
+	int32_t freqSyncMethod;    /* 0,1,2 as ofdmDecoder (main.cpp:91 default 1)                     */
+	int32_t reserved [4];
+} dabgpu_config;
+
+/* one MSC sub-channel, the fields of audiodata/packetdata the decode path uses (dab-constants.h:151-175;
+ * msc-handler.cpp:91-105).  uepFlag keeps the reference's inverted meaning: 0 = UEP table, else EEP;
+ * protLevel for EEP is 0100+level (A) / 0200+level (B) (fib-processor.cpp:313,330). */
+typedef struct {
+	int32_t startAddr;         /* first capacity unit (CU = 64 soft bits)                          */
+	int32_t length;            /* size in CUs; fragmentSize = length * 64                          */
+	int32_t bitRate;           /* kbit/s; decoded block = 24 * bitRate bits per CIF                */
+	int32_t uepFlag;
+	int32_t protLevel;
+} dabgpu_subch;
+
+int  dabgpu_create (const dabgpu_config *cfg, dabgpu_t **out);
+void dabgpu_destroy (dabgpu_t *h);
+const char *dabgpu_last_error (const dabgpu_t *h);      /* h may be NULL: error of the last failed create */
+int  dabgpu_sync (dabgpu_t *h);                          /* wait for the handle's stream                   */
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t dabgpu_launch_count (const dabgpu_t *h);
+/* CUDA-event stopwatch on the handle's stream: begin records an event, end records a second one, waits for
+ * it and returns the device time between them in milliseconds */
+int  dabgpu_timer_begin (dabgpu_t *h);
+int  dabgpu_timer_end (dabgpu_t *h, float *ms);
+
+/* ------------------------------------------------------------------------------------------------
+ * Channel decoding (Viterbi group)
+ * ---------------------------------------------------------------------------------------------- */
+/* viterbi::deconvolve (viterbi.cpp:225-242) on nblocks independent terminated code words:
+ * soft[nblocks][4*(frameBits+6)] -> bits[nblocks][frameBits] */
+int dabgpu_viterbi (dabgpu_t *h, const int16_t *soft, int32_t frameBits, int32_t nblocks, uint8_t *bits);
+int dabgpu_viterbi_dev (dabgpu_t *h, const int16_t *soft, int32_t frameBits, int32_t nblocks, uint8_t *bits);
+
+/* eep_deconvolve::deconvolve / uep_deconvolve::deconvolve (deconvolve.cpp:338-366 / 186-237): depuncture +
+ * Viterbi, NO energy dispersal.  v[nblocks][size] -> bits[nblocks][24*bitRate]; size >= the number of
+ * punctured bits of the profile (the reference ignores it, deconvolve.cpp:184). */
+int dabgpu_protect_decode (dabgpu_t *h, int32_t bitRate, int32_t uepFlag, int32_t protLevel,
+                           const int16_t *v, int32_t size, int32_t nblocks, uint8_t *bits);
+
+/* ficHandler::process_ficInput (fic-handler.cpp:241-321) on ngroups 2304-soft-bit FIC code words:
+ * depuncture (21xPI_16, 3xPI_15, PI_X), Viterbi(768), PRBS, CRC of the three FIBs.
+ * soft[ngroups][2304] -> bits[ngroups][768], crc_ok[ngroups][3] (crc_ok may be NULL) */
+int dabgpu_fic_decode (dabgpu_t *h, const int16_t *soft, int32_t ngroups, uint8_t *bits, uint8_t *crc_ok);
+
+/* dabConcurrent::run (dab-concurrent.cpp:144-193) for one sub-channel over ncif consecutive CIF fragments:
+ * 16-CIF time de-interleaving, 16-CIF warm-up skip, eep/uep depuncture + Viterbi, energy dispersal.
+ * A backend object carries the de-interleaver history across calls like the reference object does.
+ * frags[ncif][fragmentSize] -> out[*nout][24*bitRate]; *nout = blocks produced (ncif minus what the warm-up
+ * swallowed). */
+typedef struct dabgpu_backend dabgpu_backend_t;
+int  dabgpu_backend_create (dabgpu_t *h, const dabgpu_subch *sc, dabgpu_backend_t **out);
+void dabgpu_backend_destroy (dabgpu_backend_t *b);
+int  dabgpu_backend_process (dabgpu_backend_t *b, const int16_t *frags, int32_t ncif, uint8_t *out, int32_t *nout);
+/* the de-interleaver state (the multi-GPU halo): the last 15 fragments seen plus the warm-up counter.
+ * hist[15][fragmentSize], oldest first. */
+int  dabgpu_backend_get_state (dabgpu_backend_t *b, int16_t *hist, int32_t *cifs_seen);
+int  dabgpu_backend_set_state (dabgpu_backend_t *b, const int16_t *hist, int32_t cifs_seen);
+
+/* ------------------------------------------------------------------------------------------------
+ * OFDM front end (FFT + demod group), per-call parity entry points
+ * ---------------------------------------------------------------------------------------------- */
+/* phaseReference::findIndex (phasereference.cpp:60-88) on n windows v[n][T_u] (interleaved re,im):
+ * idx[i] = index of the correlation peak, or the reference's negative code when below threshold */
+int dabgpu_find_index (dabgpu_t *h, const float *v, int32_t n, int32_t *idx);
+/* ofdmDecoder::processBlock_0 (ofdm-decoder.cpp:85-162): v[T_u] is the PRS block; sets the handle's phase
+ * reference; *correction = coarse offset in carriers (100 = not found; 0 when flag == 0) */
+int dabgpu_block0 (dabgpu_t *h, const float *v, int32_t flag, int16_t *correction);
+/* ofdmDecoder::processToken (ofdm-decoder.cpp:167-207) on nsym CONSECUTIVE symbols inv[nsym][T_s]:
+ * ibits[nsym][2K]; the phase reference advances symbol by symbol as in the reference */
+int dabgpu_token (dabgpu_t *h, const float *inv, int32_t nsym, int16_t *ibits);
+/* copy of the current phaseReference[T_u] (tests) */
+int dabgpu_get_phase_reference (dabgpu_t *h, float *out);
+/* common_fft::do_FFT / common_ifft::do_IFFT (fft.cpp:53-55, 109-112) on n vectors of T_u complex floats */
+int dabgpu_fft (dabgpu_t *h, float *v, int32_t n, int32_t inverse);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batch decode: ofdmProcessor::run + ficHandler + mscHandler/dabConcurrent over a block of u8 IQ
+ * (ofdm-processor.cpp:247-474; rawfiles.cpp:113-116 sample format).  The handle is a stream: sync/AFC
+ * state, the unconsumed sample tail and the de-interleaver histories persist between calls.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {               /* per decoded frame, what the reference shows on its GUI + replay state */
+	int64_t pos;               /* absolute sample index where SyncOnPhase started reading               */
+	int32_t startIndex;        /* findIndex result                                                      */
+	int32_t coarse, fine;      /* correctors while the data symbols were read                           */
+	int32_t phase0;            /* NCO phase index before the first SyncOnPhase sample                   */
+	int32_t correction;        /* processBlock_0 result                                                 */
+	float   freqCorrRe, freqCorrIm;
+} dabgpu_frame_info;
+
+typedef struct {
+	/* capacities (in), set by the caller */
+	int32_t max_frames;
+	/* outputs; any pointer may be NULL to skip that output */
+	int32_t nframes;           /* frames decoded by this call                                           */
+	dabgpu_frame_info *info;   /* [max_frames]                                                          */
+	int16_t *soft;             /* [max_frames][L-1][2K] soft bits as handed to process_fic/mscBlock     */
+	uint8_t *fic_bits;         /* [max_frames*ficGroups][768]                                           */
+	uint8_t *fic_crc;          /* [max_frames*ficGroups][3]                                             */
+	uint8_t **msc_bits;        /* [nsub] -> [max_frames*cifsPerFrame][24*bitRate]                       */
+	int32_t *msc_nblocks;      /* [nsub] blocks written per sub-channel                                 */
+	int64_t consumed;          /* samples of this call's input consumed (rest is kept in the handle)    */
+} dabgpu_result;
+
+int dabgpu_set_subchannels (dabgpu_t *h, const dabgpu_subch *sc, int32_t nsub);   /* set_audioChannel x nsub */
+int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out);
+int dabgpu_reset (dabgpu_t *h);                                                   /* ofdmProcessor::reset  */
+
+/* stream state for splitting a recording across calls / GPUs */
+typedef struct {
+	int32_t synced;            /* 0 = acquisition (notSynced), 1 = tracking (SyncOnPhase)               */
+	int32_t coarse, fine, f2Correction, previous_1, previous_2, localPhase;
+	int64_t abs_pos;           /* absolute index of the next sample to read                             */
+	int64_t frames, cifs;
+} dabgpu_stream_state;
+int dabgpu_state_get (dabgpu_t *h, dabgpu_stream_state *s);
+int dabgpu_state_set (dabgpu_t *h, const dabgpu_stream_state *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

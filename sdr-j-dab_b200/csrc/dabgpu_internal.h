@@ -1,0 +1,105 @@
+// dabgpu_internal.h -- shared declarations of libdabgpu.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/dabgpu.h"
+
+#define DAB_INPUT_RATE 2048000          // includes/dab-constants.h:79
+
+struct DabParams {                      // gui.cpp:1328-1372 + derived geometry
+	int dabMode, L, K, T_null, T_F, T_s, T_u, T_g, carrierDiff;
+	int ficGroups, cifsPerFrame, blocksPerCIF;
+};
+int dab_mode_params (int mode, DabParams *p);
+
+// growable device / pinned-host buffers
+struct DevBuf {
+	void *p = nullptr; size_t cap = 0;
+	cudaError_t ensure (size_t bytes) {
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFree (p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaMalloc (&p, want);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release () { if (p) cudaFree (p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+	void *p = nullptr; size_t cap = 0;
+	cudaError_t ensure (size_t bytes) {
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFreeHost (p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaMallocHost (&p, want);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release () { if (p) cudaFreeHost (p); p = nullptr; cap = 0; }
+};
+
+// ---- puncturing / protection profiles (host side, dabgpu_tables.cpp) ----
+// mother-code index -> input index LUT (int16, -1 = punctured/erasure), 4*(frameBits+6) entries
+struct ProtProfile {
+	int frameBits = 0;                  // 24 * bitRate (768 for the FIC)
+	int nPunctured = 0;                 // input soft bits consumed per code word
+	std::vector<int16_t> lut;
+};
+int  prot_build_fic (ProtProfile *pp);                                        // fic-handler.cpp:254-288
+int  prot_build_msc (int bitRate, int uepFlag, int protLevel, ProtProfile *pp); // deconvolve.cpp:142-182, 244-319
+void prbs_packed (int nbits, std::vector<uint32_t> *words);                   // fic-handler.cpp:100-108
+
+// ---- Viterbi group (dabgpu_viterbi.cu) ----
+struct VitJob {
+	const int16_t *in;        // soft-bit source
+	long long in_stride;      // elements between consecutive code words (rows when deint)
+	int first_row;            // deint: buffer row of the CIF decoded by block 0
+	const int16_t *lut;       // device LUT [4*nsteps] or nullptr (identity)
+	int frameBits, nsteps, nblocks;
+	int deint;                // 1: value(idx) is read from row (blk + first_row - D[idx & 15])
+	const uint32_t *prbs;     // packed energy-dispersal sequence or nullptr
+	uint8_t *out;             // [nblocks][frameBits], one bit per byte
+};
+cudaError_t vit_launch (const VitJob &job, cudaStream_t st, int64_t *launches);
+cudaError_t fib_crc_launch (const uint8_t *bits, int nfibs, uint8_t *ok, cudaStream_t st, int64_t *launches);
+
+struct dabgpu {
+	int device = 0;
+	dabgpu_config cfg {};
+	DabParams p {};
+	cudaStream_t stream = nullptr;
+	std::string err;
+	int64_t launches = 0;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	// staging
+	DevBuf d_in, d_out, d_aux;
+	PinBuf h_in, h_out;
+	// cached device tables
+	std::map<long long, void *> d_tables;          // key -> device pointer (LUTs, PRBS)
+	std::map<long long, ProtProfile> profiles;
+};
+
+extern thread_local std::string g_create_error;
+int  dab_fail (dabgpu *h, int code, const char *fmt, ...);
+#define CUDA_TRY(h, expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) \
+	return dab_fail ((h), DABGPU_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString (e__), __FILE__, __LINE__); } while (0)
+
+// device copy of a host table, cached in the handle under `key`
+int  dab_device_table (dabgpu *h, long long key, const void *host, size_t bytes, void **dev);
+int  dab_get_profile (dabgpu *h, int kind /*0 fic, 1 msc*/, int bitRate, int uepFlag, int protLevel,
+                      const ProtProfile **pp, const int16_t **d_lut);
+int  dab_get_prbs (dabgpu *h, int nbits, const uint32_t **d_prbs);
+int  dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, uint8_t *d_crc);
+struct dabgpu_backend;
+int  dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row_stride, int ncif, uint8_t *d_out, int *nout);
+// OFDM / stream engine state (dabgpu_ofdm.cu, dabgpu_engine.cu)
+int  dab_engine_init (dabgpu *h);
+void dab_engine_free (dabgpu *h);
