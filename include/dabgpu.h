@@ -148,6 +148,8 @@ typedef struct {
 
 int dabgpu_set_subchannels (dabgpu_t *h, const dabgpu_subch *sc, int32_t nsub);   /* set_audioChannel x nsub */
 int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out);
+/* same with the input already resident on the handle's device (result pointers stay host pointers) */
+int dabgpu_decode_dev (dabgpu_t *h, const uint8_t *d_iq_u8, size_t nsamples, dabgpu_result *out);
 int dabgpu_reset (dabgpu_t *h);                                                   /* ofdmProcessor::reset  */
 
 /* stream state for splitting a recording across calls / GPUs */

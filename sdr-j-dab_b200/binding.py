@@ -70,8 +70,29 @@ def load_library():
     L.dabgpu_backend_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]
     L.dabgpu_backend_get_state.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     L.dabgpu_backend_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.dabgpu_fft.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    L.dabgpu_find_index.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.dabgpu_block0.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int16)]
+    L.dabgpu_token.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.dabgpu_get_phase_reference.argtypes = [C.c_void_p, C.c_void_p]
+    L.dabgpu_set_subchannels.argtypes = [C.c_void_p, C.POINTER(SubCh), C.c_int32]
+    L.dabgpu_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Result)]
+    L.dabgpu_decode_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Result)]
+    L.dabgpu_reset.argtypes = [C.c_void_p]
+    L.dabgpu_state_get.argtypes = [C.c_void_p, C.POINTER(StreamState)]
+    L.dabgpu_state_set.argtypes = [C.c_void_p, C.POINTER(StreamState)]
     _lib = L
     return L
+
+
+MODE_PARAMS = {  # L, K, T_null, T_F, T_s, T_u, cifsPerFrame (gui.cpp:1328-1372, msc-handler.cpp:61-71)
+    1: (76, 1536, 2656, 196608, 2552, 2048, 4), 2: (76, 384, 664, 49152, 638, 512, 1),
+    3: (153, 192, 345, 49152, 319, 256, 0), 4: (76, 768, 1328, 98304, 1276, 1024, 2)}
+
+
+class DecodeOut:
+    """Host-side result buffers of one dabgpu_decode call."""
+    pass
 
 
 class DabGpu:
@@ -138,6 +159,103 @@ class DabGpu:
         self._check(self.lib.dabgpu_fic_decode(self.h, soft.ctypes.data, soft.shape[0], bits.ctypes.data,
                                                crc.ctypes.data))
         return bits, crc
+
+    # ---- OFDM group, per-call ----
+    def fft(self, v, inverse=False):
+        T_u = MODE_PARAMS[self.mode][5]
+        a = np.ascontiguousarray(v, np.complex64).reshape(-1, T_u).copy()
+        self._check(self.lib.dabgpu_fft(self.h, a.ctypes.data, a.shape[0], int(inverse)))
+        return a
+
+    def find_index(self, v):
+        T_u = MODE_PARAMS[self.mode][5]
+        a = np.ascontiguousarray(v, np.complex64).reshape(-1, T_u)
+        idx = np.empty(a.shape[0], np.int32)
+        self._check(self.lib.dabgpu_find_index(self.h, a.ctypes.data, a.shape[0], idx.ctypes.data))
+        return idx
+
+    def block0(self, v, flag=True):
+        a = np.ascontiguousarray(v, np.complex64)
+        assert a.size == MODE_PARAMS[self.mode][5]
+        c = C.c_int16(0)
+        self._check(self.lib.dabgpu_block0(self.h, a.ctypes.data, int(flag), C.byref(c)))
+        return c.value
+
+    def token(self, inv):
+        L, K, _, _, T_s, _, _ = MODE_PARAMS[self.mode]
+        a = np.ascontiguousarray(inv, np.complex64).reshape(-1, T_s)
+        out = np.empty((a.shape[0], 2 * K), np.int16)
+        self._check(self.lib.dabgpu_token(self.h, a.ctypes.data, a.shape[0], out.ctypes.data))
+        return out
+
+    def phase_reference(self):
+        out = np.empty(MODE_PARAMS[self.mode][5], np.complex64)
+        self._check(self.lib.dabgpu_get_phase_reference(self.h, out.ctypes.data))
+        return out
+
+    # ---- stream decode ----
+    def set_subchannels(self, subs):
+        """subs: list of (startAddr, length, bitRate, uepFlag, protLevel)"""
+        self._subs = [SubCh(*s) for s in subs]
+        arr = (SubCh * max(len(subs), 1))(*self._subs)
+        self._check(self.lib.dabgpu_set_subchannels(self.h, arr, len(subs)))
+
+    def alloc_result(self, max_frames, want_soft=True):
+        L, K, _, _, _, _, cpf = MODE_PARAMS[self.mode]
+        subs = getattr(self, "_subs", [])
+        o = DecodeOut()
+        o.max_frames = max_frames
+        o.info = (FrameInfo * max(max_frames, 1))()
+        o.soft = np.zeros((max_frames, L - 1, 2 * K), np.int16) if want_soft else None
+        groups = 3 * 2 * K // 2304
+        o.fic_bits = np.zeros((max_frames * groups, 768), np.uint8)
+        o.fic_crc = np.zeros((max_frames * groups, 3), np.uint8)
+        o.msc = [np.zeros((max_frames * cpf, 24 * s.bitRate), np.uint8) for s in subs]
+        o.ptrs = (C.POINTER(C.c_uint8) * max(len(subs), 1))(*[m.ctypes.data_as(C.POINTER(C.c_uint8)) for m in o.msc])
+        o.nblocks = (C.c_int32 * max(len(subs), 1))()
+        o.res = Result(max_frames=max_frames, nframes=0, info=o.info,
+                       soft=o.soft.ctypes.data_as(C.POINTER(C.c_int16)) if want_soft else None,
+                       fic_bits=o.fic_bits.ctypes.data_as(C.POINTER(C.c_uint8)),
+                       fic_crc=o.fic_crc.ctypes.data_as(C.POINTER(C.c_uint8)),
+                       msc_bits=o.ptrs, msc_nblocks=o.nblocks, consumed=0)
+        return o
+
+    def decode(self, iq_u8, out):
+        """iq_u8: numpy uint8 (interleaved I,Q) or an int host address with `nsamples` given via a tuple"""
+        if isinstance(iq_u8, tuple):
+            ptr, nsamples = iq_u8
+        else:
+            iq = np.ascontiguousarray(iq_u8, np.uint8)
+            ptr, nsamples = iq.ctypes.data, iq.size // 2
+        self._check(self.lib.dabgpu_decode(self.h, ptr, nsamples, C.byref(out.res)))
+        return self._trim(out)
+
+    def decode_dev(self, d_ptr, nsamples, out):
+        self._check(self.lib.dabgpu_decode_dev(self.h, d_ptr, nsamples, C.byref(out.res)))
+        return self._trim(out)
+
+    def _trim(self, o):
+        L, K, _, _, _, _, cpf = MODE_PARAMS[self.mode]
+        n = o.res.nframes
+        groups = 3 * 2 * K // 2304
+        r = DecodeOut()
+        r.nframes, r.consumed = n, o.res.consumed
+        r.info = [o.info[i] for i in range(n)]
+        r.soft = o.soft[:n] if o.soft is not None else None
+        r.fic_bits, r.fic_crc = o.fic_bits[:n * groups], o.fic_crc[:n * groups]
+        r.msc = [m[:o.nblocks[i]] for i, m in enumerate(o.msc)]
+        return r
+
+    def reset(self):
+        self._check(self.lib.dabgpu_reset(self.h))
+
+    def state_get(self):
+        s = StreamState()
+        self._check(self.lib.dabgpu_state_get(self.h, C.byref(s)))
+        return s
+
+    def state_set(self, s):
+        self._check(self.lib.dabgpu_state_set(self.h, C.byref(s)))
 
     def backend(self, startAddr, length, bitRate, uepFlag, protLevel):
         return Backend(self, SubCh(startAddr, length, bitRate, uepFlag, protLevel))

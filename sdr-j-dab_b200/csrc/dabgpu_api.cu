@@ -292,6 +292,8 @@ int dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row
 	return DABGPU_OK;
 }
 
+void dab_backend_note_cifs (dabgpu_backend *b, int ncif) { b -> cifs_seen += ncif; }
+
 extern "C" int dabgpu_backend_process (dabgpu_backend_t *b, const int16_t *frags, int32_t ncif, uint8_t *out, int32_t *nout) {
 	if (!b || !frags || !out || !nout || ncif < 0) return dab_fail (b ? b -> h : nullptr, DABGPU_ERR_ARG, "dabgpu_backend_process: bad argument");
 	dabgpu *h = b -> h;

@@ -1,4 +1,520 @@
-// dabgpu_engine.cu -- stream engine (placeholder until the OFDM group lands)
-#include "dabgpu_internal.h"
-int  dab_engine_init (dabgpu *h) { (void) h; return DABGPU_OK; }
-void dab_engine_free (dabgpu *h) { (void) h; }
+// dabgpu_engine.cu -- the stream engine: ofdmProcessor::run (ofdm-processor.cpp:247-474) re-designed for a
+// frame-parallel GPU, feeding the FIC and MSC decoders (fic-handler.cpp, msc-handler.cpp, dab-concurrent.cpp).
+//
+// The reference loop is sequential through three couplings: the frame position (findIndex of frame n fixes
+// where frame n+1 is read), the NCO phase/frequency (coarse/fine correctors updated once per frame) and the
+// 16-CIF time de-interleaver.  The engine speculates: a pass decodes a chunk of frames in parallel assuming
+// the tracking state stays what it is at the chunk start (start index T_g, correctors unchanged -- the steady
+// state of a locked receiver), then a single-thread scan kernel replays the reference's scalar state machine
+// over the per-frame results (findIndex, coarse correction, cyclic-prefix correlation) and accepts frames up
+// to the first one whose assumed inputs differ from the replayed truth; the next pass restarts there with the
+// true state.  Accepted frames are therefore computed from exactly the inputs the reference would have used.
+// Acquisition (null-symbol search) is a sample-serial scan done once per (re)synchronisation.
+#include <math.h>
+#include "dabgpu_engine.h"
+
+__device__ __forceinline__ uchar2 win_fetch (const SampleWin &w, long long i) {
+	return i < w. len0 ? __ldg (&w. seg0 [i]) : __ldg (&w. seg1 [i - w. len0]);
+}
+
+// dst[i] = sample (first + i) after u8 conversion and NCO, i < n (rawfiles.cpp:113-116; ofdm-processor.cpp:217-226)
+__device__ __forceinline__ void load_win_nco (float2 *dst, const SampleWin &w, long long first, int n,
+                                              int lp_before, int phase, const OfdmTables &T) {
+	const int tid = threadIdx. x;
+	const int ph = mod_rate (phase);
+	int lp = mod_rate ((long long) lp_before - (long long) (tid + 1) * ph);
+	const int step = mod_rate ((long long) OFDM_THREADS * ph);
+	for (int i = tid; i < n; i += OFDM_THREADS) {
+		const uchar2 s = win_fetch (w, first + i);
+		const float2 v = make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f));
+		dst [i] = cmul (v, nco (T, lp));
+		lp -= step;
+		if (lp < 0) lp += DAB_INPUT_RATE;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// acquisition: notSynced -> SyncOnNull -> SyncOnEndNull (ofdm-processor.cpp:275-338), one warp.
+// Lanes convert / mix a chunk of samples in parallel, lane 0 runs the sample-serial recurrences
+// (signal level IIR, 50-sample envelope window, thresholds) exactly in the reference's order.
+// ---------------------------------------------------------------------------------------------------
+#define ACQ_CHUNK 256
+__global__ void __launch_bounds__ (32) acquire_kernel (SampleWin w, OfdmTables T, int T_F, int T_null, StreamCtl *ctl) {
+	__shared__ float s_ja [ACQ_CHUNK], s_ha [ACQ_CHUNK];
+	__shared__ int s_n, s_phase, s_lp, s_done;
+	__shared__ long long s_pos;
+	const int lane = threadIdx. x;
+	const long long total = w. len0 + w. len1;
+	// lane-0 state
+	int stage = 0, cnt = 0, counter = 0, idx = 0;
+	float sLevel = 0.f, cs = 0.f, env [64];
+	long long attempt_pos = ctl -> pos; int attempt_lp = ctl -> lp;
+	const int phi = ctl -> coarse + ctl -> fine;
+	if (lane == 0) { s_pos = attempt_pos; s_lp = attempt_lp; s_done = 0; }
+	__syncwarp ();
+	while (true) {
+		if (lane == 0) {
+			int n;                                        // samples until the NCO frequency can change
+			if (stage == 0) n = 20 * T. T_s - cnt + 50;
+			else if (stage == 1) n = 50 - cnt;
+			else if (stage == 2) n = T_F + 1 - counter;
+			else n = T_null + 51 - counter;
+			if (n > ACQ_CHUNK) n = ACQ_CHUNK;
+			if (s_pos + n > total) { s_done = 2; n = 0; }          // out of data: rewind to the attempt start
+			s_n = n; s_phase = stage < 2 ? 0 : phi;
+		}
+		__syncwarp ();
+		if (s_done) break;
+		const int n = s_n, ph = mod_rate (s_phase);
+		{
+			int lp = mod_rate ((long long) s_lp - (long long) (lane + 1) * ph);
+			const int step = mod_rate (32ll * ph);
+			for (int i = lane; i < n; i += 32) {
+				const uchar2 s = win_fetch (w, s_pos + i);
+				const float2 v = cmul (make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f)), nco (T, lp));
+				s_ja [i] = fabsf (v. x) + fabsf (v. y);           // jan_abs
+				s_ha [i] = hypotf (v. x, v. y);                   // abs
+				lp -= step; if (lp < 0) lp += DAB_INPUT_RATE;
+			}
+		}
+		__syncwarp ();
+		if (lane == 0) {
+			int used = n, restart = 0;
+			for (int i = 0; i < n; i ++) {
+				if (stage == 2 && !((double) (cs / 50.0f) > 0.40 * (double) sLevel)) { stage = 3; counter = 0; }   // :301
+				if (stage == 3 && !((double) (cs / 50.0f) < 0.75 * (double) sLevel)) { s_done = 1; used = i; break; }   // :323
+				const float ja = s_ja [i];
+				sLevel = (float) __dadd_rn (__dmul_rn (0.00001, (double) ja), __dmul_rn (1 - 0.00001, (double) sLevel));   // :168
+				if (stage == 0) {
+					if (++ cnt == 20 * T. T_s) { stage = 1; cnt = 0; idx = 0; cs = 0.f; }
+				} else if (stage == 1) {
+					env [idx & 63] = ja; cs = __fadd_rn (cs, ja); idx ++;
+					if (++ cnt == 50) { stage = 2; counter = 0; }
+				} else {
+					const float e = stage == 2 ? ja : s_ha [i];
+					env [idx & 63] = e;
+					cs = __fadd_rn (cs, __fsub_rn (e, env [(idx - 50) & 63]));
+					idx ++;
+					counter ++;
+					if ((stage == 2 && counter > T_F) || (stage == 3 && counter > T_null + 50)) { restart = 1; used = i + 1; break; }
+				}
+			}
+			s_pos += used;
+			s_lp = mod_rate ((long long) s_lp - (long long) used * ph);
+			if (restart) {                                   // goto notSynced (:315, :337)
+				stage = 0; cnt = 0; counter = 0; idx = 0; cs = 0.f; sLevel = 0.f;
+				attempt_pos = s_pos; attempt_lp = s_lp;
+			}
+		}
+		__syncwarp ();
+		if (s_done) break;
+	}
+	if (lane == 0) {
+		if (s_done == 1) { ctl -> synced = 1; ctl -> pos = s_pos; ctl -> lp = s_lp; ctl -> acq_done = 1; }
+		else             { ctl -> synced = 0; ctl -> pos = attempt_pos; ctl -> lp = attempt_lp; ctl -> acq_done = 0; }
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// front kernel, one CTA per frame of the chunk: SyncOnPhase + OFDM_PRS (ofdm-processor.cpp:344-406)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__ (OFDM_THREADS) front_kernel (SampleWin w, OfdmTables T, PassParams pp, int T_F,
+                                                               FrameOut *fo, float2 *spec0) {
+	extern __shared__ float2 sm [];
+	__shared__ float cv [96];
+	const int N = T. T_u, c = blockIdx. x;
+	float2 *a = sm, *b = sm + N;
+	const long long P = pp. pos0 + (long long) c * T_F;
+	const int lpP = mod_rate ((long long) pp. lp0 - (long long) c * T_F % DAB_INPUT_RATE * mod_rate (pp. phiA));
+	load_win_nco (a, w, P, N, lpP, pp. phiA, T);                       // :347-348
+	const int s = find_index_block (a, b, T);                          // :352
+	int corr = 0;
+	if (s >= 0) {
+		// block 0 = the T_u samples from P + s on (:362-388), same NCO run
+		const int lp0 = mod_rate ((long long) lpP - (long long) s * mod_rate (pp. phiA));
+		__syncthreads ();
+		load_win_nco (a, w, P + s, N, lp0, pp. phiA, T);
+		float2 *f = block_fft (a, b, N, T. tw);
+		float2 *g = spec0 + (size_t) c * N;
+		for (int i = threadIdx. x; i < N; i += OFDM_THREADS) g [i] = f [i];   // phaseReference (ofdm-decoder.cpp:91)
+		corr = coarse_offset_warp0 (f, T, cv);                         // always computed; the scan applies the flag
+	}
+	if (threadIdx. x == 0) { fo [c]. startIndex = s; fo [c]. correction = corr; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// symbol kernel, CTA (c, g) = frame c of the chunk, symbol group g: OFDM_SYMBOLS (ofdm-processor.cpp:414-442)
+// with processToken (ofdm-decoder.cpp:167-190) and the cyclic-prefix correlation (:424-425) fused.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__ (OFDM_THREADS) symbol_kernel (SampleWin w, OfdmTables T, PassParams pp, int T_F, int groups,
+                                                                int blocksPerCIF, int cifsPerFrame, const FrameOut *fo,
+                                                                const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc) {
+	extern __shared__ float2 sm [];
+	__shared__ float2 s_fc [OFDM_THREADS / 32];
+	const int N = T. T_u, Ts = T. T_s, Tg = T. T_g, c = blockIdx. x / groups, g = blockIdx. x % groups;
+	const int s = fo [c]. startIndex;
+	if (s < 0) { if (threadIdx. x == 0) fcpart [c * MAX_GROUPS + g] = make_float2 (0.f, 0.f); return; }
+	float2 *symbuf = sm, *scratch = sm + Ts, *prev = sm + Ts + N;
+	const int nsym = T. L - 1, per = (nsym + groups - 1) / groups;
+	const int l0 = 1 + g * per, l1 = min (nsym + 1, l0 + per);             // symbols [l0, l1)
+	const long long P = pp. pos0 + (long long) c * T_F;
+	const int phA = mod_rate (pp. phiA), phiB = c == 0 ? pp. phiB0 : pp. phiA, phB = mod_rate (phiB);
+	const int lpP = mod_rate ((long long) pp. lp0 - (long long) c * T_F % DAB_INPUT_RATE * phA);
+	const long long F = P + s;                                             // first sample of the PRS
+	const int lpD = mod_rate ((long long) lpP - (long long) (s + N) * phA);  // localPhase after the PRS
+	// symbol l (>= 1) occupies samples [F + N + (l-1) Ts, + Ts): guard first, then the useful part
+	if (l0 == 1) {
+		const float2 *p0 = spec0 + (size_t) c * N;
+		for (int i = threadIdx. x; i < N; i += OFDM_THREADS) prev [i] = p0 [i];
+	} else {
+		const long long first = F + N + (long long) (l0 - 2) * Ts + Tg;
+		const int lpb = mod_rate ((long long) lpD - ((long long) (l0 - 2) * Ts + Tg) % DAB_INPUT_RATE * phB);
+		load_win_nco (symbuf, w, first, N, lpb, phiB, T);
+		float2 *f = block_fft (symbuf, scratch, N, T. tw);
+		for (int i = threadIdx. x; i < N; i += OFDM_THREADS) prev [i] = f [i];
+	}
+	float2 acc = make_float2 (0.f, 0.f);
+	const int slot = pp. slot0 + c;
+	for (int l = l0; l < l1; l ++) {
+		const long long first = F + N + (long long) (l - 1) * Ts;
+		const int lpb = mod_rate ((long long) lpD - ((long long) (l - 1) * Ts) % DAB_INPUT_RATE * phB);
+		__syncthreads ();
+		load_win_nco (symbuf, w, first, Ts, lpb, phiB, T);
+		__syncthreads ();
+		for (int i = N + threadIdx. x; i < Ts; i += OFDM_THREADS) {        // FreqCorr += x[i] * conj (x[i - T_u])
+			const float2 r = cmulc (symbuf [i], symbuf [i - N]);
+			acc. x += r. x; acc. y += r. y;
+		}
+		float2 *f = block_fft (symbuf + Tg, scratch, N, T. tw);
+		int16_t *out;
+		if (l < 4) out = fic + ((size_t) slot * 3 + (l - 1)) * 2 * T. K;
+		else {
+			const int m = l - 4;
+			out = msc + ((size_t) 15 + (size_t) slot * cifsPerFrame + m / blocksPerCIF) * CIF_BITS + (size_t) (m % blocksPerCIF) * 2 * T. K;
+		}
+		demod_symbol (f, prev, T, out);
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		acc. x += __shfl_xor_sync (0xffffffffu, acc. x, o);
+		acc. y += __shfl_xor_sync (0xffffffffu, acc. y, o);
+	}
+	if ((threadIdx. x & 31) == 0) s_fc [threadIdx. x >> 5] = acc;
+	__syncthreads ();
+	if (threadIdx. x == 0) {
+		float2 t = make_float2 (0.f, 0.f);
+		for (int k = 0; k < OFDM_THREADS / 32; k ++) { t. x += s_fc [k]. x; t. y += s_fc [k]. y; }
+		fcpart [c * MAX_GROUPS + g] = t;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// scan kernel (one thread): the scalar state machine of ofdmProcessor::run replayed over the chunk
+// ---------------------------------------------------------------------------------------------------
+__global__ void scan_kernel (StreamCtl *ctl, PassParams pp, int groups, DabParams dp, const FrameOut *fo,
+                             const float2 *fcpart, dabgpu_frame_info *info, long long abs_base) {
+	if (threadIdx. x != 0 || blockIdx. x != 0) return;
+	StreamCtl s = *ctl;
+	const int cd = dp. carrierDiff;
+	s. n_valid = 0; s. lost = 0; s. override_valid = 0;
+	for (int c = 0; c < pp. nframes; c ++) {
+		const long long Pa = pp. pos0 + (long long) c * dp. T_F;
+		const int lpa = mod_rate ((long long) pp. lp0 - (long long) c * dp. T_F % DAB_INPUT_RATE * mod_rate (pp. phiA));
+		if (c > 0 && (s. pos != Pa || s. lp != lpa || s. coarse + s. fine != pp. phiA)) break;   // speculation failed here
+		const int si = fo [c]. startIndex;
+		const int phiA = s. coarse + s. fine;
+		if (si < 0) {                                        // :353-356 -> notSynced; T_u samples were consumed
+			s. pos += dp. T_u;
+			s. lp = mod_rate ((long long) s. lp - (long long) dp. T_u * mod_rate (phiA));
+			s. synced = 0; s. lost = 1;
+			break;
+		}
+		StreamCtl before = s;
+		int correction = 0;
+		if (s. f2) {                                         // :390-405
+			correction = fo [c]. correction;
+			if (correction == 0 && s. prev1 == 0 && s. prev2 == 0) s. f2 = 0;
+			else if (correction != 100) {
+				s. coarse += correction * cd;
+				if (abs (s. coarse) > 35000) s. coarse = 0;
+				s. prev2 = s. prev1; s. prev1 = correction;
+			}
+		}
+		const int phiB = s. coarse + s. fine;
+		const int usedB = c == 0 ? pp. phiB0 : pp. phiA;
+		if (phiB != usedB) {                                 // the data symbols were mixed with the wrong frequency: redo
+			s = before; s. override_valid = 1; s. override_phiB = phiB;
+			break;
+		}
+		float2 fc = make_float2 (0.f, 0.f);
+		for (int g = 0; g < groups; g ++) { fc. x += fcpart [c * MAX_GROUPS + g]. x; fc. y += fcpart [c * MAX_GROUPS + g]. y; }
+		dabgpu_frame_info fi;
+		fi. pos = abs_base + s. pos; fi. startIndex = si; fi. coarse = s. coarse; fi. fine = s. fine;
+		fi. phase0 = s. lp; fi. correction = correction; fi. freqCorrRe = fc. x; fi. freqCorrIm = fc. y;
+		info [pp. slot0 + c] = fi;
+		// :445-446  fineCorrector (int16) += 0.1 * arg (FreqCorr) / M_PI * (carrierDiff / 2)
+		const double inc = __dmul_rn (__ddiv_rn (__dmul_rn (0.1, (double) atan2f (fc. y, fc. x)), 3.14159265358979323846), (double) (cd / 2));
+		s. fine = (int) (short) __double2int_rz (__dadd_rn ((double) s. fine, inc));
+		const int phiC = s. coarse + s. fine;
+		long long lp = (long long) s. lp - (long long) (si + dp. T_u) * mod_rate (phiA);
+		lp -= ((long long) (dp. L - 1) * dp. T_s) % DAB_INPUT_RATE * mod_rate (phiB);
+		lp -= (long long) dp. T_null * mod_rate (phiC);                // :453
+		s. lp = mod_rate (lp);
+		s. pos += si + dp. T_u + (long long) (dp. L - 1) * dp. T_s + dp. T_null;
+		if (s. fine > cd / 2) { s. coarse += cd; s. fine -= cd; }      // :458-465
+		else if (s. fine < - cd / 2) { s. coarse -= cd; s. fine += cd; }
+		s. n_valid = c + 1;
+	}
+	*ctl = s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+int dab_engine_init (dabgpu *h) {
+	Engine *E = new Engine ();
+	h -> engine = E;
+	int rc = ofdm_tables_init (h, &E -> T);
+	if (rc) return rc;
+	CUDA_TRY (h, cudaMalloc ((void **) &E -> d_phaseRef, (size_t) h -> p. T_u * sizeof (float2)));
+	CUDA_TRY (h, E -> d_ctl. ensure (sizeof (StreamCtl)));
+	CUDA_TRY (h, E -> h_ctl. ensure (sizeof (StreamCtl)));
+	memset (&E -> ctl, 0, sizeof (StreamCtl));
+	E -> ctl. f2 = 1; E -> ctl. prev1 = 1000; E -> ctl. prev2 = 999;     // ofdm-processor.cpp:258-259, 73
+	E -> groups = h -> p. L > 100 ? 8 : 5;
+	const int big = 100 * 1024;
+	CUDA_TRY (h, cudaFuncSetAttribute (front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	CUDA_TRY (h, cudaFuncSetAttribute (symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	return DABGPU_OK;
+}
+
+void dab_engine_free (dabgpu *h) {
+	Engine *E = h -> engine;
+	if (!E) return;
+	for (auto *b : E -> backends) dabgpu_backend_destroy (b);
+	if (E -> d_phaseRef) cudaFree (E -> d_phaseRef);
+	E -> tail. release (); E -> d_ctl. release (); E -> h_ctl. release ();
+	E -> d_frameout. release (); E -> d_fcpart. release (); E -> d_spec0. release (); E -> d_info. release ();
+	E -> d_fic. release (); E -> d_msc. release (); E -> d_histtmp. release ();
+	E -> d_ficbits. release (); E -> d_ficcrc. release ();
+	for (auto &b : E -> d_mscbits) b. release ();
+	delete E;
+	h -> engine = nullptr;
+}
+
+extern "C" int dabgpu_reset (dabgpu_t *h) {                 // ofdmProcessor::reset (ofdm-processor.cpp:476-479)
+	if (!h) return DABGPU_ERR_ARG;
+	h -> engine -> ctl. fine = h -> engine -> ctl. coarse = 0;
+	h -> engine -> ctl. f2 = 1;
+	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_set_subchannels (dabgpu_t *h, const dabgpu_subch *sc, int32_t nsub) {
+	if (!h || nsub < 0 || (nsub > 0 && !sc)) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_set_subchannels: bad argument");
+	Engine *E = h -> engine;
+	std::vector<dabgpu_backend *> nb;
+	for (int i = 0; i < nsub; i ++) {
+		dabgpu_backend *b = nullptr;
+		int rc = dabgpu_backend_create (h, &sc [i], &b);
+		if (rc) { for (auto *x : nb) dabgpu_backend_destroy (x); return rc; }
+		nb. push_back (b);
+	}
+	for (auto *b : E -> backends) dabgpu_backend_destroy (b);
+	E -> backends = nb;
+	E -> subch. assign (sc, sc + nsub);
+	for (auto &b : E -> d_mscbits) b. release ();
+	E -> d_mscbits. assign (nsub, DevBuf ());
+	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_state_get (dabgpu_t *h, dabgpu_stream_state *s) {
+	if (!h || !s) return DABGPU_ERR_ARG;
+	const Engine *E = h -> engine;
+	s -> synced = E -> ctl. synced; s -> coarse = E -> ctl. coarse; s -> fine = E -> ctl. fine;
+	s -> f2Correction = E -> ctl. f2; s -> previous_1 = E -> ctl. prev1; s -> previous_2 = E -> ctl. prev2;
+	s -> localPhase = E -> ctl. lp; s -> abs_pos = E -> abs_base + E -> ctl. pos;
+	s -> frames = E -> frames_total; s -> cifs = E -> cifs_total;
+	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_state_set (dabgpu_t *h, const dabgpu_stream_state *s) {
+	if (!h || !s) return DABGPU_ERR_ARG;
+	Engine *E = h -> engine;
+	E -> ctl. synced = s -> synced; E -> ctl. coarse = s -> coarse; E -> ctl. fine = s -> fine;
+	E -> ctl. f2 = s -> f2Correction; E -> ctl. prev1 = s -> previous_1; E -> ctl. prev2 = s -> previous_2;
+	E -> ctl. lp = s -> localPhase;
+	E -> tail_len = 0; E -> ctl. pos = 0; E -> abs_base = s -> abs_pos;      // the next input starts at abs_pos
+	E -> frames_total = s -> frames; E -> cifs_total = s -> cifs;
+	return DABGPU_OK;
+}
+
+static int ensure_frame_capacity (dabgpu *h, long long frames) {
+	Engine *E = h -> engine;
+	const DabParams &p = h -> p;
+	if (frames <= E -> cap_frames) return DABGPU_OK;
+	const long long cap = frames + frames / 8 + 4;
+	// the MSC row buffer carries 15 CIFs of history in front: preserve them across a re-allocation
+	DevBuf nmsc;
+	const size_t rowb = (size_t) CIF_BITS * sizeof (int16_t);
+	CUDA_TRY (h, nmsc. ensure ((15 + (size_t) cap * p. cifsPerFrame) * rowb));
+	if (E -> d_msc. p && E -> hist_init)
+		CUDA_TRY (h, cudaMemcpyAsync (nmsc. p, E -> d_msc. p, 15 * rowb, cudaMemcpyDeviceToDevice, h -> stream));
+	else
+		CUDA_TRY (h, cudaMemsetAsync (nmsc. p, 0, 15 * rowb, h -> stream));
+	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+	E -> d_msc. release ();
+	E -> d_msc = nmsc;
+	E -> hist_init = true;
+	CUDA_TRY (h, E -> d_fic. ensure ((size_t) cap * 3 * 2 * p. K * sizeof (int16_t)));
+	CUDA_TRY (h, E -> d_info. ensure ((size_t) cap * sizeof (dabgpu_frame_info)));
+	CUDA_TRY (h, E -> d_histtmp. ensure (15 * rowb));
+	E -> cap_frames = cap;
+	return DABGPU_OK;
+}
+
+// decode core on a device-resident input segment
+static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_result *out) {
+	Engine *E = h -> engine;
+	const DabParams &p = h -> p;
+	if (p. dabMode == 3)
+		return dab_fail (h, DABGPU_ERR_ARG, "stream decode is not available for Mode III (the reference has no Mode III framing either)");
+	SampleWin w { (const uchar2 *) E -> tail. p, E -> tail_len, d_new, nnew };
+	const long long total = E -> tail_len + nnew;
+	const long long frame_need = 2ll * p. T_u + (long long) (p. L - 1) * p. T_s + p. T_null;   // worst case from P
+	const long long max_frames_possible = total / p. T_F + 2;
+	long long want = out -> max_frames < max_frames_possible ? out -> max_frames : max_frames_possible;
+	if (want < 0) want = 0;
+	int rc = ensure_frame_capacity (h, want);
+	if (rc) return rc;
+	CUDA_TRY (h, E -> d_frameout. ensure ((size_t) E -> max_chunk * sizeof (FrameOut)));
+	CUDA_TRY (h, E -> d_fcpart. ensure ((size_t) E -> max_chunk * MAX_GROUPS * sizeof (float2)));
+	CUDA_TRY (h, E -> d_spec0. ensure ((size_t) E -> max_chunk * p. T_u * sizeof (float2)));
+	StreamCtl *hctl = (StreamCtl *) E -> h_ctl. p;
+	int nframes = 0;
+	const size_t sm_front = 2 * (size_t) p. T_u * sizeof (float2), sm_sym = ((size_t) p. T_s + 2 * p. T_u) * sizeof (float2);
+	while (nframes < want) {
+		if (!E -> ctl. synced) {
+			*hctl = E -> ctl;
+			CUDA_TRY (h, cudaMemcpyAsync (E -> d_ctl. p, hctl, sizeof (StreamCtl), cudaMemcpyHostToDevice, h -> stream));
+			acquire_kernel<<<1, 32, 0, h -> stream>>> (w, E -> T, p. T_F, p. T_null, (StreamCtl *) E -> d_ctl. p);
+			h -> launches ++;
+			CUDA_TRY (h, cudaGetLastError ());
+			CUDA_TRY (h, cudaMemcpyAsync (hctl, E -> d_ctl. p, sizeof (StreamCtl), cudaMemcpyDeviceToHost, h -> stream));
+			CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+			E -> ctl = *hctl;
+			if (!E -> ctl. synced) break;                   // ran out of samples inside the attempt
+			E -> chunk = 1;
+		}
+		long long avail = (total - E -> ctl. pos - frame_need) / p. T_F + 1;
+		if (total - E -> ctl. pos < frame_need) avail = 0;
+		if (avail <= 0) break;
+		long long C = E -> chunk;
+		if (E -> ctl. override_valid) C = 1;
+		if (C > avail) C = avail;
+		if (C > want - nframes) C = want - nframes;
+		PassParams pp;
+		pp. pos0 = E -> ctl. pos; pp. lp0 = E -> ctl. lp; pp. phiA = E -> ctl. coarse + E -> ctl. fine;
+		pp. phiB0 = E -> ctl. override_valid ? E -> ctl. override_phiB : pp. phiA;
+		pp. nframes = (int) C; pp. slot0 = nframes;
+		*hctl = E -> ctl;
+		CUDA_TRY (h, cudaMemcpyAsync (E -> d_ctl. p, hctl, sizeof (StreamCtl), cudaMemcpyHostToDevice, h -> stream));
+		front_kernel<<<(int) C, OFDM_THREADS, sm_front, h -> stream>>> (w, E -> T, pp, p. T_F, (FrameOut *) E -> d_frameout. p, (float2 *) E -> d_spec0. p);
+		symbol_kernel<<<(int) C * E -> groups, OFDM_THREADS, sm_sym, h -> stream>>> (w, E -> T, pp, p. T_F, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
+			(const FrameOut *) E -> d_frameout. p, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p,
+			(int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p);
+		scan_kernel<<<1, 1, 0, h -> stream>>> ((StreamCtl *) E -> d_ctl. p, pp, E -> groups, p, (const FrameOut *) E -> d_frameout. p,
+			(const float2 *) E -> d_fcpart. p, (dabgpu_frame_info *) E -> d_info. p, E -> abs_base);
+		h -> launches += 3;
+		CUDA_TRY (h, cudaGetLastError ());
+		CUDA_TRY (h, cudaMemcpyAsync (hctl, E -> d_ctl. p, sizeof (StreamCtl), cudaMemcpyDeviceToHost, h -> stream));
+		CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+		E -> ctl = *hctl;
+		nframes += E -> ctl. n_valid;
+		if (E -> ctl. n_valid == C) { E -> chunk *= 2; if (E -> chunk > E -> max_chunk) E -> chunk = E -> max_chunk; }
+		else { E -> chunk = E -> chunk > 2 ? E -> chunk / 2 : 1; }
+	}
+	out -> nframes = nframes;
+	// ---- channel decoding of what the OFDM part produced ----
+	const int ngroups = nframes * p. ficGroups, ncif = nframes * p. cifsPerFrame;
+	if (ngroups > 0) {
+		CUDA_TRY (h, E -> d_ficbits. ensure ((size_t) ngroups * 768));
+		CUDA_TRY (h, E -> d_ficcrc. ensure ((size_t) ngroups * 3));
+		if ((rc = dab_fic_decode_dev (h, (const int16_t *) E -> d_fic. p, 2304, ngroups, (uint8_t *) E -> d_ficbits. p, (uint8_t *) E -> d_ficcrc. p))) return rc;
+		if (out -> fic_bits) CUDA_TRY (h, cudaMemcpyAsync (out -> fic_bits, E -> d_ficbits. p, (size_t) ngroups * 768, cudaMemcpyDeviceToHost, h -> stream));
+		if (out -> fic_crc)  CUDA_TRY (h, cudaMemcpyAsync (out -> fic_crc, E -> d_ficcrc. p, (size_t) ngroups * 3, cudaMemcpyDeviceToHost, h -> stream));
+	}
+	for (size_t i = 0; i < E -> backends. size (); i ++) {
+		int n = 0;
+		if (ncif > 0) {
+			const dabgpu_subch &sc = E -> subch [i];
+			CUDA_TRY (h, E -> d_mscbits [i]. ensure ((size_t) ncif * 24 * sc. bitRate));
+			if ((rc = dab_backend_run_dev (E -> backends [i], (const int16_t *) E -> d_msc. p + (size_t) sc. startAddr * 64, CIF_BITS, ncif,
+			                               (uint8_t *) E -> d_mscbits [i]. p, &n))) return rc;
+			dab_backend_note_cifs (E -> backends [i], ncif);
+			if (out -> msc_bits && out -> msc_bits [i] && n > 0)
+				CUDA_TRY (h, cudaMemcpyAsync (out -> msc_bits [i], E -> d_mscbits [i]. p, (size_t) n * 24 * sc. bitRate, cudaMemcpyDeviceToHost, h -> stream));
+		}
+		if (out -> msc_nblocks) out -> msc_nblocks [i] = n;
+	}
+	if (nframes > 0) {
+		if (out -> info) CUDA_TRY (h, cudaMemcpyAsync (out -> info, E -> d_info. p, (size_t) nframes * sizeof (dabgpu_frame_info), cudaMemcpyDeviceToHost, h -> stream));
+		if (out -> soft) {
+			const size_t dpitch = (size_t) (p. L - 1) * 2 * p. K * sizeof (int16_t), fw = (size_t) 3 * 2 * p. K * sizeof (int16_t);
+			const size_t mw = (size_t) p. cifsPerFrame * CIF_BITS * sizeof (int16_t);
+			CUDA_TRY (h, cudaMemcpy2DAsync (out -> soft, dpitch, E -> d_fic. p, fw, fw, nframes, cudaMemcpyDeviceToHost, h -> stream));
+			CUDA_TRY (h, cudaMemcpy2DAsync ((char *) out -> soft + fw, dpitch, (const int16_t *) E -> d_msc. p + (size_t) 15 * CIF_BITS, mw, mw, nframes,
+			                                cudaMemcpyDeviceToHost, h -> stream));
+		}
+		// time de-interleaver history for the next call: the last 15 CIF rows move to the front
+		const size_t rowb = (size_t) CIF_BITS * sizeof (int16_t);
+		CUDA_TRY (h, cudaMemcpyAsync (E -> d_histtmp. p, (const char *) E -> d_msc. p + (size_t) ncif * rowb, 15 * rowb, cudaMemcpyDeviceToDevice, h -> stream));
+		CUDA_TRY (h, cudaMemcpyAsync (E -> d_msc. p, E -> d_histtmp. p, 15 * rowb, cudaMemcpyDeviceToDevice, h -> stream));
+	}
+	// ---- keep the unconsumed samples for the next call ----
+	const long long consumed = E -> ctl. pos;               // everything before `pos` is done with
+	const long long keep = total - consumed;
+	out -> consumed = consumed - E -> tail_len;               // relative to this call's input (may be negative: none of it)
+	if (keep > 0) {
+		DevBuf nt;
+		CUDA_TRY (h, nt. ensure ((size_t) keep * sizeof (uchar2)));
+		long long from0 = consumed < E -> tail_len ? E -> tail_len - consumed : 0;     // part still in the old tail
+		if (from0 > 0)
+			CUDA_TRY (h, cudaMemcpyAsync (nt. p, (const uchar2 *) E -> tail. p + consumed, (size_t) from0 * sizeof (uchar2), cudaMemcpyDeviceToDevice, h -> stream));
+		const long long off1 = consumed > E -> tail_len ? consumed - E -> tail_len : 0;
+		CUDA_TRY (h, cudaMemcpyAsync ((uchar2 *) nt. p + from0, d_new + off1, (size_t) (nnew - off1) * sizeof (uchar2), cudaMemcpyDeviceToDevice, h -> stream));
+		CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+		E -> tail. release ();
+		E -> tail = nt;
+	} else
+		CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+	E -> tail_len = keep > 0 ? keep : 0;
+	E -> abs_base += consumed;
+	E -> ctl. pos = 0;
+	E -> frames_total += nframes; E -> cifs_total += ncif;
+	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_decode_dev (dabgpu_t *h, const uint8_t *d_iq_u8, size_t nsamples, dabgpu_result *out) {
+	if (!h || !out || (nsamples > 0 && !d_iq_u8)) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_decode: bad argument");
+	CUDA_TRY (h, cudaSetDevice (h -> device));
+	return decode_core (h, (const uchar2 *) d_iq_u8, (long long) nsamples, out);
+}
+
+extern "C" int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out) {
+	if (!h || !out || (nsamples > 0 && !iq_u8)) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_decode: bad argument");
+	CUDA_TRY (h, cudaSetDevice (h -> device));
+	const size_t bytes = nsamples * 2;
+	CUDA_TRY (h, h -> d_in. ensure (bytes + 16));
+	if (bytes) {
+		cudaPointerAttributes attr;
+		const bool pinned = cudaPointerGetAttributes (&attr, iq_u8) == cudaSuccess && attr. type == cudaMemoryTypeHost;
+		cudaGetLastError ();
+		if (pinned)
+			CUDA_TRY (h, cudaMemcpyAsync (h -> d_in. p, iq_u8, bytes, cudaMemcpyHostToDevice, h -> stream));
+		else {
+			CUDA_TRY (h, h -> h_in. ensure (bytes));
+			memcpy (h -> h_in. p, iq_u8, bytes);
+			CUDA_TRY (h, cudaMemcpyAsync (h -> d_in. p, h -> h_in. p, bytes, cudaMemcpyHostToDevice, h -> stream));
+		}
+	}
+	return decode_core (h, (const uchar2 *) h -> d_in. p, (long long) nsamples, out);
+}

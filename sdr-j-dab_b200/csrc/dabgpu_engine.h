@@ -1,0 +1,59 @@
+// dabgpu_engine.h -- stream engine state (ofdmProcessor + ficHandler + mscHandler replacement)
+#pragma once
+#include "dabgpu_ofdm.cuh"
+
+#define CIF_BITS 55296                  // 864 CUs x 64 soft bits (msc-handler.cpp:42,52)
+#define MAX_GROUPS 8                    // symbol groups (CTAs) per frame in the symbol kernel
+
+// device/host mirrored control block of the sequential part of ofdmProcessor::run
+struct StreamCtl {
+	int synced;                         // 1 = next is SyncOnPhase, 0 = notSynced
+	int lp;                             // localPhase before sample `pos`
+	long long pos;                      // next sample to read, relative to the engine's sample window
+	int coarse, fine, f2, prev1, prev2;
+	int override_valid, override_phiB;  // redo the first frame with this data-symbol NCO frequency
+	int n_valid;                        // frames accepted by the last pass
+	int lost;                           // last pass ended with a failed findIndex
+	int acq_done;                       // acquisition kernel: 1 = found the end of a null symbol
+	int pad;
+};
+
+struct SampleWin {                      // two-segment sample window: [tail of earlier calls | this call's input]
+	const uchar2 *seg0; long long len0;
+	const uchar2 *seg1; long long len1;
+};
+
+struct PassParams {
+	long long pos0; int lp0, phiA, phiB0, nframes, slot0;
+};
+
+struct FrameOut {                       // per chunk slot, written by the front / symbol kernels
+	int startIndex, correction;
+};
+
+struct dabgpu_backend;
+
+struct Engine {
+	OfdmTables T {};
+	float2 *d_phaseRef = nullptr;       // per-call API phase reference
+	bool have_phase_ref = false;
+	// stream state
+	StreamCtl ctl {};
+	long long abs_base = 0;             // absolute sample index of window position 0
+	long long frames_total = 0, cifs_total = 0;
+	DevBuf tail; long long tail_len = 0;     // unconsumed samples (uchar2)
+	DevBuf d_ctl;                       // StreamCtl on the device
+	PinBuf h_ctl;
+	int chunk = 1, max_chunk = 256;
+	DevBuf d_frameout, d_fcpart, d_spec0, d_info;
+	DevBuf d_fic, d_msc, d_histtmp;     // soft bits: FIC [frames][3*2K], MSC rows [15 + cifs][55296]
+	long long cap_frames = 0;
+	DevBuf d_ficbits, d_ficcrc;
+	std::vector<DevBuf> d_mscbits;
+	bool hist_init = false;
+	std::vector<dabgpu_subch> subch;
+	std::vector<dabgpu_backend *> backends;
+	int groups = 5;
+};
+
+int ofdm_tables_init (dabgpu *h, OfdmTables *T);

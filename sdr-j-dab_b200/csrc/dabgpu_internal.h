@@ -71,8 +71,10 @@ struct VitJob {
 cudaError_t vit_launch (const VitJob &job, cudaStream_t st, int64_t *launches);
 cudaError_t fib_crc_launch (const uint8_t *bits, int nfibs, uint8_t *ok, cudaStream_t st, int64_t *launches);
 
+struct Engine;
 struct dabgpu {
 	int device = 0;
+	Engine *engine = nullptr;
 	dabgpu_config cfg {};
 	DabParams p {};
 	cudaStream_t stream = nullptr;
@@ -100,6 +102,7 @@ int  dab_get_prbs (dabgpu *h, int nbits, const uint32_t **d_prbs);
 int  dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, uint8_t *d_crc);
 struct dabgpu_backend;
 int  dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row_stride, int ncif, uint8_t *d_out, int *nout);
+void dab_backend_note_cifs (dabgpu_backend *b, int ncif);
 // OFDM / stream engine state (dabgpu_ofdm.cu, dabgpu_engine.cu)
 int  dab_engine_init (dabgpu *h);
 void dab_engine_free (dabgpu *h);

@@ -1,0 +1,233 @@
+// dabgpu_ofdm.cuh -- device building blocks of the FFT + demod group (shared by the per-call parity entry
+// points in dabgpu_ofdm.cu and the stream engine in dabgpu_engine.cu).  sm_100a.
+#pragma once
+#include "dabgpu_internal.h"
+
+#define OFDM_THREADS 256
+
+struct OfdmTables {                   // device pointers, built once per handle (dab_engine_init)
+	const float2  *tw;                // [T_u]  exp (-2 pi i k / T_u), double -> float
+	const float2  *ref;               // [T_u]  PRS spectrum (phasereference.cpp:41-47)
+	const int16_t *perm;              // [K]    frequency de-interleaver, wrapped to [0, T_u) (mapper.cpp, ofdm-decoder.cpp:179-181)
+	const float   *refArg;            // [18]   ofdm-decoder.cpp:73-76
+	const float2  *osc_hi;            // [1000] exp (2 pi i 2048 h / 2048000)   NCO = osc_hi[lp >> 11] * osc_lo[lp & 2047]
+	const float2  *osc_lo;            // [2048] exp (2 pi i l / 2048000)        (ofdm-processor.cpp:76-81, 165-167)
+	int T_u, T_s, T_g, K, L, log2n;
+	int level, method;
+};
+
+__device__ __forceinline__ float2 cmul (float2 a, float2 b) { return make_float2 (a. x * b. x - a. y * b. y, a. x * b. y + a. y * b. x); }
+__device__ __forceinline__ float2 cmulc (float2 a, float2 b) { return make_float2 (a. x * b. x + a. y * b. y, a. y * b. x - a. x * b. y); }   // a * conj (b)
+
+// In-shared-memory Stockham autosort FFT, radix 4 with a final radix-2 pass when log2 N is odd; forward,
+// unnormalised (fft.cpp:53-55).  x holds the input, y is scratch; returns the buffer holding the result.
+// All OFDM_THREADS threads of the block must call it; ends with a __syncthreads.
+__device__ __forceinline__ float2 *block_fft (float2 *x, float2 *y, const int N, const float2 *__restrict__ tw) {
+	const int tid = threadIdx. x;
+	int n = N, s = 1, ls = 0;
+	__syncthreads ();
+	while (n >= 4) {
+		const int quarter = N >> 2, tstep = N / n;
+		for (int j = tid; j < quarter; j += OFDM_THREADS) {
+			const int q = j & (s - 1), p = j >> ls;
+			const float2 a = x [j], b = x [j + quarter], c = x [j + 2 * quarter], d = x [j + 3 * quarter];
+			const float2 apc = make_float2 (a. x + c. x, a. y + c. y), amc = make_float2 (a. x - c. x, a. y - c. y);
+			const float2 bpd = make_float2 (b. x + d. x, b. y + d. y);
+			const float2 jbmd = make_float2 (-(b. y - d. y), b. x - d. x);            // j * (b - d)
+			const int o = q + s * 4 * p;
+			y [o] = make_float2 (apc. x + bpd. x, apc. y + bpd. y);
+			if (p == 0) {                                                               // twiddles are 1
+				y [o + s]     = make_float2 (amc. x - jbmd. x, amc. y - jbmd. y);
+				y [o + 2 * s] = make_float2 (apc. x - bpd. x, apc. y - bpd. y);
+				y [o + 3 * s] = make_float2 (amc. x + jbmd. x, amc. y + jbmd. y);
+			} else {
+				const float2 w1 = __ldg (&tw [p * tstep]), w2 = __ldg (&tw [2 * p * tstep]), w3 = __ldg (&tw [3 * p * tstep]);
+				y [o + s]     = cmul (make_float2 (amc. x - jbmd. x, amc. y - jbmd. y), w1);
+				y [o + 2 * s] = cmul (make_float2 (apc. x - bpd. x, apc. y - bpd. y), w2);
+				y [o + 3 * s] = cmul (make_float2 (amc. x + jbmd. x, amc. y + jbmd. y), w3);
+			}
+		}
+		n >>= 2; s <<= 2; ls += 2;
+		float2 *t = x; x = y; y = t;
+		__syncthreads ();
+	}
+	if (n == 2) {
+		for (int j = tid; j < s; j += OFDM_THREADS) {
+			const float2 a = x [j], b = x [j + s];
+			y [j]     = make_float2 (a. x + b. x, a. y + b. y);
+			y [j + s] = make_float2 (a. x - b. x, a. y - b. y);
+		}
+		float2 *t = x; x = y; y = t;
+		__syncthreads ();
+	}
+	return x;
+}
+
+// NCO phasor for localPhase index lp in [0, 2048000)
+__device__ __forceinline__ float2 nco (const OfdmTables &T, int lp) {
+	return cmul (__ldg (&T. osc_hi [lp >> 11]), __ldg (&T. osc_lo [lp & 2047]));
+}
+
+__device__ __forceinline__ int mod_rate (long long v) {          // v mod 2048000 into [0, 2048000)
+	int r = (int) (v % DAB_INPUT_RATE);
+	return r < 0 ? r + DAB_INPUT_RATE : r;
+}
+
+// dst[i] = ((iq[first+i] - 128) / 128) * osc[(lp_before - (i+1) * phase) mod RATE], i < n
+// (rawfiles.cpp:113-116 + ofdm-processor.cpp:217-226).  iq = interleaved u8 I,Q.
+__device__ __forceinline__ void load_u8_nco (float2 *dst, const uchar2 *__restrict__ iq, long long first, int n,
+                                             int lp_before, int phase, const OfdmTables &T) {
+	const int tid = threadIdx. x;
+	const int ph = mod_rate (phase);
+	int lp = mod_rate ((long long) lp_before - (long long) (tid + 1) * ph);
+	const int step = mod_rate ((long long) OFDM_THREADS * ph);
+	for (int i = tid; i < n; i += OFDM_THREADS) {
+		const uchar2 s = __ldg (&iq [first + i]);
+		const float2 v = make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f));
+		dst [i] = cmul (v, nco (T, lp));
+		lp -= step;
+		if (lp < 0) lp += DAB_INPUT_RATE;
+	}
+}
+
+// soft-bit quantisation of ofdm-decoder.cpp:183-189: float negate + divide, double multiply, truncation
+__device__ __forceinline__ short quant127 (float num, float ab1) {
+	const double x = (double) (- num / ab1) * 127.0;
+	return (short) __double2int_rz (x);               // NaN (ab1 == 0) -> 0, as x86's conversion ends up (App. B-5)
+}
+
+// DQPSK demod + frequency de-interleave of one symbol (ofdm-decoder.cpp:178-190): cur = FFT of the symbol,
+// prev = running phase reference (updated in place on the K used bins), ibits[2K]
+__device__ __forceinline__ void demod_symbol (const float2 *cur, float2 *prev, const OfdmTables &T, int16_t *__restrict__ ibits) {
+	for (int i = threadIdx. x; i < T. K; i += OFDM_THREADS) {
+		const int idx = __ldg (&T. perm [i]);
+		const float2 c = cur [idx];
+		const float2 r1 = cmulc (c, prev [idx]);
+		prev [idx] = c;
+		const float ab1 = fabsf (r1. x) + fabsf (r1. y);                 // jan_abs, dab-constants.h:127-134
+		ibits [i]        = quant127 (r1. x, ab1);
+		ibits [T. K + i] = quant127 (r1. y, ab1);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device routines shared with the engine
+// ---------------------------------------------------------------------------------------------------
+// phaseReference::findIndex on the T_u samples in buf (destroyed); scratch = second T_u buffer.
+// Returns (to every thread) the reference's result: peak index, or -|Max/mean| - 1 when below threshold.
+static __device__ int find_index_block (float2 *buf, float2 *scratch, const OfdmTables &T) {
+	__shared__ float s_red [OFDM_THREADS / 32];
+	__shared__ float s_max [OFDM_THREADS / 32];
+	__shared__ int   s_idx [OFDM_THREADS / 32];
+	__shared__ int   s_result;
+	const int N = T. T_u, tid = threadIdx. x;
+	float2 *spec = block_fft (buf, scratch, N, T. tw);
+	float2 *other = spec == buf ? scratch : buf;
+	// res = conj (fft * conj (ref)): the backward transform is conj (forward (conj (x)))
+	for (int i = tid; i < N; i += OFDM_THREADS) {
+		const float2 r = cmulc (spec [i], __ldg (&T. ref [i]));
+		spec [i] = make_float2 (r. x, - r. y);
+	}
+	float2 *res = block_fft (spec, other, N, T. tw);
+	const float factor = (float) (1.0 / (float) N);          // fft.cpp:114-121
+	float sum = 0.f, mx = -10000.f;
+	int mi = -1;
+	for (int i = tid; i < N; i += OFDM_THREADS) {
+		const float2 v = res [i];
+		const float a = hypotf (v. x * factor, (- v. y) * factor);
+		sum += a;
+		if (a > mx) { mx = a; mi = i; }
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		sum += __shfl_xor_sync (0xffffffffu, sum, o);
+		const float om = __shfl_xor_sync (0xffffffffu, mx, o);
+		const int   oi = __shfl_xor_sync (0xffffffffu, mi, o);
+		if (om > mx || (om == mx && oi >= 0 && (mi < 0 || oi < mi))) { mx = om; mi = oi; }   // first maximum wins
+	}
+	if ((tid & 31) == 0) { s_red [tid >> 5] = sum; s_max [tid >> 5] = mx; s_idx [tid >> 5] = mi; }
+	__syncthreads ();
+	if (tid == 0) {
+		float tsum = 0.f, tmx = -10000.f;
+		int tmi = -1;
+		for (int w = 0; w < OFDM_THREADS / 32; w ++) {
+			tsum += s_red [w];
+			if (s_max [w] > tmx || (s_max [w] == tmx && s_idx [w] >= 0 && (tmi < 0 || s_idx [w] < tmi))) { tmx = s_max [w]; tmi = s_idx [w]; }
+		}
+		if (tmx < (float) T. level * tsum / (float) N)                       // phasereference.cpp:84-85
+			s_result = (int) (- fabsf (tmx / (tsum / (float) N)) - 1.0f);
+		else
+			s_result = tmi;
+	}
+	__syncthreads ();
+	return s_result;
+}
+
+static __device__ __forceinline__ float arg_mulconj (float2 a, float2 b) {
+	const float2 r = cmulc (a, b);
+	return atan2f (r. y, r. x);
+}
+
+// coarse frequency offset from the PRS spectrum (ofdm-decoder.cpp:99-161), executed by warp 0; the result
+// is returned to thread 0 only.
+static __device__ int coarse_offset_warp0 (const float2 *f, const OfdmTables &T, float *cv /* smem, >= 90 floats */) {
+	const int N = T. T_u, tid = threadIdx. x;
+	int result = 100;
+	if (T. method == 1) {                                    // :106-127
+		if (tid < 90) {
+			const int base = N - 36 + tid;
+			cv [tid] = arg_mulconj (f [base % N], f [(base + 1) % N]);
+		}
+		__syncthreads ();
+		if (tid < 32) {
+			float best = 0.f; int bi = 100;                  // index_1 stays 100 when no sum exceeds 0
+			for (int i = tid; i < 72; i += 32) {
+				float sum = 0.f;
+				for (int j = 1; j < 18; j ++) sum += fabsf (__ldg (&T. refArg [j]) * cv [i + j]);
+				if (sum > best) { best = sum; bi = i; }
+			}
+			for (int o = 16; o > 0; o >>= 1) {
+				const float ob = __shfl_xor_sync (0xffffffffu, best, o);
+				const int   oi = __shfl_xor_sync (0xffffffffu, bi, o);
+				if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+			}
+			result = N - 36 + bi - N;
+		}
+	} else if (T. method == 2) {                             // :132-161
+		__syncthreads ();
+		if (tid < 32) {
+			float best = 1000.f; int bi = 100;
+			for (int k = tid; k < 72; k += 32) {
+				const int i = N - 36 + k;
+#define ARGP(x, y) arg_mulconj (f [(x) % N], f [(y) % N])
+				const float a1 = (float) fabs ((double) fabsf (ARGP (i + 1, i + 2)) / M_PI - 1);
+				const float a2 = (float) fabs ((double) fabsf (ARGP (i + 2, i + 3)) / M_PI - 1);
+				const float a3 = fabsf (ARGP (i + 3, i + 4)), a4 = fabsf (ARGP (i + 4, i + 5)), a5 = fabsf (ARGP (i + 5, i + 6));
+				const float b1 = (float) fabs ((double) fabsf (ARGP (i + 17, i + 19)) / M_PI - 1);
+				const float b2 = fabsf (ARGP (i + 19, i + 20)), b3 = fabsf (ARGP (i + 20, i + 21)), b4 = fabsf (ARGP (i + 21, i + 22));
+#undef ARGP
+				const float sum = a1 + a2 + a3 + a4 + a5 + b1 + b2 + b3 + b4;
+				if (sum < best) { best = sum; bi = i; }
+			}
+			for (int o = 16; o > 0; o >>= 1) {
+				const float ob = __shfl_xor_sync (0xffffffffu, best, o);
+				const int   oi = __shfl_xor_sync (0xffffffffu, bi, o);
+				if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+			}
+			result = bi - N;
+		}
+	} else {                                                 // method 0: getMiddle, :233-258, bug included
+		__syncthreads ();
+		if (tid == 0) {
+			float sum = 0.f; const float oldMax = 0.f; int maxIndex = 0;
+			for (int i = 40; i < 1536 + 40; i ++) { const float2 v = f [(N / 2 + i) % N]; sum += hypotf (v. x, v. y); }
+			for (int i = 40; i < N - (1536 - 40); i ++) {
+				float2 v = f [(N / 2 + i) % N];        sum -= hypotf (v. x, v. y);
+				v = f [(N / 2 + i + 1536) % N];        sum += hypotf (v. x, v. y);
+				if (sum > oldMax) { sum = oldMax; maxIndex = i; }
+			}
+			result = (int16_t) (maxIndex - (N - 1536) / 2);
+		}
+	}
+	return result;
+}
+

@@ -1,0 +1,95 @@
+"""End-to-end GPU parity of the stream engine (dabgpu_decode = ofdmProcessor::run + ficHandler + mscHandler /
+dabConcurrent) against the oracle on the same synthetic u8 IQ: AFC trajectory and frame positions exact,
+soft bits within +-1, decoded FIC / MSC bits bit-exact."""
+import numpy as np
+import pytest
+
+import dabmod
+from util import engine_pkg
+
+pytestmark = pytest.mark.gpu
+
+SUBS = [(0, 128, 1, 0o103), (96, 128, 0, 3), (200, 64, 1, 0o202)]
+
+
+def _oracle_chain(port, mode, iq, nmax, subs_objs):
+    sym, info = port.ofdm_run(mode, iq, nmax)
+    bits, crc = port.fic_frames(mode, sym)
+    msc = []
+    for s in subs_objs:
+        frag = port.msc_slice(mode, sym, s.startAddr, s.length)
+        msc.append(port.msc_backend(frag, s.bitRate, s.uepFlag, s.protLevel))
+    return sym, info, bits, crc, msc
+
+
+def _compare(res, want, nframes=None):
+    sym, info, bits, crc, msc = want
+    n = len(info) if nframes is None else nframes
+    assert res.nframes == n
+    for a, b in zip(res.info, info[:n]):
+        assert (a.pos, a.startIndex, a.coarse, a.fine, a.phase0, a.correction) == \
+               (b.pos, b.startIndex, b.coarse, b.fine, b.phase0, b.correction)
+    d = np.abs(res.soft.astype(int) - sym[:n].astype(int))
+    assert d.max() <= 1, (d.max(), np.argwhere(d > 1)[:5])
+    return d
+
+
+@pytest.mark.parametrize("mode,cfo,snr", [(1, 0.0, 25.0), (1, 7137.0, 20.0), (2, -9300.0, 18.0), (4, 3050.0, 15.0)])
+def test_decode_matches_oracle(port, mode, cfo, snr):
+    pkg = engine_pkg()
+    subs = SUBS if mode != 2 else SUBS[:2]
+    mod = dabmod.Modulator(port, mode, subs, 1001)
+    nframes = 28 if mode == 1 else 40
+    tr = mod.generate(nframes, cfo_hz=cfo, snr_db=snr, lead=12345, tail=5000)
+    want = _oracle_chain(port, mode, tr["iq"], nframes + 4, mod.sub)
+    eng = pkg.DabGpu(mode=mode)
+    eng.set_subchannels([(s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel) for s in mod.sub])
+    out = eng.alloc_result(nframes + 4)
+    res = eng.decode(tr["iq"], out)
+    # the oracle counts a frame whose trailing null symbol is cut off by the end of the input; the engine
+    # waits for those samples (as the reference would block), so compare on what the engine decoded
+    assert len(want[1]) - res.nframes in (0, 1)
+    _compare(res, want, res.nframes)
+    g = mod.p.ficGroups
+    assert np.array_equal(res.fic_bits, want[2][:res.nframes * g])
+    assert np.array_equal(res.fic_crc, want[3][:res.nframes * g])
+    assert res.fic_crc[-4 * g:].all()
+    for got, w, pay in zip(res.msc, want[4], tr["payloads"]):
+        assert got.shape[0] > 0 and np.array_equal(got, w[:got.shape[0]])
+    eng.close()
+
+
+def test_decode_in_pieces_equals_one_shot(port):
+    """a stream fed in ragged pieces: sync state, sample tail and de-interleaver history carry over"""
+    pkg = engine_pkg()
+    mod = dabmod.Modulator(port, 1, SUBS[:1], 77)
+    tr = mod.generate(30, cfo_hz=-2210.0, snr_db=22.0, lead=5000, tail=8000)
+    iq = tr["iq"]
+    e1 = pkg.DabGpu(mode=1); e1.set_subchannels([(0, 96, 128, 1, 0o103)])
+    one = e1.decode(iq, e1.alloc_result(40))
+    e2 = pkg.DabGpu(mode=1); e2.set_subchannels([(0, 96, 128, 1, 0o103)])
+    cuts = [0, 100000, 1500000, 1500002, 4000000, iq.size // 2]
+    cuts = [2 * c for c in cuts]
+    parts = [e2.decode(iq[a:b], e2.alloc_result(40)) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert sum(p.nframes for p in parts) == one.nframes
+    assert np.array_equal(np.concatenate([p.soft for p in parts]), one.soft)
+    assert np.array_equal(np.concatenate([p.fic_bits for p in parts]), one.fic_bits)
+    assert np.array_equal(np.concatenate([p.msc[0] for p in parts]), one.msc[0])
+    pay = tr["payloads"][0]
+    assert one.msc[0].shape[0] > 40
+    # the tail of the decoded stream is the transmitted payload
+    tailblk = one.msc[0][-20:]
+    hits = [np.array_equal(tailblk, pay[k:k + 20]) for k in range(pay.shape[0] - 20)]
+    assert any(hits)
+    e1.close(); e2.close()
+
+
+def test_noise_only_never_syncs(port):
+    pkg = engine_pkg()
+    rng = np.random.default_rng(5)
+    iq = np.clip(np.rint(rng.standard_normal(2 * 600000) * 20 + 128), 0, 255).astype(np.uint8)
+    eng = pkg.DabGpu(mode=1)
+    res = eng.decode(iq, eng.alloc_result(8))
+    sym, info = port.ofdm_run(1, iq, 8)
+    assert res.nframes == len(info) == 0
+    eng.close()
