@@ -68,6 +68,20 @@ int64_t dabgpu_launch_count (const dabgpu_t *h);
 int  dabgpu_timer_begin (dabgpu_t *h);
 int  dabgpu_timer_end (dabgpu_t *h, float *ms);
 
+/* optional per-kernel-class CUDA-event profile (bench.py's roofline numbers): when enabled every kernel
+ * launch is bracketed by two events on the handle's stream; get() waits for the stream and returns the
+ * accumulated launch count and device milliseconds of one class since the last reset */
+enum { DABGPU_KC_ACQUIRE = 0, DABGPU_KC_FRONT, DABGPU_KC_SYMBOL, DABGPU_KC_SCAN, DABGPU_KC_VITERBI_MSC,
+       DABGPU_KC_VITERBI_FIC, DABGPU_KC_VITERBI_API, DABGPU_KC_CRC, DABGPU_KC_COUNT };
+int  dabgpu_profile_enable (dabgpu_t *h, int32_t on);
+int  dabgpu_profile_reset (dabgpu_t *h);
+int  dabgpu_profile_get (dabgpu_t *h, int32_t kernel_class, int64_t *launches, double *ms);
+
+/* integer-pipe peak of this GPU, measured live (the roofline denominator of the Viterbi group, which
+ * MEASURED_PEAKS.json does not hold): ops[0] = add only, ops[1] = min only, ops[2] = add + mad.lo mix,
+ * in 32-bit integer operations per second */
+int  dabgpu_int_peak (dabgpu_t *h, double *ops);
+
 /* ------------------------------------------------------------------------------------------------
  * Channel decoding (Viterbi group)
  * ---------------------------------------------------------------------------------------------- */

@@ -70,6 +70,10 @@ def load_library():
     L.dabgpu_backend_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]
     L.dabgpu_backend_get_state.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     L.dabgpu_backend_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.dabgpu_profile_enable.argtypes = [C.c_void_p, C.c_int32]
+    L.dabgpu_profile_reset.argtypes = [C.c_void_p]
+    L.dabgpu_profile_get.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.dabgpu_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.dabgpu_fft.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
     L.dabgpu_find_index.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.dabgpu_block0.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int16)]
@@ -129,6 +133,28 @@ class DabGpu:
         ms = C.c_float(0)
         self._check(self.lib.dabgpu_timer_end(self.h, C.byref(ms)))
         return ms.value
+
+    KERNEL_CLASSES = ("acquire", "front", "symbol", "scan", "viterbi_msc", "viterbi_fic", "viterbi_api", "crc")
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.dabgpu_profile_enable(self.h, int(on)))
+
+    def profile_reset(self):
+        self._check(self.lib.dabgpu_profile_reset(self.h))
+
+    def profile(self):
+        """{class: (launches, device ms)} since the last reset"""
+        out = {}
+        for i, name in enumerate(self.KERNEL_CLASSES):
+            n, ms = C.c_int64(0), C.c_double(0)
+            self._check(self.lib.dabgpu_profile_get(self.h, i, C.byref(n), C.byref(ms)))
+            out[name] = (n.value, ms.value)
+        return out
+
+    def int_peak(self):
+        ops = (C.c_double * 3)()
+        self._check(self.lib.dabgpu_int_peak(self.h, ops))
+        return {"add": ops[0], "min": ops[1], "add_mad": ops[2]}
 
     def launch_count(self):
         return int(self.lib.dabgpu_launch_count(self.h))
@@ -200,17 +226,19 @@ class DabGpu:
         arr = (SubCh * max(len(subs), 1))(*self._subs)
         self._check(self.lib.dabgpu_set_subchannels(self.h, arr, len(subs)))
 
-    def alloc_result(self, max_frames, want_soft=True):
+    def alloc_result(self, max_frames, want_soft=True, alloc=None):
+        """alloc(shape, dtype) -> ndarray lets the caller place the result buffers (e.g. in pinned memory)"""
+        alloc = alloc or (lambda shape, dtype: np.zeros(shape, dtype))
         L, K, _, _, _, _, cpf = MODE_PARAMS[self.mode]
         subs = getattr(self, "_subs", [])
         o = DecodeOut()
         o.max_frames = max_frames
         o.info = (FrameInfo * max(max_frames, 1))()
-        o.soft = np.zeros((max_frames, L - 1, 2 * K), np.int16) if want_soft else None
+        o.soft = alloc((max_frames, L - 1, 2 * K), np.int16) if want_soft else None
         groups = 3 * 2 * K // 2304
-        o.fic_bits = np.zeros((max_frames * groups, 768), np.uint8)
-        o.fic_crc = np.zeros((max_frames * groups, 3), np.uint8)
-        o.msc = [np.zeros((max_frames * cpf, 24 * s.bitRate), np.uint8) for s in subs]
+        o.fic_bits = alloc((max_frames * groups, 768), np.uint8)
+        o.fic_crc = alloc((max_frames * groups, 3), np.uint8)
+        o.msc = [alloc((max_frames * cpf, 24 * s.bitRate), np.uint8) for s in subs]
         o.ptrs = (C.POINTER(C.c_uint8) * max(len(subs), 1))(*[m.ctypes.data_as(C.POINTER(C.c_uint8)) for m in o.msc])
         o.nblocks = (C.c_int32 * max(len(subs), 1))()
         o.res = Result(max_frames=max_frames, nframes=0, info=o.info,

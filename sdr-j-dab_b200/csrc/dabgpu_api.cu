@@ -56,6 +56,8 @@ extern "C" void dabgpu_destroy (dabgpu_t *h) {
 	h -> d_in. release (); h -> d_out. release (); h -> d_aux. release ();
 	h -> h_in. release (); h -> h_out. release ();
 	if (h -> ev0) { cudaEventDestroy (h -> ev0); cudaEventDestroy (h -> ev1); }
+	for (auto &pp : h -> prof_pending) { cudaEventDestroy (pp. a); cudaEventDestroy (pp. b); }
+	for (auto e : h -> prof_pool) cudaEventDestroy (e);
 	if (h -> stream) cudaStreamDestroy (h -> stream);
 	delete h;
 }
@@ -81,6 +83,49 @@ extern "C" int dabgpu_timer_end (dabgpu_t *h, float *ms) {
 	CUDA_TRY (h, cudaEventRecord (h -> ev1, h -> stream));
 	CUDA_TRY (h, cudaEventSynchronize (h -> ev1));
 	CUDA_TRY (h, cudaEventElapsedTime (ms, h -> ev0, h -> ev1));
+	return DABGPU_OK;
+}
+
+ProfScope::ProfScope (dabgpu *h_, int cls_) : h (h_), cls (cls_) {
+	if (!h -> profiling) return;
+	for (cudaEvent_t *e : { &a, &b }) {
+		if (!h -> prof_pool. empty ()) { *e = h -> prof_pool. back (); h -> prof_pool. pop_back (); }
+		else if (cudaEventCreate (e) != cudaSuccess) { *e = nullptr; }
+	}
+	if (a && b) cudaEventRecord (a, h -> stream);
+}
+ProfScope::~ProfScope () {
+	if (!a || !b) return;
+	cudaEventRecord (b, h -> stream);
+	h -> prof_pending. push_back ({ cls, a, b });
+}
+
+extern "C" int dabgpu_profile_enable (dabgpu_t *h, int32_t on) {
+	if (!h) return DABGPU_ERR_ARG;
+	h -> profiling = on != 0;
+	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_profile_reset (dabgpu_t *h) {
+	if (!h) return DABGPU_ERR_ARG;
+	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+	for (auto &pp : h -> prof_pending) { h -> prof_pool. push_back (pp. a); h -> prof_pool. push_back (pp. b); }
+	h -> prof_pending. clear ();
+	for (int i = 0; i < KC_COUNT; i ++) { h -> prof_ms [i] = 0; h -> prof_n [i] = 0; }
+	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_profile_get (dabgpu_t *h, int32_t kernel_class, int64_t *launches, double *ms) {
+	if (!h || kernel_class < 0 || kernel_class >= KC_COUNT || !launches || !ms) return DABGPU_ERR_ARG;
+	CUDA_TRY (h, cudaSetDevice (h -> device));
+	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+	for (auto &pp : h -> prof_pending) {
+		float t = 0;
+		if (cudaEventElapsedTime (&t, pp. a, pp. b) == cudaSuccess) { h -> prof_ms [pp. cls] += t; h -> prof_n [pp. cls] ++; }
+		h -> prof_pool. push_back (pp. a); h -> prof_pool. push_back (pp. b);
+	}
+	h -> prof_pending. clear ();
+	*launches = h -> prof_n [kernel_class]; *ms = h -> prof_ms [kernel_class];
 	return DABGPU_OK;
 }
 
@@ -159,7 +204,7 @@ extern "C" int dabgpu_viterbi_dev (dabgpu_t *h, const int16_t *soft, int32_t fra
 	j. in = soft; j. in_stride = 4ll * (frameBits + 6); j. lut = nullptr;
 	j. frameBits = frameBits; j. nsteps = frameBits + 6; j. nblocks = nblocks;
 	j. deint = 0; j. prbs = nullptr; j. out = bits;
-	CUDA_TRY (h, vit_launch (j, h -> stream, &h -> launches));
+	CUDA_TRY (h, vit_launch (h, KC_VITERBI_API, j));
 	return DABGPU_OK;
 }
 
@@ -196,7 +241,7 @@ extern "C" int dabgpu_protect_decode (dabgpu_t *h, int32_t bitRate, int32_t uepF
 	j. in = (const int16_t *) d_in; j. in_stride = size; j. lut = d_lut;
 	j. frameBits = pp -> frameBits; j. nsteps = pp -> frameBits + 6; j. nblocks = nblocks;
 	j. out = (uint8_t *) h -> d_out. p;
-	CUDA_TRY (h, vit_launch (j, h -> stream, &h -> launches));
+	CUDA_TRY (h, vit_launch (h, KC_VITERBI_API, j));
 	return stage_out (h, bits, h -> d_out. p, obytes);
 }
 
@@ -210,8 +255,8 @@ int dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, long long stride, int 
 	j. in = d_soft; j. in_stride = stride; j. lut = d_lut;
 	j. frameBits = 768; j. nsteps = 774; j. nblocks = ngroups;
 	j. prbs = d_prbs; j. out = d_bits;
-	CUDA_TRY (h, vit_launch (j, h -> stream, &h -> launches));
-	if (d_crc) CUDA_TRY (h, fib_crc_launch (d_bits, 3 * ngroups, d_crc, h -> stream, &h -> launches));
+	CUDA_TRY (h, vit_launch (h, KC_VITERBI_FIC, j));
+	if (d_crc) CUDA_TRY (h, fib_crc_launch (h, d_bits, 3 * ngroups, d_crc));
 	return DABGPU_OK;
 }
 
@@ -287,7 +332,7 @@ int dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row
 	j. in = d_rows; j. in_stride = row_stride; j. first_row = 15 + (int) skip; j. lut = b -> d_lut;
 	j. frameBits = b -> pp -> frameBits; j. nsteps = j. frameBits + 6; j. nblocks = n;
 	j. deint = 1; j. prbs = b -> d_prbs; j. out = d_out;
-	CUDA_TRY (h, vit_launch (j, h -> stream, &h -> launches));
+	CUDA_TRY (h, vit_launch (h, KC_VITERBI_MSC, j));
 	*nout = n;
 	return DABGPU_OK;
 }

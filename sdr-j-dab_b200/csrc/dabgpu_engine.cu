@@ -116,24 +116,38 @@ __global__ void __launch_bounds__ (32) acquire_kernel (SampleWin w, OfdmTables T
 }
 
 // ---------------------------------------------------------------------------------------------------
+// predict kernel: frame c of the chunk is assumed to start T_F after frame c-1 with unchanged correctors
+// ---------------------------------------------------------------------------------------------------
+__global__ void predict_kernel (const StreamCtl *ctl, FrameIn *fin, int T_F, int nframes) {
+	const int c = blockIdx. x * blockDim. x + threadIdx. x;
+	if (c >= nframes) return;
+	const int phi = ctl -> coarse + ctl -> fine;
+	FrameIn f;
+	f. P = ctl -> pos + (long long) c * T_F;
+	f. lp = mod_rate ((long long) ctl -> lp - (long long) c * T_F % DAB_INPUT_RATE * mod_rate (phi));
+	f. phiA = f. phiB = phi; f. active = 1; f. pad = 0;
+	fin [c] = f;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // front kernel, one CTA per frame of the chunk: SyncOnPhase + OFDM_PRS (ofdm-processor.cpp:344-406)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__ (OFDM_THREADS) front_kernel (SampleWin w, OfdmTables T, PassParams pp, int T_F,
+__global__ void __launch_bounds__ (OFDM_THREADS) front_kernel (SampleWin w, OfdmTables T, const FrameIn *fin,
                                                                FrameOut *fo, float2 *spec0) {
 	extern __shared__ float2 sm [];
 	__shared__ float cv [96];
 	const int N = T. T_u, c = blockIdx. x;
+	const FrameIn in = fin [c];
+	if (!in. active) return;
 	float2 *a = sm, *b = sm + N;
-	const long long P = pp. pos0 + (long long) c * T_F;
-	const int lpP = mod_rate ((long long) pp. lp0 - (long long) c * T_F % DAB_INPUT_RATE * mod_rate (pp. phiA));
-	load_win_nco (a, w, P, N, lpP, pp. phiA, T);                       // :347-348
+	load_win_nco (a, w, in. P, N, in. lp, in. phiA, T);                // :347-348
 	const int s = find_index_block (a, b, T);                          // :352
 	int corr = 0;
 	if (s >= 0) {
 		// block 0 = the T_u samples from P + s on (:362-388), same NCO run
-		const int lp0 = mod_rate ((long long) lpP - (long long) s * mod_rate (pp. phiA));
+		const int lp0 = mod_rate ((long long) in. lp - (long long) s * mod_rate (in. phiA));
 		__syncthreads ();
-		load_win_nco (a, w, P + s, N, lp0, pp. phiA, T);
+		load_win_nco (a, w, in. P + s, N, lp0, in. phiA, T);
 		float2 *f = block_fft (a, b, N, T. tw);
 		float2 *g = spec0 + (size_t) c * N;
 		for (int i = threadIdx. x; i < N; i += OFDM_THREADS) g [i] = f [i];   // phaseReference (ofdm-decoder.cpp:91)
@@ -146,22 +160,22 @@ __global__ void __launch_bounds__ (OFDM_THREADS) front_kernel (SampleWin w, Ofdm
 // symbol kernel, CTA (c, g) = frame c of the chunk, symbol group g: OFDM_SYMBOLS (ofdm-processor.cpp:414-442)
 // with processToken (ofdm-decoder.cpp:167-190) and the cyclic-prefix correlation (:424-425) fused.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__ (OFDM_THREADS) symbol_kernel (SampleWin w, OfdmTables T, PassParams pp, int T_F, int groups,
+__global__ void __launch_bounds__ (OFDM_THREADS) symbol_kernel (SampleWin w, OfdmTables T, const FrameIn *fin, int slot0, int groups,
                                                                 int blocksPerCIF, int cifsPerFrame, const FrameOut *fo,
                                                                 const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc) {
 	extern __shared__ float2 sm [];
 	__shared__ float2 s_fc [OFDM_THREADS / 32];
 	const int N = T. T_u, Ts = T. T_s, Tg = T. T_g, c = blockIdx. x / groups, g = blockIdx. x % groups;
+	const FrameIn in = fin [c];
+	if (!in. active) return;
 	const int s = fo [c]. startIndex;
 	if (s < 0) { if (threadIdx. x == 0) fcpart [c * MAX_GROUPS + g] = make_float2 (0.f, 0.f); return; }
 	float2 *symbuf = sm, *scratch = sm + Ts, *prev = sm + Ts + N;
 	const int nsym = T. L - 1, per = (nsym + groups - 1) / groups;
 	const int l0 = 1 + g * per, l1 = min (nsym + 1, l0 + per);             // symbols [l0, l1)
-	const long long P = pp. pos0 + (long long) c * T_F;
-	const int phA = mod_rate (pp. phiA), phiB = c == 0 ? pp. phiB0 : pp. phiA, phB = mod_rate (phiB);
-	const int lpP = mod_rate ((long long) pp. lp0 - (long long) c * T_F % DAB_INPUT_RATE * phA);
-	const long long F = P + s;                                             // first sample of the PRS
-	const int lpD = mod_rate ((long long) lpP - (long long) (s + N) * phA);  // localPhase after the PRS
+	const int phA = mod_rate (in. phiA), phiB = in. phiB, phB = mod_rate (phiB);
+	const long long F = in. P + s;                                         // first sample of the PRS
+	const int lpD = mod_rate ((long long) in. lp - (long long) (s + N) * phA);  // localPhase after the PRS
 	// symbol l (>= 1) occupies samples [F + N + (l-1) Ts, + Ts): guard first, then the useful part
 	if (l0 == 1) {
 		const float2 *p0 = spec0 + (size_t) c * N;
@@ -174,7 +188,7 @@ __global__ void __launch_bounds__ (OFDM_THREADS) symbol_kernel (SampleWin w, Ofd
 		for (int i = threadIdx. x; i < N; i += OFDM_THREADS) prev [i] = f [i];
 	}
 	float2 acc = make_float2 (0.f, 0.f);
-	const int slot = pp. slot0 + c;
+	const int slot = slot0 + c;
 	for (int l = l0; l < l1; l ++) {
 		const long long first = F + N + (long long) (l - 1) * Ts;
 		const int lpb = mod_rate ((long long) lpD - ((long long) (l - 1) * Ts) % DAB_INPUT_RATE * phB);
@@ -208,28 +222,38 @@ __global__ void __launch_bounds__ (OFDM_THREADS) symbol_kernel (SampleWin w, Ofd
 }
 
 // ---------------------------------------------------------------------------------------------------
-// scan kernel (one thread): the scalar state machine of ofdmProcessor::run replayed over the chunk
+// scan kernel (one thread): the scalar state machine of ofdmProcessor::run replayed over the chunk.
+//   derive = 1: optimistic pass.  Walks ALL frames, replacing fin[c] by the inputs the replayed state asks
+//     for and marking the frames whose inputs changed for recomputation.  Where the data symbols were mixed
+//     with another frequency than the replay wants, the cyclic-prefix correlation is corrected by the exact
+//     identity  FreqCorr(f') = FreqCorr(f) * exp (-j 2 pi (f' - f) T_u / 2048000).  Nothing is committed.
+//   derive = 0: verification pass.  Accepts frames only while the inputs they were actually computed from
+//     equal the replayed state, commits the stream state and the per-frame records.
 // ---------------------------------------------------------------------------------------------------
-__global__ void scan_kernel (StreamCtl *ctl, PassParams pp, int groups, DabParams dp, const FrameOut *fo,
-                             const float2 *fcpart, dabgpu_frame_info *info, long long abs_base) {
+__global__ void scan_kernel (StreamCtl *ctl, FrameIn *fin, int nframes, int slot0, int groups, DabParams dp, const FrameOut *fo,
+                             const float2 *fcpart, dabgpu_frame_info *info, long long abs_base, int derive) {
 	if (threadIdx. x != 0 || blockIdx. x != 0) return;
 	StreamCtl s = *ctl;
 	const int cd = dp. carrierDiff;
-	s. n_valid = 0; s. lost = 0; s. override_valid = 0;
-	for (int c = 0; c < pp. nframes; c ++) {
-		const long long Pa = pp. pos0 + (long long) c * dp. T_F;
-		const int lpa = mod_rate ((long long) pp. lp0 - (long long) c * dp. T_F % DAB_INPUT_RATE * mod_rate (pp. phiA));
-		if (c > 0 && (s. pos != Pa || s. lp != lpa || s. coarse + s. fine != pp. phiA)) break;   // speculation failed here
-		const int si = fo [c]. startIndex;
+	int n_redo = 0;
+	s. n_valid = 0; s. lost = 0;
+	for (int c = 0; c < nframes; c ++) {
+		FrameIn in = fin [c];
 		const int phiA = s. coarse + s. fine;
+		bool changed = in. P != s. pos || in. lp != s. lp || in. phiA != phiA;
+		if (derive) { in. P = s. pos; in. lp = s. lp; in. phiA = phiA; }
+		else if (changed) break;                             // computed from other inputs than the replay wants
+		const int si = fo [c]. startIndex;                   // (derive: from the old window if `changed`; verified later)
 		if (si < 0) {                                        // :353-356 -> notSynced; T_u samples were consumed
+			if (derive) { in. phiB = phiA; in. active = changed; fin [c] = in; n_redo += changed; c ++;
+			              for (; c < nframes; c ++) fin [c]. active = 0; break; }
 			s. pos += dp. T_u;
 			s. lp = mod_rate ((long long) s. lp - (long long) dp. T_u * mod_rate (phiA));
 			s. synced = 0; s. lost = 1;
 			break;
 		}
-		StreamCtl before = s;
 		int correction = 0;
+		StreamCtl before = s;
 		if (s. f2) {                                         // :390-405
 			correction = fo [c]. correction;
 			if (correction == 0 && s. prev1 == 0 && s. prev2 == 0) s. f2 = 0;
@@ -240,19 +264,26 @@ __global__ void scan_kernel (StreamCtl *ctl, PassParams pp, int groups, DabParam
 			}
 		}
 		const int phiB = s. coarse + s. fine;
-		const int usedB = c == 0 ? pp. phiB0 : pp. phiA;
-		if (phiB != usedB) {                                 // the data symbols were mixed with the wrong frequency: redo
-			s = before; s. override_valid = 1; s. override_phiB = phiB;
-			break;
-		}
+		const int usedB = in. phiB;
+		if (derive) {
+			changed = changed || usedB != phiB;
+			in. phiB = phiB; in. active = changed; fin [c] = in; n_redo += changed;
+		} else if (usedB != phiB) { s = before; break; }
 		float2 fc = make_float2 (0.f, 0.f);
 		for (int g = 0; g < groups; g ++) { fc. x += fcpart [c * MAX_GROUPS + g]. x; fc. y += fcpart [c * MAX_GROUPS + g]. y; }
-		dabgpu_frame_info fi;
-		fi. pos = abs_base + s. pos; fi. startIndex = si; fi. coarse = s. coarse; fi. fine = s. fine;
-		fi. phase0 = s. lp; fi. correction = correction; fi. freqCorrRe = fc. x; fi. freqCorrIm = fc. y;
-		info [pp. slot0 + c] = fi;
+		double ang = (double) atan2f (fc. y, fc. x);
+		if (derive && usedB != phiB) {
+			ang -= 2.0 * 3.14159265358979323846 * (double) (phiB - usedB) * (double) dp. T_u / (double) DAB_INPUT_RATE;
+			ang = remainder (ang, 2.0 * 3.14159265358979323846);
+		}
+		if (!derive) {
+			dabgpu_frame_info fi;
+			fi. pos = abs_base + s. pos; fi. startIndex = si; fi. coarse = s. coarse; fi. fine = s. fine;
+			fi. phase0 = s. lp; fi. correction = correction; fi. freqCorrRe = fc. x; fi. freqCorrIm = fc. y;
+			info [slot0 + c] = fi;
+		}
 		// :445-446  fineCorrector (int16) += 0.1 * arg (FreqCorr) / M_PI * (carrierDiff / 2)
-		const double inc = __dmul_rn (__ddiv_rn (__dmul_rn (0.1, (double) atan2f (fc. y, fc. x)), 3.14159265358979323846), (double) (cd / 2));
+		const double inc = __dmul_rn (__ddiv_rn (__dmul_rn (0.1, ang), 3.14159265358979323846), (double) (cd / 2));
 		s. fine = (int) (short) __double2int_rz (__dadd_rn ((double) s. fine, inc));
 		const int phiC = s. coarse + s. fine;
 		long long lp = (long long) s. lp - (long long) (si + dp. T_u) * mod_rate (phiA);
@@ -264,7 +295,8 @@ __global__ void scan_kernel (StreamCtl *ctl, PassParams pp, int groups, DabParam
 		else if (s. fine < - cd / 2) { s. coarse -= cd; s. fine += cd; }
 		s. n_valid = c + 1;
 	}
-	*ctl = s;
+	if (derive) ctl -> n_redo = n_redo;
+	else { s. n_redo = ctl -> n_redo; *ctl = s; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -293,7 +325,7 @@ void dab_engine_free (dabgpu *h) {
 	for (auto *b : E -> backends) dabgpu_backend_destroy (b);
 	if (E -> d_phaseRef) cudaFree (E -> d_phaseRef);
 	E -> tail. release (); E -> d_ctl. release (); E -> h_ctl. release ();
-	E -> d_frameout. release (); E -> d_fcpart. release (); E -> d_spec0. release (); E -> d_info. release ();
+	E -> d_frameout. release (); E -> d_framein. release (); E -> d_fcpart. release (); E -> d_spec0. release (); E -> d_info. release ();
 	E -> d_fic. release (); E -> d_msc. release (); E -> d_histtmp. release ();
 	E -> d_ficbits. release (); E -> d_ficcrc. release ();
 	for (auto &b : E -> d_mscbits) b. release ();
@@ -386,6 +418,7 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 	int rc = ensure_frame_capacity (h, want);
 	if (rc) return rc;
 	CUDA_TRY (h, E -> d_frameout. ensure ((size_t) E -> max_chunk * sizeof (FrameOut)));
+	CUDA_TRY (h, E -> d_framein. ensure ((size_t) E -> max_chunk * sizeof (FrameIn)));
 	CUDA_TRY (h, E -> d_fcpart. ensure ((size_t) E -> max_chunk * MAX_GROUPS * sizeof (float2)));
 	CUDA_TRY (h, E -> d_spec0. ensure ((size_t) E -> max_chunk * p. T_u * sizeof (float2)));
 	StreamCtl *hctl = (StreamCtl *) E -> h_ctl. p;
@@ -395,7 +428,8 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 		if (!E -> ctl. synced) {
 			*hctl = E -> ctl;
 			CUDA_TRY (h, cudaMemcpyAsync (E -> d_ctl. p, hctl, sizeof (StreamCtl), cudaMemcpyHostToDevice, h -> stream));
-			acquire_kernel<<<1, 32, 0, h -> stream>>> (w, E -> T, p. T_F, p. T_null, (StreamCtl *) E -> d_ctl. p);
+			{ ProfScope prof (h, KC_ACQUIRE);
+			acquire_kernel<<<1, 32, 0, h -> stream>>> (w, E -> T, p. T_F, p. T_null, (StreamCtl *) E -> d_ctl. p); }
 			h -> launches ++;
 			CUDA_TRY (h, cudaGetLastError ());
 			CUDA_TRY (h, cudaMemcpyAsync (hctl, E -> d_ctl. p, sizeof (StreamCtl), cudaMemcpyDeviceToHost, h -> stream));
@@ -408,22 +442,27 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 		if (total - E -> ctl. pos < frame_need) avail = 0;
 		if (avail <= 0) break;
 		long long C = E -> chunk;
-		if (E -> ctl. override_valid) C = 1;
 		if (C > avail) C = avail;
 		if (C > want - nframes) C = want - nframes;
-		PassParams pp;
-		pp. pos0 = E -> ctl. pos; pp. lp0 = E -> ctl. lp; pp. phiA = E -> ctl. coarse + E -> ctl. fine;
-		pp. phiB0 = E -> ctl. override_valid ? E -> ctl. override_phiB : pp. phiA;
-		pp. nframes = (int) C; pp. slot0 = nframes;
 		*hctl = E -> ctl;
 		CUDA_TRY (h, cudaMemcpyAsync (E -> d_ctl. p, hctl, sizeof (StreamCtl), cudaMemcpyHostToDevice, h -> stream));
-		front_kernel<<<(int) C, OFDM_THREADS, sm_front, h -> stream>>> (w, E -> T, pp, p. T_F, (FrameOut *) E -> d_frameout. p, (float2 *) E -> d_spec0. p);
-		symbol_kernel<<<(int) C * E -> groups, OFDM_THREADS, sm_sym, h -> stream>>> (w, E -> T, pp, p. T_F, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
-			(const FrameOut *) E -> d_frameout. p, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p,
-			(int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p);
-		scan_kernel<<<1, 1, 0, h -> stream>>> ((StreamCtl *) E -> d_ctl. p, pp, E -> groups, p, (const FrameOut *) E -> d_frameout. p,
-			(const float2 *) E -> d_fcpart. p, (dabgpu_frame_info *) E -> d_info. p, E -> abs_base);
-		h -> launches += 3;
+		StreamCtl *dctl = (StreamCtl *) E -> d_ctl. p;
+		FrameIn *fin = (FrameIn *) E -> d_framein. p;
+		FrameOut *fo = (FrameOut *) E -> d_frameout. p;
+		{ ProfScope prof (h, KC_SCAN);
+		predict_kernel<<<((int) C + 127) / 128, 128, 0, h -> stream>>> (dctl, fin, p. T_F, (int) C); }
+		for (int pass = 0; pass < 2; pass ++) {
+			// pass 0: speculative inputs, then the optimistic replay (derive); pass 1: recompute what changed, then verify
+			{ ProfScope prof (h, KC_FRONT);
+			front_kernel<<<(int) C, OFDM_THREADS, sm_front, h -> stream>>> (w, E -> T, fin, fo, (float2 *) E -> d_spec0. p); }
+			{ ProfScope prof (h, KC_SYMBOL);
+			symbol_kernel<<<(int) C * E -> groups, OFDM_THREADS, sm_sym, h -> stream>>> (w, E -> T, fin, nframes, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
+				fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p); }
+			{ ProfScope prof (h, KC_SCAN);
+			scan_kernel<<<1, 1, 0, h -> stream>>> (dctl, fin, (int) C, nframes, E -> groups, p, fo, (const float2 *) E -> d_fcpart. p,
+				(dabgpu_frame_info *) E -> d_info. p, E -> abs_base, pass == 0 ? 1 : 0); }
+		}
+		h -> launches += 7;
 		CUDA_TRY (h, cudaGetLastError ());
 		CUDA_TRY (h, cudaMemcpyAsync (hctl, E -> d_ctl. p, sizeof (StreamCtl), cudaMemcpyDeviceToHost, h -> stream));
 		CUDA_TRY (h, cudaStreamSynchronize (h -> stream));

@@ -11,7 +11,7 @@ struct StreamCtl {
 	int lp;                             // localPhase before sample `pos`
 	long long pos;                      // next sample to read, relative to the engine's sample window
 	int coarse, fine, f2, prev1, prev2;
-	int override_valid, override_phiB;  // redo the first frame with this data-symbol NCO frequency
+	int n_redo, pad0;                   // derive scan: frames whose inputs changed
 	int n_valid;                        // frames accepted by the last pass
 	int lost;                           // last pass ended with a failed findIndex
 	int acq_done;                       // acquisition kernel: 1 = found the end of a null symbol
@@ -23,8 +23,12 @@ struct SampleWin {                      // two-segment sample window: [tail of e
 	const uchar2 *seg1; long long len1;
 };
 
-struct PassParams {
-	long long pos0; int lp0, phiA, phiB0, nframes, slot0;
+struct FrameIn {                        // per chunk slot: the inputs a frame is (re)computed from
+	long long P;                        // SyncOnPhase window start (window relative)
+	int lp;                             // localPhase before sample P
+	int phiA, phiB;                     // NCO frequency (Hz) for the PRS part / for the data symbols
+	int active;                         // compute this slot in the current pass
+	int pad;
 };
 
 struct FrameOut {                       // per chunk slot, written by the front / symbol kernels
@@ -45,7 +49,7 @@ struct Engine {
 	DevBuf d_ctl;                       // StreamCtl on the device
 	PinBuf h_ctl;
 	int chunk = 1, max_chunk = 256;
-	DevBuf d_frameout, d_fcpart, d_spec0, d_info;
+	DevBuf d_frameout, d_fcpart, d_spec0, d_info, d_framein;
 	DevBuf d_fic, d_msc, d_histtmp;     // soft bits: FIC [frames][3*2K], MSC rows [15 + cifs][55296]
 	long long cap_frames = 0;
 	DevBuf d_ficbits, d_ficcrc;

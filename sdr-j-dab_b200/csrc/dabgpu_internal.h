@@ -68,8 +68,12 @@ struct VitJob {
 	const uint32_t *prbs;     // packed energy-dispersal sequence or nullptr
 	uint8_t *out;             // [nblocks][frameBits], one bit per byte
 };
-cudaError_t vit_launch (const VitJob &job, cudaStream_t st, int64_t *launches);
-cudaError_t fib_crc_launch (const uint8_t *bits, int nfibs, uint8_t *ok, cudaStream_t st, int64_t *launches);
+cudaError_t vit_launch (dabgpu *h, int cls, const VitJob &job);
+cudaError_t fib_crc_launch (dabgpu *h, const uint8_t *bits, int nfibs, uint8_t *ok);
+
+// kernel classes for the optional per-launch CUDA-event profile (dabgpu_profile_*)
+enum { KC_ACQUIRE = 0, KC_FRONT, KC_SYMBOL, KC_SCAN, KC_VITERBI_MSC, KC_VITERBI_FIC, KC_VITERBI_API, KC_CRC, KC_COUNT };
+struct ProfPair { int cls; cudaEvent_t a, b; };
 
 struct Engine;
 struct dabgpu {
@@ -81,6 +85,11 @@ struct dabgpu {
 	std::string err;
 	int64_t launches = 0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	bool profiling = false;
+	std::vector<ProfPair> prof_pending;
+	std::vector<cudaEvent_t> prof_pool;
+	double prof_ms [KC_COUNT] = {0};
+	int64_t prof_n [KC_COUNT] = {0};
 	// staging
 	DevBuf d_in, d_out, d_aux;
 	PinBuf h_in, h_out;
@@ -89,6 +98,12 @@ struct dabgpu {
 	std::map<long long, ProtProfile> profiles;
 };
 
+// brackets one kernel launch with events when profiling is on
+struct ProfScope {
+	dabgpu *h; int cls; cudaEvent_t a = nullptr, b = nullptr;
+	ProfScope (dabgpu *h_, int cls_);
+	~ProfScope ();
+};
 extern thread_local std::string g_create_error;
 int  dab_fail (dabgpu *h, int code, const char *fmt, ...);
 #define CUDA_TRY(h, expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) \

@@ -127,8 +127,10 @@ __global__ void __launch_bounds__ (128) vit_warp_kernel (const VitJob j, const i
 	}
 }
 
-cudaError_t vit_launch (const VitJob &job, cudaStream_t st, int64_t *launches) {
+cudaError_t vit_launch (dabgpu *h, int cls, const VitJob &job) {
 	if (job. nblocks <= 0) return cudaSuccess;
+	cudaStream_t st = h -> stream;
+	ProfScope prof (h, cls);
 	const int words_per_warp = (2 * job. nsteps + (job. frameBits + 31) / 32 + 2) & ~1;   // keeps uint2 alignment
 	const size_t per_warp = (size_t) words_per_warp * 4;
 	int wpc = (int) ((110 * 1024) / per_warp);
@@ -146,7 +148,7 @@ cudaError_t vit_launch (const VitJob &job, cudaStream_t st, int64_t *launches) {
 		if (e != cudaSuccess) return e;
 		vit_warp_kernel<false><<<grid, 32 * wpc, smem, st>>> (job, words_per_warp);
 	}
-	if (launches) (*launches) ++;
+	h -> launches ++;
 	return cudaGetLastError ();
 }
 
@@ -167,9 +169,10 @@ __global__ void fib_crc_kernel (const uint8_t *bits, int nfibs, uint8_t *ok) {
 	ok [f] = reg == 0;
 }
 
-cudaError_t fib_crc_launch (const uint8_t *bits, int nfibs, uint8_t *ok, cudaStream_t st, int64_t *launches) {
+cudaError_t fib_crc_launch (dabgpu *h, const uint8_t *bits, int nfibs, uint8_t *ok) {
 	if (nfibs <= 0) return cudaSuccess;
-	fib_crc_kernel<<<(nfibs + 127) / 128, 128, 0, st>>> (bits, nfibs, ok);
-	if (launches) (*launches) ++;
+	ProfScope prof (h, KC_CRC);
+	fib_crc_kernel<<<(nfibs + 127) / 128, 128, 0, h -> stream>>> (bits, nfibs, ok);
+	h -> launches ++;
 	return cudaGetLastError ();
 }

@@ -154,38 +154,57 @@ class Modulator:
 
     # ---- waveform ----
     def modulate(self, bits):
-        """bits[nframes, L-1, 2K] -> complex128 baseband [nframes * T_F], unit-ish power in the symbols."""
+        """bits[nframes, L-1, 2K] -> complex64 baseband [nframes * T_F], unit power in the symbols."""
+        import scipy.fft
         p = self.p
         nframes = bits.shape[0]
         K, T_u, T_g = p.K, p.T_u, p.T_g
-        q = ((1.0 - 2.0 * bits[..., :K]) + 1j * (1.0 - 2.0 * bits[..., K:])) / np.sqrt(2.0)
+        # QPSK symbol ((1-2b0) + j(1-2b1))/sqrt2 = exp(j(pi/4 + k pi/2)); differential modulation = running
+        # sum of the quadrant numbers k plus pi/4 per symbol, i.e. a running sum of odd multiples of pi/4
+        b0, b1 = bits[..., :K].astype(np.int16), bits[..., K:].astype(np.int16)
+        eighth = 1 + 2 * b0 + 6 * b1 - 4 * (b0 & b1)          # (b0,b1) -> 1,3,7,5 in units of pi/4
         idx = np.where(self.perm < 0, self.perm + T_u, self.perm)
-        y = np.ones((nframes, p.L - 1, T_u), np.complex128)
-        y[..., idx] = q
-        spec = np.zeros((nframes, p.L, T_u), np.complex128)
-        spec[:, 0, :] = self.prs
-        z = np.cumprod(y, axis=1) * self.prs[None, None, :]
-        spec[:, 1:, :] = z
-        t = np.fft.ifft(spec, axis=-1) * (T_u / np.sqrt(K))           # unit power per sample
-        sym = np.concatenate([t[..., T_u - T_g:], t], axis=-1)        # cyclic prefix
-        frames = np.zeros((nframes, p.T_F), np.complex128)
-        frames[:, p.T_null:] = sym.reshape(nframes, p.L * p.T_s)
+        prs8 = np.rint(np.angle(self.prs[idx]) / (np.pi / 4)).astype(np.int16)
+        acc = (np.cumsum(eighth, axis=1, dtype=np.int16) + prs8[None, None, :]) & 7
+        table = np.exp(1j * np.pi / 4 * np.arange(8)).astype(np.complex64)
+        spec = np.zeros((nframes, p.L, T_u), np.complex64)
+        spec[:, 0, :] = self.prs.astype(np.complex64)
+        spec[:, 1:, idx] = table[acc]
+        t = scipy.fft.ifft(spec, axis=-1, workers=-1) * np.float32(T_u / np.sqrt(K))     # unit power per sample
+        frames = np.zeros((nframes, p.T_F), np.complex64)
+        sym = frames[:, p.T_null:].reshape(nframes, p.L, p.T_s)
+        sym[..., T_g:] = t
+        sym[..., :T_g] = t[..., T_u - T_g:]                                               # cyclic prefix
         return frames.reshape(-1)
 
-    def channel(self, x, cfo_hz=0.0, snr_db=30.0, rms=30.0, lead=0, tail=0, phase0=0.0):
-        """CFO, AWGN, gain, u8 quantisation.  `lead`/`tail` noise-only samples around the signal."""
+    def channel(self, x, cfo_hz=0.0, snr_db=30.0, rms=30.0, lead=0, tail=0, phase0=0.0, start_index=0):
+        """CFO, AWGN, gain, u8 quantisation.  `lead`/`tail` noise-only samples around the signal.
+        `start_index` = absolute index of the first output sample (keeps the CFO phase continuous when a
+        long stream is produced in pieces)."""
         n = lead + x.size + tail
-        sig = np.zeros(n, np.complex128)
+        sig = np.zeros(n, np.complex64)
         sig[lead:lead + x.size] = x
-        k = np.arange(n)
-        sig *= np.exp(1j * (2.0 * np.pi * cfo_hz * k / INPUT_RATE + phase0))
-        sigma = 10.0 ** (-snr_db / 20.0)
-        noise = (self.rng.standard_normal(n) + 1j * self.rng.standard_normal(n)) * (sigma / np.sqrt(2.0))
-        r = (sig + noise) * rms * np.sqrt(2.0) / np.sqrt(1.0)           # per-rail rms = `rms` LSB
-        r = r / np.sqrt(2.0)
-        iq = np.empty(2 * n, np.float64)
-        iq[0::2] = r.real; iq[1::2] = r.imag
-        return np.clip(np.rint(iq + 128.0), 0, 255).astype(np.uint8)
+        if cfo_hz != 0.0 or phase0 != 0.0:
+            blk = 1 << 16                                    # e^{j w k} = e^{j w (k0 + r)}: two small tables
+            w = 2.0 * np.pi * cfo_hz / INPUT_RATE
+            fine = np.exp(1j * w * np.arange(blk)).astype(np.complex64)
+            nb = -(-n // blk)
+            coarse = np.exp(1j * (w * (start_index + blk * np.arange(nb, dtype=np.float64)) + phase0)).astype(np.complex64)
+            pad = np.zeros(nb * blk, np.complex64)
+            pad[:n] = sig
+            pad = pad.reshape(nb, blk)
+            pad *= fine[None, :]
+            pad *= coarse[:, None]
+            sig = pad.reshape(-1)[:n]
+        sigma = np.float32(10.0 ** (-snr_db / 20.0) / np.sqrt(2.0))
+        r = np.empty(2 * n, np.float32)
+        r[0::2] = sig.real; r[1::2] = sig.imag
+        r += self.rng.standard_normal(2 * n, dtype=np.float32) * sigma
+        r *= np.float32(rms)                                 # unit-power complex signal -> |x| rms = `rms` LSB
+        r += np.float32(128.0)
+        np.rint(r, out=r)
+        np.clip(r, 0, 255, out=r)
+        return r.astype(np.uint8)
 
     def generate(self, nframes, cfo_hz=0.0, snr_db=30.0, rms=30.0, lead=0, tail=0):
         truth = self.frame_bits(nframes)
