@@ -176,6 +176,23 @@ typedef struct {
 int dabgpu_state_get (dabgpu_t *h, dabgpu_stream_state *s);
 int dabgpu_state_set (dabgpu_t *h, const dabgpu_stream_state *s);
 
+/* ------------------------------------------------------------------------------------------------
+ * Host-only helpers (no GPU needed): the constant tables the engine derives on the host, exported so the
+ * CPU test-suite can compare them with the oracle.
+ * ---------------------------------------------------------------------------------------------- */
+/* out = {dabMode, L, K, T_null, T_F, T_s, T_u, T_g, carrierDiff, ficGroups, cifsPerFrame, blocksPerCIF} (gui.cpp:1328-1372) */
+int dabgpu_host_mode_params (int32_t mode, int32_t out [12]);
+/* permVector (mapper.cpp:33-117) with negative carriers wrapped by +T_u as ofdm-decoder.cpp:179-181 does: out[K] */
+int dabgpu_host_perm_table (int32_t mode, int16_t *out);
+/* phaseReference::refTable (phasereference.cpp:25-48): out[2*T_u] interleaved re,im */
+int dabgpu_host_ref_table (int32_t mode, float *out);
+/* mother-code index -> input index (-1 = punctured) of the FIC (fic != 0; fic-handler.cpp:254-288) or of an
+ * MSC profile (deconvolve.cpp:142-182, 244-319); lut may be NULL to query the sizes only */
+int dabgpu_host_depuncture_lut (int32_t fic, int32_t bitRate, int32_t uepFlag, int32_t protLevel,
+                                int32_t *lut, int32_t lut_capacity, int32_t *lut_len, int32_t *n_punctured);
+/* energy-dispersal sequence (fic-handler.cpp:100-108), one bit per byte */
+int dabgpu_host_prbs (int32_t nbits, uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif

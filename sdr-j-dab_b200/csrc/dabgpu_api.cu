@@ -145,7 +145,7 @@ int dab_device_table (dabgpu *h, long long key, const void *host, size_t bytes, 
 }
 
 int dab_get_profile (dabgpu *h, int kind, int bitRate, int uepFlag, int protLevel,
-                     const ProtProfile **pp, const int16_t **d_lut) {
+                     const ProtProfile **pp, const uint16_t **d_lut) {
 	const long long key = ((long long) (kind ? 1 : 2) << 40) | ((long long) (uepFlag != 0) << 32) |
 	                      ((long long) (bitRate & 0xffff) << 16) | (protLevel & 0xffff);
 	auto it = h -> profiles. find (key);
@@ -158,9 +158,9 @@ int dab_get_profile (dabgpu *h, int kind, int bitRate, int uepFlag, int protLeve
 	}
 	*pp = &it -> second;
 	void *d = nullptr;
-	int rc = dab_device_table (h, key, it -> second. lut. data (), it -> second. lut. size () * sizeof (int16_t), &d);
+	int rc = dab_device_table (h, key, it -> second. lut. data (), it -> second. lut. size () * sizeof (uint16_t), &d);
 	if (rc) return rc;
-	*d_lut = (const int16_t *) d;
+	*d_lut = (const uint16_t *) d;
 	return DABGPU_OK;
 }
 
@@ -226,7 +226,7 @@ extern "C" int dabgpu_viterbi (dabgpu_t *h, const int16_t *soft, int32_t frameBi
 extern "C" int dabgpu_protect_decode (dabgpu_t *h, int32_t bitRate, int32_t uepFlag, int32_t protLevel,
                                       const int16_t *v, int32_t size, int32_t nblocks, uint8_t *bits) {
 	if (!h || !v || !bits || nblocks < 0 || size <= 0) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_protect_decode: bad argument");
-	const ProtProfile *pp; const int16_t *d_lut;
+	const ProtProfile *pp; const uint16_t *d_lut;
 	int rc = dab_get_profile (h, 1, bitRate, uepFlag, protLevel, &pp, &d_lut);
 	if (rc) return rc;
 	if (size < pp -> nPunctured)
@@ -247,7 +247,7 @@ extern "C" int dabgpu_protect_decode (dabgpu_t *h, int32_t bitRate, int32_t uepF
 
 // ---- ficHandler::process_ficInput x ngroups (fic-handler.cpp:241-321) ----
 int dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, uint8_t *d_crc) {
-	const ProtProfile *pp; const int16_t *d_lut; const uint32_t *d_prbs;
+	const ProtProfile *pp; const uint16_t *d_lut; const uint32_t *d_prbs;
 	int rc = dab_get_profile (h, 0, 0, 1, 0, &pp, &d_lut);
 	if (rc) return rc;
 	if ((rc = dab_get_prbs (h, 768, &d_prbs))) return rc;
@@ -283,7 +283,7 @@ struct dabgpu_backend {
 	dabgpu *h;
 	dabgpu_subch sc;
 	int fragmentSize;
-	const ProtProfile *pp; const int16_t *d_lut; const uint32_t *d_prbs;
+	const ProtProfile *pp; const uint16_t *d_lut; const uint32_t *d_prbs;
 	DevBuf rows;                 // [15 history + ncif][fragmentSize] int16
 	DevBuf hist;                 // the last 15 fragments (oldest first), device resident between calls
 	int64_t cifs_seen;           // countforInterleaver, unbounded
@@ -294,7 +294,7 @@ extern "C" int dabgpu_backend_create (dabgpu_t *h, const dabgpu_subch *sc, dabgp
 	*out = nullptr;
 	if (sc -> length <= 0 || sc -> length * 64 > 32767 || sc -> startAddr < 0 || sc -> startAddr + sc -> length > 864)
 		return dab_fail (h, DABGPU_ERR_ARG, "sub-channel [%d, +%d) CUs out of range", sc -> startAddr, sc -> length);
-	const ProtProfile *pp; const int16_t *d_lut; const uint32_t *d_prbs;
+	const ProtProfile *pp; const uint16_t *d_lut; const uint32_t *d_prbs;
 	int rc = dab_get_profile (h, 1, sc -> bitRate, sc -> uepFlag, sc -> protLevel, &pp, &d_lut);
 	if (rc) return rc;
 	if (pp -> nPunctured > sc -> length * 64)

@@ -47,11 +47,11 @@ struct PinBuf {
 };
 
 // ---- puncturing / protection profiles (host side, dabgpu_tables.cpp) ----
-// mother-code index -> input index LUT (int16, -1 = punctured/erasure), 4*(frameBits+6) entries
+// mother-code index -> input index LUT (uint16, 0xFFFF = punctured/erasure), 4*(frameBits+6) entries
 struct ProtProfile {
 	int frameBits = 0;                  // 24 * bitRate (768 for the FIC)
 	int nPunctured = 0;                 // input soft bits consumed per code word
-	std::vector<int16_t> lut;
+	std::vector<uint16_t> lut;
 };
 int  prot_build_fic (ProtProfile *pp);                                        // fic-handler.cpp:254-288
 int  prot_build_msc (int bitRate, int uepFlag, int protLevel, ProtProfile *pp); // deconvolve.cpp:142-182, 244-319
@@ -62,7 +62,7 @@ struct VitJob {
 	const int16_t *in;        // soft-bit source
 	long long in_stride;      // elements between consecutive code words (rows when deint)
 	int first_row;            // deint: buffer row of the CIF decoded by block 0
-	const int16_t *lut;       // device LUT [4*nsteps] or nullptr (identity)
+	const uint16_t *lut;      // device LUT [4*nsteps] or nullptr (identity); 0xFFFF = erasure
 	int frameBits, nsteps, nblocks;
 	int deint;                // 1: value(idx) is read from row (blk + first_row - D[idx & 15])
 	const uint32_t *prbs;     // packed energy-dispersal sequence or nullptr
@@ -112,7 +112,7 @@ int  dab_fail (dabgpu *h, int code, const char *fmt, ...);
 // device copy of a host table, cached in the handle under `key`
 int  dab_device_table (dabgpu *h, long long key, const void *host, size_t bytes, void **dev);
 int  dab_get_profile (dabgpu *h, int kind /*0 fic, 1 msc*/, int bitRate, int uepFlag, int protLevel,
-                      const ProtProfile **pp, const int16_t **d_lut);
+                      const ProtProfile **pp, const uint16_t **d_lut);
 int  dab_get_prbs (dabgpu *h, int nbits, const uint32_t **d_prbs);
 int  dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, uint8_t *d_crc);
 struct dabgpu_backend;

@@ -99,6 +99,59 @@ int ofdm_tables_init (dabgpu *h, OfdmTables *T) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// host-only table exports: let the CPU test-suite check the host logic without a GPU
+// ---------------------------------------------------------------------------------------------------
+extern "C" int dabgpu_host_mode_params (int32_t mode, int32_t out [12]) {
+	DabParams p;
+	if (!out || dab_mode_params (mode, &p)) return DABGPU_ERR_ARG;
+	const int v [12] = { p. dabMode, p. L, p. K, p. T_null, p. T_F, p. T_s, p. T_u, p. T_g, p. carrierDiff, p. ficGroups, p. cifsPerFrame, p. blocksPerCIF };
+	for (int i = 0; i < 12; i ++) out [i] = v [i];
+	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_host_perm_table (int32_t mode, int16_t *out) {
+	DabParams p;
+	std::vector<int16_t> perm;
+	if (!out || dab_mode_params (mode, &p) || build_perm (p, &perm)) return DABGPU_ERR_ARG;
+	memcpy (out, perm. data (), perm. size () * sizeof (int16_t));
+	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_host_ref_table (int32_t mode, float *out) {
+	DabParams p;
+	if (!out || dab_mode_params (mode, &p)) return DABGPU_ERR_ARG;
+	memset (out, 0, sizeof (float) * 2 * p. T_u);
+	for (int i = 1; i <= p. K / 2; i ++) {
+		float phi = prs_phi (mode, i);
+		out [2 * i] = cosf (phi); out [2 * i + 1] = sinf (phi);
+		phi = prs_phi (mode, -i);
+		out [2 * (p. T_u - i)] = cosf (phi); out [2 * (p. T_u - i) + 1] = sinf (phi);
+	}
+	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_host_depuncture_lut (int32_t fic, int32_t bitRate, int32_t uepFlag, int32_t protLevel,
+                                           int32_t *lut, int32_t lut_capacity, int32_t *lut_len, int32_t *n_punctured) {
+	ProtProfile pp;
+	if (!lut_len || !n_punctured) return DABGPU_ERR_ARG;
+	if (fic ? prot_build_fic (&pp) : prot_build_msc (bitRate, uepFlag, protLevel, &pp)) return DABGPU_ERR_PROFILE;
+	*lut_len = (int32_t) pp. lut. size (); *n_punctured = pp. nPunctured;
+	if (lut) {
+		if (lut_capacity < (int32_t) pp. lut. size ()) return DABGPU_ERR_ARG;
+		for (size_t i = 0; i < pp. lut. size (); i ++) lut [i] = pp. lut [i] == 0xFFFF ? -1 : (int32_t) pp. lut [i];
+	}
+	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_host_prbs (int32_t nbits, uint8_t *out) {
+	if (!out || nbits < 0) return DABGPU_ERR_ARG;
+	std::vector<uint32_t> w;
+	prbs_packed (nbits, &w);
+	for (int i = 0; i < nbits; i ++) out [i] = (w [i >> 5] >> (i & 31)) & 1;
+	return DABGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // per-call kernels (float input, as the reference's class interfaces take it)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__ (OFDM_THREADS) fft_kernel (float2 *v, OfdmTables T, int inverse) {

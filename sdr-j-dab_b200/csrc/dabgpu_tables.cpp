@@ -90,7 +90,7 @@ static int segments_for (int bitRate, int uepFlag, int protLevel, int L [4], int
 static int build_lut (int frameBits, const int L [4], const int PI [4], ProtProfile *pp) {
 	const int total = 4 * (frameBits + 6);
 	pp -> frameBits = frameBits;
-	pp -> lut. assign (total, -1);
+	pp -> lut. assign (total, (uint16_t) 0xFFFF);
 	int in = 0, pos = 0;
 	for (int s = 0; s < 4; s ++) {
 		if (L [s] <= 0) continue;
@@ -98,14 +98,14 @@ static int build_lut (int frameBits, const int L [4], const int PI [4], ProtProf
 		puncture_vector (PI [s], v);
 		for (int i = 0; i < L [s] * 128; i ++, pos ++) {
 			if (pos >= total) return -1;
-			if (v [i & 31]) pp -> lut [pos] = (int16_t) in ++;
+			if (v [i & 31]) pp -> lut [pos] = (uint16_t) in ++;
 		}
 	}
 	for (int i = 0; i < 24; i ++, pos ++) {
 		if (pos >= total) return -1;
-		if ((i & 3) < 2) pp -> lut [pos] = (int16_t) in ++;
+		if ((i & 3) < 2) pp -> lut [pos] = (uint16_t) in ++;
 	}
-	if (in > 32767) return -1;
+	if (in >= 0xFFFF) return -1;
 	pp -> nPunctured = in;
 	return 0;
 }

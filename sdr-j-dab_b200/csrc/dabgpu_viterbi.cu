@@ -26,8 +26,9 @@ __device__ __forceinline__ unsigned load_step_symbols (const VitJob &j, const in
 	if (t >= j. nsteps) return 0x7f7f7f7fu;
 	int idx [4];
 	if (j. lut) {
-		const short4 l = reinterpret_cast<const short4 *> (j. lut) [t];
-		idx [0] = l. x; idx [1] = l. y; idx [2] = l. z; idx [3] = l. w;
+		const ushort4 l = reinterpret_cast<const ushort4 *> (j. lut) [t];
+		idx [0] = l. x == 0xFFFF ? -1 : l. x; idx [1] = l. y == 0xFFFF ? -1 : l. y;
+		idx [2] = l. z == 0xFFFF ? -1 : l. z; idx [3] = l. w == 0xFFFF ? -1 : l. w;
 	} else {
 		idx [0] = 4 * t; idx [1] = 4 * t + 1; idx [2] = 4 * t + 2; idx [3] = 4 * t + 3;
 	}

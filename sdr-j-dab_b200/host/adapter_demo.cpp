@@ -1,0 +1,40 @@
+// adapter_demo.cpp -- exercises the drop-in adapter classes (dab_adapters.h) exactly the way the reference's
+// own code uses the classes they replace.  Built and run by tests/test_adapters_gpu.py on the GPU box;
+// prints one hash line per class so the test can compare with the oracle.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "dab_adapters.h"
+
+static uint32_t lcg (uint32_t &s) { s = s * 1664525u + 1013904223u; return s >> 8; }
+static unsigned long long fnv (const uint8_t *p, size_t n) { unsigned long long h = 1469598103934665603ull; for (size_t i = 0; i < n; i ++) { h ^= p [i]; h *= 1099511628211ull; } return h; }
+
+int main () {
+	try {
+		uint32_t seed = 12345;
+		{	// viterbi (768), as ficHandler does (fic-handler.cpp:84, 293)
+			viterbi v (768);
+			std::vector<int16_t> in (4 * 774); std::vector<uint8_t> out (768);
+			for (auto &x : in) x = (int16_t) (lcg (seed) % 255) - 127;
+			v. deconvolve (in. data (), out. data ());
+			printf ("viterbi768 %016llx\n", fnv (out. data (), out. size ()));
+		}
+		{	// eep_deconvolve (128, 3-A) and uep_deconvolve (128, 3), as dabConcurrent does (dab-concurrent.cpp:78-83, 177-180)
+			eep_deconvolve e (128, 0103); uep_deconvolve u (128, 3);
+			std::vector<int16_t> in (96 * 64); std::vector<uint8_t> out (3072);
+			for (auto &x : in) x = (int16_t) (lcg (seed) % 255) - 127;
+			e. deconvolve (in. data (), 96 * 64, out. data ());
+			printf ("eep128_3A %016llx\n", fnv (out. data (), out. size ()));
+			u. deconvolve (in. data (), 96 * 64, out. data ());
+			printf ("uep128_3 %016llx\n", fnv (out. data (), out. size ()));
+		}
+		{	// dabBackend = dabConcurrent: 20 CIF fragments in, 4 frames out
+			int frames = 0; unsigned long long acc = 0;
+			dabBackend b (1, 12 * 64, 16, 1, 0103, 0, [&] (uint8_t *v, int16_t n) { frames ++; acc ^= fnv (v, n) + frames; });
+			std::vector<int16_t> frag (12 * 64);
+			for (int t = 0; t < 20; t ++) { for (auto &x : frag) x = (int16_t) (lcg (seed) % 255) - 127; b. process (frag. data (), 12 * 64); }
+			printf ("backend %d %016llx\n", frames, acc);
+		}
+	} catch (const std::exception &e) { fprintf (stderr, "adapter_demo: %s\n", e. what ()); return 1; }
+	return 0;
+}
