@@ -175,6 +175,12 @@ typedef struct {
 } dabgpu_stream_state;
 int dabgpu_state_get (dabgpu_t *h, dabgpu_stream_state *s);
 int dabgpu_state_set (dabgpu_t *h, const dabgpu_stream_state *s);
+/* the complete stream state as one opaque blob: sync/AFC state, the unconsumed sample tail, the 15-CIF soft-bit
+ * halo of the time de-interleaver (dab-concurrent.cpp:41-43, 162-175) and the warm-up counters of the configured
+ * sub-channels.  This is what one GPU hands to the next when a recording is split (<= ~2.1 MB).
+ * export with buf == NULL returns the size needed in *used. */
+int dabgpu_state_export (dabgpu_t *h, void *buf, size_t capacity, size_t *used);
+int dabgpu_state_import (dabgpu_t *h, const void *buf, size_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-only helpers (no GPU needed): the constant tables the engine derives on the host, exported so the

@@ -85,6 +85,8 @@ def load_library():
     L.dabgpu_reset.argtypes = [C.c_void_p]
     L.dabgpu_state_get.argtypes = [C.c_void_p, C.POINTER(StreamState)]
     L.dabgpu_state_set.argtypes = [C.c_void_p, C.POINTER(StreamState)]
+    L.dabgpu_state_export.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.dabgpu_state_import.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     _lib = L
     return L
 
@@ -284,6 +286,18 @@ class DabGpu:
 
     def state_set(self, s):
         self._check(self.lib.dabgpu_state_set(self.h, C.byref(s)))
+
+    def export_state(self):
+        """-> uint8 ndarray: the whole stream state (sync, sample tail, de-interleaver halo)"""
+        n = C.c_size_t(0)
+        self._check(self.lib.dabgpu_state_export(self.h, None, 0, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        self._check(self.lib.dabgpu_state_export(self.h, buf.ctypes.data, buf.size, C.byref(n)))
+        return buf
+
+    def import_state(self, blob):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        self._check(self.lib.dabgpu_state_import(self.h, blob.ctypes.data, blob.size))
 
     def backend(self, startAddr, length, bitRate, uepFlag, protLevel):
         return Backend(self, SubCh(startAddr, length, bitRate, uepFlag, protLevel))

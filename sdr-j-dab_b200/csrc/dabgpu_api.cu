@@ -338,6 +338,8 @@ int dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row
 }
 
 void dab_backend_note_cifs (dabgpu_backend *b, int ncif) { b -> cifs_seen += ncif; }
+int64_t dab_backend_cifs_seen (const dabgpu_backend *b) { return b -> cifs_seen; }
+void dab_backend_set_cifs_seen (dabgpu_backend *b, int64_t n) { b -> cifs_seen = n; }
 
 extern "C" int dabgpu_backend_process (dabgpu_backend_t *b, const int16_t *frags, int32_t ncif, uint8_t *out, int32_t *nout) {
 	if (!b || !frags || !out || !nout || ncif < 0) return dab_fail (b ? b -> h : nullptr, DABGPU_ERR_ARG, "dabgpu_backend_process: bad argument");

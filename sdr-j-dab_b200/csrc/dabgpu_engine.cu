@@ -379,6 +379,66 @@ extern "C" int dabgpu_state_set (dabgpu_t *h, const dabgpu_stream_state *s) {
 	return DABGPU_OK;
 }
 
+static int ensure_frame_capacity (dabgpu *h, long long frames);
+
+// ---- whole stream state as one blob (the multi-GPU hand-over: sync/AFC state + unconsumed samples + the
+// 15-CIF soft-bit halo of the time de-interleaver + per-sub-channel warm-up counters) ----
+struct StateBlobHeader {
+	uint32_t magic; int32_t mode, nsub, hist_valid;
+	StreamCtl ctl; long long abs_base, frames_total, cifs_total, tail_len;
+};
+#define STATE_MAGIC 0x44414247u
+
+extern "C" int dabgpu_state_export (dabgpu_t *h, void *buf, size_t capacity, size_t *used) {
+	if (!h || !used) return DABGPU_ERR_ARG;
+	Engine *E = h -> engine;
+	const size_t rowb = (size_t) CIF_BITS * sizeof (int16_t);
+	const size_t need = sizeof (StateBlobHeader) + E -> backends. size () * sizeof (int64_t) + (size_t) E -> tail_len * sizeof (uchar2) + 15 * rowb;
+	*used = need;
+	if (!buf) return DABGPU_OK;
+	if (capacity < need) return dab_fail (h, DABGPU_ERR_ARG, "state blob needs %zu bytes", need);
+	CUDA_TRY (h, cudaSetDevice (h -> device));
+	StateBlobHeader hd {};
+	hd. magic = STATE_MAGIC; hd. mode = h -> p. dabMode; hd. nsub = (int32_t) E -> backends. size (); hd. hist_valid = E -> hist_init;
+	hd. ctl = E -> ctl; hd. abs_base = E -> abs_base; hd. frames_total = E -> frames_total; hd. cifs_total = E -> cifs_total; hd. tail_len = E -> tail_len;
+	char *q = (char *) buf;
+	memcpy (q, &hd, sizeof (hd)); q += sizeof (hd);
+	for (auto *b : E -> backends) { int64_t c = dab_backend_cifs_seen (b); memcpy (q, &c, sizeof (c)); q += sizeof (c); }
+	if (E -> tail_len) CUDA_TRY (h, cudaMemcpyAsync (q, E -> tail. p, (size_t) E -> tail_len * sizeof (uchar2), cudaMemcpyDeviceToHost, h -> stream));
+	q += (size_t) E -> tail_len * sizeof (uchar2);
+	if (E -> hist_init) CUDA_TRY (h, cudaMemcpyAsync (q, E -> d_msc. p, 15 * rowb, cudaMemcpyDeviceToHost, h -> stream));
+	else memset (q, 0, 15 * rowb);
+	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_state_import (dabgpu_t *h, const void *buf, size_t n) {
+	if (!h || !buf || n < sizeof (StateBlobHeader)) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_state_import: bad argument");
+	Engine *E = h -> engine;
+	StateBlobHeader hd;
+	memcpy (&hd, buf, sizeof (hd));
+	const size_t rowb = (size_t) CIF_BITS * sizeof (int16_t);
+	if (hd. magic != STATE_MAGIC || hd. mode != h -> p. dabMode || hd. nsub != (int32_t) E -> backends. size () || hd. tail_len < 0 ||
+	    n != sizeof (hd) + (size_t) hd. nsub * sizeof (int64_t) + (size_t) hd. tail_len * sizeof (uchar2) + 15 * rowb)
+		return dab_fail (h, DABGPU_ERR_ARG, "state blob does not match this handle (mode / sub-channel count / size)");
+	CUDA_TRY (h, cudaSetDevice (h -> device));
+	int rc = ensure_frame_capacity (h, 1);
+	if (rc) return rc;
+	const char *q = (const char *) buf + sizeof (hd);
+	for (auto *b : E -> backends) { int64_t c; memcpy (&c, q, sizeof (c)); q += sizeof (c); dab_backend_set_cifs_seen (b, c); }
+	E -> ctl = hd. ctl; E -> abs_base = hd. abs_base; E -> frames_total = hd. frames_total; E -> cifs_total = hd. cifs_total;
+	E -> tail_len = hd. tail_len;
+	if (hd. tail_len) {
+		CUDA_TRY (h, E -> tail. ensure ((size_t) hd. tail_len * sizeof (uchar2)));
+		CUDA_TRY (h, cudaMemcpyAsync (E -> tail. p, q, (size_t) hd. tail_len * sizeof (uchar2), cudaMemcpyHostToDevice, h -> stream));
+	}
+	q += (size_t) hd. tail_len * sizeof (uchar2);
+	CUDA_TRY (h, cudaMemcpyAsync (E -> d_msc. p, q, 15 * rowb, cudaMemcpyHostToDevice, h -> stream));
+	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+	E -> hist_init = true;
+	return DABGPU_OK;
+}
+
 static int ensure_frame_capacity (dabgpu *h, long long frames) {
 	Engine *E = h -> engine;
 	const DabParams &p = h -> p;

@@ -118,6 +118,8 @@ int  dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, long long stride, int
 struct dabgpu_backend;
 int  dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row_stride, int ncif, uint8_t *d_out, int *nout);
 void dab_backend_note_cifs (dabgpu_backend *b, int ncif);
+int64_t dab_backend_cifs_seen (const dabgpu_backend *b);
+void dab_backend_set_cifs_seen (dabgpu_backend *b, int64_t n);
 // OFDM / stream engine state (dabgpu_ofdm.cu, dabgpu_engine.cu)
 int  dab_engine_init (dabgpu *h);
 void dab_engine_free (dabgpu *h);
