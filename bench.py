@@ -299,7 +299,7 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         ip = eng.int_peak()
-        int_peak = max(ip.values())
+        int_peak = max(ip[k] for k in ("add", "min", "add_mad"))
         n_vit, ms_vit = prof["viterbi_msc"]
         n_sym, ms_sym = prof["symbol"]
         steps_msc = frames_per_step * 4 * (3072 + 6)          # trellis steps per viterbi_msc launch

@@ -43,7 +43,8 @@ typedef struct {
 	int32_t dabMode;           /* 1..4 (DabParams.dabMode, gui.cpp:1328-1372)                      */
 	int32_t threshold;         /* phaseReference level, default 3 (gui.cpp:98-99)                  */
 	int32_t freqSyncMethod;    /* 0,1,2 as ofdmDecoder (main.cpp:91 default 1)                     */
-	int32_t reserved [4];
+	int32_t viterbi_path;      /* 0 = auto (by batch size), 1 = warp-per-code-word kernel, 2 = code-word-per-thread kernel */
+	int32_t reserved [3];
 } dabgpu_config;
 
 /* one MSC sub-channel, the fields of audiodata/packetdata the decode path uses (dab-constants.h:151-175;
@@ -72,14 +73,15 @@ int  dabgpu_timer_end (dabgpu_t *h, float *ms);
  * launch is bracketed by two events on the handle's stream; get() waits for the stream and returns the
  * accumulated launch count and device milliseconds of one class since the last reset */
 enum { DABGPU_KC_ACQUIRE = 0, DABGPU_KC_FRONT, DABGPU_KC_SYMBOL, DABGPU_KC_SCAN, DABGPU_KC_VITERBI_MSC,
-       DABGPU_KC_VITERBI_FIC, DABGPU_KC_VITERBI_API, DABGPU_KC_CRC, DABGPU_KC_COUNT };
+       DABGPU_KC_VITERBI_FIC, DABGPU_KC_VITERBI_API, DABGPU_KC_CRC, DABGPU_KC_VITERBI_TB, DABGPU_KC_COUNT };
 int  dabgpu_profile_enable (dabgpu_t *h, int32_t on);
 int  dabgpu_profile_reset (dabgpu_t *h);
 int  dabgpu_profile_get (dabgpu_t *h, int32_t kernel_class, int64_t *launches, double *ms);
 
 /* integer-pipe peak of this GPU, measured live (the roofline denominator of the Viterbi group, which
  * MEASURED_PEAKS.json does not hold): ops[0] = add only, ops[1] = min only, ops[2] = add + mad.lo mix,
- * in 32-bit integer operations per second */
+ * ops[3] = packed 16x2 add, ops[4] = packed 16x2 min, ops[5] = packed min + predicates + two predicated ORs
+ * (one count per group); ops must hold 6 doubles; unit = instructions x 32-bit lanes per second */
 int  dabgpu_int_peak (dabgpu_t *h, double *ops);
 
 /* ------------------------------------------------------------------------------------------------

@@ -14,7 +14,7 @@ class DabGpuError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("dabMode", C.c_int32), ("threshold", C.c_int32),
-                ("freqSyncMethod", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("freqSyncMethod", C.c_int32), ("viterbi_path", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class SubCh(C.Structure):
@@ -104,9 +104,9 @@ class DecodeOut:
 class DabGpu:
     """One engine handle (dabgpu_t)."""
 
-    def __init__(self, mode=1, device=0, threshold=3, freqSyncMethod=1):
+    def __init__(self, mode=1, device=0, threshold=3, freqSyncMethod=1, viterbi_path=0):
         self.lib = load_library()
-        cfg = Config(device=device, dabMode=mode, threshold=threshold, freqSyncMethod=freqSyncMethod)
+        cfg = Config(device=device, dabMode=mode, threshold=threshold, freqSyncMethod=freqSyncMethod, viterbi_path=viterbi_path)
         self.h = C.c_void_p()
         rc = self.lib.dabgpu_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:
@@ -136,7 +136,7 @@ class DabGpu:
         self._check(self.lib.dabgpu_timer_end(self.h, C.byref(ms)))
         return ms.value
 
-    KERNEL_CLASSES = ("acquire", "front", "symbol", "scan", "viterbi_msc", "viterbi_fic", "viterbi_api", "crc")
+    KERNEL_CLASSES = ("acquire", "front", "symbol", "scan", "viterbi_msc", "viterbi_fic", "viterbi_api", "crc", "viterbi_tb")
 
     def profile_enable(self, on=True):
         self._check(self.lib.dabgpu_profile_enable(self.h, int(on)))
@@ -154,9 +154,9 @@ class DabGpu:
         return out
 
     def int_peak(self):
-        ops = (C.c_double * 3)()
+        ops = (C.c_double * 6)()
         self._check(self.lib.dabgpu_int_peak(self.h, ops))
-        return {"add": ops[0], "min": ops[1], "add_mad": ops[2]}
+        return {"add": ops[0], "min": ops[1], "add_mad": ops[2], "vadd2": ops[3], "vmin2": ops[4], "vibmin2_or2": ops[5]}
 
     def launch_count(self):
         return int(self.lib.dabgpu_launch_count(self.h))

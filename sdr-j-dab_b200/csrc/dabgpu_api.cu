@@ -53,7 +53,7 @@ extern "C" void dabgpu_destroy (dabgpu_t *h) {
 	if (h -> stream) cudaStreamSynchronize (h -> stream);
 	dab_engine_free (h);
 	for (auto &kv : h -> d_tables) cudaFree (kv. second);
-	h -> d_in. release (); h -> d_out. release (); h -> d_aux. release ();
+	h -> d_in. release (); h -> d_out. release (); h -> d_aux. release (); h -> d_dec. release (); h -> d_jobs. release (); h -> h_jobs. release ();
 	h -> h_in. release (); h -> h_out. release ();
 	if (h -> ev0) { cudaEventDestroy (h -> ev0); cudaEventDestroy (h -> ev1); }
 	for (auto &pp : h -> prof_pending) { cudaEventDestroy (pp. a); cudaEventDestroy (pp. b); }
@@ -164,6 +164,50 @@ int dab_get_profile (dabgpu *h, int kind, int bitRate, int uepFlag, int protLeve
 	return DABGPU_OK;
 }
 
+int dab_get_profile_simd (dabgpu *h, int kind, int bitRate, int uepFlag, int protLevel, const uint16_t **d_inv, const uint16_t **d_chunk) {
+	const ProtProfile *pp; const uint16_t *d_lut;
+	int rc = dab_get_profile (h, kind, bitRate, uepFlag, protLevel, &pp, &d_lut);
+	if (rc) return rc;
+	const long long key = ((long long) (kind ? 1 : 2) << 40) | ((long long) (uepFlag != 0) << 32) |
+	                      ((long long) (bitRate & 0xffff) << 16) | (protLevel & 0xffff);
+	void *d = nullptr;
+	if ((rc = dab_device_table (h, key | (5ll << 44), pp -> inv. data (), pp -> inv. size () * sizeof (uint16_t), &d))) return rc;
+	*d_inv = (const uint16_t *) d;
+	if ((rc = dab_device_table (h, key | (6ll << 44), pp -> chunk_i0. data (), pp -> chunk_i0. size () * sizeof (uint16_t), &d))) return rc;
+	*d_chunk = (const uint16_t *) d;
+	return DABGPU_OK;
+}
+
+// the one-code-word-per-thread kernels need ~20k code words in flight to fill 148 SMs; below that the
+// warp-per-code-word kernel has the lower latency.  cfg.viterbi_path: 0 = auto, 1 = always warp, 2 = always SIMD.
+bool dab_use_simd (const dabgpu *h, long long ncodewords) {
+	if (h -> cfg. viterbi_path == 1) return false;
+	if (h -> cfg. viterbi_path == 2) return true;
+	return ncodewords >= 8192;
+}
+
+int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
+	if (jobs. empty ()) return DABGPU_OK;
+	size_t dec_words = 0;
+	int ctas = 0;
+	for (auto &j : jobs) {
+		j. cta_first = ctas;
+		ctas += (j. ncw + 63) / 64;
+		dec_words += (size_t) ((j. nsteps + 39) / 40 * 40) * j. ncw;
+	}
+	CUDA_TRY (h, h -> d_dec. ensure (dec_words * sizeof (uint2)));
+	size_t off = 0;
+	for (auto &j : jobs) { j. dec = (uint2 *) h -> d_dec. p + off; off += (size_t) ((j. nsteps + 39) / 40 * 40) * j. ncw; }
+	const size_t jb = jobs. size () * sizeof (VitSimdJob);
+	CUDA_TRY (h, h -> d_jobs. ensure (jb));
+	CUDA_TRY (h, h -> h_jobs. ensure (jb));
+	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));           // the pinned job table may still be read by an earlier launch
+	memcpy (h -> h_jobs. p, jobs. data (), jb);
+	CUDA_TRY (h, cudaMemcpyAsync (h -> d_jobs. p, h -> h_jobs. p, jb, cudaMemcpyHostToDevice, h -> stream));
+	CUDA_TRY (h, vit_simd_launch (h, (const VitSimdJob *) h -> d_jobs. p, (int) jobs. size (), ctas));
+	return DABGPU_OK;
+}
+
 int dab_get_prbs (dabgpu *h, int nbits, const uint32_t **d_prbs) {
 	const long long key = (3ll << 40) | nbits;
 	auto it = h -> d_tables. find (key);
@@ -204,6 +248,13 @@ extern "C" int dabgpu_viterbi_dev (dabgpu_t *h, const int16_t *soft, int32_t fra
 	j. in = soft; j. in_stride = 4ll * (frameBits + 6); j. lut = nullptr;
 	j. frameBits = frameBits; j. nsteps = frameBits + 6; j. nblocks = nblocks;
 	j. deint = 0; j. prbs = nullptr; j. out = bits;
+	if (dab_use_simd (h, nblocks)) {
+		std::vector<VitSimdJob> jobs (1);
+		VitSimdJob &s = jobs [0];
+		memset (&s, 0, sizeof (s));
+		s. in = soft; s. in_stride = j. in_stride; s. frameBits = frameBits; s. nsteps = frameBits + 6; s. ncw = nblocks; s. out = bits;
+		return dab_vit_simd_run (h, jobs);
+	}
 	CUDA_TRY (h, vit_launch (h, KC_VITERBI_API, j));
 	return DABGPU_OK;
 }
@@ -241,11 +292,28 @@ extern "C" int dabgpu_protect_decode (dabgpu_t *h, int32_t bitRate, int32_t uepF
 	j. in = (const int16_t *) d_in; j. in_stride = size; j. lut = d_lut;
 	j. frameBits = pp -> frameBits; j. nsteps = pp -> frameBits + 6; j. nblocks = nblocks;
 	j. out = (uint8_t *) h -> d_out. p;
-	CUDA_TRY (h, vit_launch (h, KC_VITERBI_API, j));
+	if (dab_use_simd (h, nblocks)) {
+		std::vector<VitSimdJob> jobs (1);
+		VitSimdJob &s = jobs [0];
+		memset (&s, 0, sizeof (s));
+		if ((rc = dab_get_profile_simd (h, 1, bitRate, uepFlag, protLevel, &s. inv, &s. chunk_i0))) return rc;
+		s. in = j. in; s. in_stride = size; s. frameBits = j. frameBits; s. nsteps = j. nsteps; s. ncw = nblocks; s. out = j. out;
+		if ((rc = dab_vit_simd_run (h, jobs))) return rc;
+	} else
+		CUDA_TRY (h, vit_launch (h, KC_VITERBI_API, j));
 	return stage_out (h, bits, h -> d_out. p, obytes);
 }
 
 // ---- ficHandler::process_ficInput x ngroups (fic-handler.cpp:241-321) ----
+int dab_fic_simd_job (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, VitSimdJob *s) {
+	memset (s, 0, sizeof (*s));
+	int rc = dab_get_profile_simd (h, 0, 0, 1, 0, &s -> inv, &s -> chunk_i0);
+	if (rc) return rc;
+	if ((rc = dab_get_prbs (h, 768, &s -> prbs))) return rc;
+	s -> in = d_soft; s -> in_stride = stride; s -> frameBits = 768; s -> nsteps = 774; s -> ncw = ngroups; s -> out = d_bits;
+	return DABGPU_OK;
+}
+
 int dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, uint8_t *d_crc) {
 	const ProtProfile *pp; const uint16_t *d_lut; const uint32_t *d_prbs;
 	int rc = dab_get_profile (h, 0, 0, 1, 0, &pp, &d_lut);
@@ -255,7 +323,12 @@ int dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, long long stride, int 
 	j. in = d_soft; j. in_stride = stride; j. lut = d_lut;
 	j. frameBits = 768; j. nsteps = 774; j. nblocks = ngroups;
 	j. prbs = d_prbs; j. out = d_bits;
-	CUDA_TRY (h, vit_launch (h, KC_VITERBI_FIC, j));
+	if (dab_use_simd (h, ngroups)) {
+		std::vector<VitSimdJob> jobs (1);
+		if ((rc = dab_fic_simd_job (h, d_soft, stride, ngroups, d_bits, &jobs [0]))) return rc;
+		if ((rc = dab_vit_simd_run (h, jobs))) return rc;
+	} else
+		CUDA_TRY (h, vit_launch (h, KC_VITERBI_FIC, j));
 	if (d_crc) CUDA_TRY (h, fib_crc_launch (h, d_bits, 3 * ngroups, d_crc));
 	return DABGPU_OK;
 }
@@ -321,7 +394,7 @@ extern "C" void dabgpu_backend_destroy (dabgpu_backend_t *b) {
 
 // device-side core: rows = [15 history][ncif new] fragments; decodes the CIFs past the warm-up
 int dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row_stride, int ncif,
-                         uint8_t *d_out, int *nout) {
+                         uint8_t *d_out, int *nout, VitSimdJob *simd_job) {
 	dabgpu *h = b -> h;
 	// dab-concurrent.cpp:172-175: the first 16 CIFs only fill the de-interleaver
 	int64_t skip = 16 - b -> cifs_seen;
@@ -332,8 +405,16 @@ int dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row
 	j. in = d_rows; j. in_stride = row_stride; j. first_row = 15 + (int) skip; j. lut = b -> d_lut;
 	j. frameBits = b -> pp -> frameBits; j. nsteps = j. frameBits + 6; j. nblocks = n;
 	j. deint = 1; j. prbs = b -> d_prbs; j. out = d_out;
-	CUDA_TRY (h, vit_launch (h, KC_VITERBI_MSC, j));
 	*nout = n;
+	if (simd_job) {                       // the caller batches several sub-channels into one SIMD launch
+		memset (simd_job, 0, sizeof (*simd_job));
+		int rc = dab_get_profile_simd (h, 1, b -> sc. bitRate, b -> sc. uepFlag, b -> sc. protLevel, &simd_job -> inv, &simd_job -> chunk_i0);
+		if (rc) return rc;
+		simd_job -> in = d_rows; simd_job -> in_stride = row_stride; simd_job -> first_row = j. first_row; simd_job -> deint = 1;
+		simd_job -> frameBits = j. frameBits; simd_job -> nsteps = j. nsteps; simd_job -> ncw = n; simd_job -> prbs = b -> d_prbs; simd_job -> out = d_out;
+		return DABGPU_OK;
+	}
+	CUDA_TRY (h, vit_launch (h, KC_VITERBI_MSC, j));
 	return DABGPU_OK;
 }
 
@@ -357,8 +438,12 @@ extern "C" int dabgpu_backend_process (dabgpu_backend_t *b, const int16_t *frags
 	const size_t obytes = (size_t) ncif * b -> pp -> frameBits;
 	CUDA_TRY (h, h -> d_out. ensure (obytes));
 	int n = 0;
-	int rc = dab_backend_run_dev (b, d_rows, (long long) fs, ncif, (uint8_t *) h -> d_out. p, &n);
-	if (rc) return rc;
+	int rc;
+	if (dab_use_simd (h, ncif)) {
+		std::vector<VitSimdJob> jobs (1);
+		if ((rc = dab_backend_run_dev (b, d_rows, (long long) fs, ncif, (uint8_t *) h -> d_out. p, &n, &jobs [0]))) return rc;
+		if (n > 0 && (rc = dab_vit_simd_run (h, jobs))) return rc;
+	} else if ((rc = dab_backend_run_dev (b, d_rows, (long long) fs, ncif, (uint8_t *) h -> d_out. p, &n, nullptr))) return rc;
 	// new history = last 15 rows of [history | new]
 	CUDA_TRY (h, cudaMemcpyAsync (b -> hist. p, d_rows + (size_t) ncif * fs, 15 * rowb, cudaMemcpyDeviceToDevice, h -> stream));
 	b -> cifs_seen += ncif;

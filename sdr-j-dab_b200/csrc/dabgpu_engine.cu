@@ -230,73 +230,101 @@ __global__ void __launch_bounds__ (OFDM_THREADS) symbol_kernel (SampleWin w, Ofd
 //   derive = 0: verification pass.  Accepts frames only while the inputs they were actually computed from
 //     equal the replayed state, commits the stream state and the per-frame records.
 // ---------------------------------------------------------------------------------------------------
-__global__ void scan_kernel (StreamCtl *ctl, FrameIn *fin, int nframes, int slot0, int groups, DabParams dp, const FrameOut *fo,
+#define SCAN_MAX 256
+__global__ void __launch_bounds__ (32) scan_kernel (StreamCtl *ctl, FrameIn *fin, int nframes, int slot0, int groups, DabParams dp, const FrameOut *fo,
                              const float2 *fcpart, dabgpu_frame_info *info, long long abs_base, int derive) {
-	if (threadIdx. x != 0 || blockIdx. x != 0) return;
-	StreamCtl s = *ctl;
-	const int cd = dp. carrierDiff;
-	int n_redo = 0;
-	s. n_valid = 0; s. lost = 0;
-	for (int c = 0; c < nframes; c ++) {
-		FrameIn in = fin [c];
-		const int phiA = s. coarse + s. fine;
-		bool changed = in. P != s. pos || in. lp != s. lp || in. phiA != phiA;
-		if (derive) { in. P = s. pos; in. lp = s. lp; in. phiA = phiA; }
-		else if (changed) break;                             // computed from other inputs than the replay wants
-		const int si = fo [c]. startIndex;                   // (derive: from the old window if `changed`; verified later)
-		if (si < 0) {                                        // :353-356 -> notSynced; T_u samples were consumed
-			if (derive) { in. phiB = phiA; in. active = changed; fin [c] = in; n_redo += changed; c ++;
-			              for (; c < nframes; c ++) fin [c]. active = 0; break; }
-			s. pos += dp. T_u;
-			s. lp = mod_rate ((long long) s. lp - (long long) dp. T_u * mod_rate (phiA));
-			s. synced = 0; s. lost = 1;
-			break;
-		}
-		int correction = 0;
-		StreamCtl before = s;
-		if (s. f2) {                                         // :390-405
-			correction = fo [c]. correction;
-			if (correction == 0 && s. prev1 == 0 && s. prev2 == 0) s. f2 = 0;
-			else if (correction != 100) {
-				s. coarse += correction * cd;
-				if (abs (s. coarse) > 35000) s. coarse = 0;
-				s. prev2 = s. prev1; s. prev1 = correction;
-			}
-		}
-		const int phiB = s. coarse + s. fine;
-		const int usedB = in. phiB;
-		if (derive) {
-			changed = changed || usedB != phiB;
-			in. phiB = phiB; in. active = changed; fin [c] = in; n_redo += changed;
-		} else if (usedB != phiB) { s = before; break; }
+	__shared__ FrameIn s_in [SCAN_MAX];
+	__shared__ FrameOut s_fo [SCAN_MAX];
+	__shared__ float2 s_fc [SCAN_MAX];
+	__shared__ double s_inc [SCAN_MAX];              // 0.1 * arg (FreqCorr) / M_PI * (carrierDiff / 2), state independent
+	__shared__ dabgpu_frame_info s_info [SCAN_MAX];
+	__shared__ int s_ninfo;
+	const int lane = threadIdx. x;
+	if (!derive && ctl -> n_redo == 0) return;               // the derive pass found nothing to redo and committed already
+	// parallel preload of the per-frame records (the serial replay then runs out of shared memory)
+	for (int c = lane; c < nframes; c += 32) {
+		s_in [c] = fin [c]; s_fo [c] = fo [c];
 		float2 fc = make_float2 (0.f, 0.f);
 		for (int g = 0; g < groups; g ++) { fc. x += fcpart [c * MAX_GROUPS + g]. x; fc. y += fcpart [c * MAX_GROUPS + g]. y; }
-		double ang = (double) atan2f (fc. y, fc. x);
-		if (derive && usedB != phiB) {
-			ang -= 2.0 * 3.14159265358979323846 * (double) (phiB - usedB) * (double) dp. T_u / (double) DAB_INPUT_RATE;
-			ang = remainder (ang, 2.0 * 3.14159265358979323846);
-		}
-		if (!derive) {
+		s_fc [c] = fc;
+		s_inc [c] = __dmul_rn (__ddiv_rn (__dmul_rn (0.1, (double) atan2f (fc. y, fc. x)), 3.14159265358979323846), (double) (dp. carrierDiff / 2));
+	}
+	__syncwarp ();
+	if (lane == 0) {
+		StreamCtl s = *ctl;
+		const int cd = dp. carrierDiff;
+		int n_redo = 0, ninfo = 0;
+		s. n_valid = 0; s. lost = 0;
+		for (int c = 0; c < nframes; c ++) {
+			FrameIn in = s_in [c];
+			const int phiA = s. coarse + s. fine;
+			bool changed = in. P != s. pos || in. lp != s. lp || in. phiA != phiA;
+			if (derive) { in. P = s. pos; in. lp = s. lp; in. phiA = phiA; }
+			else if (changed) break;                             // computed from other inputs than the replay wants
+			const int si = s_fo [c]. startIndex;                 // (derive: from the old window if `changed`; verified later)
+			if (si < 0) {                                        // :353-356 -> notSynced; T_u samples were consumed
+				if (derive && changed) {
+					in. phiB = phiA; in. active = 1; s_in [c] = in; n_redo ++;
+					for (int k = c + 1; k < nframes; k ++) s_in [k]. active = 0;
+					nframes = c + 1;
+					break;
+				}
+				if (derive) for (int k = c; k < nframes; k ++) s_in [k]. active = 0;
+				s. pos += dp. T_u;
+				s. lp = mod_rate ((long long) s. lp - (long long) dp. T_u * mod_rate (phiA));
+				s. synced = 0; s. lost = 1;
+				break;
+			}
+			int correction = 0;
+			const StreamCtl before = s;
+			if (s. f2) {                                         // :390-405
+				correction = s_fo [c]. correction;
+				if (correction == 0 && s. prev1 == 0 && s. prev2 == 0) s. f2 = 0;
+				else if (correction != 100) {
+					s. coarse += correction * cd;
+					if (abs (s. coarse) > 35000) s. coarse = 0;
+					s. prev2 = s. prev1; s. prev1 = correction;
+				}
+			}
+			const int phiB = s. coarse + s. fine;
+			const int usedB = in. phiB;
+			if (derive) {
+				changed = changed || usedB != phiB;
+				in. phiB = phiB; in. active = changed; s_in [c] = in; n_redo += changed;
+			} else if (usedB != phiB) { s = before; break; }
+			const float2 fc = s_fc [c];
+			double inc = s_inc [c];                              // :445-446
+			if (derive && usedB != phiB) {                       // the symbols were mixed with another frequency: rotate
+				double ang = (double) atan2f (fc. y, fc. x);
+				ang -= 2.0 * 3.14159265358979323846 * (double) (phiB - usedB) * (double) dp. T_u / (double) DAB_INPUT_RATE;
+				ang = remainder (ang, 2.0 * 3.14159265358979323846);
+				inc = __dmul_rn (__ddiv_rn (__dmul_rn (0.1, ang), 3.14159265358979323846), (double) (cd / 2));
+			}
 			dabgpu_frame_info fi;
 			fi. pos = abs_base + s. pos; fi. startIndex = si; fi. coarse = s. coarse; fi. fine = s. fine;
 			fi. phase0 = s. lp; fi. correction = correction; fi. freqCorrRe = fc. x; fi. freqCorrIm = fc. y;
-			info [slot0 + c] = fi;
+			s_info [c] = fi; ninfo = c + 1;
+			// fineCorrector (int16) += 0.1 * arg (FreqCorr) / M_PI * (carrierDiff / 2)
+			s. fine = (int) (short) __double2int_rz (__dadd_rn ((double) s. fine, inc));
+			const int phiC = s. coarse + s. fine;
+			long long lp = (long long) s. lp - (long long) (si + dp. T_u) * mod_rate (phiA);
+			lp -= ((long long) (dp. L - 1) * dp. T_s) % DAB_INPUT_RATE * mod_rate (phiB);
+			lp -= (long long) dp. T_null * mod_rate (phiC);                // :453
+			s. lp = mod_rate (lp);
+			s. pos += si + dp. T_u + (long long) (dp. L - 1) * dp. T_s + dp. T_null;
+			if (s. fine > cd / 2) { s. coarse += cd; s. fine -= cd; }      // :458-465
+			else if (s. fine < - cd / 2) { s. coarse -= cd; s. fine += cd; }
+			s. n_valid = c + 1;
 		}
-		// :445-446  fineCorrector (int16) += 0.1 * arg (FreqCorr) / M_PI * (carrierDiff / 2)
-		const double inc = __dmul_rn (__ddiv_rn (__dmul_rn (0.1, ang), 3.14159265358979323846), (double) (cd / 2));
-		s. fine = (int) (short) __double2int_rz (__dadd_rn ((double) s. fine, inc));
-		const int phiC = s. coarse + s. fine;
-		long long lp = (long long) s. lp - (long long) (si + dp. T_u) * mod_rate (phiA);
-		lp -= ((long long) (dp. L - 1) * dp. T_s) % DAB_INPUT_RATE * mod_rate (phiB);
-		lp -= (long long) dp. T_null * mod_rate (phiC);                // :453
-		s. lp = mod_rate (lp);
-		s. pos += si + dp. T_u + (long long) (dp. L - 1) * dp. T_s + dp. T_null;
-		if (s. fine > cd / 2) { s. coarse += cd; s. fine -= cd; }      // :458-465
-		else if (s. fine < - cd / 2) { s. coarse -= cd; s. fine += cd; }
-		s. n_valid = c + 1;
+		if (derive) {
+			ctl -> n_redo = n_redo;
+			if (n_redo == 0) { s. n_redo = 0; *ctl = s; s_ninfo = ninfo; }   // nothing changes: this replay IS the verification
+			else s_ninfo = 0;
+		} else { s. n_redo = ctl -> n_redo; *ctl = s; s_ninfo = ninfo; }
 	}
-	if (derive) ctl -> n_redo = n_redo;
-	else { s. n_redo = ctl -> n_redo; *ctl = s; }
+	__syncwarp ();
+	if (derive) for (int c = lane; c < nframes; c += 32) fin [c] = s_in [c];
+	for (int c = lane; c < s_ninfo; c += 32) info [slot0 + c] = s_info [c];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -519,7 +547,7 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 			symbol_kernel<<<(int) C * E -> groups, OFDM_THREADS, sm_sym, h -> stream>>> (w, E -> T, fin, nframes, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
 				fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p); }
 			{ ProfScope prof (h, KC_SCAN);
-			scan_kernel<<<1, 1, 0, h -> stream>>> (dctl, fin, (int) C, nframes, E -> groups, p, fo, (const float2 *) E -> d_fcpart. p,
+			scan_kernel<<<1, 32, 0, h -> stream>>> (dctl, fin, (int) C, nframes, E -> groups, p, fo, (const float2 *) E -> d_fcpart. p,
 				(dabgpu_frame_info *) E -> d_info. p, E -> abs_base, pass == 0 ? 1 : 0); }
 		}
 		h -> launches += 7;
@@ -534,24 +562,38 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 	out -> nframes = nframes;
 	// ---- channel decoding of what the OFDM part produced ----
 	const int ngroups = nframes * p. ficGroups, ncif = nframes * p. cifsPerFrame;
+	const bool simd = dab_use_simd (h, (long long) ngroups + (long long) ncif * (long long) E -> backends. size ());
+	std::vector<VitSimdJob> jobs;
+	std::vector<int> nblk (E -> backends. size (), 0);
 	if (ngroups > 0) {
 		CUDA_TRY (h, E -> d_ficbits. ensure ((size_t) ngroups * 768));
 		CUDA_TRY (h, E -> d_ficcrc. ensure ((size_t) ngroups * 3));
-		if ((rc = dab_fic_decode_dev (h, (const int16_t *) E -> d_fic. p, 2304, ngroups, (uint8_t *) E -> d_ficbits. p, (uint8_t *) E -> d_ficcrc. p))) return rc;
+		if (simd) {
+			jobs. emplace_back ();
+			if ((rc = dab_fic_simd_job (h, (const int16_t *) E -> d_fic. p, 2304, ngroups, (uint8_t *) E -> d_ficbits. p, &jobs. back ()))) return rc;
+		} else if ((rc = dab_fic_decode_dev (h, (const int16_t *) E -> d_fic. p, 2304, ngroups, (uint8_t *) E -> d_ficbits. p, (uint8_t *) E -> d_ficcrc. p))) return rc;
+	}
+	for (size_t i = 0; i < E -> backends. size () && ncif > 0; i ++) {
+		const dabgpu_subch &sc = E -> subch [i];
+		CUDA_TRY (h, E -> d_mscbits [i]. ensure ((size_t) ncif * 24 * sc. bitRate));
+		VitSimdJob job;
+		if ((rc = dab_backend_run_dev (E -> backends [i], (const int16_t *) E -> d_msc. p + (size_t) sc. startAddr * 64, CIF_BITS, ncif,
+		                               (uint8_t *) E -> d_mscbits [i]. p, &nblk [i], simd ? &job : nullptr))) return rc;
+		if (simd && nblk [i] > 0) jobs. push_back (job);
+		dab_backend_note_cifs (E -> backends [i], ncif);
+	}
+	if (simd) {
+		if ((rc = dab_vit_simd_run (h, jobs))) return rc;
+		if (ngroups > 0) CUDA_TRY (h, fib_crc_launch (h, (const uint8_t *) E -> d_ficbits. p, 3 * ngroups, (uint8_t *) E -> d_ficcrc. p));
+	}
+	if (ngroups > 0) {
 		if (out -> fic_bits) CUDA_TRY (h, cudaMemcpyAsync (out -> fic_bits, E -> d_ficbits. p, (size_t) ngroups * 768, cudaMemcpyDeviceToHost, h -> stream));
 		if (out -> fic_crc)  CUDA_TRY (h, cudaMemcpyAsync (out -> fic_crc, E -> d_ficcrc. p, (size_t) ngroups * 3, cudaMemcpyDeviceToHost, h -> stream));
 	}
 	for (size_t i = 0; i < E -> backends. size (); i ++) {
-		int n = 0;
-		if (ncif > 0) {
-			const dabgpu_subch &sc = E -> subch [i];
-			CUDA_TRY (h, E -> d_mscbits [i]. ensure ((size_t) ncif * 24 * sc. bitRate));
-			if ((rc = dab_backend_run_dev (E -> backends [i], (const int16_t *) E -> d_msc. p + (size_t) sc. startAddr * 64, CIF_BITS, ncif,
-			                               (uint8_t *) E -> d_mscbits [i]. p, &n))) return rc;
-			dab_backend_note_cifs (E -> backends [i], ncif);
-			if (out -> msc_bits && out -> msc_bits [i] && n > 0)
-				CUDA_TRY (h, cudaMemcpyAsync (out -> msc_bits [i], E -> d_mscbits [i]. p, (size_t) n * 24 * sc. bitRate, cudaMemcpyDeviceToHost, h -> stream));
-		}
+		const int n = nblk [i];
+		if (out -> msc_bits && out -> msc_bits [i] && n > 0)
+			CUDA_TRY (h, cudaMemcpyAsync (out -> msc_bits [i], E -> d_mscbits [i]. p, (size_t) n * 24 * E -> subch [i]. bitRate, cudaMemcpyDeviceToHost, h -> stream));
 		if (out -> msc_nblocks) out -> msc_nblocks [i] = n;
 	}
 	if (nframes > 0) {

@@ -52,6 +52,8 @@ struct ProtProfile {
 	int frameBits = 0;                  // 24 * bitRate (768 for the FIC)
 	int nPunctured = 0;                 // input soft bits consumed per code word
 	std::vector<uint16_t> lut;
+	std::vector<uint16_t> inv;          // input index -> mother index (for the SIMD kernel's staging)
+	std::vector<uint16_t> chunk_i0;     // per 40-step chunk: first input index (+ end)
 };
 int  prot_build_fic (ProtProfile *pp);                                        // fic-handler.cpp:254-288
 int  prot_build_msc (int bitRate, int uepFlag, int protLevel, ProtProfile *pp); // deconvolve.cpp:142-182, 244-319
@@ -69,10 +71,26 @@ struct VitJob {
 	uint8_t *out;             // [nblocks][frameBits], one bit per byte
 };
 cudaError_t vit_launch (dabgpu *h, int cls, const VitJob &job);
+
+// ---- throughput Viterbi (dabgpu_vit_simd.cu): one code word per thread, several jobs per launch ----
+struct VitSimdJob {
+	const int16_t *in;        // soft-bit source
+	long long in_stride;      // elements between consecutive code words (rows when deint)
+	int first_row;            // deint: buffer row of the CIF decoded by code word 0
+	int deint;
+	const uint16_t *inv;      // device: input index -> mother-code index, or nullptr (identity)
+	const uint16_t *chunk_i0; // device: first input index of every 40-step chunk (+ one past the end), with inv
+	int frameBits, nsteps, ncw;
+	int cta_first;            // first CTA of this job in the launch (64 code words per CTA)
+	uint2 *dec;               // [nsteps padded to 40][ncw] decision words
+	const uint32_t *prbs;     // packed dispersal sequence or nullptr
+	uint8_t *out;             // [ncw][frameBits]
+};
+cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas);
 cudaError_t fib_crc_launch (dabgpu *h, const uint8_t *bits, int nfibs, uint8_t *ok);
 
 // kernel classes for the optional per-launch CUDA-event profile (dabgpu_profile_*)
-enum { KC_ACQUIRE = 0, KC_FRONT, KC_SYMBOL, KC_SCAN, KC_VITERBI_MSC, KC_VITERBI_FIC, KC_VITERBI_API, KC_CRC, KC_COUNT };
+enum { KC_ACQUIRE = 0, KC_FRONT, KC_SYMBOL, KC_SCAN, KC_VITERBI_MSC, KC_VITERBI_FIC, KC_VITERBI_API, KC_CRC, KC_VITERBI_TB, KC_COUNT };
 struct ProfPair { int cls; cudaEvent_t a, b; };
 
 struct Engine;
@@ -91,7 +109,8 @@ struct dabgpu {
 	double prof_ms [KC_COUNT] = {0};
 	int64_t prof_n [KC_COUNT] = {0};
 	// staging
-	DevBuf d_in, d_out, d_aux;
+	DevBuf d_in, d_out, d_aux, d_dec, d_jobs;
+	PinBuf h_jobs;
 	PinBuf h_in, h_out;
 	// cached device tables
 	std::map<long long, void *> d_tables;          // key -> device pointer (LUTs, PRBS)
@@ -114,9 +133,14 @@ int  dab_device_table (dabgpu *h, long long key, const void *host, size_t bytes,
 int  dab_get_profile (dabgpu *h, int kind /*0 fic, 1 msc*/, int bitRate, int uepFlag, int protLevel,
                       const ProtProfile **pp, const uint16_t **d_lut);
 int  dab_get_prbs (dabgpu *h, int nbits, const uint32_t **d_prbs);
+int  dab_get_profile_simd (dabgpu *h, int kind, int bitRate, int uepFlag, int protLevel, const uint16_t **d_inv, const uint16_t **d_chunk);
+// runs a set of jobs on the one-code-word-per-thread kernels (fills cta_first / dec itself)
+int  dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs);
+bool dab_use_simd (const dabgpu *h, long long ncodewords);
 int  dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, uint8_t *d_crc);
 struct dabgpu_backend;
-int  dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row_stride, int ncif, uint8_t *d_out, int *nout);
+int  dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row_stride, int ncif, uint8_t *d_out, int *nout, VitSimdJob *simd_job);
+int  dab_fic_simd_job (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, VitSimdJob *s);
 void dab_backend_note_cifs (dabgpu_backend *b, int ncif);
 int64_t dab_backend_cifs_seen (const dabgpu_backend *b);
 void dab_backend_set_cifs_seen (dabgpu_backend *b, int64_t n);

@@ -107,6 +107,17 @@ static int build_lut (int frameBits, const int L [4], const int PI [4], ProtProf
 	}
 	if (in >= 0xFFFF) return -1;
 	pp -> nPunctured = in;
+	// inverse map and per-chunk input ranges for the one-code-word-per-thread kernel (40 steps = 160 mother bits)
+	pp -> inv. assign (in, 0);
+	const int nchunks = (frameBits + 6 + 39) / 40;
+	pp -> chunk_i0. assign (nchunks + 1, (uint16_t) in);
+	for (int m = total - 1; m >= 0; m --)
+		if (pp -> lut [m] != 0xFFFF) { pp -> inv [pp -> lut [m]] = (uint16_t) m; }
+	int next = 0;
+	for (int k = 0; k < nchunks; k ++) {
+		while (next < in && pp -> inv [next] < 160 * k) next ++;
+		pp -> chunk_i0 [k] = (uint16_t) next;
+	}
 	return 0;
 }
 

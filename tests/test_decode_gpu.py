@@ -45,7 +45,7 @@ def test_decode_matches_oracle(port, mode, cfo, snr, locks):
     nframes = 28 if mode == 1 else 40
     tr = mod.generate(nframes, cfo_hz=cfo, snr_db=snr, lead=12345, tail=5000)
     want = _oracle_chain(port, mode, tr["iq"], nframes + 4, mod.sub)
-    eng = pkg.DabGpu(mode=mode)
+    eng = pkg.DabGpu(mode=mode, viterbi_path=2 if mode == 1 else 0)
     eng.set_subchannels([(s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel) for s in mod.sub])
     out = eng.alloc_result(nframes + 4)
     res = eng.decode(tr["iq"], out)

@@ -9,9 +9,10 @@ from util import engine_pkg
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def eng():
-    e = engine_pkg().DabGpu(mode=1)
+@pytest.fixture(scope="module", params=[1, 2], ids=["warp", "simd"])
+def eng(request):
+    """both Viterbi kernels are forced in turn: 1 = warp per code word, 2 = code word per thread (SIMD)"""
+    e = engine_pkg().DabGpu(mode=1, viterbi_path=request.param)
     yield e
     e.close()
 
