@@ -222,6 +222,102 @@ __global__ void __launch_bounds__ (OFDM_THREADS) symbol_kernel (SampleWin w, Ofd
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Mode I symbol kernel: same work as symbol_kernel, built on the 8-points-per-thread register FFT.
+// Samples go global -> registers (u8 convert + NCO by a per-thread phasor recurrence) -> first butterflies,
+// the spectrum stays in shared memory in the FFT's own digit-reversed order (the carrier table is pre-permuted),
+// the previous symbol's spectrum is simply the other shared buffer (pointer swap instead of a copy).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 u8_to_c (uchar2 s) {
+	return make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f));
+}
+
+__global__ void __launch_bounds__ (256) symbol_kernel_r8 (SampleWin w, OfdmTables T, const FrameIn *fin, int slot0, int groups,
+                                                          int blocksPerCIF, int cifsPerFrame, const FrameOut *fo,
+                                                          const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc) {
+	__shared__ float2 bufA [R8_SMEM], bufB [R8_SMEM], G [512];
+	__shared__ float2 s_fc [8];
+	const int N = R8_N, Ts = T. T_s, Tg = T. T_g, t = threadIdx. x;
+	const int c = blockIdx. x / groups, g = blockIdx. x % groups;
+	const FrameIn in = fin [c];
+	if (!in. active) return;
+	const int s = fo [c]. startIndex;
+	if (s < 0) { if (t == 0) fcpart [c * MAX_GROUPS + g] = make_float2 (0.f, 0.f); return; }
+	const int nsym = T. L - 1, per = (nsym + groups - 1) / groups;
+	const int l0 = 1 + g * per, l1 = min (nsym + 1, l0 + per);             // symbols [l0, l1)
+	const int phA = mod_rate (in. phiA), phB = mod_rate (in. phiB);
+	const long long F = in. P + s;                                         // first sample of the PRS
+	const int lpD = mod_rate ((long long) in. lp - (long long) (s + N) * phA);  // localPhase after the PRS
+	const float2 rot256 = nco (T, mod_rate (- 256ll * phB));               // 256 samples further: phase index - 256 f
+	float2 *cur = bufA, *prev = bufB;
+	float2 x [8];
+	if (l0 == 1) {
+		const float2 *p0 = spec0 + (size_t) c * N;
+		for (int k = t; k < N; k += 256) prev [r8_pad (r8_pos (k))] = p0 [k];
+		__syncthreads ();
+	} else {                                                               // spectrum of symbol l0-1 as reference
+		const long long first = F + N + (long long) (l0 - 2) * Ts + Tg;
+		const int lpb = mod_rate ((long long) lpD - ((long long) (l0 - 2) * Ts + Tg) % DAB_INPUT_RATE * phB);
+		float2 ph = nco (T, mod_rate ((long long) lpb - (long long) (t + 1) * phB));
+#pragma unroll
+		for (int k = 0; k < 8; k ++) { x [k] = cmul (u8_to_c (win_fetch (w, first + t + 256 * k)), ph); ph = cmul (ph, rot256); }
+		fft2048_r8 (x, prev, T. tw);
+	}
+	float2 acc = make_float2 (0.f, 0.f);
+	const int slot = slot0 + c;
+	for (int l = l0; l < l1; l ++) {
+		const long long first = F + N + (long long) (l - 1) * Ts;          // guard interval starts here
+		const int lpb = mod_rate ((long long) lpD - ((long long) (l - 1) * Ts) % DAB_INPUT_RATE * phB);
+		// issue every load of the symbol first
+		uchar2 raw [8], rg0, rg1;
+#pragma unroll
+		for (int k = 0; k < 8; k ++) raw [k] = win_fetch (w, first + Tg + t + 256 * k);
+		rg0 = win_fetch (w, first + t);
+		rg1 = t + 256 < Tg ? win_fetch (w, first + t + 256) : make_uchar2 (128, 128);
+		float2 phg = nco (T, mod_rate ((long long) lpb - (long long) (t + 1) * phB));          // guard sample t
+		float2 ph  = nco (T, mod_rate ((long long) lpb - (long long) (Tg + t + 1) * phB));     // useful sample t
+		G [t] = cmul (u8_to_c (rg0), phg);
+		G [t + 256] = cmul (u8_to_c (rg1), cmul (phg, rot256));
+#pragma unroll
+		for (int k = 0; k < 8; k ++) { x [k] = cmul (u8_to_c (raw [k]), ph); ph = cmul (ph, rot256); }
+		__syncthreads ();                                                  // G visible; last symbol's demod reads done
+		// FreqCorr += x[i] * conj (x[i - T_u]), i in [T_u, T_s): useful element e = i - T_g pairs with guard sample e - (T_u - T_g)
+		{
+			const int e6 = t + 1536 - (N - Tg), e7 = t + 1792 - (N - Tg);
+			if (e6 >= 0) { const float2 r = cmulc (x [6], G [e6]); acc. x += r. x; acc. y += r. y; }
+			{ const float2 r = cmulc (x [7], G [e7]); acc. x += r. x; acc. y += r. y; }
+		}
+		fft2048_r8 (x, cur, T. tw);
+		int16_t *out;
+		if (l < 4) out = fic + ((size_t) slot * 3 + (l - 1)) * 2 * T. K;
+		else {
+			const int m = l - 4;
+			out = msc + ((size_t) 15 + (size_t) slot * cifsPerFrame + m / blocksPerCIF) * CIF_BITS + (size_t) (m % blocksPerCIF) * 2 * T. K;
+		}
+#pragma unroll
+		for (int m = 0; m < 6; m ++) {                                      // K = 1536 = 6 x 256 carriers
+			const int i = t + 256 * m;
+			const int idx = __ldg (&T. permpos [i]);
+			const float2 r1 = cmulc (cur [idx], prev [idx]);
+			const float ab1 = fabsf (r1. x) + fabsf (r1. y);
+			out [i]        = quant127 (r1. x, ab1);
+			out [T. K + i] = quant127 (r1. y, ab1);
+		}
+		float2 *tmp = cur; cur = prev; prev = tmp;
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		acc. x += __shfl_xor_sync (0xffffffffu, acc. x, o);
+		acc. y += __shfl_xor_sync (0xffffffffu, acc. y, o);
+	}
+	if ((t & 31) == 0) s_fc [t >> 5] = acc;
+	__syncthreads ();
+	if (t == 0) {
+		float2 sum = make_float2 (0.f, 0.f);
+		for (int k = 0; k < 8; k ++) { sum. x += s_fc [k]. x; sum. y += s_fc [k]. y; }
+		fcpart [c * MAX_GROUPS + g] = sum;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
 // scan kernel (one thread): the scalar state machine of ofdmProcessor::run replayed over the chunk.
 //   derive = 1: optimistic pass.  Walks ALL frames, replacing fin[c] by the inputs the replayed state asks
 //     for and marking the frames whose inputs changed for recomputation.  Where the data symbols were mixed
@@ -254,6 +350,7 @@ __global__ void __launch_bounds__ (32) scan_kernel (StreamCtl *ctl, FrameIn *fin
 		StreamCtl s = *ctl;
 		const int cd = dp. carrierDiff;
 		int n_redo = 0, ninfo = 0;
+		int k_a = 0x7fffffff, k_b = 0, k_c = 0, k_si = -1, k_delta = 0;
 		s. n_valid = 0; s. lost = 0;
 		for (int c = 0; c < nframes; c ++) {
 			FrameIn in = s_in [c];
@@ -307,10 +404,16 @@ __global__ void __launch_bounds__ (32) scan_kernel (StreamCtl *ctl, FrameIn *fin
 			// fineCorrector (int16) += 0.1 * arg (FreqCorr) / M_PI * (carrierDiff / 2)
 			s. fine = (int) (short) __double2int_rz (__dadd_rn ((double) s. fine, inc));
 			const int phiC = s. coarse + s. fine;
-			long long lp = (long long) s. lp - (long long) (si + dp. T_u) * mod_rate (phiA);
-			lp -= ((long long) (dp. L - 1) * dp. T_s) % DAB_INPUT_RATE * mod_rate (phiB);
-			lp -= (long long) dp. T_null * mod_rate (phiC);                // :453
-			s. lp = mod_rate (lp);
+			// localPhase after the whole frame: -(si + T_u) fA - (L-1) T_s fB - T_null fC (mod rate).  In lock all
+			// three frequencies and si repeat from frame to frame, so the 64-bit reductions are cached.
+			if (phiA != k_a || phiB != k_b || phiC != k_c || si != k_si) {
+				long long d = (long long) (si + dp. T_u) * mod_rate (phiA);
+				d += ((long long) (dp. L - 1) * dp. T_s) % DAB_INPUT_RATE * mod_rate (phiB);
+				d += (long long) dp. T_null * mod_rate (phiC);                // :453
+				k_delta = mod_rate (d); k_a = phiA; k_b = phiB; k_c = phiC; k_si = si;
+			}
+			s. lp -= k_delta;
+			if (s. lp < 0) s. lp += DAB_INPUT_RATE;
 			s. pos += si + dp. T_u + (long long) (dp. L - 1) * dp. T_s + dp. T_null;
 			if (s. fine > cd / 2) { s. coarse += cd; s. fine -= cd; }      // :458-465
 			else if (s. fine < - cd / 2) { s. coarse -= cd; s. fine += cd; }
@@ -544,8 +647,12 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 			{ ProfScope prof (h, KC_FRONT);
 			front_kernel<<<(int) C, OFDM_THREADS, sm_front, h -> stream>>> (w, E -> T, fin, fo, (float2 *) E -> d_spec0. p); }
 			{ ProfScope prof (h, KC_SYMBOL);
-			symbol_kernel<<<(int) C * E -> groups, OFDM_THREADS, sm_sym, h -> stream>>> (w, E -> T, fin, nframes, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
-				fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p); }
+			if (p. T_u == R8_N && p. K == 1536)
+				symbol_kernel_r8<<<(int) C * E -> groups, 256, 0, h -> stream>>> (w, E -> T, fin, nframes, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
+					fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p);
+			else
+				symbol_kernel<<<(int) C * E -> groups, OFDM_THREADS, sm_sym, h -> stream>>> (w, E -> T, fin, nframes, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
+					fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p); }
 			{ ProfScope prof (h, KC_SCAN);
 			scan_kernel<<<1, 32, 0, h -> stream>>> (dctl, fin, (int) C, nframes, E -> groups, p, fo, (const float2 *) E -> d_fcpart. p,
 				(dabgpu_frame_info *) E -> d_info. p, E -> abs_base, pass == 0 ? 1 : 0); }

@@ -92,6 +92,13 @@ int ofdm_tables_init (dabgpu *h, OfdmTables *T) {
 	if ((rc = dab_device_table (h, base + 4, refArg, sizeof (refArg), &d))) return rc;            T -> refArg = (const float *) d;
 	if ((rc = dab_device_table (h, base + 5, hi. data (), 1000 * sizeof (float2), &d))) return rc; T -> osc_hi = (const float2 *) d;
 	if ((rc = dab_device_table (h, base + 6, lo. data (), 2048 * sizeof (float2), &d))) return rc; T -> osc_lo = (const float2 *) d;
+	T -> permpos = nullptr;
+	if (N == R8_N) {
+		std::vector<uint16_t> pp (p. K);
+		for (int i = 0; i < p. K; i ++) pp [i] = (uint16_t) r8_pad (r8_pos (perm [i]));
+		if ((rc = dab_device_table (h, base + 7, pp. data (), p. K * sizeof (uint16_t), &d))) return rc;
+		T -> permpos = (const uint16_t *) d;
+	}
 	T -> T_u = N; T -> T_s = p. T_s; T -> T_g = p. T_g; T -> K = p. K; T -> L = p. L;
 	T -> log2n = 0; while ((1 << T -> log2n) < N) T -> log2n ++;
 	T -> level = h -> cfg. threshold; T -> method = h -> cfg. freqSyncMethod;
@@ -157,11 +164,23 @@ extern "C" int dabgpu_host_prbs (int32_t nbits, uint8_t *out) {
 __global__ void __launch_bounds__ (OFDM_THREADS) fft_kernel (float2 *v, OfdmTables T, int inverse) {
 	extern __shared__ float2 sm [];
 	const int N = T. T_u;
-	float2 *a = sm, *b = sm + N;
 	float2 *g = v + (size_t) blockIdx. x * N;
+	const float factor = (float) (1.0 / (float) N);
+	if (N == R8_N) {                                     // the register FFT of the Mode I symbol kernel
+		float2 x [8];
+#pragma unroll
+		for (int k = 0; k < 8; k ++) { x [k] = g [threadIdx. x + 256 * k]; if (inverse) x [k]. y = - x [k]. y; }
+		fft2048_r8 (x, sm, T. tw);
+		for (int k = threadIdx. x; k < N; k += OFDM_THREADS) {
+			float2 r = sm [r8_pad (r8_pos (k))];
+			if (inverse) r = make_float2 (r. x * factor, (- r. y) * factor);
+			g [k] = r;
+		}
+		return;
+	}
+	float2 *a = sm, *b = sm + N;
 	for (int i = threadIdx. x; i < N; i += OFDM_THREADS) { float2 x = g [i]; if (inverse) x. y = - x. y; a [i] = x; }
 	float2 *r = block_fft (a, b, N, T. tw);
-	const float factor = (float) (1.0 / (float) N);
 	for (int i = threadIdx. x; i < N; i += OFDM_THREADS) {
 		float2 x = r [i];
 		if (inverse) x = make_float2 (x. x * factor, (- x. y) * factor);
@@ -234,7 +253,7 @@ extern "C" int dabgpu_fft (dabgpu_t *h, float *v, int32_t n, int32_t inverse) {
 	const size_t bytes = (size_t) n * h -> p. T_u * sizeof (float2);
 	int rc = upload (h, v, bytes);
 	if (rc) return rc;
-	fft_kernel<<<n, OFDM_THREADS, 2 * h -> p. T_u * sizeof (float2), h -> stream>>> ((float2 *) h -> d_in. p, E -> T, inverse);
+	fft_kernel<<<n, OFDM_THREADS, (2 * h -> p. T_u + 512) * sizeof (float2), h -> stream>>> ((float2 *) h -> d_in. p, E -> T, inverse);
 	h -> launches ++;
 	CUDA_TRY (h, cudaGetLastError ());
 	return download (h, v, h -> d_in. p, bytes);

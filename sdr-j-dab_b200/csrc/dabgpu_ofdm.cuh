@@ -9,6 +9,7 @@ struct OfdmTables {                   // device pointers, built once per handle 
 	const float2  *tw;                // [T_u]  exp (-2 pi i k / T_u), double -> float
 	const float2  *ref;               // [T_u]  PRS spectrum (phasereference.cpp:41-47)
 	const int16_t *perm;              // [K]    frequency de-interleaver, wrapped to [0, T_u) (mapper.cpp, ofdm-decoder.cpp:179-181)
+	const uint16_t *permpos;          // [K]    Mode I only: position of that carrier in the register FFT's shared layout
 	const float   *refArg;            // [18]   ofdm-decoder.cpp:73-76
 	const float2  *osc_hi;            // [1000] exp (2 pi i 2048 h / 2048000)   NCO = osc_hi[lp >> 11] * osc_lo[lp & 2047]
 	const float2  *osc_lo;            // [2048] exp (2 pi i l / 2048000)        (ofdm-processor.cpp:76-81, 165-167)
@@ -231,3 +232,91 @@ static __device__ int coarse_offset_warp0 (const float2 *f, const OfdmTables &T,
 	return result;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// 2048-point forward FFT for 256 threads, 8 points per thread in registers, decimation in frequency with
+// radices 4 x 8 x 8 x 8: three shared-memory exchanges instead of the six passes of the generic routine.
+// Thread t enters with x[t + 256 k], k = 0..7 (so the first butterflies need no shared memory at all).
+// The result is left in shared memory in digit-reversed order: X[k] sits at r8_pos (k) = 512 (k & 3) +
+// 64 ((k >> 2) & 7) + 8 ((k >> 5) & 7) + (k >> 8); consumers index through that map (the demodulator's carrier
+// table is pre-permuted on the host), so no reordering pass exists.  Shared index i is padded to i + (i >> 3).
+// ---------------------------------------------------------------------------------------------------
+#define R8_N      2048
+#define R8_SMEM   (R8_N + R8_N / 8)            // float2 elements
+__host__ __device__ __forceinline__ int r8_pad (int i) { return i + (i >> 3); }
+__host__ __device__ __forceinline__ int r8_pos (int k) { return 512 * (k & 3) + 64 * ((k >> 2) & 7) + 8 * ((k >> 5) & 7) + (k >> 8); }
+
+__device__ __forceinline__ float2 cadd (float2 a, float2 b) { return make_float2 (a. x + b. x, a. y + b. y); }
+__device__ __forceinline__ float2 csub (float2 a, float2 b) { return make_float2 (a. x - b. x, a. y - b. y); }
+__device__ __forceinline__ float2 cmulmj (float2 a) { return make_float2 (a. y, - a. x); }          // a * (-j)
+
+// 4-point DFT (forward): y_q = sum_m c_m exp (-2 pi i m q / 4)
+__device__ __forceinline__ void dft4 (float2 c0, float2 c1, float2 c2, float2 c3, float2 &y0, float2 &y1, float2 &y2, float2 &y3) {
+	const float2 d0 = cadd (c0, c2), d2 = csub (c0, c2), d1 = cadd (c1, c3), d3 = cmulmj (csub (c1, c3));
+	y0 = cadd (d0, d1); y2 = csub (d0, d1); y1 = cadd (d2, d3); y3 = csub (d2, d3);
+}
+// 8-point DFT (forward), in place: a[q] <- sum_m a[m] exp (-2 pi i m q / 8)
+__device__ __forceinline__ void dft8 (float2 (&a) [8]) {
+	const float h = 0.70710678118654752440f;
+	const float2 b0 = cadd (a [0], a [4]), b4 = csub (a [0], a [4]);
+	const float2 b1 = cadd (a [1], a [5]), t5 = csub (a [1], a [5]);
+	const float2 b2 = cadd (a [2], a [6]), t6 = csub (a [2], a [6]);
+	const float2 b3 = cadd (a [3], a [7]), t7 = csub (a [3], a [7]);
+	const float2 b5 = make_float2 (h * (t5. x + t5. y), h * (t5. y - t5. x));      // * (1 - j) / sqrt 2
+	const float2 b6 = cmulmj (t6);                                                 // * (-j)
+	const float2 b7 = make_float2 (h * (t7. y - t7. x), - h * (t7. x + t7. y));    // * (-1 - j) / sqrt 2
+	dft4 (b0, b1, b2, b3, a [0], a [2], a [4], a [6]);
+	dft4 (b4, b5, b6, b7, a [1], a [3], a [5], a [7]);
+}
+
+// x[k] = sample t + 256 k on entry; A = R8_SMEM float2 of shared memory; tw = exp (-2 pi i j / 2048) table
+__device__ __forceinline__ void fft2048_r8 (float2 (&x) [8], float2 *A, const float2 *__restrict__ tw) {
+	const int t = threadIdx. x;
+	// stage 1: two radix-4 butterflies, n = t (k even) and n = t + 256 (k odd); twiddle W_2048^(n q)
+	{
+		float2 y [4];
+#pragma unroll
+		for (int g = 0; g < 2; g ++) {
+			const int n = t + 256 * g;
+			dft4 (x [g], x [g + 2], x [g + 4], x [g + 6], y [0], y [1], y [2], y [3]);
+			A [r8_pad (n)] = y [0];
+#pragma unroll
+			for (int q = 1; q < 4; q ++) A [r8_pad (n + 512 * q)] = cmul (y [q], __ldg (&tw [(n * q) & 2047]));
+		}
+	}
+	__syncthreads ();
+	// stage 2: radix 8 inside blocks of 512: n = t & 63, twiddle W_512^(n q) = W_2048^(4 n q)
+	{
+		const int b = t >> 6, n = t & 63, base = 512 * b + n;
+		float2 a [8];
+#pragma unroll
+		for (int m = 0; m < 8; m ++) a [m] = A [r8_pad (base + 64 * m)];
+		dft8 (a);
+		A [r8_pad (base)] = a [0];
+#pragma unroll
+		for (int q = 1; q < 8; q ++) A [r8_pad (base + 64 * q)] = cmul (a [q], __ldg (&tw [(4 * n * q) & 2047]));
+	}
+	__syncthreads ();
+	// stage 3: radix 8 inside blocks of 64: n = t & 7, twiddle W_64^(n q) = W_2048^(32 n q)
+	{
+		const int b = t >> 3, n = t & 7, base = 64 * b + n;
+		float2 a [8];
+#pragma unroll
+		for (int m = 0; m < 8; m ++) a [m] = A [r8_pad (base + 8 * m)];
+		dft8 (a);
+		A [r8_pad (base)] = a [0];
+#pragma unroll
+		for (int q = 1; q < 8; q ++) A [r8_pad (base + 8 * q)] = cmul (a [q], __ldg (&tw [(32 * n * q) & 2047]));
+	}
+	__syncthreads ();
+	// stage 4: radix 8 on 8 consecutive points, no twiddles
+	{
+		float2 a [8];
+#pragma unroll
+		for (int m = 0; m < 8; m ++) a [m] = A [r8_pad (8 * t + m)];
+		dft8 (a);
+#pragma unroll
+		for (int q = 0; q < 8; q ++) A [r8_pad (8 * t + q)] = a [q];
+	}
+	__syncthreads ();
+}
