@@ -41,6 +41,13 @@ extern "C" int dabgpu_create (const dabgpu_config *cfg, dabgpu_t **out) {
 		delete h;
 		return dab_fail (nullptr, DABGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString (e));
 	}
+	h -> vctx [0]. st = h -> stream;
+	for (int i = 1; i < 4; i ++)
+		if ((e = cudaStreamCreateWithFlags (&h -> vctx [i]. st, cudaStreamNonBlocking)) != cudaSuccess) {
+			g_create_error = std::string ("cudaStreamCreate: ") + cudaGetErrorString (e);
+			dabgpu_destroy (h);
+			return DABGPU_ERR_CUDA;
+		}
 	int rc = dab_engine_init (h);
 	if (rc) { g_create_error = h -> err; dabgpu_destroy (h); return rc; }
 	*out = h;
@@ -53,7 +60,12 @@ extern "C" void dabgpu_destroy (dabgpu_t *h) {
 	if (h -> stream) cudaStreamSynchronize (h -> stream);
 	dab_engine_free (h);
 	for (auto &kv : h -> d_tables) cudaFree (kv. second);
-	h -> d_in. release (); h -> d_out. release (); h -> d_aux. release (); h -> d_dec. release (); h -> d_jobs. release (); h -> h_jobs. release ();
+	h -> d_in. release (); h -> d_out. release (); h -> d_aux. release ();
+	for (int i = 0; i < 4; i ++) {
+		dabgpu::VitCtx &c = h -> vctx [i];
+		if (i > 0 && c. st) { cudaStreamSynchronize (c. st); cudaStreamDestroy (c. st); }
+		c. d_dec. release (); c. d_jobs. release (); c. h_jobs. release ();
+	}
 	h -> h_in. release (); h -> h_out. release ();
 	if (h -> ev0) { cudaEventDestroy (h -> ev0); cudaEventDestroy (h -> ev1); }
 	for (auto &pp : h -> prof_pending) { cudaEventDestroy (pp. a); cudaEventDestroy (pp. b); }
@@ -86,17 +98,17 @@ extern "C" int dabgpu_timer_end (dabgpu_t *h, float *ms) {
 	return DABGPU_OK;
 }
 
-ProfScope::ProfScope (dabgpu *h_, int cls_) : h (h_), cls (cls_) {
+ProfScope::ProfScope (dabgpu *h_, int cls_, cudaStream_t st_) : h (h_), cls (cls_), st (st_ ? st_ : h_ -> stream) {
 	if (!h -> profiling) return;
 	for (cudaEvent_t *e : { &a, &b }) {
 		if (!h -> prof_pool. empty ()) { *e = h -> prof_pool. back (); h -> prof_pool. pop_back (); }
 		else if (cudaEventCreate (e) != cudaSuccess) { *e = nullptr; }
 	}
-	if (a && b) cudaEventRecord (a, h -> stream);
+	if (a && b) cudaEventRecord (a, st);
 }
 ProfScope::~ProfScope () {
 	if (!a || !b) return;
-	cudaEventRecord (b, h -> stream);
+	cudaEventRecord (b, st);
 	h -> prof_pending. push_back ({ cls, a, b });
 }
 
@@ -118,7 +130,7 @@ extern "C" int dabgpu_profile_reset (dabgpu_t *h) {
 extern "C" int dabgpu_profile_get (dabgpu_t *h, int32_t kernel_class, int64_t *launches, double *ms) {
 	if (!h || kernel_class < 0 || kernel_class >= KC_COUNT || !launches || !ms) return DABGPU_ERR_ARG;
 	CUDA_TRY (h, cudaSetDevice (h -> device));
-	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+	for (auto &c : h -> vctx) if (c. st) CUDA_TRY (h, cudaStreamSynchronize (c. st));
 	for (auto &pp : h -> prof_pending) {
 		float t = 0;
 		if (cudaEventElapsedTime (&t, pp. a, pp. b) == cudaSuccess) { h -> prof_ms [pp. cls] += t; h -> prof_n [pp. cls] ++; }
@@ -188,6 +200,7 @@ bool dab_use_simd (const dabgpu *h, long long ncodewords) {
 
 int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
 	if (jobs. empty ()) return DABGPU_OK;
+	dabgpu::VitCtx &cx = h -> vctx [h -> cur];
 	size_t dec_words = 0;
 	int ctas = 0;
 	for (auto &j : jobs) {
@@ -195,16 +208,17 @@ int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
 		ctas += (j. ncw + 63) / 64;
 		dec_words += (size_t) ((j. nsteps + 39) / 40 * 40) * j. ncw;
 	}
-	CUDA_TRY (h, h -> d_dec. ensure (dec_words * sizeof (uint2)));
-	size_t off = 0;
-	for (auto &j : jobs) { j. dec = (uint2 *) h -> d_dec. p + off; off += (size_t) ((j. nsteps + 39) / 40 * 40) * j. ncw; }
+	// (re)allocation and the pinned job table are only touched once everything queued on this context is done
 	const size_t jb = jobs. size () * sizeof (VitSimdJob);
-	CUDA_TRY (h, h -> d_jobs. ensure (jb));
-	CUDA_TRY (h, h -> h_jobs. ensure (jb));
-	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));           // the pinned job table may still be read by an earlier launch
-	memcpy (h -> h_jobs. p, jobs. data (), jb);
-	CUDA_TRY (h, cudaMemcpyAsync (h -> d_jobs. p, h -> h_jobs. p, jb, cudaMemcpyHostToDevice, h -> stream));
-	CUDA_TRY (h, vit_simd_launch (h, (const VitSimdJob *) h -> d_jobs. p, (int) jobs. size (), ctas));
+	CUDA_TRY (h, cudaStreamSynchronize (cx. st));
+	CUDA_TRY (h, cx. d_dec. ensure (dec_words * sizeof (uint2)));
+	size_t off = 0;
+	for (auto &j : jobs) { j. dec = (uint2 *) cx. d_dec. p + off; off += (size_t) ((j. nsteps + 39) / 40 * 40) * j. ncw; }
+	CUDA_TRY (h, cx. d_jobs. ensure (jb));
+	CUDA_TRY (h, cx. h_jobs. ensure (jb));
+	memcpy (cx. h_jobs. p, jobs. data (), jb);
+	CUDA_TRY (h, cudaMemcpyAsync (cx. d_jobs. p, cx. h_jobs. p, jb, cudaMemcpyHostToDevice, cx. st));
+	CUDA_TRY (h, vit_simd_launch (h, (const VitSimdJob *) cx. d_jobs. p, (int) jobs. size (), ctas));
 	return DABGPU_OK;
 }
 
@@ -393,7 +407,7 @@ extern "C" void dabgpu_backend_destroy (dabgpu_backend_t *b) {
 }
 
 // device-side core: rows = [15 history][ncif new] fragments; decodes the CIFs past the warm-up
-int dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row_stride, int ncif,
+int dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row_stride, int row0, int ncif,
                          uint8_t *d_out, int *nout, VitSimdJob *simd_job) {
 	dabgpu *h = b -> h;
 	// dab-concurrent.cpp:172-175: the first 16 CIFs only fill the de-interleaver
@@ -402,7 +416,7 @@ int dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row
 	if (skip > ncif) skip = ncif;
 	const int n = ncif - (int) skip;
 	VitJob j {};
-	j. in = d_rows; j. in_stride = row_stride; j. first_row = 15 + (int) skip; j. lut = b -> d_lut;
+	j. in = d_rows; j. in_stride = row_stride; j. first_row = 15 + row0 + (int) skip; j. lut = b -> d_lut;
 	j. frameBits = b -> pp -> frameBits; j. nsteps = j. frameBits + 6; j. nblocks = n;
 	j. deint = 1; j. prbs = b -> d_prbs; j. out = d_out;
 	*nout = n;
@@ -441,9 +455,9 @@ extern "C" int dabgpu_backend_process (dabgpu_backend_t *b, const int16_t *frags
 	int rc;
 	if (dab_use_simd (h, ncif)) {
 		std::vector<VitSimdJob> jobs (1);
-		if ((rc = dab_backend_run_dev (b, d_rows, (long long) fs, ncif, (uint8_t *) h -> d_out. p, &n, &jobs [0]))) return rc;
+		if ((rc = dab_backend_run_dev (b, d_rows, (long long) fs, 0, ncif, (uint8_t *) h -> d_out. p, &n, &jobs [0]))) return rc;
 		if (n > 0 && (rc = dab_vit_simd_run (h, jobs))) return rc;
-	} else if ((rc = dab_backend_run_dev (b, d_rows, (long long) fs, ncif, (uint8_t *) h -> d_out. p, &n, nullptr))) return rc;
+	} else if ((rc = dab_backend_run_dev (b, d_rows, (long long) fs, 0, ncif, (uint8_t *) h -> d_out. p, &n, nullptr))) return rc;
 	// new history = last 15 rows of [history | new]
 	CUDA_TRY (h, cudaMemcpyAsync (b -> hist. p, d_rows + (size_t) ncif * fs, 15 * rowb, cudaMemcpyDeviceToDevice, h -> stream));
 	b -> cifs_seen += ncif;

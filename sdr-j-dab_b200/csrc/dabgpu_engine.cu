@@ -444,6 +444,7 @@ int dab_engine_init (dabgpu *h) {
 	memset (&E -> ctl, 0, sizeof (StreamCtl));
 	E -> ctl. f2 = 1; E -> ctl. prev1 = 1000; E -> ctl. prev2 = 999;     // ofdm-processor.cpp:258-259, 73
 	E -> groups = h -> p. L > 100 ? 8 : 5;
+	CUDA_TRY (h, cudaStreamCreateWithFlags (&E -> copy_st, cudaStreamNonBlocking));
 	const int big = 100 * 1024;
 	CUDA_TRY (h, cudaFuncSetAttribute (front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 	CUDA_TRY (h, cudaFuncSetAttribute (symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -455,6 +456,8 @@ void dab_engine_free (dabgpu *h) {
 	if (!E) return;
 	for (auto *b : E -> backends) dabgpu_backend_destroy (b);
 	if (E -> d_phaseRef) cudaFree (E -> d_phaseRef);
+	if (E -> copy_st) { cudaStreamSynchronize (E -> copy_st); cudaStreamDestroy (E -> copy_st); }
+	for (auto e : E -> copy_events) cudaEventDestroy (e);
 	E -> tail. release (); E -> d_ctl. release (); E -> h_ctl. release ();
 	E -> d_frameout. release (); E -> d_framein. release (); E -> d_fcpart. release (); E -> d_spec0. release (); E -> d_info. release ();
 	E -> d_fic. release (); E -> d_msc. release (); E -> d_histtmp. release ();
@@ -594,8 +597,63 @@ static int ensure_frame_capacity (dabgpu *h, long long frames) {
 	return DABGPU_OK;
 }
 
-// decode core on a device-resident input segment
-static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_result *out) {
+// channel decoding (FIC + every configured sub-channel) of the frames [f0, f0 + nv) just accepted by the OFDM part,
+// queued on a side stream so that it overlaps the OFDM work of the next chunk; results are copied to the caller's
+// buffers on the same stream
+static int channel_chunk (dabgpu *h, int f0, int nv, dabgpu_result *out, std::vector<int> &nblk) {
+	Engine *E = h -> engine;
+	const DabParams &p = h -> p;
+	const int ngroups = nv * p. ficGroups, g0 = f0 * p. ficGroups, ncif = nv * p. cifsPerFrame, r0 = f0 * p. cifsPerFrame;
+	if (nv <= 0) return DABGPU_OK;
+	h -> cur = 1 + (E -> vrr ++ % 3);
+	cudaStream_t st = h -> vst ();
+	int rc = DABGPU_OK;
+	const bool simd = dab_use_simd (h, (long long) ngroups + (long long) ncif * (long long) E -> backends. size ());
+	std::vector<VitSimdJob> jobs;
+	uint8_t *ficbits = (uint8_t *) E -> d_ficbits. p + (size_t) g0 * 768, *ficcrc = (uint8_t *) E -> d_ficcrc. p + (size_t) g0 * 3;
+	do {
+		if (ngroups > 0) {
+			const int16_t *soft = (const int16_t *) E -> d_fic. p + (size_t) f0 * 3 * 2 * p. K;
+			if (simd) {
+				jobs. emplace_back ();
+				if ((rc = dab_fic_simd_job (h, soft, 2304, ngroups, ficbits, &jobs. back ()))) break;
+			} else if ((rc = dab_fic_decode_dev (h, soft, 2304, ngroups, ficbits, ficcrc))) break;
+		}
+		std::vector<int> n_here (E -> backends. size (), 0);
+		for (size_t i = 0; i < E -> backends. size () && ncif > 0; i ++) {
+			const dabgpu_subch &sc = E -> subch [i];
+			VitSimdJob job;
+			uint8_t *dst = (uint8_t *) E -> d_mscbits [i]. p + (size_t) nblk [i] * 24 * sc. bitRate;
+			if ((rc = dab_backend_run_dev (E -> backends [i], (const int16_t *) E -> d_msc. p + (size_t) sc. startAddr * 64, CIF_BITS, r0, ncif,
+			                               dst, &n_here [i], simd ? &job : nullptr))) break;
+			if (simd && n_here [i] > 0) jobs. push_back (job);
+			dab_backend_note_cifs (E -> backends [i], ncif);
+		}
+		if (rc) break;
+		if (simd) {
+			if ((rc = dab_vit_simd_run (h, jobs))) break;
+			if (ngroups > 0) { cudaError_t e = fib_crc_launch (h, ficbits, 3 * ngroups, ficcrc); if (e != cudaSuccess) { rc = dab_fail (h, DABGPU_ERR_CUDA, "crc launch: %s", cudaGetErrorString (e)); break; } }
+		}
+		cudaError_t e = cudaSuccess;
+		if (ngroups > 0 && out -> fic_bits) e = cudaMemcpyAsync (out -> fic_bits + (size_t) g0 * 768, ficbits, (size_t) ngroups * 768, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess && ngroups > 0 && out -> fic_crc) e = cudaMemcpyAsync (out -> fic_crc + (size_t) g0 * 3, ficcrc, (size_t) ngroups * 3, cudaMemcpyDeviceToHost, st);
+		for (size_t i = 0; i < E -> backends. size () && e == cudaSuccess; i ++) {
+			const size_t fb = (size_t) 24 * E -> subch [i]. bitRate;
+			if (out -> msc_bits && out -> msc_bits [i] && n_here [i] > 0)
+				e = cudaMemcpyAsync (out -> msc_bits [i] + (size_t) nblk [i] * fb, (uint8_t *) E -> d_mscbits [i]. p + (size_t) nblk [i] * fb,
+				                     (size_t) n_here [i] * fb, cudaMemcpyDeviceToHost, st);
+			nblk [i] += n_here [i];
+		}
+		if (e != cudaSuccess) rc = dab_fail (h, DABGPU_ERR_CUDA, "result copy: %s", cudaGetErrorString (e));
+	} while (0);
+	h -> cur = 0;
+	return rc;
+}
+
+// decode core on a device-resident input segment.  `ready` (optional): events of the piecewise host-to-device copy
+// of the input; piece k covers new-segment samples [k * piece, (k+1) * piece).
+static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_result *out,
+                        const std::vector<cudaEvent_t> *ready = nullptr, long long piece = 0, int vit_batch_frames = 0x7fffffff) {
 	Engine *E = h -> engine;
 	const DabParams &p = h -> p;
 	if (p. dabMode == 3)
@@ -612,11 +670,30 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 	CUDA_TRY (h, E -> d_framein. ensure ((size_t) E -> max_chunk * sizeof (FrameIn)));
 	CUDA_TRY (h, E -> d_fcpart. ensure ((size_t) E -> max_chunk * MAX_GROUPS * sizeof (float2)));
 	CUDA_TRY (h, E -> d_spec0. ensure ((size_t) E -> max_chunk * p. T_u * sizeof (float2)));
+	// result buffers on the device for the whole call (side streams write into them chunk by chunk)
+	for (int i = 1; i < 4; i ++) CUDA_TRY (h, cudaStreamSynchronize (h -> vctx [i]. st));
+	CUDA_TRY (h, E -> d_ficbits. ensure ((size_t) (want * p. ficGroups + 1) * 768));
+	CUDA_TRY (h, E -> d_ficcrc. ensure ((size_t) (want * p. ficGroups + 1) * 3));
+	for (size_t i = 0; i < E -> backends. size (); i ++)
+		CUDA_TRY (h, E -> d_mscbits [i]. ensure ((size_t) (want * p. cifsPerFrame + 1) * 24 * E -> subch [i]. bitRate));
+	std::vector<int> nblk (E -> backends. size (), 0);
 	StreamCtl *hctl = (StreamCtl *) E -> h_ctl. p;
-	int nframes = 0;
+	int nframes = 0, decoded_upto = 0;
+	long long waited = -1;                                   // input pieces [0, waited] are known to have arrived on the main stream
+	auto need_input = [&] (long long upto_window_pos) -> cudaError_t {      // samples before this window position must be resident
+		if (!ready || ready -> empty ()) return cudaSuccess;
+		long long rel = upto_window_pos - E -> tail_len;
+		if (rel <= 0) return cudaSuccess;
+		long long k = (rel - 1) / piece;
+		if (k >= (long long) ready -> size ()) k = (long long) ready -> size () - 1;
+		cudaError_t e = cudaSuccess;
+		if (k > waited) { e = cudaStreamWaitEvent (h -> stream, (*ready) [k], 0); waited = k; }    // copies are in order on one stream
+		return e;
+	};
 	const size_t sm_front = 2 * (size_t) p. T_u * sizeof (float2), sm_sym = ((size_t) p. T_s + 2 * p. T_u) * sizeof (float2);
 	while (nframes < want) {
 		if (!E -> ctl. synced) {
+			CUDA_TRY (h, need_input (total));                // the null search reads until it finds one
 			*hctl = E -> ctl;
 			CUDA_TRY (h, cudaMemcpyAsync (E -> d_ctl. p, hctl, sizeof (StreamCtl), cudaMemcpyHostToDevice, h -> stream));
 			{ ProfScope prof (h, KC_ACQUIRE);
@@ -635,6 +712,7 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 		long long C = E -> chunk;
 		if (C > avail) C = avail;
 		if (C > want - nframes) C = want - nframes;
+		CUDA_TRY (h, need_input (E -> ctl. pos + (C - 1) * p. T_F + frame_need));
 		*hctl = E -> ctl;
 		CUDA_TRY (h, cudaMemcpyAsync (E -> d_ctl. p, hctl, sizeof (StreamCtl), cudaMemcpyHostToDevice, h -> stream));
 		StreamCtl *dctl = (StreamCtl *) E -> d_ctl. p;
@@ -663,46 +741,21 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 		CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
 		E -> ctl = *hctl;
 		nframes += E -> ctl. n_valid;
+		// the accepted frames' soft bits are final: once enough of them have piled up to fill the GPU, decode them on a
+		// side stream while the OFDM part (and the input copy) of the following frames goes on
+		if (nframes - decoded_upto >= vit_batch_frames) {
+			if ((rc = channel_chunk (h, decoded_upto, nframes - decoded_upto, out, nblk))) return rc;
+			decoded_upto = nframes;
+		}
 		if (E -> ctl. n_valid == C) { E -> chunk *= 2; if (E -> chunk > E -> max_chunk) E -> chunk = E -> max_chunk; }
 		else { E -> chunk = E -> chunk > 2 ? E -> chunk / 2 : 1; }
 	}
 	out -> nframes = nframes;
-	// ---- channel decoding of what the OFDM part produced ----
-	const int ngroups = nframes * p. ficGroups, ncif = nframes * p. cifsPerFrame;
-	const bool simd = dab_use_simd (h, (long long) ngroups + (long long) ncif * (long long) E -> backends. size ());
-	std::vector<VitSimdJob> jobs;
-	std::vector<int> nblk (E -> backends. size (), 0);
-	if (ngroups > 0) {
-		CUDA_TRY (h, E -> d_ficbits. ensure ((size_t) ngroups * 768));
-		CUDA_TRY (h, E -> d_ficcrc. ensure ((size_t) ngroups * 3));
-		if (simd) {
-			jobs. emplace_back ();
-			if ((rc = dab_fic_simd_job (h, (const int16_t *) E -> d_fic. p, 2304, ngroups, (uint8_t *) E -> d_ficbits. p, &jobs. back ()))) return rc;
-		} else if ((rc = dab_fic_decode_dev (h, (const int16_t *) E -> d_fic. p, 2304, ngroups, (uint8_t *) E -> d_ficbits. p, (uint8_t *) E -> d_ficcrc. p))) return rc;
-	}
-	for (size_t i = 0; i < E -> backends. size () && ncif > 0; i ++) {
-		const dabgpu_subch &sc = E -> subch [i];
-		CUDA_TRY (h, E -> d_mscbits [i]. ensure ((size_t) ncif * 24 * sc. bitRate));
-		VitSimdJob job;
-		if ((rc = dab_backend_run_dev (E -> backends [i], (const int16_t *) E -> d_msc. p + (size_t) sc. startAddr * 64, CIF_BITS, ncif,
-		                               (uint8_t *) E -> d_mscbits [i]. p, &nblk [i], simd ? &job : nullptr))) return rc;
-		if (simd && nblk [i] > 0) jobs. push_back (job);
-		dab_backend_note_cifs (E -> backends [i], ncif);
-	}
-	if (simd) {
-		if ((rc = dab_vit_simd_run (h, jobs))) return rc;
-		if (ngroups > 0) CUDA_TRY (h, fib_crc_launch (h, (const uint8_t *) E -> d_ficbits. p, 3 * ngroups, (uint8_t *) E -> d_ficcrc. p));
-	}
-	if (ngroups > 0) {
-		if (out -> fic_bits) CUDA_TRY (h, cudaMemcpyAsync (out -> fic_bits, E -> d_ficbits. p, (size_t) ngroups * 768, cudaMemcpyDeviceToHost, h -> stream));
-		if (out -> fic_crc)  CUDA_TRY (h, cudaMemcpyAsync (out -> fic_crc, E -> d_ficcrc. p, (size_t) ngroups * 3, cudaMemcpyDeviceToHost, h -> stream));
-	}
-	for (size_t i = 0; i < E -> backends. size (); i ++) {
-		const int n = nblk [i];
-		if (out -> msc_bits && out -> msc_bits [i] && n > 0)
-			CUDA_TRY (h, cudaMemcpyAsync (out -> msc_bits [i], E -> d_mscbits [i]. p, (size_t) n * 24 * E -> subch [i]. bitRate, cudaMemcpyDeviceToHost, h -> stream));
-		if (out -> msc_nblocks) out -> msc_nblocks [i] = n;
-	}
+	const int ncif = nframes * p. cifsPerFrame;
+	if ((rc = channel_chunk (h, decoded_upto, nframes - decoded_upto, out, nblk))) return rc;
+	for (int i = 1; i < 4; i ++) CUDA_TRY (h, cudaStreamSynchronize (h -> vctx [i]. st));
+	for (size_t i = 0; i < E -> backends. size (); i ++)
+		if (out -> msc_nblocks) out -> msc_nblocks [i] = nblk [i];
 	if (nframes > 0) {
 		if (out -> info) CUDA_TRY (h, cudaMemcpyAsync (out -> info, E -> d_info. p, (size_t) nframes * sizeof (dabgpu_frame_info), cudaMemcpyDeviceToHost, h -> stream));
 		if (out -> soft) {
@@ -718,6 +771,7 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 		CUDA_TRY (h, cudaMemcpyAsync (E -> d_msc. p, E -> d_histtmp. p, 15 * rowb, cudaMemcpyDeviceToDevice, h -> stream));
 	}
 	// ---- keep the unconsumed samples for the next call ----
+	CUDA_TRY (h, need_input (total));
 	const long long consumed = E -> ctl. pos;               // everything before `pos` is done with
 	const long long keep = total - consumed;
 	out -> consumed = consumed - E -> tail_len;               // relative to this call's input (may be negative: none of it)
@@ -750,19 +804,39 @@ extern "C" int dabgpu_decode_dev (dabgpu_t *h, const uint8_t *d_iq_u8, size_t ns
 extern "C" int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out) {
 	if (!h || !out || (nsamples > 0 && !iq_u8)) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_decode: bad argument");
 	CUDA_TRY (h, cudaSetDevice (h -> device));
+	Engine *E = h -> engine;
 	const size_t bytes = nsamples * 2;
+	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
 	CUDA_TRY (h, h -> d_in. ensure (bytes + 16));
+	// the input goes up in pieces on its own stream; every chunk of frames waits only for the pieces it reads, so
+	// the host-to-device copy overlaps the decode of the frames already there
+	const long long piece = 8ll << 20;                       // samples per piece (16 MB)
+	std::vector<cudaEvent_t> ready;
 	if (bytes) {
 		cudaPointerAttributes attr;
 		const bool pinned = cudaPointerGetAttributes (&attr, iq_u8) == cudaSuccess && attr. type == cudaMemoryTypeHost;
 		cudaGetLastError ();
-		if (pinned)
-			CUDA_TRY (h, cudaMemcpyAsync (h -> d_in. p, iq_u8, bytes, cudaMemcpyHostToDevice, h -> stream));
-		else {
+		const uint8_t *src = iq_u8;
+		if (!pinned) {
 			CUDA_TRY (h, h -> h_in. ensure (bytes));
 			memcpy (h -> h_in. p, iq_u8, bytes);
-			CUDA_TRY (h, cudaMemcpyAsync (h -> d_in. p, h -> h_in. p, bytes, cudaMemcpyHostToDevice, h -> stream));
+			src = (const uint8_t *) h -> h_in. p;
+		}
+		const size_t npieces = (nsamples + piece - 1) / piece;
+		while (E -> copy_events. size () < npieces) {
+			cudaEvent_t e;
+			CUDA_TRY (h, cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
+			E -> copy_events. push_back (e);
+		}
+		for (size_t k = 0; k < npieces; k ++) {
+			const size_t off = k * (size_t) piece * 2, len = (k + 1 == npieces ? bytes - off : (size_t) piece * 2);
+			CUDA_TRY (h, cudaMemcpyAsync ((char *) h -> d_in. p + off, src + off, len, cudaMemcpyHostToDevice, E -> copy_st));
+			CUDA_TRY (h, cudaEventRecord (E -> copy_events [k], E -> copy_st));
+			ready. push_back (E -> copy_events [k]);
 		}
 	}
-	return decode_core (h, (const uchar2 *) h -> d_in. p, (long long) nsamples, out);
+	// host input: the PCIe copy paces the call, so channel decoding starts as soon as 512 frames are demodulated
+	int rc = decode_core (h, (const uchar2 *) h -> d_in. p, (long long) nsamples, out, &ready, piece, E -> vit_batch_frames);
+	cudaStreamSynchronize (E -> copy_st);
+	return rc;
 }

@@ -58,6 +58,10 @@ struct Engine {
 	std::vector<dabgpu_subch> subch;
 	std::vector<dabgpu_backend *> backends;
 	int groups = 5;
+	cudaStream_t copy_st = nullptr;     // piecewise host-to-device input copies
+	std::vector<cudaEvent_t> copy_events;
+	int vit_batch_frames = 512;         // frames per channel-decoding launch (enough code words to fill the GPU)
+	unsigned vrr = 0;                   // round robin over the channel-decoding side streams
 };
 
 int ofdm_tables_init (dabgpu *h, OfdmTables *T);

@@ -109,8 +109,14 @@ struct dabgpu {
 	double prof_ms [KC_COUNT] = {0};
 	int64_t prof_n [KC_COUNT] = {0};
 	// staging
-	DevBuf d_in, d_out, d_aux, d_dec, d_jobs;
-	PinBuf h_jobs;
+	DevBuf d_in, d_out, d_aux;
+	// channel-decoding contexts: 0 = the handle's main stream, 1..3 = side streams the stream engine uses to
+	// overlap the Viterbi work of finished chunks with the OFDM work of the next one.  Launch helpers use the
+	// current context (the handle is not re-entrant, so an implicit current context is safe).
+	struct VitCtx { cudaStream_t st = nullptr; DevBuf d_dec, d_jobs; PinBuf h_jobs; };
+	VitCtx vctx [4];
+	int cur = 0;
+	cudaStream_t vst () const { return vctx [cur]. st; }
 	PinBuf h_in, h_out;
 	// cached device tables
 	std::map<long long, void *> d_tables;          // key -> device pointer (LUTs, PRBS)
@@ -119,8 +125,8 @@ struct dabgpu {
 
 // brackets one kernel launch with events when profiling is on
 struct ProfScope {
-	dabgpu *h; int cls; cudaEvent_t a = nullptr, b = nullptr;
-	ProfScope (dabgpu *h_, int cls_);
+	dabgpu *h; int cls; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+	ProfScope (dabgpu *h_, int cls_, cudaStream_t st_ = nullptr);
 	~ProfScope ();
 };
 extern thread_local std::string g_create_error;
@@ -139,7 +145,7 @@ int  dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs);
 bool dab_use_simd (const dabgpu *h, long long ncodewords);
 int  dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, uint8_t *d_crc);
 struct dabgpu_backend;
-int  dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row_stride, int ncif, uint8_t *d_out, int *nout, VitSimdJob *simd_job);
+int  dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row_stride, int row0, int ncif, uint8_t *d_out, int *nout, VitSimdJob *simd_job);
 int  dab_fic_simd_job (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, VitSimdJob *s);
 void dab_backend_note_cifs (dabgpu_backend *b, int ncif);
 int64_t dab_backend_cifs_seen (const dabgpu_backend *b);

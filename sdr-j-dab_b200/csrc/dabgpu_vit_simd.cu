@@ -233,10 +233,11 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 
 cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas) {
 	if (njobs <= 0 || total_ctas <= 0) return cudaSuccess;
-	{ ProfScope prof (h, KC_VITERBI_MSC);
-	  vit_simd_forward<<<total_ctas, VS_THREADS, 0, h -> stream>>> (d_jobs, njobs); }
-	{ ProfScope prof (h, KC_VITERBI_TB);
-	  vit_simd_traceback<<<total_ctas, TB_THREADS, 0, h -> stream>>> (d_jobs, njobs); }
+	cudaStream_t st = h -> vst ();
+	{ ProfScope prof (h, KC_VITERBI_MSC, st);
+	  vit_simd_forward<<<total_ctas, VS_THREADS, 0, st>>> (d_jobs, njobs); }
+	{ ProfScope prof (h, KC_VITERBI_TB, st);
+	  vit_simd_traceback<<<total_ctas, TB_THREADS, 0, st>>> (d_jobs, njobs); }
 	h -> launches += 2;
 	return cudaGetLastError ();
 }

@@ -130,8 +130,8 @@ __global__ void __launch_bounds__ (128) vit_warp_kernel (const VitJob j, const i
 
 cudaError_t vit_launch (dabgpu *h, int cls, const VitJob &job) {
 	if (job. nblocks <= 0) return cudaSuccess;
-	cudaStream_t st = h -> stream;
-	ProfScope prof (h, cls);
+	cudaStream_t st = h -> vst ();
+	ProfScope prof (h, cls, st);
 	const int words_per_warp = (2 * job. nsteps + (job. frameBits + 31) / 32 + 2) & ~1;   // keeps uint2 alignment
 	const size_t per_warp = (size_t) words_per_warp * 4;
 	int wpc = (int) ((110 * 1024) / per_warp);
@@ -172,8 +172,8 @@ __global__ void fib_crc_kernel (const uint8_t *bits, int nfibs, uint8_t *ok) {
 
 cudaError_t fib_crc_launch (dabgpu *h, const uint8_t *bits, int nfibs, uint8_t *ok) {
 	if (nfibs <= 0) return cudaSuccess;
-	ProfScope prof (h, KC_CRC);
-	fib_crc_kernel<<<(nfibs + 127) / 128, 128, 0, h -> stream>>> (bits, nfibs, ok);
+	ProfScope prof (h, KC_CRC, h -> vst ());
+	fib_crc_kernel<<<(nfibs + 127) / 128, 128, 0, h -> vst ()>>> (bits, nfibs, ok);
 	h -> launches ++;
 	return cudaGetLastError ();
 }
