@@ -28,7 +28,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 MODE = 1
 T_F = 196608
 SUBS = [(96 * i, 128, 1, 0o103) for i in range(9)]          # (startAddr, bitRate, uepFlag, protLevel)
-LEAD_FRAMES = 16
+LEAD_FRAMES = 64                                             # lead-in decoded before the timed region: acquisition, AFC convergence, de-interleaver fill
 ALG_BYTES_PER_FRAME = 2 * T_F + 2 * 75 * 3072                # u8 IQ read once + int16 soft bits written once
 INT_OPS_PER_STEP = 272                                       # 64 ACS x 4 + 16 branch-metric ops
 STEPS_PER_FRAME = 4 * 9 * (3072 + 6) + 4 * (768 + 6)         # trellis steps per Mode I frame of this workload

@@ -326,47 +326,78 @@ __global__ void __launch_bounds__ (256) symbol_kernel_r8 (SampleWin w, OfdmTable
 //   derive = 0: verification pass.  Accepts frames only while the inputs they were actually computed from
 //     equal the replayed state, commits the stream state and the per-frame records.
 // ---------------------------------------------------------------------------------------------------
-#define SCAN_MAX 256
+#define SCAN_MAX 1024
+struct ScanSmem { FrameIn in [SCAN_MAX]; FrameOut fo [SCAN_MAX]; float2 fc [SCAN_MAX]; double inc [SCAN_MAX]; };
 __global__ void __launch_bounds__ (32) scan_kernel (StreamCtl *ctl, FrameIn *fin, int nframes, int slot0, int groups, DabParams dp, const FrameOut *fo,
                              const float2 *fcpart, dabgpu_frame_info *info, long long abs_base, int derive) {
-	__shared__ FrameIn s_in [SCAN_MAX];
-	__shared__ FrameOut s_fo [SCAN_MAX];
-	__shared__ float2 s_fc [SCAN_MAX];
-	__shared__ double s_inc [SCAN_MAX];              // 0.1 * arg (FreqCorr) / M_PI * (carrierDiff / 2), state independent
-	__shared__ dabgpu_frame_info s_info [SCAN_MAX];
-	__shared__ int s_ninfo;
+	extern __shared__ unsigned char scan_raw [];
+	ScanSmem &S = *reinterpret_cast<ScanSmem *> (scan_raw);
+	__shared__ int s_ninfo, s_start;
 	const int lane = threadIdx. x;
 	if (!derive && ctl -> n_redo == 0) return;               // the derive pass found nothing to redo and committed already
-	// parallel preload of the per-frame records (the serial replay then runs out of shared memory)
+	const StreamCtl s0 = *ctl;
+	const int cd = dp. carrierDiff;
+	// parallel preload of the per-frame records; the serial replay then runs out of shared memory
 	for (int c = lane; c < nframes; c += 32) {
-		s_in [c] = fin [c]; s_fo [c] = fo [c];
+		S. in [c] = fin [c]; S. fo [c] = fo [c];
 		float2 fc = make_float2 (0.f, 0.f);
 		for (int g = 0; g < groups; g ++) { fc. x += fcpart [c * MAX_GROUPS + g]. x; fc. y += fcpart [c * MAX_GROUPS + g]. y; }
-		s_fc [c] = fc;
-		s_inc [c] = __dmul_rn (__ddiv_rn (__dmul_rn (0.1, (double) atan2f (fc. y, fc. x)), 3.14159265358979323846), (double) (dp. carrierDiff / 2));
+		S. fc [c] = fc;
+		S. inc [c] = __dmul_rn (__ddiv_rn (__dmul_rn (0.1, (double) atan2f (fc. y, fc. x)), 3.14159265358979323846), (double) (cd / 2));
 	}
 	__syncwarp ();
+	// Fast path for a locked receiver.  A frame leaves the tracking state as it found it (apart from advancing by one
+	// frame length) when its window was placed where the replay wants it, the coarse search is off, findIndex returned
+	// T_g and the fine integrator's truncated sum is unchanged.  Such frames are accepted in parallel; the serial replay
+	// starts at the first frame that is not of this kind.
+	const int phi0 = s0. coarse + s0. fine;
+	const int phm = mod_rate (phi0);
+	int first_slow = nframes;
+	if (!s0. f2 && s0. fine <= cd / 2 && s0. fine >= - cd / 2) {
+		for (int c0 = 0; c0 < nframes && first_slow == nframes; c0 += 32) {
+			const int c = c0 + lane;
+			bool ok = true;
+			if (c < nframes) {
+				const FrameIn in = S. in [c];
+				const long long P = s0. pos + (long long) c * dp. T_F;
+				const int lp = mod_rate ((long long) s0. lp - (long long) c * dp. T_F % DAB_INPUT_RATE * phm);
+				ok = in. P == P && in. lp == lp && in. phiA == phi0 && in. phiB == phi0 && S. fo [c]. startIndex == dp. T_s - dp. T_u &&
+				     (int) (short) __double2int_rz (__dadd_rn ((double) s0. fine, S. inc [c])) == s0. fine;
+				if (ok) {
+					dabgpu_frame_info fi;
+					fi. pos = abs_base + P; fi. startIndex = dp. T_s - dp. T_u; fi. coarse = s0. coarse; fi. fine = s0. fine;
+					fi. phase0 = lp; fi. correction = 0; fi. freqCorrRe = S. fc [c]. x; fi. freqCorrIm = S. fc [c]. y;
+					info [slot0 + c] = fi;                       // harmless if the chunk is redone: rewritten then
+					if (derive) S. in [c]. active = 0;
+				}
+			}
+			const unsigned bad = __ballot_sync (0xffffffffu, !ok);
+			if (bad) first_slow = c0 + __ffs (bad) - 1;
+		}
+	} else first_slow = 0;
+	__syncwarp ();
 	if (lane == 0) {
-		StreamCtl s = *ctl;
-		const int cd = dp. carrierDiff;
-		int n_redo = 0, ninfo = 0;
+		StreamCtl s = s0;
+		int n_redo = 0, ninfo = first_slow;
 		int k_a = 0x7fffffff, k_b = 0, k_c = 0, k_si = -1, k_delta = 0;
-		s. n_valid = 0; s. lost = 0;
-		for (int c = 0; c < nframes; c ++) {
-			FrameIn in = s_in [c];
+		s. n_valid = first_slow; s. lost = 0;
+		s. pos = s0. pos + (long long) first_slow * dp. T_F;
+		s. lp = mod_rate ((long long) s0. lp - (long long) first_slow * dp. T_F % DAB_INPUT_RATE * phm);
+		for (int c = first_slow; c < nframes; c ++) {
+			FrameIn in = S. in [c];
 			const int phiA = s. coarse + s. fine;
 			bool changed = in. P != s. pos || in. lp != s. lp || in. phiA != phiA;
 			if (derive) { in. P = s. pos; in. lp = s. lp; in. phiA = phiA; }
 			else if (changed) break;                             // computed from other inputs than the replay wants
-			const int si = s_fo [c]. startIndex;                 // (derive: from the old window if `changed`; verified later)
+			const int si = S. fo [c]. startIndex;                // (derive: from the old window if `changed`; verified later)
 			if (si < 0) {                                        // :353-356 -> notSynced; T_u samples were consumed
 				if (derive && changed) {
-					in. phiB = phiA; in. active = 1; s_in [c] = in; n_redo ++;
-					for (int k = c + 1; k < nframes; k ++) s_in [k]. active = 0;
+					in. phiB = phiA; in. active = 1; S. in [c] = in; n_redo ++;
+					for (int k = c + 1; k < nframes; k ++) S. in [k]. active = 0;
 					nframes = c + 1;
 					break;
 				}
-				if (derive) for (int k = c; k < nframes; k ++) s_in [k]. active = 0;
+				if (derive) for (int k = c; k < nframes; k ++) S. in [k]. active = 0;
 				s. pos += dp. T_u;
 				s. lp = mod_rate ((long long) s. lp - (long long) dp. T_u * mod_rate (phiA));
 				s. synced = 0; s. lost = 1;
@@ -375,7 +406,7 @@ __global__ void __launch_bounds__ (32) scan_kernel (StreamCtl *ctl, FrameIn *fin
 			int correction = 0;
 			const StreamCtl before = s;
 			if (s. f2) {                                         // :390-405
-				correction = s_fo [c]. correction;
+				correction = S. fo [c]. correction;
 				if (correction == 0 && s. prev1 == 0 && s. prev2 == 0) s. f2 = 0;
 				else if (correction != 100) {
 					s. coarse += correction * cd;
@@ -387,10 +418,10 @@ __global__ void __launch_bounds__ (32) scan_kernel (StreamCtl *ctl, FrameIn *fin
 			const int usedB = in. phiB;
 			if (derive) {
 				changed = changed || usedB != phiB;
-				in. phiB = phiB; in. active = changed; s_in [c] = in; n_redo += changed;
+				in. phiB = phiB; in. active = changed; S. in [c] = in; n_redo += changed;
 			} else if (usedB != phiB) { s = before; break; }
-			const float2 fc = s_fc [c];
-			double inc = s_inc [c];                              // :445-446
+			const float2 fc = S. fc [c];
+			double inc = S. inc [c];                             // :445-446
 			if (derive && usedB != phiB) {                       // the symbols were mixed with another frequency: rotate
 				double ang = (double) atan2f (fc. y, fc. x);
 				ang -= 2.0 * 3.14159265358979323846 * (double) (phiB - usedB) * (double) dp. T_u / (double) DAB_INPUT_RATE;
@@ -400,12 +431,11 @@ __global__ void __launch_bounds__ (32) scan_kernel (StreamCtl *ctl, FrameIn *fin
 			dabgpu_frame_info fi;
 			fi. pos = abs_base + s. pos; fi. startIndex = si; fi. coarse = s. coarse; fi. fine = s. fine;
 			fi. phase0 = s. lp; fi. correction = correction; fi. freqCorrRe = fc. x; fi. freqCorrIm = fc. y;
-			s_info [c] = fi; ninfo = c + 1;
+			info [slot0 + c] = fi; ninfo = c + 1;
 			// fineCorrector (int16) += 0.1 * arg (FreqCorr) / M_PI * (carrierDiff / 2)
 			s. fine = (int) (short) __double2int_rz (__dadd_rn ((double) s. fine, inc));
 			const int phiC = s. coarse + s. fine;
-			// localPhase after the whole frame: -(si + T_u) fA - (L-1) T_s fB - T_null fC (mod rate).  In lock all
-			// three frequencies and si repeat from frame to frame, so the 64-bit reductions are cached.
+			// localPhase after the whole frame: -(si + T_u) fA - (L-1) T_s fB - T_null fC (mod rate); cached while nothing moves
 			if (phiA != k_a || phiB != k_b || phiC != k_c || si != k_si) {
 				long long d = (long long) (si + dp. T_u) * mod_rate (phiA);
 				d += ((long long) (dp. L - 1) * dp. T_s) % DAB_INPUT_RATE * mod_rate (phiB);
@@ -419,15 +449,16 @@ __global__ void __launch_bounds__ (32) scan_kernel (StreamCtl *ctl, FrameIn *fin
 			else if (s. fine < - cd / 2) { s. coarse -= cd; s. fine += cd; }
 			s. n_valid = c + 1;
 		}
+		(void) ninfo;
 		if (derive) {
 			ctl -> n_redo = n_redo;
-			if (n_redo == 0) { s. n_redo = 0; *ctl = s; s_ninfo = ninfo; }   // nothing changes: this replay IS the verification
-			else s_ninfo = 0;
-		} else { s. n_redo = ctl -> n_redo; *ctl = s; s_ninfo = ninfo; }
+			if (n_redo == 0) { s. n_redo = 0; *ctl = s; }    // nothing changes: this replay IS the verification
+		} else { s. n_redo = ctl -> n_redo; *ctl = s; }
+		s_start = first_slow;
 	}
 	__syncwarp ();
-	if (derive) for (int c = lane; c < nframes; c += 32) fin [c] = s_in [c];
-	for (int c = lane; c < s_ninfo; c += 32) info [slot0 + c] = s_info [c];
+	if (derive) for (int c = lane; c < nframes; c += 32) fin [c] = S. in [c];
+	(void) s_ninfo; (void) s_start;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -448,6 +479,7 @@ int dab_engine_init (dabgpu *h) {
 	const int big = 100 * 1024;
 	CUDA_TRY (h, cudaFuncSetAttribute (front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 	CUDA_TRY (h, cudaFuncSetAttribute (symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	CUDA_TRY (h, cudaFuncSetAttribute (scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (ScanSmem)));
 	return DABGPU_OK;
 }
 
@@ -458,7 +490,7 @@ void dab_engine_free (dabgpu *h) {
 	if (E -> d_phaseRef) cudaFree (E -> d_phaseRef);
 	if (E -> copy_st) { cudaStreamSynchronize (E -> copy_st); cudaStreamDestroy (E -> copy_st); }
 	for (auto e : E -> copy_events) cudaEventDestroy (e);
-	E -> tail. release (); E -> d_ctl. release (); E -> h_ctl. release ();
+	E -> tail. release (); E -> tail_spare. release (); E -> d_ctl. release (); E -> h_ctl. release ();
 	E -> d_frameout. release (); E -> d_framein. release (); E -> d_fcpart. release (); E -> d_spec0. release (); E -> d_info. release ();
 	E -> d_fic. release (); E -> d_msc. release (); E -> d_histtmp. release ();
 	E -> d_ficbits. release (); E -> d_ficcrc. release ();
@@ -679,6 +711,8 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 	std::vector<int> nblk (E -> backends. size (), 0);
 	StreamCtl *hctl = (StreamCtl *) E -> h_ctl. p;
 	int nframes = 0, decoded_upto = 0;
+	// host input arrives piecewise: smaller chunks let the first frames start before the last samples are up
+	const int chunk_cap = ready && !ready -> empty () ? (E -> max_chunk < 128 ? E -> max_chunk : 128) : E -> max_chunk;
 	long long waited = -1;                                   // input pieces [0, waited] are known to have arrived on the main stream
 	auto need_input = [&] (long long upto_window_pos) -> cudaError_t {      // samples before this window position must be resident
 		if (!ready || ready -> empty ()) return cudaSuccess;
@@ -709,7 +743,7 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 		long long avail = (total - E -> ctl. pos - frame_need) / p. T_F + 1;
 		if (total - E -> ctl. pos < frame_need) avail = 0;
 		if (avail <= 0) break;
-		long long C = E -> chunk;
+		long long C = E -> chunk < chunk_cap ? E -> chunk : chunk_cap;
 		if (C > avail) C = avail;
 		if (C > want - nframes) C = want - nframes;
 		CUDA_TRY (h, need_input (E -> ctl. pos + (C - 1) * p. T_F + frame_need));
@@ -732,7 +766,7 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 				symbol_kernel<<<(int) C * E -> groups, OFDM_THREADS, sm_sym, h -> stream>>> (w, E -> T, fin, nframes, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
 					fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p); }
 			{ ProfScope prof (h, KC_SCAN);
-			scan_kernel<<<1, 32, 0, h -> stream>>> (dctl, fin, (int) C, nframes, E -> groups, p, fo, (const float2 *) E -> d_fcpart. p,
+			scan_kernel<<<1, 32, sizeof (ScanSmem), h -> stream>>> (dctl, fin, (int) C, nframes, E -> groups, p, fo, (const float2 *) E -> d_fcpart. p,
 				(dabgpu_frame_info *) E -> d_info. p, E -> abs_base, pass == 0 ? 1 : 0); }
 		}
 		h -> launches += 7;
@@ -747,7 +781,10 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 			if ((rc = channel_chunk (h, decoded_upto, nframes - decoded_upto, out, nblk))) return rc;
 			decoded_upto = nframes;
 		}
-		if (E -> ctl. n_valid == C) { E -> chunk *= 2; if (E -> chunk > E -> max_chunk) E -> chunk = E -> max_chunk; }
+		// chunk policy: grow while the speculation holds outright; a chunk that needed recomputation (correctors still
+		// moving) or was cut short shrinks, so a converging loop costs little and a locked one runs in one pass
+		if (E -> ctl. n_valid == C && E -> ctl. n_redo == 0) { E -> chunk *= 2; if (E -> chunk > chunk_cap) E -> chunk = chunk_cap; }
+		else if (E -> ctl. n_valid == C) { E -> chunk = E -> chunk > 16 ? E -> chunk / 2 : (E -> chunk < 8 ? E -> chunk * 2 : E -> chunk); }
 		else { E -> chunk = E -> chunk > 2 ? E -> chunk / 2 : 1; }
 	}
 	out -> nframes = nframes;
@@ -776,7 +813,7 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 	const long long keep = total - consumed;
 	out -> consumed = consumed - E -> tail_len;               // relative to this call's input (may be negative: none of it)
 	if (keep > 0) {
-		DevBuf nt;
+		DevBuf &nt = E -> tail_spare;                       // ping-pong: no allocation once both buffers are big enough
 		CUDA_TRY (h, nt. ensure ((size_t) keep * sizeof (uchar2)));
 		long long from0 = consumed < E -> tail_len ? E -> tail_len - consumed : 0;     // part still in the old tail
 		if (from0 > 0)
@@ -784,8 +821,7 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 		const long long off1 = consumed > E -> tail_len ? consumed - E -> tail_len : 0;
 		CUDA_TRY (h, cudaMemcpyAsync ((uchar2 *) nt. p + from0, d_new + off1, (size_t) (nnew - off1) * sizeof (uchar2), cudaMemcpyDeviceToDevice, h -> stream));
 		CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
-		E -> tail. release ();
-		E -> tail = nt;
+		DevBuf t = E -> tail; E -> tail = E -> tail_spare; E -> tail_spare = t;
 	} else
 		CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
 	E -> tail_len = keep > 0 ? keep : 0;

@@ -45,10 +45,10 @@ struct Engine {
 	StreamCtl ctl {};
 	long long abs_base = 0;             // absolute sample index of window position 0
 	long long frames_total = 0, cifs_total = 0;
-	DevBuf tail; long long tail_len = 0;     // unconsumed samples (uchar2)
+	DevBuf tail, tail_spare; long long tail_len = 0;     // unconsumed samples (uchar2), ping-pong
 	DevBuf d_ctl;                       // StreamCtl on the device
 	PinBuf h_ctl;
-	int chunk = 1, max_chunk = 256;
+	int chunk = 1, max_chunk = 1024;
 	DevBuf d_frameout, d_fcpart, d_spec0, d_info, d_framein;
 	DevBuf d_fic, d_msc, d_histtmp;     // soft bits: FIC [frames][3*2K], MSC rows [15 + cifs][55296]
 	long long cap_frames = 0;
