@@ -300,11 +300,12 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         ip = eng.int_peak()
         int_peak = max(ip[k] for k in ("add", "min", "add_mad"))
-        n_vit, ms_vit = prof["viterbi_msc"]
+        n_vit, ms_vit = prof["viterbi_msc"]                   # forward (add-compare-select) launches: FIC + all sub-channels per launch
+        n_tb, ms_tb = prof["viterbi_tb"]
         n_sym, ms_sym = prof["symbol"]
-        steps_msc = frames_per_step * 4 * (3072 + 6)          # trellis steps per viterbi_msc launch
+        steps_per_launch = frames_per_step * STEPS_PER_FRAME * args.steps / max(n_vit, 1)   # trellis steps per forward launch
         vit_avg_ms = ms_vit / max(n_vit, 1)
-        vit_ops = INT_OPS_PER_STEP * steps_msc / (vit_avg_ms * 1e-3) if n_vit else 0.0
+        vit_ops = INT_OPS_PER_STEP * steps_per_launch / (vit_avg_ms * 1e-3) if n_vit else 0.0
         sym_frames = frames_per_step * args.steps / max(n_sym, 1)
         sym_avg_ms = ms_sym / max(n_sym, 1)
         sym_gbs = ALG_BYTES_PER_FRAME * sym_frames / (sym_avg_ms * 1e-3) / 1e9 if n_sym else 0.0
@@ -316,19 +317,19 @@ def main():
             "config": dict(config, frames_decoded_per_step=frames_per_step, parallelism="1 stream per GPU, frame-parallel inside",
                            fic_crc_ok=crc_ok),
             "msamples_per_s": value * T_F / 1e6,
-            "viterbi_gbit_per_s": (frames_per_step * 4 * 3072) / (vit_avg_ms * 1e-3) / 1e9 if n_vit else None,
+            "viterbi_gbit_per_s": (frames_per_step * args.steps * (4 * 9 * 3072 + 4 * 768)) / ((ms_vit + ms_tb) * 1e-3) / 1e9 if n_vit else None,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(nsamp * 2),
                     "d2h_bytes_per_step": int(frames_per_step * (4 * 768 + 12) + sum(m.shape[0] * m.shape[1] for m in r.msc)),
                     "ms_per_step": e2e_wall * 1e3 / args.steps, "timing": "wall clock, synchronised on both sides, pinned host buffers"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            # dominant kernel by time: the MSC Viterbi launch (one per sub-channel per step); integer-ALU bound
-            "roofline": {"kernel": "vit_warp_kernel<deint> (viterbi_msc)", "bound": "alu", "achieved": vit_ops / 1e12, "peak": int_peak / 1e12,
+            # dominant kernel by time: the Viterbi forward pass; integer-ALU bound
+            "roofline": {"kernel": "vit_simd2_forward (add-compare-select of FIC + 9 sub-channels, one launch per step)", "bound": "alu", "achieved": vit_ops / 1e12, "peak": int_peak / 1e12,
                          "unit": "Tint-op/s", "frac": vit_ops / int_peak if int_peak else None, "traffic": None,
                          "avg_launch_ms": vit_avg_ms, "launches": n_vit, "share_of_step": shares.get("viterbi_msc"),
                          "peak_source": "measured live by dabgpu_int_peak (add / min / add+mad.lo micro-benchmark): %s" %
                                         {k: round(v / 1e12, 2) for k, v in ip.items()},
-                         "algorithmic": "272 int-ops per trellis step (SURVEY.md 8d) x %d steps per launch" % steps_msc},
+                         "algorithmic": "272 int-ops per trellis step (SURVEY.md 8d) x %d steps per launch" % steps_per_launch},
             "roofline_hbm": {"kernel": "symbol_kernel (FFT+demod group)", "bound": "hbm", "achieved": sym_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": sym_gbs / hbm_peak, "traffic": None, "avg_launch_ms": sym_avg_ms, "launches": n_sym,
                              "share_of_step": shares.get("symbol"), "peak_source": peak_src,

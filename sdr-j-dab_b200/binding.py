@@ -104,9 +104,10 @@ class DecodeOut:
 class DabGpu:
     """One engine handle (dabgpu_t)."""
 
-    def __init__(self, mode=1, device=0, threshold=3, freqSyncMethod=1, viterbi_path=0):
+    def __init__(self, mode=1, device=0, threshold=3, freqSyncMethod=1, viterbi_path=0, simd_single_lane=False):
         self.lib = load_library()
         cfg = Config(device=device, dabMode=mode, threshold=threshold, freqSyncMethod=freqSyncMethod, viterbi_path=viterbi_path)
+        cfg.reserved[0] = 1 if simd_single_lane else 0
         self.h = C.c_void_p()
         rc = self.lib.dabgpu_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:

@@ -204,7 +204,7 @@ int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
 	size_t dec_words = 0;
 	int ctas = 0;
 	for (auto &j : jobs) {
-		j. cta_first = ctas;
+		j. cta_first = ctas; j. one = 1u;
 		ctas += (j. ncw + 63) / 64;
 		dec_words += (size_t) ((j. nsteps + 39) / 40 * 40) * j. ncw;
 	}

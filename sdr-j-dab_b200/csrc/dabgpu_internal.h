@@ -82,6 +82,7 @@ struct VitSimdJob {
 	const uint16_t *chunk_i0; // device: first input index of every 40-step chunk (+ one past the end), with inv
 	int frameBits, nsteps, ncw;
 	int cta_first;            // first CTA of this job in the launch (64 code words per CTA)
+	unsigned one;             // = 1, set by dab_vit_simd_run; opaque to the compiler on purpose (see vs_acs)
 	uint2 *dec;               // [nsteps padded to 40][ncw] decision words
 	const uint32_t *prbs;     // packed dispersal sequence or nullptr
 	uint8_t *out;             // [ncw][frameBits]
