@@ -202,10 +202,10 @@ int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
 	if (jobs. empty ()) return DABGPU_OK;
 	dabgpu::VitCtx &cx = h -> vctx [h -> cur];
 	size_t dec_words = 0;
-	int ctas = 0;
+	int ctas = 0, ctas2 = 0;
 	for (auto &j : jobs) {
-		j. cta_first = ctas; j. one = 1u;
-		ctas += (j. ncw + 63) / 64;
+		j. cta_first = ctas; j. cta_first2 = ctas2; j. one = 1u;
+		ctas += (j. ncw + 63) / 64; ctas2 += (j. ncw + 63) / 64;
 		dec_words += (size_t) ((j. nsteps + 39) / 40 * 40) * j. ncw;
 	}
 	// (re)allocation and the pinned job table are only touched once everything queued on this context is done
@@ -218,7 +218,7 @@ int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
 	CUDA_TRY (h, cx. h_jobs. ensure (jb));
 	memcpy (cx. h_jobs. p, jobs. data (), jb);
 	CUDA_TRY (h, cudaMemcpyAsync (cx. d_jobs. p, cx. h_jobs. p, jb, cudaMemcpyHostToDevice, cx. st));
-	CUDA_TRY (h, vit_simd_launch (h, (const VitSimdJob *) cx. d_jobs. p, (int) jobs. size (), ctas));
+	CUDA_TRY (h, vit_simd_launch (h, (const VitSimdJob *) cx. d_jobs. p, (int) jobs. size (), ctas, ctas2));
 	return DABGPU_OK;
 }
 

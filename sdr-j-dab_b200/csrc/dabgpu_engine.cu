@@ -231,7 +231,7 @@ __device__ __forceinline__ float2 u8_to_c (uchar2 s) {
 	return make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f));
 }
 
-__global__ void __launch_bounds__ (256) symbol_kernel_r8 (SampleWin w, OfdmTables T, const FrameIn *fin, int slot0, int groups,
+__global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTables T, const FrameIn *fin, int slot0, int groups,
                                                           int blocksPerCIF, int cifsPerFrame, const FrameOut *fo,
                                                           const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc) {
 	__shared__ float2 bufA [R8_SMEM], bufB [R8_SMEM], G [512];
@@ -264,21 +264,24 @@ __global__ void __launch_bounds__ (256) symbol_kernel_r8 (SampleWin w, OfdmTable
 	}
 	float2 acc = make_float2 (0.f, 0.f);
 	const int slot = slot0 + c;
+	int pidx [6];                                                          // this thread's six carriers (K = 1536 = 6 x 256)
+#pragma unroll
+	for (int m = 0; m < 6; m ++) pidx [m] = __ldg (&T. permpos [t + 256 * m]);
 	for (int l = l0; l < l1; l ++) {
 		const long long first = F + N + (long long) (l - 1) * Ts;          // guard interval starts here
 		const int lpb = mod_rate ((long long) lpD - ((long long) (l - 1) * Ts) % DAB_INPUT_RATE * phB);
 		// issue every load of the symbol first
-		uchar2 raw [8], rg0, rg1;
+		uchar2 cur_raw [8], cg0, cg1;
 #pragma unroll
-		for (int k = 0; k < 8; k ++) raw [k] = win_fetch (w, first + Tg + t + 256 * k);
-		rg0 = win_fetch (w, first + t);
-		rg1 = t + 256 < Tg ? win_fetch (w, first + t + 256) : make_uchar2 (128, 128);
+		for (int k = 0; k < 8; k ++) cur_raw [k] = win_fetch (w, first + Tg + t + 256 * k);
+		cg0 = win_fetch (w, first + t);
+		cg1 = t + 256 < Tg ? win_fetch (w, first + t + 256) : make_uchar2 (128, 128);
 		float2 phg = nco (T, mod_rate ((long long) lpb - (long long) (t + 1) * phB));          // guard sample t
 		float2 ph  = nco (T, mod_rate ((long long) lpb - (long long) (Tg + t + 1) * phB));     // useful sample t
-		G [t] = cmul (u8_to_c (rg0), phg);
-		G [t + 256] = cmul (u8_to_c (rg1), cmul (phg, rot256));
+		G [t] = cmul (u8_to_c (cg0), phg);
+		G [t + 256] = cmul (u8_to_c (cg1), cmul (phg, rot256));
 #pragma unroll
-		for (int k = 0; k < 8; k ++) { x [k] = cmul (u8_to_c (raw [k]), ph); ph = cmul (ph, rot256); }
+		for (int k = 0; k < 8; k ++) { x [k] = cmul (u8_to_c (cur_raw [k]), ph); ph = cmul (ph, rot256); }
 		__syncthreads ();                                                  // G visible; last symbol's demod reads done
 		// FreqCorr += x[i] * conj (x[i - T_u]), i in [T_u, T_s): useful element e = i - T_g pairs with guard sample e - (T_u - T_g)
 		{
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__ (256) symbol_kernel_r8 (SampleWin w, OfdmTable
 #pragma unroll
 		for (int m = 0; m < 6; m ++) {                                      // K = 1536 = 6 x 256 carriers
 			const int i = t + 256 * m;
-			const int idx = __ldg (&T. permpos [i]);
+			const int idx = pidx [m];
 			const float2 r1 = cmulc (cur [idx], prev [idx]);
 			const float ab1 = fabsf (r1. x) + fabsf (r1. y);
 			out [i]        = quant127 (r1. x, ab1);

@@ -81,13 +81,14 @@ struct VitSimdJob {
 	const uint16_t *inv;      // device: input index -> mother-code index, or nullptr (identity)
 	const uint16_t *chunk_i0; // device: first input index of every 40-step chunk (+ one past the end), with inv
 	int frameBits, nsteps, ncw;
-	int cta_first;            // first CTA of this job in the launch (64 code words per CTA)
+	int cta_first;            // first CTA of this job in the launch (64 code words per CTA: single-lane forward, chain-back)
+	int cta_first2;           // same for the lane-pair forward kernel (VS2_CW code words per CTA)
 	unsigned one;             // = 1, set by dab_vit_simd_run; opaque to the compiler on purpose (see vs_acs)
 	uint2 *dec;               // [nsteps padded to 40][ncw] decision words
 	const uint32_t *prbs;     // packed dispersal sequence or nullptr
 	uint8_t *out;             // [ncw][frameBits]
 };
-cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas);
+cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas, int total_ctas2);
 cudaError_t fib_crc_launch (dabgpu *h, const uint8_t *bits, int nfibs, uint8_t *ok);
 
 // kernel classes for the optional per-launch CUDA-event profile (dabgpu_profile_*)

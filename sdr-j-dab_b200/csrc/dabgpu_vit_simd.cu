@@ -94,11 +94,11 @@ __device__ __forceinline__ void vs_renorm (uint32_t (&R) [32]) {
 // symbols of the step (erasure = 127).  Source rows are read coalesced (a warp reads consecutive soft bits of one row)
 // and scattered through the inverse puncturing map; with time de-interleaving the soft bit of code word c, position i
 // comes from row c - D[i & 15] (dab-concurrent.cpp:162-169).
-template <int NT, int VS_RB>
+template <int NT, int VS_RB, int CW>
 __device__ __forceinline__ void vs_stage (uint32_t *tile, const VitSimdJob &j, int k, int c0, int nrows, long long g_lo, int dmax) {
 	const int tid = threadIdx. x, lane = tid & 31, warp = tid >> 5;
 	__syncthreads ();
-	for (int w = tid; w < VS_THREADS * VS_CHUNK; w += NT)
+	for (int w = tid; w < CW * VS_CHUNK; w += NT)
 		tile [(w / VS_CHUNK) * VS_ROWW + (w % VS_CHUNK)] = 0x7f7f7f7fu;          // erasure = 127 (deconvolve.cpp:185)
 	__syncthreads ();
 	const int m0 = 4 * VS_CHUNK * k;
@@ -128,7 +128,7 @@ __device__ __forceinline__ void vs_stage (uint32_t *tile, const VitSimdJob &j, i
 #pragma unroll
 			for (int rr = 0; rr < VS_RB; rr ++) {
 				const int c = row0 + rr - dmax + dl;
-				if (row0 + rr < nrows && c >= 0 && c < VS_THREADS && c0 + c < j. ncw)
+				if (row0 + rr < nrows && c >= 0 && c < CW && c0 + c < j. ncw)
 					tb [c * (VS_ROWW * 4) + m] = (uint8_t) min (max (v [rr][cc] + 127, 0), 255);   // viterbi.cpp:229-235
 			}
 		}
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__ (VS_THREADS) vit_simd_forward (const VitSimdJo
 	uint2 *dec = j. dec + cw;
 	const int nchunks = (j. nsteps + VS_CHUNK - 1) / VS_CHUNK;
 	for (int k = 0; k < nchunks; k ++) {
-		vs_stage<VS_THREADS, 16> (tile, j, k, c0, nrows, g_lo, dmax);
+		vs_stage<VS_THREADS, 16, VS_THREADS> (tile, j, k, c0, nrows, g_lo, dmax);
 		// ---- 8 layout cycles of 5 steps ----
 		const uint32_t *my = &tile [tid * VS_ROWW];
 		uint2 *d = dec + (size_t) (VS_CHUNK * k) * j. ncw;
@@ -190,7 +190,8 @@ __global__ void __launch_bounds__ (VS_THREADS) vit_simd_forward (const VitSimdJo
 // as above.  After four steps the lane bit has reached s5 and the half bit s4; one round of 8 lane-pair shuffles and
 // 16 PRMTs (plus a compile-time renaming) moves them back to s1 / s0.
 // ---------------------------------------------------------------------------------------------------------------
-#define VS2_THREADS 128
+#define VS2_CW      64          // code words per CTA (two threads each)
+#define VS2_THREADS (2 * VS2_CW)
 __host__ __device__ constexpr int vs_insert00 (int r, int p) { return ((r >> p) << (p + 2)) | (r & ((1 << p) - 1)); }
 
 template <int K>
@@ -241,18 +242,18 @@ __device__ __forceinline__ void vs2_fixup (uint32_t (&Q) [16], uint32_t (&R) [16
 }
 
 __global__ void __launch_bounds__ (VS2_THREADS) vit_simd2_forward (const VitSimdJob *jobs, int njobs) {
-	__shared__ uint32_t tile [VS_THREADS * VS_ROWW];
+	__shared__ uint32_t tile [VS2_CW * VS_ROWW];
 	int jb = 0;
-	while (jb + 1 < njobs && (int) blockIdx. x >= jobs [jb + 1]. cta_first) jb ++;
+	while (jb + 1 < njobs && (int) blockIdx. x >= jobs [jb + 1]. cta_first2) jb ++;
 	const VitSimdJob j = jobs [jb];
-	const int c0 = ((int) blockIdx. x - j. cta_first) * VS_THREADS;
+	const int c0 = ((int) blockIdx. x - j. cta_first2) * VS2_CW;
 	const int tid = threadIdx. x;
 	const int cl = tid >> 1;                                   // code word within the CTA
 	const bool lanebit = tid & 1;
 	const int cw = c0 + cl;
 	const bool live = cw < j. ncw;
 	const int dmax = j. deint ? 15 : 0;
-	const int nrows = min (VS_THREADS, j. ncw - c0) + dmax;
+	const int nrows = min (VS2_CW, j. ncw - c0) + dmax;
 	const long long g_lo = (long long) c0 + j. first_row - dmax;
 
 	uint32_t R [16], Q [16];
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__ (VS2_THREADS) vit_simd2_forward (const VitSimd
 	const size_t dstride = 2 * (size_t) j. ncw;
 	const int nchunks = (j. nsteps + VS_CHUNK - 1) / VS_CHUNK;
 	for (int k = 0; k < nchunks; k ++) {
-		vs_stage<VS2_THREADS, 8> (tile, j, k, c0, nrows, g_lo, dmax);
+		vs_stage<VS2_THREADS, 8, VS2_CW> (tile, j, k, c0, nrows, g_lo, dmax);
 		const uint32_t *my = &tile [cl * VS_ROWW];
 		uint32_t *d = dec + (size_t) (VS_CHUNK * k) * dstride;
 #pragma unroll 1
@@ -314,18 +315,22 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 		const int base = 128 * rd, top = min (j. frameBits, base + 128);
 		uint32_t w [4] = { 0, 0, 0, 0 };
 		if (live) {
-			// the loads do not depend on the state: fetch 16 decision words, then walk them
-			for (int hi = top - 1; hi >= base; hi -= 16) {
-				uint2 dd [16];
+			// the loads do not depend on the state: fetch 32 decision words (one output word), then walk them
 #pragma unroll
-				for (int u = 0; u < 16; u ++) {
+			for (int wd = 3; wd >= 0; wd --) {
+				const int hi = base + 32 * wd + 31;              // highest information bit of this output word
+				if (base + 32 * wd >= top) continue;
+				uint2 dd [32];
+#pragma unroll
+				for (int u = 0; u < 32; u ++) {
 					const int i = hi - u;
-					dd [u] = i >= base ? dec [(size_t) (i + 6) * j. ncw] : make_uint2 (0u, 0u);
+					dd [u] = i < top ? dec [(size_t) (i + 6) * j. ncw] : make_uint2 (0u, 0u);
 				}
+				uint32_t acc = 0;
 #pragma unroll
-				for (int u = 0; u < 16; u ++) {
+				for (int u = 0; u < 32; u ++) {
 					const int i = hi - u;
-					if (i < base) break;
+					if (i >= top) continue;
 					const int t = i + 6;                        // decision of step i+6 = information bit i
 					unsigned bit;
 					if (LANES == 1) {                            // one thread per code word: word = half, bit = state without bit pp
@@ -340,8 +345,9 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 						bit = ((l ? dd [u]. y : dd [u]. x) >> (16u * h + q)) & 1u;
 					}
 					state = (state >> 1) | (bit << 5);
-					w [(i - base) >> 5] |= bit << (i & 31);
+					acc |= bit << (31 - u);
 				}
+				w [wd] = acc;
 			}
 		}
 		__syncthreads ();
@@ -366,12 +372,12 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 	}
 }
 
-cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas) {
+cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas, int total_ctas2) {
 	if (njobs <= 0 || total_ctas <= 0) return cudaSuccess;
 	cudaStream_t st = h -> vst ();
 	const bool pair = h -> cfg. reserved [0] != 1;           // reserved[0] = 1: one thread per code word (kept for comparison)
 	{ ProfScope prof (h, KC_VITERBI_MSC, st);
-	  if (pair) vit_simd2_forward<<<total_ctas, VS2_THREADS, 0, st>>> (d_jobs, njobs);
+	  if (pair) vit_simd2_forward<<<total_ctas2, VS2_THREADS, 0, st>>> (d_jobs, njobs);
 	  else      vit_simd_forward<<<total_ctas, VS_THREADS, 0, st>>> (d_jobs, njobs); }
 	{ ProfScope prof (h, KC_VITERBI_TB, st);
 	  if (pair) vit_simd_traceback<2><<<total_ctas, TB_THREADS, 0, st>>> (d_jobs, njobs);
