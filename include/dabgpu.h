@@ -73,7 +73,7 @@ int  dabgpu_timer_end (dabgpu_t *h, float *ms);
  * launch is bracketed by two events on the handle's stream; get() waits for the stream and returns the
  * accumulated launch count and device milliseconds of one class since the last reset */
 enum { DABGPU_KC_ACQUIRE = 0, DABGPU_KC_FRONT, DABGPU_KC_SYMBOL, DABGPU_KC_SCAN, DABGPU_KC_VITERBI_MSC,
-       DABGPU_KC_VITERBI_FIC, DABGPU_KC_VITERBI_API, DABGPU_KC_CRC, DABGPU_KC_VITERBI_TB, DABGPU_KC_COUNT };
+       DABGPU_KC_VITERBI_FIC, DABGPU_KC_VITERBI_API, DABGPU_KC_CRC, DABGPU_KC_VITERBI_TB, DABGPU_KC_VITERBI_SYM, DABGPU_KC_COUNT };
 int  dabgpu_profile_enable (dabgpu_t *h, int32_t on);
 int  dabgpu_profile_reset (dabgpu_t *h);
 int  dabgpu_profile_get (dabgpu_t *h, int32_t kernel_class, int64_t *launches, double *ms);

@@ -137,7 +137,7 @@ class DabGpu:
         self._check(self.lib.dabgpu_timer_end(self.h, C.byref(ms)))
         return ms.value
 
-    KERNEL_CLASSES = ("acquire", "front", "symbol", "scan", "viterbi_msc", "viterbi_fic", "viterbi_api", "crc", "viterbi_tb")
+    KERNEL_CLASSES = ("acquire", "front", "symbol", "scan", "viterbi_msc", "viterbi_fic", "viterbi_api", "crc", "viterbi_tb", "viterbi_sym")
 
     def profile_enable(self, on=True):
         self._check(self.lib.dabgpu_profile_enable(self.h, int(on)))

@@ -156,14 +156,18 @@ int dab_device_table (dabgpu *h, long long key, const void *host, size_t bytes, 
 	return DABGPU_OK;
 }
 
+static long long profile_key (int kind, int bitRate, int uepFlag, int protLevel) {
+	return ((long long) (kind == 3 ? 4 : kind ? 1 : 2) << 40) | ((long long) (uepFlag != 0) << 32) |
+	       ((long long) (bitRate & 0xffff) << 16) | (protLevel & 0xffff);
+}
+
 int dab_get_profile (dabgpu *h, int kind, int bitRate, int uepFlag, int protLevel,
                      const ProtProfile **pp, const uint16_t **d_lut) {
-	const long long key = ((long long) (kind ? 1 : 2) << 40) | ((long long) (uepFlag != 0) << 32) |
-	                      ((long long) (bitRate & 0xffff) << 16) | (protLevel & 0xffff);
+	const long long key = profile_key (kind, bitRate, uepFlag, protLevel);
 	auto it = h -> profiles. find (key);
 	if (it == h -> profiles. end ()) {
 		ProtProfile prof;
-		const int rc = kind == 0 ? prot_build_fic (&prof) : prot_build_msc (bitRate, uepFlag, protLevel, &prof);
+		const int rc = kind == 0 ? prot_build_fic (&prof) : kind == 3 ? prot_build_identity (bitRate, &prof) : prot_build_msc (bitRate, uepFlag, protLevel, &prof);
 		if (rc) return dab_fail (h, DABGPU_ERR_PROFILE, "no %s profile for bitRate %d protLevel 0%o",
 		                         uepFlag == 0 ? "UEP" : "EEP", bitRate, protLevel);
 		it = h -> profiles. emplace (key, std::move (prof)). first;
@@ -176,17 +180,18 @@ int dab_get_profile (dabgpu *h, int kind, int bitRate, int uepFlag, int protLeve
 	return DABGPU_OK;
 }
 
-int dab_get_profile_simd (dabgpu *h, int kind, int bitRate, int uepFlag, int protLevel, const uint16_t **d_inv, const uint16_t **d_chunk) {
+int dab_simd_job_profile (dabgpu *h, int kind, int bitRate, int uepFlag, int protLevel, int deint, VitSimdJob *job) {
 	const ProtProfile *pp; const uint16_t *d_lut;
 	int rc = dab_get_profile (h, kind, bitRate, uepFlag, protLevel, &pp, &d_lut);
 	if (rc) return rc;
-	const long long key = ((long long) (kind ? 1 : 2) << 40) | ((long long) (uepFlag != 0) << 32) |
-	                      ((long long) (bitRate & 0xffff) << 16) | (protLevel & 0xffff);
+	const long long key = profile_key (kind, bitRate, uepFlag, protLevel);
 	void *d = nullptr;
-	if ((rc = dab_device_table (h, key | (5ll << 44), pp -> inv. data (), pp -> inv. size () * sizeof (uint16_t), &d))) return rc;
-	*d_inv = (const uint16_t *) d;
-	if ((rc = dab_device_table (h, key | (6ll << 44), pp -> chunk_i0. data (), pp -> chunk_i0. size () * sizeof (uint16_t), &d))) return rc;
-	*d_chunk = (const uint16_t *) d;
+	const std::vector<uint32_t> &g = pp -> gather [deint ? 1 : 0];
+	if ((rc = dab_device_table (h, key | ((deint ? 5ll : 7ll) << 44), g. data (), g. size () * sizeof (uint32_t), &d))) return rc;
+	job -> gather = (const uint4 *) d;
+	if ((rc = dab_device_table (h, key | (6ll << 44), pp -> chunk. data (), pp -> chunk. size () * sizeof (int32_t), &d))) return rc;
+	job -> chunk = (const int2 *) d;
+	job -> deint = deint ? 1 : 0; job -> ncols = pp -> nPunctured; job -> frameBits = pp -> frameBits; job -> nsteps = pp -> frameBits + 6;
 	return DABGPU_OK;
 }
 
@@ -201,19 +206,27 @@ bool dab_use_simd (const dabgpu *h, long long ncodewords) {
 int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
 	if (jobs. empty ()) return DABGPU_OK;
 	dabgpu::VitCtx &cx = h -> vctx [h -> cur];
-	size_t dec_words = 0;
+	size_t dec_words = 0, sym_bytes = 0;
 	int ctas = 0, ctas2 = 0;
+	const int cw2 = vit_simd_cw_per_cta ();
+	auto padded = [] (int nsteps) { return (size_t) ((nsteps + VS_CHUNK - 1) / VS_CHUNK * VS_CHUNK); };
 	for (auto &j : jobs) {
 		j. cta_first = ctas; j. cta_first2 = ctas2; j. one = 1u;
-		ctas += (j. ncw + 63) / 64; ctas2 += (j. ncw + 63) / 64;
-		dec_words += (size_t) ((j. nsteps + 39) / 40 * 40) * j. ncw;
+		ctas += (j. ncw + 63) / 64; ctas2 += (j. ncw + cw2 - 1) / cw2;
+		dec_words += padded (j. nsteps) * j. ncw;
+		j. stride8 = ((long long) j. ncols + 7 + 8) / 8 * 8;     // the staging may read up to 7 bytes past the last column
+		sym_bytes += (size_t) (j. ncw + (j. deint ? 15 : 0)) * j. stride8;
 	}
 	// (re)allocation and the pinned job table are only touched once everything queued on this context is done
 	const size_t jb = jobs. size () * sizeof (VitSimdJob);
 	CUDA_TRY (h, cudaStreamSynchronize (cx. st));
 	CUDA_TRY (h, cx. d_dec. ensure (dec_words * sizeof (uint2)));
-	size_t off = 0;
-	for (auto &j : jobs) { j. dec = (uint2 *) cx. d_dec. p + off; off += (size_t) ((j. nsteps + 39) / 40 * 40) * j. ncw; }
+	CUDA_TRY (h, cx. d_sym8. ensure (sym_bytes + 64));
+	size_t off = 0, soff = 0;
+	for (auto &j : jobs) {
+		j. dec = (uint2 *) cx. d_dec. p + off; off += padded (j. nsteps) * j. ncw;
+		j. sym8 = (uint8_t *) cx. d_sym8. p + soff; soff += (size_t) (j. ncw + (j. deint ? 15 : 0)) * j. stride8;
+	}
 	CUDA_TRY (h, cx. d_jobs. ensure (jb));
 	CUDA_TRY (h, cx. h_jobs. ensure (jb));
 	memcpy (cx. h_jobs. p, jobs. data (), jb);
@@ -262,11 +275,13 @@ extern "C" int dabgpu_viterbi_dev (dabgpu_t *h, const int16_t *soft, int32_t fra
 	j. in = soft; j. in_stride = 4ll * (frameBits + 6); j. lut = nullptr;
 	j. frameBits = frameBits; j. nsteps = frameBits + 6; j. nblocks = nblocks;
 	j. deint = 0; j. prbs = nullptr; j. out = bits;
-	if (dab_use_simd (h, nblocks)) {
+	if (dab_use_simd (h, nblocks) && 4 * (frameBits + 6) < 0xFFFF) {
 		std::vector<VitSimdJob> jobs (1);
 		VitSimdJob &s = jobs [0];
 		memset (&s, 0, sizeof (s));
-		s. in = soft; s. in_stride = j. in_stride; s. frameBits = frameBits; s. nsteps = frameBits + 6; s. ncw = nblocks; s. out = bits;
+		int rc = dab_simd_job_profile (h, 3, frameBits, 1, 0, 0, &s);
+		if (rc) return rc;
+		s. in = soft; s. in_stride = j. in_stride; s. ncw = nblocks; s. out = bits;
 		return dab_vit_simd_run (h, jobs);
 	}
 	CUDA_TRY (h, vit_launch (h, KC_VITERBI_API, j));
@@ -310,8 +325,8 @@ extern "C" int dabgpu_protect_decode (dabgpu_t *h, int32_t bitRate, int32_t uepF
 		std::vector<VitSimdJob> jobs (1);
 		VitSimdJob &s = jobs [0];
 		memset (&s, 0, sizeof (s));
-		if ((rc = dab_get_profile_simd (h, 1, bitRate, uepFlag, protLevel, &s. inv, &s. chunk_i0))) return rc;
-		s. in = j. in; s. in_stride = size; s. frameBits = j. frameBits; s. nsteps = j. nsteps; s. ncw = nblocks; s. out = j. out;
+		if ((rc = dab_simd_job_profile (h, 1, bitRate, uepFlag, protLevel, 0, &s))) return rc;
+		s. in = j. in; s. in_stride = size; s. ncw = nblocks; s. out = j. out;
 		if ((rc = dab_vit_simd_run (h, jobs))) return rc;
 	} else
 		CUDA_TRY (h, vit_launch (h, KC_VITERBI_API, j));
@@ -321,10 +336,10 @@ extern "C" int dabgpu_protect_decode (dabgpu_t *h, int32_t bitRate, int32_t uepF
 // ---- ficHandler::process_ficInput x ngroups (fic-handler.cpp:241-321) ----
 int dab_fic_simd_job (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, VitSimdJob *s) {
 	memset (s, 0, sizeof (*s));
-	int rc = dab_get_profile_simd (h, 0, 0, 1, 0, &s -> inv, &s -> chunk_i0);
+	int rc = dab_simd_job_profile (h, 0, 0, 1, 0, 0, s);
 	if (rc) return rc;
 	if ((rc = dab_get_prbs (h, 768, &s -> prbs))) return rc;
-	s -> in = d_soft; s -> in_stride = stride; s -> frameBits = 768; s -> nsteps = 774; s -> ncw = ngroups; s -> out = d_bits;
+	s -> in = d_soft; s -> in_stride = stride; s -> ncw = ngroups; s -> out = d_bits;
 	return DABGPU_OK;
 }
 
@@ -422,10 +437,10 @@ int dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row
 	*nout = n;
 	if (simd_job) {                       // the caller batches several sub-channels into one SIMD launch
 		memset (simd_job, 0, sizeof (*simd_job));
-		int rc = dab_get_profile_simd (h, 1, b -> sc. bitRate, b -> sc. uepFlag, b -> sc. protLevel, &simd_job -> inv, &simd_job -> chunk_i0);
+		int rc = dab_simd_job_profile (h, 1, b -> sc. bitRate, b -> sc. uepFlag, b -> sc. protLevel, 1, simd_job);
 		if (rc) return rc;
-		simd_job -> in = d_rows; simd_job -> in_stride = row_stride; simd_job -> first_row = j. first_row; simd_job -> deint = 1;
-		simd_job -> frameBits = j. frameBits; simd_job -> nsteps = j. nsteps; simd_job -> ncw = n; simd_job -> prbs = b -> d_prbs; simd_job -> out = d_out;
+		simd_job -> in = d_rows; simd_job -> in_stride = row_stride; simd_job -> first_row = j. first_row;
+		simd_job -> ncw = n; simd_job -> prbs = b -> d_prbs; simd_job -> out = d_out;
 		return DABGPU_OK;
 	}
 	CUDA_TRY (h, vit_launch (h, KC_VITERBI_MSC, j));

@@ -52,9 +52,13 @@ struct ProtProfile {
 	int frameBits = 0;                  // 24 * bitRate (768 for the FIC)
 	int nPunctured = 0;                 // input soft bits consumed per code word
 	std::vector<uint16_t> lut;
-	std::vector<uint16_t> inv;          // input index -> mother index (for the SIMD kernel's staging)
-	std::vector<uint16_t> chunk_i0;     // per 40-step chunk: first input index (+ end)
+	std::vector<int32_t>  chunk;        // throughput kernel: per VS_CHUNK-step chunk {first staged column a_k, 8-byte granules G_k}
+	std::vector<uint32_t> gather [2];   // [deint][4 * step + j]: tile byte offset of symbol j relative to the code word's row
 };
+#define VS_CHUNK 40                     // trellis steps per staged chunk of the throughput Viterbi (one renormalisation each)
+#define VS_PITCH 184                    // tile row pitch in bytes: 8 x odd (conflict-free over 16 code words), >= 21 granules + pad column
+void prot_build_gather (ProtProfile *pp);
+int  prot_build_identity (int frameBits, ProtProfile *pp);                    // viterbi.cpp:225-242 (no puncturing)
 int  prot_build_fic (ProtProfile *pp);                                        // fic-handler.cpp:254-288
 int  prot_build_msc (int bitRate, int uepFlag, int protLevel, ProtProfile *pp); // deconvolve.cpp:142-182, 244-319
 void prbs_packed (int nbits, std::vector<uint32_t> *words);                   // fic-handler.cpp:100-108
@@ -72,27 +76,31 @@ struct VitJob {
 };
 cudaError_t vit_launch (dabgpu *h, int cls, const VitJob &job);
 
-// ---- throughput Viterbi (dabgpu_vit_simd.cu): one code word per thread, several jobs per launch ----
+// ---- throughput Viterbi (dabgpu_vit_simd.cu): two threads per code word, several jobs per launch ----
 struct VitSimdJob {
 	const int16_t *in;        // soft-bit source
 	long long in_stride;      // elements between consecutive code words (rows when deint)
 	int first_row;            // deint: buffer row of the CIF decoded by code word 0
 	int deint;
-	const uint16_t *inv;      // device: input index -> mother-code index, or nullptr (identity)
-	const uint16_t *chunk_i0; // device: first input index of every 40-step chunk (+ one past the end), with inv
+	int ncols;                // input columns a code word consumes (punctured length)
+	const uint4 *gather;      // device: per trellis step the four tile byte offsets (ProtProfile::gather)
+	const int2 *chunk;        // device: per chunk {a_k, G_k}
+	uint8_t *sym8;            // 0..255 symbols of the rows this job reads: row r = source row first_row - dmax + r
+	long long stride8;        // bytes between sym8 rows (multiple of 8)
 	int frameBits, nsteps, ncw;
-	int cta_first;            // first CTA of this job in the launch (64 code words per CTA: single-lane forward, chain-back)
-	int cta_first2;           // same for the lane-pair forward kernel (VS2_CW code words per CTA)
+	int cta_first;            // first CTA of this job in the chain-back launch (64 code words per CTA)
+	int cta_first2;           // same for the forward kernel (VS_CW code words per CTA)
 	unsigned one;             // = 1, set by dab_vit_simd_run; opaque to the compiler on purpose (see vs_acs)
-	uint2 *dec;               // [nsteps padded to 40][ncw] decision words
+	uint2 *dec;               // [nsteps padded to VS_CHUNK][ncw] decision words
 	const uint32_t *prbs;     // packed dispersal sequence or nullptr
 	uint8_t *out;             // [ncw][frameBits]
 };
 cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas, int total_ctas2);
+int vit_simd_cw_per_cta ();
 cudaError_t fib_crc_launch (dabgpu *h, const uint8_t *bits, int nfibs, uint8_t *ok);
 
 // kernel classes for the optional per-launch CUDA-event profile (dabgpu_profile_*)
-enum { KC_ACQUIRE = 0, KC_FRONT, KC_SYMBOL, KC_SCAN, KC_VITERBI_MSC, KC_VITERBI_FIC, KC_VITERBI_API, KC_CRC, KC_VITERBI_TB, KC_COUNT };
+enum { KC_ACQUIRE = 0, KC_FRONT, KC_SYMBOL, KC_SCAN, KC_VITERBI_MSC, KC_VITERBI_FIC, KC_VITERBI_API, KC_CRC, KC_VITERBI_TB, KC_VITERBI_SYM, KC_COUNT };
 struct ProfPair { int cls; cudaEvent_t a, b; };
 
 struct Engine;
@@ -115,7 +123,7 @@ struct dabgpu {
 	// channel-decoding contexts: 0 = the handle's main stream, 1..3 = side streams the stream engine uses to
 	// overlap the Viterbi work of finished chunks with the OFDM work of the next one.  Launch helpers use the
 	// current context (the handle is not re-entrant, so an implicit current context is safe).
-	struct VitCtx { cudaStream_t st = nullptr; DevBuf d_dec, d_jobs; PinBuf h_jobs; };
+	struct VitCtx { cudaStream_t st = nullptr; DevBuf d_dec, d_jobs, d_sym8; PinBuf h_jobs; };
 	VitCtx vctx [4];
 	int cur = 0;
 	cudaStream_t vst () const { return vctx [cur]. st; }
@@ -141,7 +149,8 @@ int  dab_device_table (dabgpu *h, long long key, const void *host, size_t bytes,
 int  dab_get_profile (dabgpu *h, int kind /*0 fic, 1 msc*/, int bitRate, int uepFlag, int protLevel,
                       const ProtProfile **pp, const uint16_t **d_lut);
 int  dab_get_prbs (dabgpu *h, int nbits, const uint32_t **d_prbs);
-int  dab_get_profile_simd (dabgpu *h, int kind, int bitRate, int uepFlag, int protLevel, const uint16_t **d_inv, const uint16_t **d_chunk);
+// fills the profile-dependent fields of a throughput-Viterbi job (gather / chunk tables, ncols, frameBits, nsteps); kind 0 fic, 1 msc, 3 unpunctured (bitRate = frameBits)
+int  dab_simd_job_profile (dabgpu *h, int kind, int bitRate, int uepFlag, int protLevel, int deint, VitSimdJob *job);
 // runs a set of jobs on the one-code-word-per-thread kernels (fills cta_first / dec itself)
 int  dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs);
 bool dab_use_simd (const dabgpu *h, long long ncodewords);

@@ -107,17 +107,49 @@ static int build_lut (int frameBits, const int L [4], const int PI [4], ProtProf
 	}
 	if (in >= 0xFFFF) return -1;
 	pp -> nPunctured = in;
-	// inverse map and per-chunk input ranges for the one-code-word-per-thread kernel (40 steps = 160 mother bits)
-	pp -> inv. assign (in, 0);
-	const int nchunks = (frameBits + 6 + 39) / 40;
-	pp -> chunk_i0. assign (nchunks + 1, (uint16_t) in);
+	prot_build_gather (pp);
+	return 0;
+}
+
+// Tables of the throughput Viterbi (dabgpu_vit_simd.cu).  The trellis is processed in chunks of VS_CHUNK steps; for
+// chunk k the input columns [a_k, a_k + 8 G_k) of every source row are staged in shared memory (a_k = the chunk's
+// first input index rounded down to 8), and gather entry (step, j) is the byte offset of symbol j of that step
+// relative to the code word's own tile row: (15 - D[i & 15]) rows up/down for the time de-interleaver
+// (dab-concurrent.cpp:41-43, 162-169), column i - a_k; a punctured position points at the pad column, which holds
+// the erasure value 127 (deconvolve.cpp:185).
+void prot_build_gather (ProtProfile *pp) {
+	static const int D [16] = { 15, 7, 11, 3, 13, 5, 9, 1, 14, 6, 10, 2, 12, 4, 8, 0 };
+	const int nsteps = pp -> frameBits + 6, total = 4 * nsteps, in = pp -> nPunctured;
+	const int nchunks = (nsteps + VS_CHUNK - 1) / VS_CHUNK;
+	std::vector<int> first (nchunks + 1, in);           // first input index whose mother position is in chunk >= k
 	for (int m = total - 1; m >= 0; m --)
-		if (pp -> lut [m] != 0xFFFF) { pp -> inv [pp -> lut [m]] = (uint16_t) m; }
-	int next = 0;
+		if (pp -> lut [m] != 0xFFFF) first [m / (4 * VS_CHUNK)] = pp -> lut [m];
+	for (int k = nchunks - 1; k >= 0; k --) if (first [k] > first [k + 1]) first [k] = first [k + 1];
+	pp -> chunk. assign (2 * nchunks, 0);
+	for (int d = 0; d < 2; d ++) pp -> gather [d]. assign ((size_t) 4 * nchunks * VS_CHUNK + 4, 0);      // + one entry: the kernel prefetches one step ahead
 	for (int k = 0; k < nchunks; k ++) {
-		while (next < in && pp -> inv [next] < 160 * k) next ++;
-		pp -> chunk_i0 [k] = (uint16_t) next;
+		const int a = first [k] & ~7, g = (first [k + 1] - a + 7) / 8;
+		pp -> chunk [2 * k] = a; pp -> chunk [2 * k + 1] = first [k + 1] > first [k] ? g : 0;
+		for (int s = 0; s < VS_CHUNK; s ++)
+			for (int j = 0; j < 4; j ++) {
+				const int m = 4 * (VS_CHUNK * k + s) + j;
+				const int i = m < total && pp -> lut [m] != 0xFFFF ? pp -> lut [m] : -1;
+				for (int d = 0; d < 2; d ++) {
+					const int dmax = d ? 15 : 0;
+					pp -> gather [d][(size_t) m] = i < 0 ? dmax * VS_PITCH + VS_PITCH - 1
+					                                     : (dmax - (d ? D [i & 15] : 0)) * VS_PITCH + (i - a);
+				}
+			}
 	}
+}
+
+int prot_build_identity (int frameBits, ProtProfile *pp) {  // viterbi::deconvolve on unpunctured input (viterbi.cpp:225-242)
+	if (frameBits <= 0 || 4 * (frameBits + 6) >= 0xFFFF) return -1;
+	const int total = 4 * (frameBits + 6);
+	pp -> frameBits = frameBits; pp -> nPunctured = total;
+	pp -> lut. resize (total);
+	for (int m = 0; m < total; m ++) pp -> lut [m] = (uint16_t) m;
+	prot_build_gather (pp);
 	return 0;
 }
 

@@ -1,234 +1,104 @@
-// dabgpu_vit_simd.cu -- throughput Viterbi: one terminated code word per THREAD, all 64 path metrics of the
-// word in 32 registers as packed 16-bit pairs, add-compare-select with the sm_100a packed integer instructions
-// (VIADD.16x2, VIMNMX.U16x2 with its two predicate outputs = the two decisions), decisions streamed to HBM as
-// one coalesced uint2 per step, chain-back in a second kernel.  Used when a launch has enough code words to
-// fill the GPU (the stream engine, large API batches); small batches use the warp-cooperative kernel of
-// dabgpu_viterbi.cu.  Same arithmetic as the reference (viterbi.cpp:225-357, spiral-*.c), bit-exact:
+// dabgpu_vit_simd.cu -- throughput Viterbi: TWO threads per terminated code word, the 64 path metrics of the word
+// in 2 x 16 registers as packed 16-bit pairs, add-compare-select with the sm_100a packed integer instructions
+// (32-bit IADD on carry-free pairs, VIMNMX.U16x2 whose two predicate outputs are the two decisions), decisions
+// streamed to HBM as one coalesced word per thread and step, chain-back in a second kernel.  Used when a launch has
+// enough code words to fill the GPU (the stream engine, large API batches); small batches use the warp-cooperative
+// kernel of dabgpu_viterbi.cu.  Same arithmetic as the reference (viterbi.cpp:225-357, spiral-*.c), bit-exact:
 //   * metrics start 63 / state 0 = 0; branch metric sum_j (Branchtab_j ^ sym_j), complement 1020 - m;
 //   * VIMNMX's predicate is (upper <= lower): a tie keeps predecessor i, exactly the reference's strict '>';
 //   * the common minimum is subtracted every 40 steps (differences, hence decisions, unchanged) so that the
 //     16-bit lanes never wrap: spread <= 6*1020+63 and 40 steps add <= 40800  ->  < 2^16.
 //
-// Register layout.  State s = (s5..s0).  At the start of step k (k = t mod 5) "half position" p = k: register
-// r holds the two states whose index is r with a 0 / 1 inserted at bit p (low / high half).  The butterfly pairs
-// states differing in s5, i.e. registers r and r+16, same halves, so one packed op does two butterflies; the
-// results 2i and 2i+1 go to registers 2r and 2r+1 and the half position becomes p+1.  After five steps the half
-// position is 5 = the butterfly bit itself, and 32 PRMTs bring it back to 0.  All indices are compile-time, the
-// code is unrolled over the five-step cycle.
+// Input path.  A streaming pre-pass turns the int16 soft bits of the rows a job reads into 0..255 symbols
+// (viterbi.cpp:229-235) in a byte plane.  The forward kernel stages, per chunk of 40 trellis steps, the byte columns
+// of that chunk for its CW + 15 source rows with 8-byte cp.async copies into a double-buffered shared-memory tile --
+// no arithmetic at all -- and every thread then gathers the four symbols of a step through a per-profile table that
+// already contains depuncturing (deconvolve.cpp:186-231) AND the time de-interleaver's row offset
+// (dab-concurrent.cpp:162-169); a punctured position points at a pad column holding the erasure value 127.
+//
+// Register layout.  State s = (s5..s0).  At step k of a 4-step cycle the half bit is state bit k and the lane bit
+// is state bit k+1; register q (16 per thread) holds the remaining four bits.  The butterfly pairs states differing
+// in s5, i.e. registers q and q+8, same halves / lanes, so one packed op does two butterflies; the results 2i and
+// 2i+1 go to registers 2q and 2q+1 and both special bits move up by one.  After four steps the lane bit has reached
+// s5 and the half bit s4; one round of 8 lane-pair shuffles and 16 PRMTs (plus a compile-time renaming) moves them
+// back to s1 / s0.  All indices are compile-time, the code is unrolled over the four-step cycle.
 #include "dabgpu_internal.h"
 
-#define VS_THREADS 64          // code words per CTA
-#define VS_CHUNK   40          // trellis steps staged per round (8 layout cycles, one renormalisation)
-#define VS_ROWW   41          // tile row stride in words (odd: conflict-free)
-
-__constant__ int8_t c_vs_delay [16] = { 15, 7, 11, 3, 13, 5, 9, 1, 14, 6, 10, 2, 12, 4, 8, 0 };   // dab-concurrent.cpp:41-43
+#define VS_CW      32          // code words per forward CTA (two threads each)
+#define VS_THREADS (2 * VS_CW)
+#define VS_ROWS    (VS_CW + 15)
+#define VS_TILE    (VS_ROWS * VS_PITCH)
 
 __host__ __device__ constexpr int vs_parity (unsigned x) { x ^= x >> 4; x ^= x >> 2; x ^= x >> 1; return x & 1; }
 // branch pattern of butterfly i: bit0 = polys 0155 (used twice: j = 0 and 3), bit1 = 0117, bit2 = 0123 (viterbi.cpp:63, 159-164)
 __host__ __device__ constexpr int vs_pat (int i) {
 	return vs_parity ((2u * i) & 0155u) | (vs_parity ((2u * i) & 0117u) << 1) | (vs_parity ((2u * i) & 0123u) << 2);
 }
-__host__ __device__ constexpr int vs_insert0 (int r, int p) { return ((r >> p) << (p + 1)) | (r & ((1 << p) - 1)); }
+__host__ __device__ constexpr int vs_insert00 (int r, int p) { return ((r >> p) << (p + 2)) | (r & ((1 << p) - 1)); }
 
 // packed compare-select: min (upper, lower) per 16-bit lane; `bit` is ORed into wlo / whi where the lower candidate
 // won (decision = upper > lower; a tie keeps the upper one).  __vibmin_u16x2 is one VIMNMX.U16x2 with two predicate
 // outputs (predicate = upper <= lower) on sm_100a.
-__device__ __forceinline__ uint32_t vs_acs (uint32_t upper, uint32_t lower, uint32_t &wlo, uint32_t &whi, const uint32_t bit, const uint32_t one) {
+__device__ __forceinline__ uint32_t vs_acs (uint32_t upper, uint32_t lower, uint32_t &acc, const uint32_t bit, const uint32_t one) {
 	bool ph, pl;
 	const uint32_t r = __vibmin_u16x2 (upper, lower, &ph, &pl);
 	// decision bits are accumulated with predicated multiply-adds (acc += one * bit): `one` is 1 at run time but opaque
 	// to the compiler, which keeps these on the FMA pipe; the ALU pipe, busy with the packed min and everything else,
-	// is the scarce one here (ncu: ALU 75 % vs FMA 22 % before this change)
-	asm ("{ .reg .pred p; setp.eq.u32 p, %1, 0; @p mad.lo.u32 %0, %3, %2, %0; }" : "+r" (wlo) : "r" ((uint32_t) pl), "r" (bit), "r" (one));
-	asm ("{ .reg .pred p; setp.eq.u32 p, %1, 0; @p mad.lo.u32 %0, %3, %2, %0; }" : "+r" (whi) : "r" ((uint32_t) ph), "r" (bit), "r" (one));
+	// is the scarce one here
+	asm ("{ .reg .pred p; setp.eq.u32 p, %1, 0; @p mad.lo.u32 %0, %3, %2, %0; }" : "+r" (acc) : "r" ((uint32_t) pl), "r" (bit), "r" (one));
+	asm ("{ .reg .pred p; setp.eq.u32 p, %1, 0; @p mad.lo.u32 %0, %3, %2, %0; }" : "+r" (acc) : "r" ((uint32_t) ph), "r" (bit << 16), "r" (one));
 	return r;
 }
 
-template <int P>
-__device__ __forceinline__ void vs_step (const uint32_t (&R) [32], uint32_t (&Q) [32], const uint32_t sym, uint2 &dec, const uint32_t one) {
-	// the 8 branch metrics B[x], x = pattern, and their packed pairs PM[x] = B[x] | B[x ^ delta] << 16
-	const uint32_t s0 = sym & 255u, s1 = (sym >> 8) & 255u, s2 = (sym >> 16) & 255u, s3 = sym >> 24;
-	const uint32_t a0 = s0 + s3, a1 = 510u - a0, b1 = 255u - s1, c1 = 255u - s2;
-	uint32_t B [8];
-	B [0] = a0 + s1 + s2; B [1] = a1 + s1 + s2; B [2] = a0 + b1 + s2; B [3] = a1 + b1 + s2;
-	B [4] = a0 + s1 + c1; B [5] = a1 + s1 + c1; B [6] = a0 + b1 + c1; B [7] = a1 + b1 + c1;
-	constexpr int delta = vs_pat (1 << P);
-	uint32_t PM [8];
-#pragma unroll
-	for (int x = 0; x < 8; x ++) PM [x] = B [x] + (B [x ^ delta] << 16);
-	uint32_t wlo = 0, whi = 0;
-#pragma unroll
-	for (int r = 0; r < 16; r ++) {
-		constexpr int dummy = 0; (void) dummy;
-		const int x = vs_pat (vs_insert0 (r, P));
-		const uint32_t a = R [r], b = R [r + 16];
-		// plain 32-bit adds: every 16-bit lane stays below 2^16 (see the renormalisation bound), so no carry
-		// crosses the halves and the full-rate IADD replaces the half-rate VIADD.16x2
-		const uint32_t m0 = a + PM [x],     m1 = b + PM [7 - x];
-		const uint32_t m2 = a + PM [7 - x], m3 = b + PM [x];
-		Q [2 * r]     = vs_acs (m0, m1, wlo, whi, 1u << (2 * r), one);
-		Q [2 * r + 1] = vs_acs (m2, m3, wlo, whi, 1u << (2 * r + 1), one);
-	}
-	dec = make_uint2 (wlo, whi);
-}
+__device__ __forceinline__ uint32_t vs_sel (uint32_t a, uint32_t b, uint32_t mask) { return (a & ~mask) | (b & mask); }   // one LOP3
 
-// half position 5 -> 0
-__device__ __forceinline__ void vs_repack (const uint32_t (&Q) [32], uint32_t (&R) [32]) {
-#pragma unroll
-	for (int q = 0; q < 32; q ++)
-		R [q] = q < 16 ? __byte_perm (Q [(2 * q) & 31], Q [(2 * q + 1) & 31], 0x5410)
-		               : __byte_perm (Q [(2 * q) & 31], Q [(2 * q + 1) & 31], 0x7632);
-}
-
-__device__ __forceinline__ void vs_renorm (uint32_t (&R) [32]) {
-	uint32_t m = R [0];
-#pragma unroll
-	for (int q = 1; q < 32; q ++) m = __vminu2 (m, R [q]);
-	const uint32_t mm = min (m & 0xffffu, m >> 16);
-	const uint32_t neg = ((0u - mm) & 0xffffu) * 0x10001u;
-#pragma unroll
-	for (int q = 0; q < 32; q ++) R [q] = __vadd2 (R [q], neg);     // wraps per lane on purpose (subtraction)
-}
-
-// Stages the symbols of trellis steps [40k, 40k+40) of the CTA's 64 code words: tile[c][step] = the four 0..255
-// symbols of the step (erasure = 127).  Source rows are read coalesced (a warp reads consecutive soft bits of one row)
-// and scattered through the inverse puncturing map; with time de-interleaving the soft bit of code word c, position i
-// comes from row c - D[i & 15] (dab-concurrent.cpp:162-169).
-template <int NT, int VS_RB, int CW>
-__device__ __forceinline__ void vs_stage (uint32_t *tile, const VitSimdJob &j, int k, int c0, int nrows, long long g_lo, int dmax) {
-	const int tid = threadIdx. x, lane = tid & 31, warp = tid >> 5;
-	__syncthreads ();
-	for (int w = tid; w < CW * VS_CHUNK; w += NT)
-		tile [(w / VS_CHUNK) * VS_ROWW + (w % VS_CHUNK)] = 0x7f7f7f7fu;          // erasure = 127 (deconvolve.cpp:185)
-	__syncthreads ();
-	const int m0 = 4 * VS_CHUNK * k;
-	int i0, i1;
-	if (j. inv) { i0 = j. chunk_i0 [k]; i1 = j. chunk_i0 [k + 1]; }
-	else { i0 = m0; i1 = min (m0 + 4 * VS_CHUNK, 4 * j. nsteps); }
-	uint8_t *tb = reinterpret_cast<uint8_t *> (tile);
-	// VS_RB rows x up to 5 column groups of independent loads in flight per thread (the chunk has <= 160 columns):
-	// the staging is latency bound, so memory-level parallelism is what matters here
-	for (int row0 = warp * VS_RB; row0 < nrows; row0 += (NT / 32) * VS_RB) {
-		int v [VS_RB][5];
-#pragma unroll
-		for (int rr = 0; rr < VS_RB; rr ++) {
-			const int16_t *src = j. in + (g_lo + row0 + rr) * j. in_stride;
-#pragma unroll
-			for (int cc = 0; cc < 5; cc ++) {
-				const int col = i0 + lane + 32 * cc;
-				v [rr][cc] = (row0 + rr < nrows && col < i1) ? (int) __ldg (&src [col]) : 0;
-			}
-		}
-#pragma unroll
-		for (int cc = 0; cc < 5; cc ++) {
-			const int col = i0 + lane + 32 * cc;
-			if (col >= i1) continue;
-			const int m = (j. inv ? (int) __ldg (&j. inv [col]) : col) - m0;
-			const int dl = j. deint ? (int) c_vs_delay [col & 15] : 0;
-#pragma unroll
-			for (int rr = 0; rr < VS_RB; rr ++) {
-				const int c = row0 + rr - dmax + dl;
-				if (row0 + rr < nrows && c >= 0 && c < CW && c0 + c < j. ncw)
-					tb [c * (VS_ROWW * 4) + m] = (uint8_t) min (max (v [rr][cc] + 127, 0), 255);   // viterbi.cpp:229-235
-			}
-		}
-	}
-	__syncthreads ();
-}
-
-__global__ void __launch_bounds__ (VS_THREADS) vit_simd_forward (const VitSimdJob *jobs, int njobs) {
-	__shared__ uint32_t tile [VS_THREADS * VS_ROWW];
-	// which job does this CTA belong to?
-	int jb = 0;
-	while (jb + 1 < njobs && (int) blockIdx. x >= jobs [jb + 1]. cta_first) jb ++;
-	const VitSimdJob j = jobs [jb];
-	const int c0 = ((int) blockIdx. x - j. cta_first) * VS_THREADS;       // first code word of this CTA
-	const int tid = threadIdx. x;
-	const int cw = c0 + tid;
-	const bool live = cw < j. ncw;
-	const int dmax = j. deint ? 15 : 0;
-	const int nrows = min (VS_THREADS, j. ncw - c0) + dmax;
-	const long long g_lo = (long long) c0 + j. first_row - dmax;          // first source row this CTA touches
-
-	uint32_t R [32], Q [32];
-	R [0] = 0u | (63u << 16);                                             // viterbi.cpp:364-370
-#pragma unroll
-	for (int q = 1; q < 32; q ++) R [q] = 63u | (63u << 16);
-
-	uint2 *dec = j. dec + cw;
-	const int nchunks = (j. nsteps + VS_CHUNK - 1) / VS_CHUNK;
-	for (int k = 0; k < nchunks; k ++) {
-		vs_stage<VS_THREADS, 16, VS_THREADS> (tile, j, k, c0, nrows, g_lo, dmax);
-		// ---- 8 layout cycles of 5 steps ----
-		const uint32_t *my = &tile [tid * VS_ROWW];
-		uint2 *d = dec + (size_t) (VS_CHUNK * k) * j. ncw;
-#pragma unroll 1
-		for (int u = 0; u < VS_CHUNK / 5; u ++) {
-			uint2 d0, d1, d2, d3, d4;
-			vs_step<0> (R, Q, my [5 * u + 0], d0, j. one);
-			vs_step<1> (Q, R, my [5 * u + 1], d1, j. one);
-			vs_step<2> (R, Q, my [5 * u + 2], d2, j. one);
-			vs_step<3> (Q, R, my [5 * u + 3], d3, j. one);
-			vs_step<4> (R, Q, my [5 * u + 4], d4, j. one);
-			vs_repack (Q, R);
-			if (live) {
-				d [(size_t) (5 * u + 0) * j. ncw] = d0; d [(size_t) (5 * u + 1) * j. ncw] = d1;
-				d [(size_t) (5 * u + 2) * j. ncw] = d2; d [(size_t) (5 * u + 3) * j. ncw] = d3;
-				d [(size_t) (5 * u + 4) * j. ncw] = d4;
-			}
-		}
-		vs_renorm (R);
-	}
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------
-// Two threads per code word.  One code word per thread leaves a 1024-frame batch with only ~8 warps per SM and every
-// warp latency bound; splitting the 64 states over a lane pair doubles the warps in flight and halves the work per
-// thread.  Layout: at step k of a 4-step cycle the half bit is state bit k and the lane bit is state bit k+1; register
-// q (16 per thread) holds the remaining four bits.  Butterflies pair registers q and q+8 and write 2q, 2q+1, exactly
-// as above.  After four steps the lane bit has reached s5 and the half bit s4; one round of 8 lane-pair shuffles and
-// 16 PRMTs (plus a compile-time renaming) moves them back to s1 / s0.
-// ---------------------------------------------------------------------------------------------------------------
-#define VS2_CW      64          // code words per CTA (two threads each)
-#define VS2_THREADS (2 * VS2_CW)
-__host__ __device__ constexpr int vs_insert00 (int r, int p) { return ((r >> p) << (p + 2)) | (r & ((1 << p) - 1)); }
-
+// One trellis step.  a0 = sym0 + sym3 (both use polynomial 0155), s1, s2 = the other two symbols.  The branch metric
+// of pattern x is B[x] = sum_j (x_j ? C_j - v_j : v_j) with (v, C) = (a0, 510), (s1, 255), (s2, 255); a register needs
+// it for the low-half state and, 16 bits up, for the high-half state (pattern x ^ dh); the odd lane of a pair sees
+// pattern x ^ dl (lm = all ones in the odd lane, 0 in the even one).  Built per component, so that PL[x] is a sum of
+// three terms.  The 32 decisions of the step are disjoint bits spread over four accumulators (short dependency chains:
+// the predicates of the packed min are consumed as fast as they are produced).
 template <int K>
-__device__ __forceinline__ void vs2_step (const uint32_t (&R) [16], uint32_t (&Q) [16], const uint32_t sym, const bool lanebit, uint32_t &dec, const uint32_t one) {
-	const uint32_t s0 = sym & 255u, s1 = (sym >> 8) & 255u, s2 = (sym >> 16) & 255u, s3 = sym >> 24;
-	const uint32_t a0 = s0 + s3, a1 = 510u - a0, b1 = 255u - s1, c1 = 255u - s2;
-	uint32_t B [8];
-	B [0] = a0 + s1 + s2; B [1] = a1 + s1 + s2; B [2] = a0 + b1 + s2; B [3] = a1 + b1 + s2;
-	B [4] = a0 + s1 + c1; B [5] = a1 + s1 + c1; B [6] = a0 + b1 + c1; B [7] = a1 + b1 + c1;
+__device__ __forceinline__ void vs_step (const uint32_t (&R) [16], uint32_t (&Q) [16], const uint32_t a0, const uint32_t s1, const uint32_t s2,
+                                         const uint32_t lm, uint32_t &dec, const uint32_t one) {
 	constexpr int dh = vs_pat (1 << K), dl = vs_pat (1 << (K + 1));
-	uint32_t PM [8], PL [8];
+	uint32_t c [3][2];
 #pragma unroll
-	for (int x = 0; x < 8; x ++) PM [x] = B [x] + (B [x ^ dh] << 16);
+	for (int j = 0; j < 3; j ++) {
+		const uint32_t v = j == 0 ? a0 : j == 1 ? s1 : s2;
+		const uint32_t C = j == 0 ? 510u : 255u;
+		const uint32_t c0 = ((dh >> j) & 1) ? ((C - v) << 16) + v : v * 0x00010001u;     // low: v, high: C - v or v
+		const uint32_t c1 = C * 0x00010001u - c0;
+		if ((dl >> j) & 1) { c [j][0] = vs_sel (c0, c1, lm); c [j][1] = vs_sel (c1, c0, lm); }
+		else               { c [j][0] = c0; c [j][1] = c1; }
+	}
+	uint32_t PL [8];
 #pragma unroll
-	for (int x = 0; x < 8; x ++) PL [x] = lanebit ? PM [x ^ dl] : PM [x];
-	uint32_t wlo = 0, whi = 0;
+	for (int x = 0; x < 8; x ++)                                // one three-input add each (kept from being split into shared partial sums)
+		asm ("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r" (PL [x]) : "r" (c [0][x & 1]), "r" (c [1][(x >> 1) & 1]), "r" (c [2][(x >> 2) & 1]));
+	uint32_t acc [8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 #pragma unroll
 	for (int r = 0; r < 8; r ++) {
 		const int x = vs_pat (vs_insert00 (r, K));
 		const uint32_t a = R [r], b = R [r + 8];
+		// plain 32-bit adds: every 16-bit lane stays below 2^16 (see the renormalisation bound), so no carry crosses
+		// the halves and the full-rate IADD replaces the half-rate VIADD.16x2
 		const uint32_t m0 = a + PL [x],     m1 = b + PL [7 - x];
 		const uint32_t m2 = a + PL [7 - x], m3 = b + PL [x];
-		Q [2 * r]     = vs_acs (m0, m1, wlo, whi, 1u << (2 * r), one);
-		Q [2 * r + 1] = vs_acs (m2, m3, wlo, whi, 1u << (2 * r + 1), one);
+		Q [2 * r]     = vs_acs (m0, m1, acc [r], 1u << (2 * r), one);
+		Q [2 * r + 1] = vs_acs (m2, m3, acc [r], 1u << (2 * r + 1), one);
 	}
-	dec = wlo | (whi << 16);
+	dec = ((acc [0] + acc [1]) + (acc [2] + acc [3])) + ((acc [4] + acc [5]) + (acc [6] + acc [7]));
 }
 
 // lane = s5, half = s4, q = (s3 s2 s1 s0)  ->  lane = s1, half = s0, q = (s5 s4 s3 s2)
-__device__ __forceinline__ void vs2_fixup (uint32_t (&Q) [16], uint32_t (&R) [16], const bool lanebit) {
+__device__ __forceinline__ void vs_fixup (uint32_t (&Q) [16], uint32_t (&R) [16], const uint32_t lm) {
 #pragma unroll
 	for (int qa = 0; qa < 16; qa ++) {
 		if (qa & 2) continue;
 		const int qb = qa | 2;                                  // lane (s5) <-> register bit 1 (s1)
-		const uint32_t send = lanebit ? Q [qa] : Q [qb];
-		const uint32_t recv = __shfl_xor_sync (0xffffffffu, send, 1);
-		if (lanebit) Q [qa] = recv; else Q [qb] = recv;
+		const uint32_t recv = __shfl_xor_sync (0xffffffffu, vs_sel (Q [qb], Q [qa], lm), 1);
+		Q [qa] = vs_sel (Q [qa], recv, lm); Q [qb] = vs_sel (recv, Q [qb], lm);
 	}
 	uint32_t T [16];
 #pragma unroll
@@ -241,20 +111,60 @@ __device__ __forceinline__ void vs2_fixup (uint32_t (&Q) [16], uint32_t (&R) [16
 	for (int q = 0; q < 16; q ++) R [q] = T [((q & 3) << 2) | (q >> 2)];
 }
 
-__global__ void __launch_bounds__ (VS2_THREADS) vit_simd2_forward (const VitSimdJob *jobs, int njobs) {
-	__shared__ uint32_t tile [VS2_CW * VS_ROWW];
+// int16 soft bits -> 0..255 symbols (viterbi.cpp:229-235) for the rows and columns the jobs of a launch read.
+// blockIdx.y = job; sym8 row r = source row first_row - dmax + r.
+__global__ void __launch_bounds__ (256) vit_sym8_kernel (const VitSimdJob *jobs) {
+	const VitSimdJob j = jobs [blockIdx. y];
+	const int dmax = j. deint ? 15 : 0, nrows = j. ncw + dmax;
+	const int wpr = (int) (j. stride8 >> 2);                      // 4-byte words per row
+	const long long total = (long long) nrows * wpr;
+	const int16_t *src0 = j. in + (long long) (j. first_row - dmax) * j. in_stride;
+	for (long long w = (long long) blockIdx. x * blockDim. x + threadIdx. x; w < total; w += (long long) gridDim. x * blockDim. x) {
+		const int r = (int) (w / wpr), c = 4 * (int) (w % wpr);
+		const int16_t *src = src0 + (long long) r * j. in_stride + c;
+		uint32_t o = 0;
+#pragma unroll
+		for (int b = 0; b < 4; b ++) {
+			const int v = c + b < j. ncols ? (int) __ldg (&src [b]) : 0;
+			o |= (uint32_t) min (max (v + 127, 0), 255) << (8 * b);
+		}
+		*reinterpret_cast<uint32_t *> (j. sym8 + (long long) r * j. stride8 + c) = o;
+	}
+}
+
+__device__ __forceinline__ void vs_cp_async8 (void *smem, const void *gmem) {
+	asm volatile ("cp.async.ca.shared.global [%0], [%1], 8;" :: "r" ((uint32_t) __cvta_generic_to_shared (smem)), "l" (gmem));
+}
+
+__global__ void __launch_bounds__ (VS_THREADS, 10) vit_simd_forward (const VitSimdJob *jobs, int njobs) {
+	__shared__ __align__ (16) uint8_t tile [2 * VS_TILE];
 	int jb = 0;
 	while (jb + 1 < njobs && (int) blockIdx. x >= jobs [jb + 1]. cta_first2) jb ++;
 	const VitSimdJob j = jobs [jb];
-	const int c0 = ((int) blockIdx. x - j. cta_first2) * VS2_CW;
+	const int c0 = ((int) blockIdx. x - j. cta_first2) * VS_CW;   // first code word of this CTA
 	const int tid = threadIdx. x;
 	const int cl = tid >> 1;                                   // code word within the CTA
 	const bool lanebit = tid & 1;
+	uint32_t lm = 0u - (uint32_t) (tid & 1);
+	asm volatile ("" : "+r" (lm));                               // keep the lane select a bit mask (LOP3), not a predicate: predicates are scarce here
 	const int cw = c0 + cl;
 	const bool live = cw < j. ncw;
 	const int dmax = j. deint ? 15 : 0;
-	const int nrows = min (VS2_CW, j. ncw - c0) + dmax;
-	const long long g_lo = (long long) c0 + j. first_row - dmax;
+	const int nrows = min (VS_CW, j. ncw - c0) + dmax;
+	const uint8_t *src = j. sym8 + (long long) c0 * j. stride8;    // tile row 0 = sym8 row c0 = source row of code word c0 minus dmax
+
+	// chunk k -> tile buffer k & 1: the 8-byte granules g < G_k of every row, one (row, granule) per thread and round
+	auto stage = [&] (int k) {
+		const int2 ch = __ldg (&j. chunk [k]);
+		uint8_t *dst = tile + (k & 1) * VS_TILE;
+		for (int idx = tid; idx < nrows * 32; idx += VS_THREADS) {
+			const int r = idx >> 5, g = idx & 31;
+			if (g < ch. y) vs_cp_async8 (dst + r * VS_PITCH + 8 * g, src + (long long) r * j. stride8 + ch. x + 8 * g);
+		}
+		asm volatile ("cp.async.commit_group;");
+	};
+	for (int r = tid; r < 2 * VS_ROWS; r += VS_THREADS) tile [r * VS_PITCH + VS_PITCH - 1] = 127;   // erasure (deconvolve.cpp:185)
+	stage (0);
 
 	uint32_t R [16], Q [16];
 #pragma unroll
@@ -265,17 +175,29 @@ __global__ void __launch_bounds__ (VS2_THREADS) vit_simd2_forward (const VitSimd
 	const size_t dstride = 2 * (size_t) j. ncw;
 	const int nchunks = (j. nsteps + VS_CHUNK - 1) / VS_CHUNK;
 	for (int k = 0; k < nchunks; k ++) {
-		vs_stage<VS2_THREADS, 8, VS2_CW> (tile, j, k, c0, nrows, g_lo, dmax);
-		const uint32_t *my = &tile [cl * VS_ROWW];
+		if (k + 1 < nchunks) stage (k + 1); else asm volatile ("cp.async.commit_group;");
+		asm volatile ("cp.async.wait_group 1;");
+		__syncthreads ();
+		const uint8_t *my = tile + (k & 1) * VS_TILE + cl * VS_PITCH;
+		const uint4 *ga = j. gather + VS_CHUNK * k;
 		uint32_t *d = dec + (size_t) (VS_CHUNK * k) * dstride;
+		// the symbols of the next step are gathered while the current one is processed
+		uint32_t sa, sb, sc;
+		{ const uint4 e = __ldg (&ga [0]); sa = (uint32_t) my [e. x] + my [e. w]; sb = my [e. y]; sc = my [e. z]; }
 #pragma unroll 1
 		for (int u = 0; u < VS_CHUNK / 4; u ++) {
-			uint32_t d0, d1, d2, d3;
-			vs2_step<0> (R, Q, my [4 * u + 0], lanebit, d0, j. one);
-			vs2_step<1> (Q, R, my [4 * u + 1], lanebit, d1, j. one);
-			vs2_step<2> (R, Q, my [4 * u + 2], lanebit, d2, j. one);
-			vs2_step<3> (Q, R, my [4 * u + 3], lanebit, d3, j. one);
-			vs2_fixup (R, Q, lanebit);
+			uint32_t d0, d1, d2, d3, na, nb, nc;
+#define VS_NEXT(i) { const uint4 e = __ldg (&ga [i]); na = (uint32_t) my [e. x] + my [e. w]; nb = my [e. y]; nc = my [e. z]; }
+			VS_NEXT (4 * u + 1); vs_step<0> (R, Q, sa, sb, sc, lm, d0, j. one);
+			sa = na; sb = nb; sc = nc;
+			VS_NEXT (4 * u + 2); vs_step<1> (Q, R, sa, sb, sc, lm, d1, j. one);
+			sa = na; sb = nb; sc = nc;
+			VS_NEXT (4 * u + 3); vs_step<2> (R, Q, sa, sb, sc, lm, d2, j. one);
+			sa = na; sb = nb; sc = nc;
+			VS_NEXT (4 * u + 4); vs_step<3> (Q, R, sa, sb, sc, lm, d3, j. one);      // (one entry past the chunk is read, not used)
+			sa = na; sb = nb; sc = nc;
+#undef VS_NEXT
+			vs_fixup (R, Q, lm);
 #pragma unroll
 			for (int q = 0; q < 16; q ++) R [q] = Q [q];
 			if (live) {
@@ -292,13 +214,14 @@ __global__ void __launch_bounds__ (VS2_THREADS) vit_simd2_forward (const VitSimd
 		const uint32_t neg = ((0u - mm) & 0xffffu) * 0x10001u;
 #pragma unroll
 		for (int q = 0; q < 16; q ++) R [q] = __vadd2 (R [q], neg);
+		__syncthreads ();                                        // everyone is done with buffer k & 1 before chunk k + 2 lands in it
 	}
 }
 
 // chain-back (viterbi.cpp:333-357) + energy dispersal + unpack, one thread per code word.  The decision of new
-// state n at step t sits in word h = bit p' of n, bit position = n with bit p' removed, p' = (t mod 5) + 1.
+// state n at step t sits in the word of lane l = bit p'+1 of n, at bit 16 h + (n without bits p', p'+1), h = bit p' of n,
+// p' = (t mod 4) + 1.
 #define TB_THREADS 64
-template <int LANES>
 __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimdJob *jobs, int njobs) {
 	__shared__ uint32_t bits [TB_THREADS * 5];               // 128 decoded bits per code word per round, row stride 5 words
 	int jb = 0;
@@ -332,18 +255,11 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 					const int i = hi - u;
 					if (i >= top) continue;
 					const int t = i + 6;                        // decision of step i+6 = information bit i
-					unsigned bit;
-					if (LANES == 1) {                            // one thread per code word: word = half, bit = state without bit pp
-						const int pp = t % 5 + 1;
-						const unsigned h = (state >> pp) & 1u;
-						const unsigned q = ((state >> (pp + 1)) << pp) | (state & ((1u << pp) - 1u));
-						bit = ((h ? dd [u]. y : dd [u]. x) >> q) & 1u;
-					} else {                                     // lane pair: word = lane bit (state bit pp+1), bit = 16 half + state without bits pp, pp+1
-						const int pp = (t & 3) + 1;
-						const unsigned h = (state >> pp) & 1u, l = (state >> (pp + 1)) & 1u;
-						const unsigned q = ((state >> (pp + 2)) << pp) | (state & ((1u << pp) - 1u));
-						bit = ((l ? dd [u]. y : dd [u]. x) >> (16u * h + q)) & 1u;
-					}
+					// word = lane bit (state bit pp+1), bit = 16 half + state without bits pp, pp+1
+					const int pp = (t & 3) + 1;
+					const unsigned h = (state >> pp) & 1u, l = (state >> (pp + 1)) & 1u;
+					const unsigned q = ((state >> (pp + 2)) << pp) | (state & ((1u << pp) - 1u));
+					const unsigned bit = ((l ? dd [u]. y : dd [u]. x) >> (16u * h + q)) & 1u;
 					state = (state >> 1) | (bit << 5);
 					acc |= bit << (31 - u);
 				}
@@ -372,16 +288,17 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 	}
 }
 
+int vit_simd_cw_per_cta () { return VS_CW; }
+
 cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas, int total_ctas2) {
 	if (njobs <= 0 || total_ctas <= 0) return cudaSuccess;
 	cudaStream_t st = h -> vst ();
-	const bool pair = h -> cfg. reserved [0] != 1;           // reserved[0] = 1: one thread per code word (kept for comparison)
+	{ ProfScope prof (h, KC_VITERBI_SYM, st);
+	  vit_sym8_kernel<<<dim3 (296, njobs), 256, 0, st>>> (d_jobs); }
 	{ ProfScope prof (h, KC_VITERBI_MSC, st);
-	  if (pair) vit_simd2_forward<<<total_ctas2, VS2_THREADS, 0, st>>> (d_jobs, njobs);
-	  else      vit_simd_forward<<<total_ctas, VS_THREADS, 0, st>>> (d_jobs, njobs); }
+	  vit_simd_forward<<<total_ctas2, VS_THREADS, 0, st>>> (d_jobs, njobs); }
 	{ ProfScope prof (h, KC_VITERBI_TB, st);
-	  if (pair) vit_simd_traceback<2><<<total_ctas, TB_THREADS, 0, st>>> (d_jobs, njobs);
-	  else      vit_simd_traceback<1><<<total_ctas, TB_THREADS, 0, st>>> (d_jobs, njobs); }
-	h -> launches += 2;
+	  vit_simd_traceback<<<total_ctas, TB_THREADS, 0, st>>> (d_jobs, njobs); }
+	h -> launches += 3;
 	return cudaGetLastError ();
 }
