@@ -43,8 +43,10 @@ typedef struct {
 	int32_t dabMode;           /* 1..4 (DabParams.dabMode, gui.cpp:1328-1372)                      */
 	int32_t threshold;         /* phaseReference level, default 3 (gui.cpp:98-99)                  */
 	int32_t freqSyncMethod;    /* 0,1,2 as ofdmDecoder (main.cpp:91 default 1)                     */
-	int32_t viterbi_path;      /* 0 = auto (by batch size), 1 = warp-per-code-word kernel, 2 = code-word-per-thread kernel */
-	int32_t reserved [3];
+	int32_t viterbi_path;      /* 0 = auto (by batch size), 1 = warp-per-code-word kernel, 2 = throughput (two threads per code word) kernel */
+	int32_t host_batch_frames; /* dabgpu_decode from HOST memory: frames per channel-decoding launch while the input is
+	                              still arriving over PCIe (0 = default 128)                                           */
+	int32_t reserved [2];
 } dabgpu_config;
 
 /* one MSC sub-channel, the fields of audiodata/packetdata the decode path uses (dab-constants.h:151-175;

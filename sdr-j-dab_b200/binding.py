@@ -14,7 +14,8 @@ class DabGpuError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("dabMode", C.c_int32), ("threshold", C.c_int32),
-                ("freqSyncMethod", C.c_int32), ("viterbi_path", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("freqSyncMethod", C.c_int32), ("viterbi_path", C.c_int32), ("host_batch_frames", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
 
 
 class SubCh(C.Structure):
@@ -104,10 +105,10 @@ class DecodeOut:
 class DabGpu:
     """One engine handle (dabgpu_t)."""
 
-    def __init__(self, mode=1, device=0, threshold=3, freqSyncMethod=1, viterbi_path=0, simd_single_lane=False):
+    def __init__(self, mode=1, device=0, threshold=3, freqSyncMethod=1, viterbi_path=0, host_batch_frames=0):
         self.lib = load_library()
         cfg = Config(device=device, dabMode=mode, threshold=threshold, freqSyncMethod=freqSyncMethod, viterbi_path=viterbi_path)
-        cfg.reserved[0] = 1 if simd_single_lane else 0
+        cfg.host_batch_frames = host_batch_frames
         self.h = C.c_void_p()
         rc = self.lib.dabgpu_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:

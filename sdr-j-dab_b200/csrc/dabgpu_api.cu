@@ -195,12 +195,12 @@ int dab_simd_job_profile (dabgpu *h, int kind, int bitRate, int uepFlag, int pro
 	return DABGPU_OK;
 }
 
-// the one-code-word-per-thread kernels need ~20k code words in flight to fill 148 SMs; below that the
+// the one-code-word-per-thread kernels need ~20k code words in flight to fill 148 SMs, but already win from ~2k on; below that the
 // warp-per-code-word kernel has the lower latency.  cfg.viterbi_path: 0 = auto, 1 = always warp, 2 = always SIMD.
 bool dab_use_simd (const dabgpu *h, long long ncodewords) {
 	if (h -> cfg. viterbi_path == 1) return false;
 	if (h -> cfg. viterbi_path == 2) return true;
-	return ncodewords >= 8192;
+	return ncodewords >= 2048;
 }
 
 int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
@@ -208,12 +208,16 @@ int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
 	dabgpu::VitCtx &cx = h -> vctx [h -> cur];
 	size_t dec_words = 0, sym_bytes = 0;
 	int ctas = 0, ctas2 = 0;
+	bool need_sym8 = false;
 	const int cw2 = vit_simd_cw_per_cta ();
 	auto padded = [] (int nsteps) { return (size_t) ((nsteps + VS_CHUNK - 1) / VS_CHUNK * VS_CHUNK); };
 	for (auto &j : jobs) {
 		j. cta_first = ctas; j. cta_first2 = ctas2; j. one = 1u;
 		ctas += (j. ncw + 63) / 64; ctas2 += (j. ncw + cw2 - 1) / cw2;
 		dec_words += padded (j. nsteps) * j. ncw;
+		j. sym8_ready = j. sym8 != nullptr;                      // the caller already holds the byte symbols (stream engine)
+		if (j. sym8_ready) continue;
+		need_sym8 = true;
 		j. stride8 = ((long long) j. ncols + 7 + 8) / 8 * 8;     // the staging may read up to 7 bytes past the last column
 		sym_bytes += (size_t) (j. ncw + (j. deint ? 15 : 0)) * j. stride8;
 	}
@@ -225,13 +229,13 @@ int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
 	size_t off = 0, soff = 0;
 	for (auto &j : jobs) {
 		j. dec = (uint2 *) cx. d_dec. p + off; off += padded (j. nsteps) * j. ncw;
-		j. sym8 = (uint8_t *) cx. d_sym8. p + soff; soff += (size_t) (j. ncw + (j. deint ? 15 : 0)) * j. stride8;
+		if (!j. sym8_ready) { j. sym8 = (uint8_t *) cx. d_sym8. p + soff; soff += (size_t) (j. ncw + (j. deint ? 15 : 0)) * j. stride8; }
 	}
 	CUDA_TRY (h, cx. d_jobs. ensure (jb));
 	CUDA_TRY (h, cx. h_jobs. ensure (jb));
 	memcpy (cx. h_jobs. p, jobs. data (), jb);
 	CUDA_TRY (h, cudaMemcpyAsync (cx. d_jobs. p, cx. h_jobs. p, jb, cudaMemcpyHostToDevice, cx. st));
-	CUDA_TRY (h, vit_simd_launch (h, (const VitSimdJob *) cx. d_jobs. p, (int) jobs. size (), ctas, ctas2));
+	CUDA_TRY (h, vit_simd_launch (h, (const VitSimdJob *) cx. d_jobs. p, (int) jobs. size (), ctas, ctas2, need_sym8));
 	return DABGPU_OK;
 }
 

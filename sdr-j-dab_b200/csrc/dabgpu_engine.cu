@@ -162,7 +162,8 @@ __global__ void __launch_bounds__ (OFDM_THREADS) front_kernel (SampleWin w, Ofdm
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__ (OFDM_THREADS) symbol_kernel (SampleWin w, OfdmTables T, const FrameIn *fin, int slot0, int groups,
                                                                 int blocksPerCIF, int cifsPerFrame, const FrameOut *fo,
-                                                                const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc) {
+                                                                const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc,
+                                                                uint8_t *fic8, uint8_t *msc8) {
 	extern __shared__ float2 sm [];
 	__shared__ float2 s_fc [OFDM_THREADS / 32];
 	const int N = T. T_u, Ts = T. T_s, Tg = T. T_g, c = blockIdx. x / groups, g = blockIdx. x % groups;
@@ -200,13 +201,14 @@ __global__ void __launch_bounds__ (OFDM_THREADS) symbol_kernel (SampleWin w, Ofd
 			acc. x += r. x; acc. y += r. y;
 		}
 		float2 *f = block_fft (symbuf + Tg, scratch, N, T. tw);
-		int16_t *out;
-		if (l < 4) out = fic + ((size_t) slot * 3 + (l - 1)) * 2 * T. K;
+		size_t o; int16_t *out; uint8_t *out8;
+		if (l < 4) { o = ((size_t) slot * 3 + (l - 1)) * 2 * T. K; out = fic + o; out8 = fic8 + o; }
 		else {
 			const int m = l - 4;
-			out = msc + ((size_t) 15 + (size_t) slot * cifsPerFrame + m / blocksPerCIF) * CIF_BITS + (size_t) (m % blocksPerCIF) * 2 * T. K;
+			o = ((size_t) 15 + (size_t) slot * cifsPerFrame + m / blocksPerCIF) * CIF_BITS + (size_t) (m % blocksPerCIF) * 2 * T. K;
+			out = msc + o; out8 = msc8 + o;
 		}
-		demod_symbol (f, prev, T, out);
+		demod_symbol (f, prev, T, out, out8);
 	}
 	for (int o = 16; o > 0; o >>= 1) {
 		acc. x += __shfl_xor_sync (0xffffffffu, acc. x, o);
@@ -223,18 +225,39 @@ __global__ void __launch_bounds__ (OFDM_THREADS) symbol_kernel (SampleWin w, Ofd
 
 // ---------------------------------------------------------------------------------------------------
 // Mode I symbol kernel: same work as symbol_kernel, built on the 8-points-per-thread register FFT.
-// Samples go global -> registers (u8 convert + NCO by a per-thread phasor recurrence) -> first butterflies,
-// the spectrum stays in shared memory in the FFT's own digit-reversed order (the carrier table is pre-permuted),
-// the previous symbol's spectrum is simply the other shared buffer (pointer swap instead of a copy).
+//   * the raw u8 IQ of symbol l+1 streams into shared memory (16-byte cp.async, double buffered) while symbol l
+//     is transformed, so no thread ever waits on HBM;
+//   * samples go shared (raw) -> registers (u8 convert + NCO by a per-thread phasor recurrence, the 1/128 of
+//     rawfiles.cpp:113-116 folded into the phasor: an exact power-of-two scaling) -> first butterflies;
+//   * the spectrum stays in shared memory in the FFT's own digit-reversed order (the carrier table is
+//     pre-permuted), the previous symbol's spectrum is simply the other buffer (pointer swap instead of a copy);
+//   * NCO phase indices advance by 32-bit adds (one 64-bit modulo per thread and CTA instead of three per symbol);
+//   * a thread demodulates carrier PAIRS, so soft bits leave as 32-bit stores and the Viterbi's byte symbols
+//     (viterbi.cpp:229-235) as 16-bit stores.
 // ---------------------------------------------------------------------------------------------------
+#define R8_RAW 5152                                                        // bytes per raw buffer: 2 T_s + alignment slack, multiple of 16
+#define R8_DYN_SMEM ((2 * R8_SMEM + 512) * (int) sizeof (float2) + 2 * R8_RAW)
+
 __device__ __forceinline__ float2 u8_to_c (uchar2 s) {
 	return make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f));
+}
+// (b - 128) as float, exactly, b = byte `which` of s: 0x4B0000bb is 2^23 + b
+__device__ __forceinline__ float u8_to_f (uint32_t s, int which) {
+	return __uint_as_float (__byte_perm (s, 0x4B000000u, which ? 0x7441 : 0x7440)) - 8388736.0f;
+}
+// soft-bit quantisation of ofdm-decoder.cpp:183-189 with the quotient from the reciprocal unit (2 ulp; the soft bits'
+// stated tolerance is +-1 step and comes from the FFT, whose rounding differs from the reference's FFTW anyway)
+__device__ __forceinline__ int quant127_fast (float num, float ab1) {
+	return __double2int_rz ((double) __fdividef (- num, ab1) * 127.0);       // NaN (ab1 == 0) -> 0 (App. B-5)
 }
 
 __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTables T, const FrameIn *fin, int slot0, int groups,
                                                           int blocksPerCIF, int cifsPerFrame, const FrameOut *fo,
-                                                          const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc) {
-	__shared__ float2 bufA [R8_SMEM], bufB [R8_SMEM], G [512];
+                                                          const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc,
+                                                          uint8_t *fic8, uint8_t *msc8) {
+	extern __shared__ __align__ (16) unsigned char r8_dyn [];
+	float2 *bufA = reinterpret_cast<float2 *> (r8_dyn), *bufB = bufA + R8_SMEM, *G = bufB + R8_SMEM;
+	unsigned char *raw = reinterpret_cast<unsigned char *> (G + 512);
 	__shared__ float2 s_fc [8];
 	const int N = R8_N, Ts = T. T_s, Tg = T. T_g, t = threadIdx. x;
 	const int c = blockIdx. x / groups, g = blockIdx. x % groups;
@@ -248,12 +271,42 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 	const long long F = in. P + s;                                         // first sample of the PRS
 	const int lpD = mod_rate ((long long) in. lp - (long long) (s + N) * phA);  // localPhase after the PRS
 	const float2 rot256 = nco (T, mod_rate (- 256ll * phB));               // 256 samples further: phase index - 256 f
+	const int offT = mod_rate ((long long) (t + 1) * phB), offU = mod_rate ((long long) (Tg + t + 1) * phB);
+	const int dTs = mod_rate ((long long) Ts * phB);
 	float2 *cur = bufA, *prev = bufB;
 	float2 x [8];
+
+	// raw u8 IQ of symbol l (guard + useful part, T_s samples from `first`) -> raw buffer b; returns the byte offset of
+	// sample 0 inside the buffer.  Fast path: 16-byte cp.async from the 16-byte-aligned address below the first sample.
+	auto stage = [&] (int l, int b) -> int {
+		const long long first = F + N + (long long) (l - 1) * Ts;
+		unsigned char *dst = raw + b * R8_RAW;
+		const uchar2 *seg = nullptr; long long rel = 0, seglen = 0;
+		if (first + Ts <= w. len0) { seg = w. seg0; rel = first; seglen = w. len0; }
+		else if (first >= w. len0) { seg = w. seg1; rel = first - w. len0; seglen = w. len1; }
+		int off = 0;
+		bool fast = seg != nullptr;
+		if (fast) {
+			const unsigned long long p = (unsigned long long) (seg + rel), pa = p & ~15ull;
+			off = (int) (p - pa);
+			const int n16 = (off + 2 * Ts + 15) >> 4;
+			fast = pa >= (unsigned long long) seg && pa + 16ull * n16 <= (unsigned long long) (seg + seglen);
+			if (fast)
+				for (int i = t; i < n16; i += 256)
+					asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r" ((uint32_t) __cvta_generic_to_shared (dst + 16 * i)), "l" (pa + 16ull * i));
+		}
+		if (!fast) {                                                       // symbol straddles the tail | input seam or touches a buffer end
+			off = 0;
+			for (int i = t; i < Ts; i += 256) reinterpret_cast<uchar2 *> (dst) [i] = win_fetch (w, first + i);
+		}
+		asm volatile ("cp.async.commit_group;");
+		return off;
+	};
+
+	int off_cur = stage (l0, 0);
 	if (l0 == 1) {
 		const float2 *p0 = spec0 + (size_t) c * N;
 		for (int k = t; k < N; k += 256) prev [r8_pad (r8_pos (k))] = p0 [k];
-		__syncthreads ();
 	} else {                                                               // spectrum of symbol l0-1 as reference
 		const long long first = F + N + (long long) (l0 - 2) * Ts + Tg;
 		const int lpb = mod_rate ((long long) lpD - ((long long) (l0 - 2) * Ts + Tg) % DAB_INPUT_RATE * phB);
@@ -264,25 +317,34 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 	}
 	float2 acc = make_float2 (0.f, 0.f);
 	const int slot = slot0 + c;
-	int pidx [6];                                                          // this thread's six carriers (K = 1536 = 6 x 256)
+	int pidx [6];                                                          // this thread's six carriers: the pairs 2t, 2t+1 (+ 512 m)
 #pragma unroll
-	for (int m = 0; m < 6; m ++) pidx [m] = __ldg (&T. permpos [t + 256 * m]);
+	for (int m = 0; m < 3; m ++) { pidx [2 * m] = __ldg (&T. permpos [2 * t + 512 * m]); pidx [2 * m + 1] = __ldg (&T. permpos [2 * t + 1 + 512 * m]); }
+	int lpb = mod_rate ((long long) lpD - ((long long) (l0 - 1) * Ts) % DAB_INPUT_RATE * phB);   // localPhase before the symbol's first sample
+	const float sc = 1.0f / 128.0f;
 	for (int l = l0; l < l1; l ++) {
-		const long long first = F + N + (long long) (l - 1) * Ts;          // guard interval starts here
-		const int lpb = mod_rate ((long long) lpD - ((long long) (l - 1) * Ts) % DAB_INPUT_RATE * phB);
-		// issue every load of the symbol first
-		uchar2 cur_raw [8], cg0, cg1;
+		const int b = (l - l0) & 1;
+		int off_next = 0;
+		if (l + 1 < l1) off_next = stage (l + 1, b ^ 1); else asm volatile ("cp.async.commit_group;");
+		asm volatile ("cp.async.wait_group 1;" ::: "memory");
+		__syncthreads ();                                                  // raw buffer b complete; last symbol's demod reads done
+		const unsigned short *rs = reinterpret_cast<const unsigned short *> (raw + b * R8_RAW + off_cur);
+		int ig = lpb - offT; if (ig < 0) ig += DAB_INPUT_RATE;             // guard sample t
+		int iu = lpb - offU; if (iu < 0) iu += DAB_INPUT_RATE;             // useful sample t
+		float2 phg = nco (T, ig), ph = nco (T, iu);
+		phg. x *= sc; phg. y *= sc; ph. x *= sc; ph. y *= sc;
+		{
+			const uint32_t g0 = rs [t], g1 = t + 256 < Tg ? rs [t + 256] : 0x8080u;
+			G [t] = cmul (make_float2 (u8_to_f (g0, 0), u8_to_f (g0, 1)), phg);
+			G [t + 256] = cmul (make_float2 (u8_to_f (g1, 0), u8_to_f (g1, 1)), cmul (phg, rot256));
+		}
 #pragma unroll
-		for (int k = 0; k < 8; k ++) cur_raw [k] = win_fetch (w, first + Tg + t + 256 * k);
-		cg0 = win_fetch (w, first + t);
-		cg1 = t + 256 < Tg ? win_fetch (w, first + t + 256) : make_uchar2 (128, 128);
-		float2 phg = nco (T, mod_rate ((long long) lpb - (long long) (t + 1) * phB));          // guard sample t
-		float2 ph  = nco (T, mod_rate ((long long) lpb - (long long) (Tg + t + 1) * phB));     // useful sample t
-		G [t] = cmul (u8_to_c (cg0), phg);
-		G [t + 256] = cmul (u8_to_c (cg1), cmul (phg, rot256));
-#pragma unroll
-		for (int k = 0; k < 8; k ++) { x [k] = cmul (u8_to_c (cur_raw [k]), ph); ph = cmul (ph, rot256); }
-		__syncthreads ();                                                  // G visible; last symbol's demod reads done
+		for (int k = 0; k < 8; k ++) {
+			const uint32_t v = rs [Tg + t + 256 * k];
+			x [k] = cmul (make_float2 (u8_to_f (v, 0), u8_to_f (v, 1)), ph);
+			ph = cmul (ph, rot256);
+		}
+		__syncthreads ();                                                  // G visible
 		// FreqCorr += x[i] * conj (x[i - T_u]), i in [T_u, T_s): useful element e = i - T_g pairs with guard sample e - (T_u - T_g)
 		{
 			const int e6 = t + 1536 - (N - Tg), e7 = t + 1792 - (N - Tg);
@@ -290,22 +352,33 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 			{ const float2 r = cmulc (x [7], G [e7]); acc. x += r. x; acc. y += r. y; }
 		}
 		fft2048_r8 (x, cur, T. tw);
-		int16_t *out;
-		if (l < 4) out = fic + ((size_t) slot * 3 + (l - 1)) * 2 * T. K;
+		size_t o;
+		if (l < 4) o = ((size_t) slot * 3 + (l - 1)) * 2 * T. K;
 		else {
 			const int m = l - 4;
-			out = msc + ((size_t) 15 + (size_t) slot * cifsPerFrame + m / blocksPerCIF) * CIF_BITS + (size_t) (m % blocksPerCIF) * 2 * T. K;
+			o = ((size_t) 15 + (size_t) slot * cifsPerFrame + m / blocksPerCIF) * CIF_BITS + (size_t) (m % blocksPerCIF) * 2 * T. K;
 		}
+		int16_t *out = (l < 4 ? fic : msc) + o;
+		uint8_t *out8 = (l < 4 ? fic8 : msc8) + o;
 #pragma unroll
-		for (int m = 0; m < 6; m ++) {                                      // K = 1536 = 6 x 256 carriers
-			const int i = t + 256 * m;
-			const int idx = pidx [m];
-			const float2 r1 = cmulc (cur [idx], prev [idx]);
-			const float ab1 = fabsf (r1. x) + fabsf (r1. y);
-			out [i]        = quant127 (r1. x, ab1);
-			out [T. K + i] = quant127 (r1. y, ab1);
+		for (int m = 0; m < 3; m ++) {                                      // K = 1536 = 3 x 256 carrier pairs
+			const int i = 2 * t + 512 * m;
+			int re [2], im [2];
+#pragma unroll
+			for (int q = 0; q < 2; q ++) {
+				const int idx = pidx [2 * m + q];
+				const float2 r1 = cmulc (cur [idx], prev [idx]);
+				const float ab1 = fabsf (r1. x) + fabsf (r1. y);
+				re [q] = quant127_fast (r1. x, ab1); im [q] = quant127_fast (r1. y, ab1);
+			}
+			*reinterpret_cast<uint32_t *> (out + i)        = (uint32_t) (re [0] & 0xffff) | ((uint32_t) re [1] << 16);
+			*reinterpret_cast<uint32_t *> (out + T. K + i) = (uint32_t) (im [0] & 0xffff) | ((uint32_t) im [1] << 16);
+			*reinterpret_cast<unsigned short *> (out8 + i)        = (unsigned short) ((re [0] + 127) | ((re [1] + 127) << 8));
+			*reinterpret_cast<unsigned short *> (out8 + T. K + i) = (unsigned short) ((im [0] + 127) | ((im [1] + 127) << 8));
 		}
 		float2 *tmp = cur; cur = prev; prev = tmp;
+		off_cur = off_next;
+		lpb -= dTs; if (lpb < 0) lpb += DAB_INPUT_RATE;
 	}
 	for (int o = 16; o > 0; o >>= 1) {
 		acc. x += __shfl_xor_sync (0xffffffffu, acc. x, o);
@@ -318,6 +391,12 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 		for (int k = 0; k < 8; k ++) { sum. x += s_fc [k]. x; sum. y += s_fc [k]. y; }
 		fcpart [c * MAX_GROUPS + g] = sum;
 	}
+}
+
+// int16 soft bits -> byte symbols for n elements (the 15 history rows of the time de-interleaver at the start of a call)
+__global__ void soft_to_sym8_kernel (const int16_t *in, uint8_t *out, long long n) {
+	for (long long i = (long long) blockIdx. x * blockDim. x + threadIdx. x; i < n; i += (long long) gridDim. x * blockDim. x)
+		out [i] = (uint8_t) min (max ((int) in [i] + 127, 0), 255);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -483,6 +562,7 @@ int dab_engine_init (dabgpu *h) {
 	CUDA_TRY (h, cudaFuncSetAttribute (front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 	CUDA_TRY (h, cudaFuncSetAttribute (symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 	CUDA_TRY (h, cudaFuncSetAttribute (scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (ScanSmem)));
+	CUDA_TRY (h, cudaFuncSetAttribute (symbol_kernel_r8, cudaFuncAttributeMaxDynamicSharedMemorySize, R8_DYN_SMEM));
 	return DABGPU_OK;
 }
 
@@ -495,7 +575,7 @@ void dab_engine_free (dabgpu *h) {
 	for (auto e : E -> copy_events) cudaEventDestroy (e);
 	E -> tail. release (); E -> tail_spare. release (); E -> d_ctl. release (); E -> h_ctl. release ();
 	E -> d_frameout. release (); E -> d_framein. release (); E -> d_fcpart. release (); E -> d_spec0. release (); E -> d_info. release ();
-	E -> d_fic. release (); E -> d_msc. release (); E -> d_histtmp. release ();
+	E -> d_fic. release (); E -> d_msc. release (); E -> d_histtmp. release (); E -> d_fic8. release (); E -> d_msc8. release ();
 	E -> d_ficbits. release (); E -> d_ficcrc. release ();
 	for (auto &b : E -> d_mscbits) b. release ();
 	delete E;
@@ -626,6 +706,8 @@ static int ensure_frame_capacity (dabgpu *h, long long frames) {
 	E -> d_msc = nmsc;
 	E -> hist_init = true;
 	CUDA_TRY (h, E -> d_fic. ensure ((size_t) cap * 3 * 2 * p. K * sizeof (int16_t)));
+	CUDA_TRY (h, E -> d_fic8. ensure ((size_t) cap * 3 * 2 * p. K + 16));
+	CUDA_TRY (h, E -> d_msc8. ensure ((15 + (size_t) cap * p. cifsPerFrame) * CIF_BITS + 16));
 	CUDA_TRY (h, E -> d_info. ensure ((size_t) cap * sizeof (dabgpu_frame_info)));
 	CUDA_TRY (h, E -> d_histtmp. ensure (15 * rowb));
 	E -> cap_frames = cap;
@@ -652,6 +734,8 @@ static int channel_chunk (dabgpu *h, int f0, int nv, dabgpu_result *out, std::ve
 			if (simd) {
 				jobs. emplace_back ();
 				if ((rc = dab_fic_simd_job (h, soft, 2304, ngroups, ficbits, &jobs. back ()))) break;
+				jobs. back (). sym8 = (uint8_t *) E -> d_fic8. p + (size_t) f0 * 3 * 2 * p. K;   // written by the symbol kernel
+				jobs. back (). stride8 = 2304;
 			} else if ((rc = dab_fic_decode_dev (h, soft, 2304, ngroups, ficbits, ficcrc))) break;
 		}
 		std::vector<int> n_here (E -> backends. size (), 0);
@@ -661,7 +745,11 @@ static int channel_chunk (dabgpu *h, int f0, int nv, dabgpu_result *out, std::ve
 			uint8_t *dst = (uint8_t *) E -> d_mscbits [i]. p + (size_t) nblk [i] * 24 * sc. bitRate;
 			if ((rc = dab_backend_run_dev (E -> backends [i], (const int16_t *) E -> d_msc. p + (size_t) sc. startAddr * 64, CIF_BITS, r0, ncif,
 			                               dst, &n_here [i], simd ? &job : nullptr))) break;
-			if (simd && n_here [i] > 0) jobs. push_back (job);
+			if (simd && n_here [i] > 0) {
+				job. sym8 = (uint8_t *) E -> d_msc8. p + (size_t) (job. first_row - 15) * CIF_BITS + (size_t) sc. startAddr * 64;
+				job. stride8 = CIF_BITS;
+				jobs. push_back (job);
+			}
 			dab_backend_note_cifs (E -> backends [i], ncif);
 		}
 		if (rc) break;
@@ -711,6 +799,10 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 	CUDA_TRY (h, E -> d_ficcrc. ensure ((size_t) (want * p. ficGroups + 1) * 3));
 	for (size_t i = 0; i < E -> backends. size (); i ++)
 		CUDA_TRY (h, E -> d_mscbits [i]. ensure ((size_t) (want * p. cifsPerFrame + 1) * 24 * E -> subch [i]. bitRate));
+	// the 15 history rows of the time de-interleaver as byte symbols (whatever put them there: the previous call, a state
+	// import, a re-allocation)
+	soft_to_sym8_kernel<<<296, 256, 0, h -> stream>>> ((const int16_t *) E -> d_msc. p, (uint8_t *) E -> d_msc8. p, 15ll * CIF_BITS);
+	h -> launches ++;
 	std::vector<int> nblk (E -> backends. size (), 0);
 	StreamCtl *hctl = (StreamCtl *) E -> h_ctl. p;
 	int nframes = 0, decoded_upto = 0;
@@ -763,11 +855,13 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 			front_kernel<<<(int) C, OFDM_THREADS, sm_front, h -> stream>>> (w, E -> T, fin, fo, (float2 *) E -> d_spec0. p); }
 			{ ProfScope prof (h, KC_SYMBOL);
 			if (p. T_u == R8_N && p. K == 1536)
-				symbol_kernel_r8<<<(int) C * E -> groups, 256, 0, h -> stream>>> (w, E -> T, fin, nframes, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
-					fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p);
+				symbol_kernel_r8<<<(int) C * E -> groups, 256, R8_DYN_SMEM, h -> stream>>> (w, E -> T, fin, nframes, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
+					fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p,
+					(uint8_t *) E -> d_fic8. p, (uint8_t *) E -> d_msc8. p);
 			else
 				symbol_kernel<<<(int) C * E -> groups, OFDM_THREADS, sm_sym, h -> stream>>> (w, E -> T, fin, nframes, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
-					fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p); }
+					fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p,
+					(uint8_t *) E -> d_fic8. p, (uint8_t *) E -> d_msc8. p); }
 			{ ProfScope prof (h, KC_SCAN);
 			scan_kernel<<<1, 32, sizeof (ScanSmem), h -> stream>>> (dctl, fin, (int) C, nframes, E -> groups, p, fo, (const float2 *) E -> d_fcpart. p,
 				(dabgpu_frame_info *) E -> d_info. p, E -> abs_base, pass == 0 ? 1 : 0); }
@@ -874,8 +968,10 @@ extern "C" int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples
 			ready. push_back (E -> copy_events [k]);
 		}
 	}
-	// host input: the PCIe copy paces the call, so channel decoding starts as soon as 512 frames are demodulated
-	int rc = decode_core (h, (const uchar2 *) h -> d_in. p, (long long) nsamples, out, &ready, piece, E -> vit_batch_frames);
+	// host input: the PCIe copy paces the call and the GPU idles most of the time, so channel decoding follows the
+	// OFDM part in small batches: what is left to do once the last sample has arrived is then short
+	int rc = decode_core (h, (const uchar2 *) h -> d_in. p, (long long) nsamples, out, &ready, piece,
+	                      h -> cfg. host_batch_frames > 0 ? h -> cfg. host_batch_frames : E -> vit_batch_frames);
 	cudaStreamSynchronize (E -> copy_st);
 	return rc;
 }

@@ -51,6 +51,7 @@ struct Engine {
 	int chunk = 1, max_chunk = 1024;
 	DevBuf d_frameout, d_fcpart, d_spec0, d_info, d_framein;
 	DevBuf d_fic, d_msc, d_histtmp;     // soft bits: FIC [frames][3*2K], MSC rows [15 + cifs][55296]
+	DevBuf d_fic8, d_msc8;              // the same as 0..255 Viterbi symbols (viterbi.cpp:229-235), written by the symbol kernels alongside
 	long long cap_frames = 0;
 	DevBuf d_ficbits, d_ficcrc;
 	std::vector<DevBuf> d_mscbits;
@@ -60,7 +61,7 @@ struct Engine {
 	int groups = 5;
 	cudaStream_t copy_st = nullptr;     // piecewise host-to-device input copies
 	std::vector<cudaEvent_t> copy_events;
-	int vit_batch_frames = 512;         // frames per channel-decoding launch (enough code words to fill the GPU)
+	int vit_batch_frames = 128;         // host-input path: frames per channel-decoding launch (cfg.host_batch_frames overrides)
 	unsigned vrr = 0;                   // round robin over the channel-decoding side streams
 };
 

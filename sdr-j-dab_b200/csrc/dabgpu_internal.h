@@ -87,6 +87,7 @@ struct VitSimdJob {
 	const int2 *chunk;        // device: per chunk {a_k, G_k}
 	uint8_t *sym8;            // 0..255 symbols of the rows this job reads: row r = source row first_row - dmax + r
 	long long stride8;        // bytes between sym8 rows (multiple of 8)
+	int sym8_ready;           // 1: sym8 was filled by the producer of the soft bits, the conversion pre-pass skips this job
 	int frameBits, nsteps, ncw;
 	int cta_first;            // first CTA of this job in the chain-back launch (64 code words per CTA)
 	int cta_first2;           // same for the forward kernel (VS_CW code words per CTA)
@@ -95,7 +96,7 @@ struct VitSimdJob {
 	const uint32_t *prbs;     // packed dispersal sequence or nullptr
 	uint8_t *out;             // [ncw][frameBits]
 };
-cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas, int total_ctas2);
+cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas, int total_ctas2, bool convert);
 int vit_simd_cw_per_cta ();
 cudaError_t fib_crc_launch (dabgpu *h, const uint8_t *bits, int nfibs, uint8_t *ok);
 

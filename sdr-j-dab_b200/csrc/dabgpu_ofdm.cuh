@@ -99,15 +99,18 @@ __device__ __forceinline__ short quant127 (float num, float ab1) {
 
 // DQPSK demod + frequency de-interleave of one symbol (ofdm-decoder.cpp:178-190): cur = FFT of the symbol,
 // prev = running phase reference (updated in place on the K used bins), ibits[2K]
-__device__ __forceinline__ void demod_symbol (const float2 *cur, float2 *prev, const OfdmTables &T, int16_t *__restrict__ ibits) {
+__device__ __forceinline__ void demod_symbol (const float2 *cur, float2 *prev, const OfdmTables &T, int16_t *__restrict__ ibits,
+                                              uint8_t *__restrict__ sym8 = nullptr) {
 	for (int i = threadIdx. x; i < T. K; i += OFDM_THREADS) {
 		const int idx = __ldg (&T. perm [i]);
 		const float2 c = cur [idx];
 		const float2 r1 = cmulc (c, prev [idx]);
 		prev [idx] = c;
 		const float ab1 = fabsf (r1. x) + fabsf (r1. y);                 // jan_abs, dab-constants.h:127-134
-		ibits [i]        = quant127 (r1. x, ab1);
-		ibits [T. K + i] = quant127 (r1. y, ab1);
+		const short re = quant127 (r1. x, ab1), im = quant127 (r1. y, ab1);
+		ibits [i]        = re;
+		ibits [T. K + i] = im;
+		if (sym8) { sym8 [i] = (uint8_t) (re + 127); sym8 [T. K + i] = (uint8_t) (im + 127); }   // the Viterbi's symbol (viterbi.cpp:229-235)
 	}
 }
 

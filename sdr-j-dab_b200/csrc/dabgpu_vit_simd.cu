@@ -115,6 +115,7 @@ __device__ __forceinline__ void vs_fixup (uint32_t (&Q) [16], uint32_t (&R) [16]
 // blockIdx.y = job; sym8 row r = source row first_row - dmax + r.
 __global__ void __launch_bounds__ (256) vit_sym8_kernel (const VitSimdJob *jobs) {
 	const VitSimdJob j = jobs [blockIdx. y];
+	if (j. sym8_ready) return;
 	const int dmax = j. deint ? 15 : 0, nrows = j. ncw + dmax;
 	const int wpr = (int) (j. stride8 >> 2);                      // 4-byte words per row
 	const long long total = (long long) nrows * wpr;
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__ (VS_THREADS, 10) vit_simd_forward (const VitSi
 #define TB_THREADS 64
 __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimdJob *jobs, int njobs) {
 	__shared__ uint32_t bits [TB_THREADS * 5];               // 128 decoded bits per code word per round, row stride 5 words
+	__shared__ __align__ (16) uint2 dq [2][32][TB_THREADS];  // the decision words of two output words (32 steps each) per thread
 	int jb = 0;
 	while (jb + 1 < njobs && (int) blockIdx. x >= jobs [jb + 1]. cta_first) jb ++;
 	const VitSimdJob j = jobs [jb];
@@ -233,38 +235,47 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 	const bool live = cw < j. ncw;
 	const uint2 *dec = j. dec + (live ? cw : 0);
 	unsigned state = 0;
-	const int nrounds = (j. frameBits + 127) / 128;
+	const int nrounds = (j. frameBits + 127) / 128, nwords = (j. frameBits + 31) / 32;
+	// The loads do not depend on the state: while output word wi is walked, the 32 decision words of word wi - 1 are
+	// already on their way into shared memory (cp.async; every thread consumes only what it copied itself, so no
+	// barrier is involved).  Slot u of a word holds information bit 32 wi + 31 - u = trellis step 32 wi + 37 - u.
+	auto fetch = [&] (int wi) {
+		if (wi >= 0 && live) {
+#pragma unroll
+			for (int u = 0; u < 32; u ++) {
+				const int i = 32 * wi + 31 - u;
+				if (i < j. frameBits) vs_cp_async8 (&dq [wi & 1][u][tid], &dec [(size_t) (i + 6) * j. ncw]);
+			}
+		}
+		asm volatile ("cp.async.commit_group;");
+	};
+	fetch (nwords - 1);
 	for (int rd = nrounds - 1; rd >= 0; rd --) {
 		const int base = 128 * rd, top = min (j. frameBits, base + 128);
 		uint32_t w [4] = { 0, 0, 0, 0 };
-		if (live) {
-			// the loads do not depend on the state: fetch 32 decision words (one output word), then walk them
 #pragma unroll
-			for (int wd = 3; wd >= 0; wd --) {
-				const int hi = base + 32 * wd + 31;              // highest information bit of this output word
-				if (base + 32 * wd >= top) continue;
-				uint2 dd [32];
+		for (int wd = 3; wd >= 0; wd --) {
+			const int wi = 4 * rd + wd;
+			if (wi >= nwords) continue;
+			fetch (wi - 1);
+			asm volatile ("cp.async.wait_group 1;" ::: "memory");
+			if (!live) continue;
+			uint32_t acc = 0;
 #pragma unroll
-				for (int u = 0; u < 32; u ++) {
-					const int i = hi - u;
-					dd [u] = i < top ? dec [(size_t) (i + 6) * j. ncw] : make_uint2 (0u, 0u);
-				}
-				uint32_t acc = 0;
-#pragma unroll
-				for (int u = 0; u < 32; u ++) {
-					const int i = hi - u;
-					if (i >= top) continue;
-					const int t = i + 6;                        // decision of step i+6 = information bit i
-					// word = lane bit (state bit pp+1), bit = 16 half + state without bits pp, pp+1
-					const int pp = (t & 3) + 1;
-					const unsigned h = (state >> pp) & 1u, l = (state >> (pp + 1)) & 1u;
-					const unsigned q = ((state >> (pp + 2)) << pp) | (state & ((1u << pp) - 1u));
-					const unsigned bit = ((l ? dd [u]. y : dd [u]. x) >> (16u * h + q)) & 1u;
-					state = (state >> 1) | (bit << 5);
-					acc |= bit << (31 - u);
-				}
-				w [wd] = acc;
+			for (int u = 0; u < 32; u ++) {
+				const int i = 32 * wi + 31 - u;
+				if (i >= top) continue;
+				const int t = i + 6;                            // decision of step i+6 = information bit i
+				const uint2 dd = dq [wi & 1][u][tid];
+				// word = lane bit (state bit pp+1), bit = 16 half + state without bits pp, pp+1
+				const int pp = (t & 3) + 1;
+				const unsigned h = (state >> pp) & 1u, l = (state >> (pp + 1)) & 1u;
+				const unsigned q = ((state >> (pp + 2)) << pp) | (state & ((1u << pp) - 1u));
+				const unsigned bit = ((l ? dd. y : dd. x) >> (16u * h + q)) & 1u;
+				state = (state >> 1) | (bit << 5);
+				acc |= bit << (31 - u);
 			}
+			w [wd] = acc;
 		}
 		__syncthreads ();
 #pragma unroll
@@ -290,15 +301,18 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 
 int vit_simd_cw_per_cta () { return VS_CW; }
 
-cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas, int total_ctas2) {
+cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas, int total_ctas2, bool convert) {
 	if (njobs <= 0 || total_ctas <= 0) return cudaSuccess;
 	cudaStream_t st = h -> vst ();
-	{ ProfScope prof (h, KC_VITERBI_SYM, st);
-	  vit_sym8_kernel<<<dim3 (296, njobs), 256, 0, st>>> (d_jobs); }
+	if (convert) {
+		ProfScope prof (h, KC_VITERBI_SYM, st);
+		vit_sym8_kernel<<<dim3 (296, njobs), 256, 0, st>>> (d_jobs);
+		h -> launches ++;
+	}
 	{ ProfScope prof (h, KC_VITERBI_MSC, st);
 	  vit_simd_forward<<<total_ctas2, VS_THREADS, 0, st>>> (d_jobs, njobs); }
 	{ ProfScope prof (h, KC_VITERBI_TB, st);
 	  vit_simd_traceback<<<total_ctas, TB_THREADS, 0, st>>> (d_jobs, njobs); }
-	h -> launches += 3;
+	h -> launches += 2;
 	return cudaGetLastError ();
 }

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 pkg = importlib.import_module("sdr-j-dab_b200")
 for path in (1, 2, 3):
-    eng = pkg.DabGpu(mode=1, viterbi_path=min(path, 2), simd_single_lane=(path == 3))
+    eng = pkg.DabGpu(mode=1, viterbi_path=min(path, 2))
     for frameBits, nblocks in ((3072, 4096), (3072, 36864), (768, 4096)):
         soft = torch.randint(-127, 128, (nblocks, 4 * (frameBits + 6)), dtype=torch.int16, device="cuda")
         out = torch.empty((nblocks, frameBits), dtype=torch.uint8, device="cuda")
