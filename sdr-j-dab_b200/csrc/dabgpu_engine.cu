@@ -236,7 +236,7 @@ __global__ void __launch_bounds__ (OFDM_THREADS) symbol_kernel (SampleWin w, Ofd
 //     (viterbi.cpp:229-235) as 16-bit stores.
 // ---------------------------------------------------------------------------------------------------
 #define R8_RAW 5152                                                        // bytes per raw buffer: 2 T_s + alignment slack, multiple of 16
-#define R8_DYN_SMEM ((2 * R8_SMEM + 512) * (int) sizeof (float2) + 2 * R8_RAW)
+#define R8_DYN_SMEM ((2 * R8_SMEM + R8_TW2 + R8_TW3) * (int) sizeof (float2) + 2 * R8_RAW)
 
 __device__ __forceinline__ float2 u8_to_c (uchar2 s) {
 	return make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f));
@@ -256,8 +256,8 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
                                                           const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc,
                                                           uint8_t *fic8, uint8_t *msc8) {
 	extern __shared__ __align__ (16) unsigned char r8_dyn [];
-	float2 *bufA = reinterpret_cast<float2 *> (r8_dyn), *bufB = bufA + R8_SMEM, *G = bufB + R8_SMEM;
-	unsigned char *raw = reinterpret_cast<unsigned char *> (G + 512);
+	float2 *bufA = reinterpret_cast<float2 *> (r8_dyn), *bufB = bufA + R8_SMEM, *tw2 = bufB + R8_SMEM, *tw3 = tw2 + R8_TW2;
+	unsigned char *raw = reinterpret_cast<unsigned char *> (tw3 + R8_TW3);
 	__shared__ float2 s_fc [8];
 	const int N = R8_N, Ts = T. T_s, Tg = T. T_g, t = threadIdx. x;
 	const int c = blockIdx. x / groups, g = blockIdx. x % groups;
@@ -271,10 +271,15 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 	const long long F = in. P + s;                                         // first sample of the PRS
 	const int lpD = mod_rate ((long long) in. lp - (long long) (s + N) * phA);  // localPhase after the PRS
 	const float2 rot256 = nco (T, mod_rate (- 256ll * phB));               // 256 samples further: phase index - 256 f
-	const int offT = mod_rate ((long long) (t + 1) * phB), offU = mod_rate ((long long) (Tg + t + 1) * phB);
+	// guard samples this thread correlates with its own useful samples 1536 + t and 1792 + t: gs and gs + 256
+	const int gs = t + 1536 - (N - Tg);                                    // = t - 8 (T_u - T_g = 1544); negative: x[6] has no partner
+	const int offT = mod_rate ((long long) (gs + 1) * phB), offU = mod_rate ((long long) (Tg + t + 1) * phB);
 	const int dTs = mod_rate ((long long) Ts * phB);
 	float2 *cur = bufA, *prev = bufB;
-	float2 x [8];
+	float2 x [8], tw1 [6];
+	r8_fill_tables (tw2, tw3, T. tw);
+	r8_load_tw1 (tw1, T. tw);
+	__syncthreads ();
 
 	// raw u8 IQ of symbol l (guard + useful part, T_s samples from `first`) -> raw buffer b; returns the byte offset of
 	// sample 0 inside the buffer.  Fast path: 16-byte cp.async from the 16-byte-aligned address below the first sample.
@@ -313,30 +318,40 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 		float2 ph = nco (T, mod_rate ((long long) lpb - (long long) (t + 1) * phB));
 #pragma unroll
 		for (int k = 0; k < 8; k ++) { x [k] = cmul (u8_to_c (win_fetch (w, first + t + 256 * k)), ph); ph = cmul (ph, rot256); }
-		fft2048_r8 (x, prev, T. tw);
+		fft2048_r8 (x, prev, tw1, tw2, tw3);
 	}
 	float2 acc = make_float2 (0.f, 0.f);
 	const int slot = slot0 + c;
-	int pidx [6];                                                          // this thread's six carriers: the pairs 2t, 2t+1 (+ 512 m)
+	uint32_t pidx [3];                                                     // this thread's six carriers: the pairs 2t, 2t+1 (+ 512 m), packed
 #pragma unroll
-	for (int m = 0; m < 3; m ++) { pidx [2 * m] = __ldg (&T. permpos [2 * t + 512 * m]); pidx [2 * m + 1] = __ldg (&T. permpos [2 * t + 1 + 512 * m]); }
+	for (int m = 0; m < 3; m ++) pidx [m] = (uint32_t) __ldg (&T. permpos [2 * t + 512 * m]) | ((uint32_t) __ldg (&T. permpos [2 * t + 1 + 512 * m]) << 16);
 	int lpb = mod_rate ((long long) lpD - ((long long) (l0 - 1) * Ts) % DAB_INPUT_RATE * phB);   // localPhase before the symbol's first sample
 	const float sc = 1.0f / 128.0f;
+	// the two NCO phasors of a symbol (guard sample gs, useful sample t) are looked up one symbol ahead
+	auto phasors = [&] (int lp, float2 &pg, float2 &pu) {
+		int ig = lp - offT; if (ig < 0) ig += DAB_INPUT_RATE;
+		int iu = lp - offU; if (iu < 0) iu += DAB_INPUT_RATE;
+		pg = nco (T, ig); pu = nco (T, iu);
+		pg. x *= sc; pg. y *= sc; pu. x *= sc; pu. y *= sc;
+	};
+	float2 phg_n, ph_n;
+	phasors (lpb, phg_n, ph_n);
 	for (int l = l0; l < l1; l ++) {
 		const int b = (l - l0) & 1;
 		int off_next = 0;
 		if (l + 1 < l1) off_next = stage (l + 1, b ^ 1); else asm volatile ("cp.async.commit_group;");
+		float2 phg = phg_n, ph = ph_n;
+		lpb -= dTs; if (lpb < 0) lpb += DAB_INPUT_RATE;
+		phasors (lpb, phg_n, ph_n);
 		asm volatile ("cp.async.wait_group 1;" ::: "memory");
 		__syncthreads ();                                                  // raw buffer b complete; last symbol's demod reads done
 		const unsigned short *rs = reinterpret_cast<const unsigned short *> (raw + b * R8_RAW + off_cur);
-		int ig = lpb - offT; if (ig < 0) ig += DAB_INPUT_RATE;             // guard sample t
-		int iu = lpb - offU; if (iu < 0) iu += DAB_INPUT_RATE;             // useful sample t
-		float2 phg = nco (T, ig), ph = nco (T, iu);
-		phg. x *= sc; phg. y *= sc; ph. x *= sc; ph. y *= sc;
+		// guard samples gs and gs + 256 (the ones x[6] and x[7] are correlated with), mixed like every other sample
+		float2 g6 = make_float2 (0.f, 0.f), g7;
 		{
-			const uint32_t g0 = rs [t], g1 = t + 256 < Tg ? rs [t + 256] : 0x8080u;
-			G [t] = cmul (make_float2 (u8_to_f (g0, 0), u8_to_f (g0, 1)), phg);
-			G [t + 256] = cmul (make_float2 (u8_to_f (g1, 0), u8_to_f (g1, 1)), cmul (phg, rot256));
+			const uint32_t r7 = rs [gs + 256];
+			g7 = cmul (make_float2 (u8_to_f (r7, 0), u8_to_f (r7, 1)), cmul (phg, rot256));
+			if (gs >= 0) { const uint32_t r6 = rs [gs]; g6 = cmul (make_float2 (u8_to_f (r6, 0), u8_to_f (r6, 1)), phg); }
 		}
 #pragma unroll
 		for (int k = 0; k < 8; k ++) {
@@ -344,14 +359,10 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 			x [k] = cmul (make_float2 (u8_to_f (v, 0), u8_to_f (v, 1)), ph);
 			ph = cmul (ph, rot256);
 		}
-		__syncthreads ();                                                  // G visible
-		// FreqCorr += x[i] * conj (x[i - T_u]), i in [T_u, T_s): useful element e = i - T_g pairs with guard sample e - (T_u - T_g)
-		{
-			const int e6 = t + 1536 - (N - Tg), e7 = t + 1792 - (N - Tg);
-			if (e6 >= 0) { const float2 r = cmulc (x [6], G [e6]); acc. x += r. x; acc. y += r. y; }
-			{ const float2 r = cmulc (x [7], G [e7]); acc. x += r. x; acc. y += r. y; }
-		}
-		fft2048_r8 (x, cur, T. tw);
+		// FreqCorr += x[i] * conj (x[i - T_u]), i in [T_u, T_s): useful sample e = i - T_g pairs with guard sample e - (T_u - T_g)
+		if (gs >= 0) { const float2 r = cmulc (x [6], g6); acc. x += r. x; acc. y += r. y; }
+		{ const float2 r = cmulc (x [7], g7); acc. x += r. x; acc. y += r. y; }
+		fft2048_r8 (x, cur, tw1, tw2, tw3);
 		size_t o;
 		if (l < 4) o = ((size_t) slot * 3 + (l - 1)) * 2 * T. K;
 		else {
@@ -366,7 +377,7 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 			int re [2], im [2];
 #pragma unroll
 			for (int q = 0; q < 2; q ++) {
-				const int idx = pidx [2 * m + q];
+				const int idx = (int) (q ? pidx [m] >> 16 : pidx [m] & 0xffffu);
 				const float2 r1 = cmulc (cur [idx], prev [idx]);
 				const float ab1 = fabsf (r1. x) + fabsf (r1. y);
 				re [q] = quant127_fast (r1. x, ab1); im [q] = quant127_fast (r1. y, ab1);
@@ -378,7 +389,6 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 		}
 		float2 *tmp = cur; cur = prev; prev = tmp;
 		off_cur = off_next;
-		lpb -= dTs; if (lpb < 0) lpb += DAB_INPUT_RATE;
 	}
 	for (int o = 16; o > 0; o >>= 1) {
 		acc. x += __shfl_xor_sync (0xffffffffu, acc. x, o);

@@ -167,10 +167,14 @@ __global__ void __launch_bounds__ (OFDM_THREADS) fft_kernel (float2 *v, OfdmTabl
 	float2 *g = v + (size_t) blockIdx. x * N;
 	const float factor = (float) (1.0 / (float) N);
 	if (N == R8_N) {                                     // the register FFT of the Mode I symbol kernel
-		float2 x [8];
+		float2 x [8], tw1 [6];
+		float2 *tw2 = sm + R8_SMEM, *tw3 = tw2 + R8_TW2;
+		r8_fill_tables (tw2, tw3, T. tw);
+		r8_load_tw1 (tw1, T. tw);
 #pragma unroll
 		for (int k = 0; k < 8; k ++) { x [k] = g [threadIdx. x + 256 * k]; if (inverse) x [k]. y = - x [k]. y; }
-		fft2048_r8 (x, sm, T. tw);
+		__syncthreads ();
+		fft2048_r8 (x, sm, tw1, tw2, tw3);
 		for (int k = threadIdx. x; k < N; k += OFDM_THREADS) {
 			float2 r = sm [r8_pad (r8_pos (k))];
 			if (inverse) r = make_float2 (r. x * factor, (- r. y) * factor);

@@ -272,8 +272,24 @@ __device__ __forceinline__ void dft8 (float2 (&a) [8]) {
 	dft4 (b4, b5, b6, b7, a [1], a [3], a [5], a [7]);
 }
 
-// x[k] = sample t + 256 k on entry; A = R8_SMEM float2 of shared memory; tw = exp (-2 pi i j / 2048) table
-__device__ __forceinline__ void fft2048_r8 (float2 (&x) [8], float2 *A, const float2 *__restrict__ tw) {
+// x[k] = sample t + 256 k on entry; A = R8_SMEM float2 of shared memory.  Twiddles: tw1[2 g + ...] = the thread's own six
+// stage-1 factors W_2048^(n q), n = t + 256 g, q = 1..3 (registers, loaded once per CTA by r8_load_tw1); tw2[j] = W_512^j
+// (512 entries) and tw3[j] = W_64^j (64 entries) in shared memory (r8_fill_tables) -- with most of the SM's on-chip
+// memory carved out as shared memory the L1 is too small to keep a global twiddle table resident.
+#define R8_TW2 512
+#define R8_TW3 64
+__device__ __forceinline__ void r8_fill_tables (float2 *tw2, float2 *tw3, const float2 *__restrict__ tw) {
+	for (int j = threadIdx. x; j < R8_TW2; j += 256) tw2 [j] = __ldg (&tw [4 * j]);
+	if (threadIdx. x < R8_TW3) tw3 [threadIdx. x] = __ldg (&tw [32 * threadIdx. x]);
+}
+__device__ __forceinline__ void r8_load_tw1 (float2 (&tw1) [6], const float2 *__restrict__ tw) {
+#pragma unroll
+	for (int g = 0; g < 2; g ++)
+#pragma unroll
+		for (int q = 1; q < 4; q ++) tw1 [3 * g + q - 1] = __ldg (&tw [(((int) threadIdx. x + 256 * g) * q) & 2047]);
+}
+
+__device__ __forceinline__ void fft2048_r8 (float2 (&x) [8], float2 *A, const float2 (&tw1) [6], const float2 *tw2, const float2 *tw3) {
 	const int t = threadIdx. x;
 	// stage 1: two radix-4 butterflies, n = t (k even) and n = t + 256 (k odd); twiddle W_2048^(n q)
 	{
@@ -284,11 +300,11 @@ __device__ __forceinline__ void fft2048_r8 (float2 (&x) [8], float2 *A, const fl
 			dft4 (x [g], x [g + 2], x [g + 4], x [g + 6], y [0], y [1], y [2], y [3]);
 			A [r8_pad (n)] = y [0];
 #pragma unroll
-			for (int q = 1; q < 4; q ++) A [r8_pad (n + 512 * q)] = cmul (y [q], __ldg (&tw [(n * q) & 2047]));
+			for (int q = 1; q < 4; q ++) A [r8_pad (n + 512 * q)] = cmul (y [q], tw1 [3 * g + q - 1]);
 		}
 	}
 	__syncthreads ();
-	// stage 2: radix 8 inside blocks of 512: n = t & 63, twiddle W_512^(n q) = W_2048^(4 n q)
+	// stage 2: radix 8 inside blocks of 512: n = t & 63, twiddle W_512^(n q)
 	{
 		const int b = t >> 6, n = t & 63, base = 512 * b + n;
 		float2 a [8];
@@ -297,10 +313,10 @@ __device__ __forceinline__ void fft2048_r8 (float2 (&x) [8], float2 *A, const fl
 		dft8 (a);
 		A [r8_pad (base)] = a [0];
 #pragma unroll
-		for (int q = 1; q < 8; q ++) A [r8_pad (base + 64 * q)] = cmul (a [q], __ldg (&tw [(4 * n * q) & 2047]));
+		for (int q = 1; q < 8; q ++) A [r8_pad (base + 64 * q)] = cmul (a [q], tw2 [(n * q) & 511]);
 	}
 	__syncthreads ();
-	// stage 3: radix 8 inside blocks of 64: n = t & 7, twiddle W_64^(n q) = W_2048^(32 n q)
+	// stage 3: radix 8 inside blocks of 64: n = t & 7, twiddle W_64^(n q)
 	{
 		const int b = t >> 3, n = t & 7, base = 64 * b + n;
 		float2 a [8];
@@ -309,7 +325,7 @@ __device__ __forceinline__ void fft2048_r8 (float2 (&x) [8], float2 *A, const fl
 		dft8 (a);
 		A [r8_pad (base)] = a [0];
 #pragma unroll
-		for (int q = 1; q < 8; q ++) A [r8_pad (base + 8 * q)] = cmul (a [q], __ldg (&tw [(32 * n * q) & 2047]));
+		for (int q = 1; q < 8; q ++) A [r8_pad (base + 8 * q)] = cmul (a [q], tw3 [n * q]);
 	}
 	__syncthreads ();
 	// stage 4: radix 8 on 8 consecutive points, no twiddles
