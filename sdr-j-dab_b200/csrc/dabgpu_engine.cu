@@ -255,7 +255,7 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
                                                           int blocksPerCIF, int cifsPerFrame, const FrameOut *fo,
                                                           const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc,
                                                           uint8_t *fic8, uint8_t *msc8) {
-	extern __shared__ __align__ (16) unsigned char r8_dyn [];
+	extern __shared__ __align__ (1024) unsigned char r8_dyn [];     // the FFT buffers must be 512-byte aligned (fft2048_r8)
 	float2 *bufA = reinterpret_cast<float2 *> (r8_dyn), *bufB = bufA + R8_SMEM, *tw2 = bufB + R8_SMEM, *tw3 = tw2 + R8_TW2;
 	unsigned char *raw = reinterpret_cast<unsigned char *> (tw3 + R8_TW3);
 	__shared__ float2 s_fc [8];
@@ -277,6 +277,7 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 	const int dTs = mod_rate ((long long) Ts * phB);
 	float2 *cur = bufA, *prev = bufB;
 	float2 x [8], tw1 [6];
+	if (((uint32_t) __cvta_generic_to_shared (bufA) & 511u) != 0) __trap ();   // layout contract of fft2048_r8
 	r8_fill_tables (tw2, tw3, T. tw);
 	r8_load_tw1 (tw1, T. tw);
 	__syncthreads ();
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 	int off_cur = stage (l0, 0);
 	if (l0 == 1) {
 		const float2 *p0 = spec0 + (size_t) c * N;
-		for (int k = t; k < N; k += 256) prev [r8_pad (r8_pos (k))] = p0 [k];
+		for (int k = t; k < N; k += 256) prev [r8_swz (r8_pos (k))] = p0 [k];
 	} else {                                                               // spectrum of symbol l0-1 as reference
 		const long long first = F + N + (long long) (l0 - 2) * Ts + Tg;
 		const int lpb = mod_rate ((long long) lpD - ((long long) (l0 - 2) * Ts + Tg) % DAB_INPUT_RATE * phB);
@@ -332,7 +333,6 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 		int ig = lp - offT; if (ig < 0) ig += DAB_INPUT_RATE;
 		int iu = lp - offU; if (iu < 0) iu += DAB_INPUT_RATE;
 		pg = nco (T, ig); pu = nco (T, iu);
-		pg. x *= sc; pg. y *= sc; pu. x *= sc; pu. y *= sc;
 	};
 	float2 phg_n, ph_n;
 	phasors (lpb, phg_n, ph_n);
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 		const int b = (l - l0) & 1;
 		int off_next = 0;
 		if (l + 1 < l1) off_next = stage (l + 1, b ^ 1); else asm volatile ("cp.async.commit_group;");
-		float2 phg = phg_n, ph = ph_n;
+		float2 phg = make_float2 (phg_n. x * sc, phg_n. y * sc), ph = make_float2 (ph_n. x * sc, ph_n. y * sc);
 		lpb -= dTs; if (lpb < 0) lpb += DAB_INPUT_RATE;
 		phasors (lpb, phg_n, ph_n);
 		asm volatile ("cp.async.wait_group 1;" ::: "memory");

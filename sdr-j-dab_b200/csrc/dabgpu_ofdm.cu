@@ -95,7 +95,7 @@ int ofdm_tables_init (dabgpu *h, OfdmTables *T) {
 	T -> permpos = nullptr;
 	if (N == R8_N) {
 		std::vector<uint16_t> pp (p. K);
-		for (int i = 0; i < p. K; i ++) pp [i] = (uint16_t) r8_pad (r8_pos (perm [i]));
+		for (int i = 0; i < p. K; i ++) pp [i] = (uint16_t) r8_swz (r8_pos (perm [i]));
 		if ((rc = dab_device_table (h, base + 7, pp. data (), p. K * sizeof (uint16_t), &d))) return rc;
 		T -> permpos = (const uint16_t *) d;
 	}
@@ -162,7 +162,7 @@ extern "C" int dabgpu_host_prbs (int32_t nbits, uint8_t *out) {
 // per-call kernels (float input, as the reference's class interfaces take it)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__ (OFDM_THREADS) fft_kernel (float2 *v, OfdmTables T, int inverse) {
-	extern __shared__ float2 sm [];
+	extern __shared__ __align__ (1024) float2 sm [];                   // 512-byte alignment: fft2048_r8
 	const int N = T. T_u;
 	float2 *g = v + (size_t) blockIdx. x * N;
 	const float factor = (float) (1.0 / (float) N);
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__ (OFDM_THREADS) fft_kernel (float2 *v, OfdmTabl
 		__syncthreads ();
 		fft2048_r8 (x, sm, tw1, tw2, tw3);
 		for (int k = threadIdx. x; k < N; k += OFDM_THREADS) {
-			float2 r = sm [r8_pad (r8_pos (k))];
+			float2 r = sm [r8_swz (r8_pos (k))];
 			if (inverse) r = make_float2 (r. x * factor, (- r. y) * factor);
 			g [k] = r;
 		}

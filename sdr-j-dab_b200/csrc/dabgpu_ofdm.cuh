@@ -242,11 +242,16 @@ static __device__ int coarse_offset_warp0 (const float2 *f, const OfdmTables &T,
 // Thread t enters with x[t + 256 k], k = 0..7 (so the first butterflies need no shared memory at all).
 // The result is left in shared memory in digit-reversed order: X[k] sits at r8_pos (k) = 512 (k & 3) +
 // 64 ((k >> 2) & 7) + 8 ((k >> 5) & 7) + (k >> 8); consumers index through that map (the demodulator's carrier
-// table is pre-permuted on the host), so no reordering pass exists.  Shared index i is padded to i + (i >> 3).
+// table is pre-permuted on the host), so no reordering pass exists.
+// Shared-memory layout: element i lives at r8_swz (i) = i ^ h, h = (i4 i5 i6) into bits 0..2 and i6 again into
+// bit 3 (iN = bit N of i).  With 8-byte elements a half-warp is conflict-free iff its 16 addresses differ in bits
+// 0..3; this XOR makes that true for all four access patterns of the transform (16 consecutive elements; two runs
+// of 8, 64 apart; stride 8) and, unlike padding, keeps every address of a thread of the form `base ^ constant`
+// or `base + constant`, so the per-symbol address arithmetic all but disappears.
 // ---------------------------------------------------------------------------------------------------
 #define R8_N      2048
-#define R8_SMEM   (R8_N + R8_N / 8)            // float2 elements
-__host__ __device__ __forceinline__ int r8_pad (int i) { return i + (i >> 3); }
+#define R8_SMEM   R8_N                         // float2 elements
+__host__ __device__ __forceinline__ int r8_swz (int i) { return i ^ (((i >> 4) & 7) | (((i >> 6) & 1) << 3)); }
 __host__ __device__ __forceinline__ int r8_pos (int k) { return 512 * (k & 3) + 64 * ((k >> 2) & 7) + 8 * ((k >> 5) & 7) + (k >> 8); }
 
 __device__ __forceinline__ float2 cadd (float2 a, float2 b) { return make_float2 (a. x + b. x, a. y + b. y); }
@@ -289,53 +294,74 @@ __device__ __forceinline__ void r8_load_tw1 (float2 (&tw1) [6], const float2 *__
 		for (int q = 1; q < 4; q ++) tw1 [3 * g + q - 1] = __ldg (&tw [(((int) threadIdx. x + 256 * g) * q) & 2047]);
 }
 
+__device__ __forceinline__ float2 r8_lds (uint32_t a) {
+	float2 v;
+	asm volatile ("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f" (v. x), "=f" (v. y) : "r" (a));
+	return v;
+}
+__device__ __forceinline__ void r8_sts (uint32_t a, float2 v) {
+	asm volatile ("st.shared.v2.f32 [%0], {%1, %2};" :: "r" (a), "f" (v. x), "f" (v. y) : "memory");
+}
+
 __device__ __forceinline__ void fft2048_r8 (float2 (&x) [8], float2 *A, const float2 (&tw1) [6], const float2 *tw2, const float2 *tw3) {
 	const int t = threadIdx. x;
-	// stage 1: two radix-4 butterflies, n = t (k even) and n = t + 256 (k odd); twiddle W_2048^(n q)
+	// 32-bit shared-window addresses throughout.  A must be 512-byte aligned: the thread bases below already contain
+	// A's address, and the per-element constants are XORed into address bits 3..8
+	const uint32_t Ab = (uint32_t) __cvta_generic_to_shared (A);
+#define R8_LD(addr)      r8_lds ((uint32_t) (addr))
+#define R8_ST(addr, v)   r8_sts ((uint32_t) (addr), (v))
+	// stage 1: two radix-4 butterflies, n = t (k even) and n = t + 256 (k odd); twiddle W_2048^(n q).
+	// element t + 256 g + 512 q: the swizzle only sees bits of t
 	{
+		const uint32_t base = Ab + r8_swz (t) * 8;
 		float2 y [4];
 #pragma unroll
 		for (int g = 0; g < 2; g ++) {
-			const int n = t + 256 * g;
 			dft4 (x [g], x [g + 2], x [g + 4], x [g + 6], y [0], y [1], y [2], y [3]);
-			A [r8_pad (n)] = y [0];
+			R8_ST (base + 8 * (256 * g), y [0]);
 #pragma unroll
-			for (int q = 1; q < 4; q ++) A [r8_pad (n + 512 * q)] = cmul (y [q], tw1 [3 * g + q - 1]);
+			for (int q = 1; q < 4; q ++) R8_ST (base + 8 * (256 * g + 512 * q), cmul (y [q], tw1 [3 * g + q - 1]));
 		}
 	}
 	__syncthreads ();
-	// stage 2: radix 8 inside blocks of 512: n = t & 63, twiddle W_512^(n q)
+	// stage 2: radix 8 inside blocks of 512: n = t & 63, twiddle W_512^(n q).  element 512 b + n + 64 m: bit 6 = m & 1
 	{
-		const int b = t >> 6, n = t & 63, base = 512 * b + n;
+		const int n = t & 63;
+		const uint32_t be = Ab + r8_swz (512 * (t >> 6) + n) * 8, bo = be ^ (0xC * 8);
 		float2 a [8];
 #pragma unroll
-		for (int m = 0; m < 8; m ++) a [m] = A [r8_pad (base + 64 * m)];
+		for (int m = 0; m < 8; m ++) a [m] = R8_LD (((m & 1) ? bo : be) + 8 * 64 * m);
 		dft8 (a);
-		A [r8_pad (base)] = a [0];
+		R8_ST (be, a [0]);
 #pragma unroll
-		for (int q = 1; q < 8; q ++) A [r8_pad (base + 64 * q)] = cmul (a [q], tw2 [(n * q) & 511]);
+		for (int q = 1; q < 8; q ++) R8_ST (((q & 1) ? bo : be) + 8 * 64 * q, cmul (a [q], tw2 [(n * q) & 511]));
 	}
 	__syncthreads ();
-	// stage 3: radix 8 inside blocks of 64: n = t & 7, twiddle W_64^(n q)
+	// stage 3: radix 8 inside blocks of 64: n = t & 7, twiddle W_64^(n q).  element 64 b + n + 8 m: bits 3 | 4,5 = m,
+	// bit 6 = b & 1, so the address is base ^ K(m) with K(m) = 8 ((m >> 1) & 3) + 64 (m & 1) + 128 (m >> 1)
 	{
-		const int b = t >> 3, n = t & 7, base = 64 * b + n;
+		const int n = t & 7, bb = t >> 3;
+		const uint32_t base = Ab + ((512 * bb + 8 * (n ^ (4 * (bb & 1)))) ^ (64 * (bb & 1)));
 		float2 a [8];
 #pragma unroll
-		for (int m = 0; m < 8; m ++) a [m] = A [r8_pad (base + 8 * m)];
+		for (int m = 0; m < 8; m ++) a [m] = R8_LD (base ^ (8 * ((m >> 1) & 3) + 64 * (m & 1) + 128 * (m >> 1)));
 		dft8 (a);
-		A [r8_pad (base)] = a [0];
+		R8_ST (base, a [0]);
 #pragma unroll
-		for (int q = 1; q < 8; q ++) A [r8_pad (base + 8 * q)] = cmul (a [q], tw3 [n * q]);
+		for (int q = 1; q < 8; q ++) R8_ST (base ^ (8 * ((q >> 1) & 3) + 64 * (q & 1) + 128 * (q >> 1)), cmul (a [q], tw3 [n * q]));
 	}
 	__syncthreads ();
-	// stage 4: radix 8 on 8 consecutive points, no twiddles
+	// stage 4: radix 8 on 8 consecutive points, no twiddles.  element 8 t + m: address = base ^ 8 m
 	{
+		const uint32_t base = Ab + r8_swz (8 * t) * 8;
 		float2 a [8];
 #pragma unroll
-		for (int m = 0; m < 8; m ++) a [m] = A [r8_pad (8 * t + m)];
+		for (int m = 0; m < 8; m ++) a [m] = R8_LD (base ^ (8 * m));
 		dft8 (a);
 #pragma unroll
-		for (int q = 0; q < 8; q ++) A [r8_pad (8 * t + q)] = a [q];
+		for (int q = 0; q < 8; q ++) R8_ST (base ^ (8 * q), a [q]);
 	}
 	__syncthreads ();
+#undef R8_LD
+#undef R8_ST
 }
