@@ -126,7 +126,7 @@ void prot_build_gather (ProtProfile *pp) {
 		if (pp -> lut [m] != 0xFFFF) first [m / (4 * VS_CHUNK)] = pp -> lut [m];
 	for (int k = nchunks - 1; k >= 0; k --) if (first [k] > first [k + 1]) first [k] = first [k + 1];
 	pp -> chunk. assign (2 * nchunks, 0);
-	for (int d = 0; d < 2; d ++) pp -> gather [d]. assign ((size_t) 4 * nchunks * VS_CHUNK + 4, 0);      // + one entry: the kernel prefetches one step ahead
+	for (int d = 0; d < 2; d ++) pp -> gather [d]. assign ((size_t) 4 * nchunks * VS_CHUNK + 8, 0);      // + two entries: the kernel's table prefetch runs two steps ahead
 	for (int k = 0; k < nchunks; k ++) {
 		const int a = first [k] & ~7, g = (first [k + 1] - a + 7) / 8;
 		pp -> chunk [2 * k] = a; pp -> chunk [2 * k + 1] = first [k + 1] > first [k] ? g : 0;

@@ -182,22 +182,23 @@ __global__ void __launch_bounds__ (VS_THREADS, 10) vit_simd_forward (const VitSi
 		const uint8_t *my = tile + (k & 1) * VS_TILE + cl * VS_PITCH;
 		const uint4 *ga = j. gather + VS_CHUNK * k;
 		uint32_t *d = dec + (size_t) (VS_CHUNK * k) * dstride;
-		// the symbols of the next step are gathered while the current one is processed
+		// two-deep software pipeline: while step s is processed, the symbols of step s + 1 are read from the tile and the
+		// gather entry of step s + 2 is on its way from the table
 		uint32_t sa, sb, sc;
-		{ const uint4 e = __ldg (&ga [0]); sa = (uint32_t) my [e. x] + my [e. w]; sb = my [e. y]; sc = my [e. z]; }
+		uint4 en;
+		{ const uint4 e = __ldg (&ga [0]); sa = (uint32_t) my [e. x] + my [e. w]; sb = my [e. y]; sc = my [e. z]; en = __ldg (&ga [1]); }
 #pragma unroll 1
 		for (int u = 0; u < VS_CHUNK / 4; u ++) {
 			uint32_t d0, d1, d2, d3, na, nb, nc;
-#define VS_NEXT(i) { const uint4 e = __ldg (&ga [i]); na = (uint32_t) my [e. x] + my [e. w]; nb = my [e. y]; nc = my [e. z]; }
-			VS_NEXT (4 * u + 1); vs_step<0> (R, Q, sa, sb, sc, lm, d0, j. one);
-			sa = na; sb = nb; sc = nc;
-			VS_NEXT (4 * u + 2); vs_step<1> (Q, R, sa, sb, sc, lm, d1, j. one);
-			sa = na; sb = nb; sc = nc;
-			VS_NEXT (4 * u + 3); vs_step<2> (R, Q, sa, sb, sc, lm, d2, j. one);
-			sa = na; sb = nb; sc = nc;
-			VS_NEXT (4 * u + 4); vs_step<3> (Q, R, sa, sb, sc, lm, d3, j. one);      // (one entry past the chunk is read, not used)
-			sa = na; sb = nb; sc = nc;
+			uint4 enn;
+#define VS_NEXT(i) enn = __ldg (&ga [(i) + 1]); na = (uint32_t) my [en. x] + my [en. w]; nb = my [en. y]; nc = my [en. z];
+#define VS_ROLL    sa = na; sb = nb; sc = nc; en = enn;
+			VS_NEXT (4 * u + 1); vs_step<0> (R, Q, sa, sb, sc, lm, d0, j. one); VS_ROLL
+			VS_NEXT (4 * u + 2); vs_step<1> (Q, R, sa, sb, sc, lm, d1, j. one); VS_ROLL
+			VS_NEXT (4 * u + 3); vs_step<2> (R, Q, sa, sb, sc, lm, d2, j. one); VS_ROLL
+			VS_NEXT (4 * u + 4); vs_step<3> (Q, R, sa, sb, sc, lm, d3, j. one); VS_ROLL     // (up to two entries past the chunk are read, not used)
 #undef VS_NEXT
+#undef VS_ROLL
 			vs_fixup (R, Q, lm);
 #pragma unroll
 			for (int q = 0; q < 16; q ++) R [q] = Q [q];
@@ -281,19 +282,35 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 #pragma unroll
 		for (int q = 0; q < 4; q ++) bits [tid * 5 + q] = w [q];
 		__syncthreads ();
-		// cooperative write-out: a warp writes the 128 bits of one code word as 128 bytes
+		// cooperative write-out, one bit per byte (viterbi.cpp:240-241) with the dispersal sequence applied
+		// (dab-concurrent.cpp:183-190).  Fast path: 8 lanes x 16 bytes cover the 128 bits of a code word, a warp does four
+		// code words per pass; 4 bits -> 4 bytes is one multiply and one mask.
 		const int ncw_here = min (TB_THREADS, j. ncw - c0);
-		for (int c = warp; c < ncw_here; c += TB_THREADS / 32) {
-			const int i = base + 4 * lane;
-			if (i < top) {
-				uint32_t v = bits [c * 5 + (lane >> 3)];
-				if (j. prbs) v ^= __ldg (&j. prbs [i >> 5]);
-				v >>= (i & 31);
-				uint8_t *o = j. out + (size_t) (c0 + c) * j. frameBits + i;
-				if (i + 4 <= top && (j. frameBits & 3) == 0)
-					*reinterpret_cast<uchar4 *> (o) = make_uchar4 (v & 1, (v >> 1) & 1, (v >> 2) & 1, (v >> 3) & 1);
-				else
-					for (int b = 0; b < 4 && i + b < top; b ++) o [b] = (v >> b) & 1;
+		if ((j. frameBits & 15) == 0 && (reinterpret_cast<size_t> (j. out) & 15) == 0) {
+			const int sub = lane & 7, i = base + 16 * sub;
+			uint32_t pr = 0;
+			if (j. prbs && i < top) pr = (__ldg (&j. prbs [i >> 5]) >> (i & 31)) & 0xffffu;
+			for (int c = 4 * warp + (lane >> 3); c < ncw_here; c += 4 * (TB_THREADS / 32)) {
+				if (i >= top) continue;
+				const uint32_t v = ((bits [c * 5 + (sub >> 1)] >> (16 * (sub & 1))) & 0xffffu) ^ pr;
+				uint4 o;
+				o. x = ((v & 15u) * 0x00204081u) & 0x01010101u;         o. y = (((v >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+				o. z = (((v >> 8) & 15u) * 0x00204081u) & 0x01010101u;  o. w = (((v >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+				*reinterpret_cast<uint4 *> (j. out + (size_t) (c0 + c) * j. frameBits + i) = o;
+			}
+		} else {
+			for (int c = warp; c < ncw_here; c += TB_THREADS / 32) {
+				const int i = base + 4 * lane;
+				if (i < top) {
+					uint32_t v = bits [c * 5 + (lane >> 3)];
+					if (j. prbs) v ^= __ldg (&j. prbs [i >> 5]);
+					v >>= (i & 31);
+					uint8_t *o = j. out + (size_t) (c0 + c) * j. frameBits + i;
+					if (i + 4 <= top && (j. frameBits & 3) == 0)
+						*reinterpret_cast<uchar4 *> (o) = make_uchar4 (v & 1, (v >> 1) & 1, (v >> 2) & 1, (v >> 3) & 1);
+					else
+						for (int b = 0; b < 4 && i + b < top; b ++) o [b] = (v >> b) & 1;
+				}
 			}
 		}
 	}
