@@ -186,6 +186,15 @@ int dabgpu_state_set (dabgpu_t *h, const dabgpu_stream_state *s);
 int dabgpu_state_export (dabgpu_t *h, void *buf, size_t capacity, size_t *used);
 int dabgpu_state_import (dabgpu_t *h, const void *buf, size_t n);
 
+/* The tracking state `nframes` frames further on for a LOCKED receiver, in closed form (host only, no GPU): every frame
+ * is T_F samples long (findIndex returns T_g), the coarse search is off and the correctors do not move, so
+ * abs_pos advances by nframes * T_F and localPhase by -(nframes * T_F) * (coarse + fine) mod 2048000
+ * (ofdm-processor.cpp:217-226, 344-474 in the steady state).  This is what lets the shards of ONE recording start
+ * in parallel on several GPUs: each shard assumes the predicted state, the assumption is verified afterwards
+ * against the previous shard's true final state (sdr-j-dab_b200/parallel.py: decode_sharded).
+ * Returns DABGPU_ERR_STATE when `in` is not a locked state (synced == 0 or coarse search still on). */
+int dabgpu_host_state_predict (int32_t mode, const dabgpu_stream_state *in, int64_t nframes, dabgpu_stream_state *out);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-only helpers (no GPU needed): the constant tables the engine derives on the host, exported so the
  * CPU test-suite can compare them with the oracle.

@@ -86,6 +86,7 @@ def load_library():
     L.dabgpu_reset.argtypes = [C.c_void_p]
     L.dabgpu_state_get.argtypes = [C.c_void_p, C.POINTER(StreamState)]
     L.dabgpu_state_set.argtypes = [C.c_void_p, C.POINTER(StreamState)]
+    L.dabgpu_host_state_predict.argtypes = [C.c_int32, C.POINTER(StreamState), C.c_int64, C.POINTER(StreamState)]
     L.dabgpu_state_export.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.dabgpu_state_import.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     _lib = L
@@ -95,6 +96,14 @@ def load_library():
 MODE_PARAMS = {  # L, K, T_null, T_F, T_s, T_u, cifsPerFrame (gui.cpp:1328-1372, msc-handler.cpp:61-71)
     1: (76, 1536, 2656, 196608, 2552, 2048, 4), 2: (76, 384, 664, 49152, 638, 512, 1),
     3: (153, 192, 345, 49152, 319, 256, 0), 4: (76, 768, 1328, 98304, 1276, 1024, 2)}
+
+
+def state_predict(mode, s, nframes):
+    out = StreamState()
+    rc = load_library().dabgpu_host_state_predict(mode, C.byref(s), int(nframes), C.byref(out))
+    if rc != 0:
+        raise DabGpuError("dabgpu_host_state_predict failed (%d): not a locked state?" % rc)
+    return out
 
 
 class DecodeOut:
@@ -281,6 +290,45 @@ class DabGpu:
     def reset(self):
         self._check(self.lib.dabgpu_reset(self.h))
 
+    # ---- geometry and result helpers used by parallel.decode_sharded
+    @property
+    def frame_len(self):
+        return MODE_PARAMS[self.mode][3]
+
+    @property
+    def cifs_per_frame(self):
+        return MODE_PARAMS[self.mode][6]
+
+    @property
+    def frame_need(self):
+        """samples a frame needs from its SyncOnPhase window start on, worst case (ofdm-processor.cpp:344-442)"""
+        L, _, T_null, _, T_s, T_u, _ = MODE_PARAMS[self.mode]
+        return 2 * T_u + (L - 1) * T_s + T_null
+
+    @staticmethod
+    def make_state(**kw):
+        return StreamState(**kw)
+
+    def drop_frames(self, r, n):
+        """the result without its first n frames (MSC blocks are not touched: a fresh engine's warm-up already swallowed them)"""
+        _, K, _, _, _, _, _ = MODE_PARAMS[self.mode]
+        g = 3 * 2 * K // 2304
+        o = DecodeOut()
+        n = min(n, r.nframes)
+        o.nframes, o.consumed, o.info = r.nframes - n, r.consumed, r.info[n:]
+        o.soft = r.soft[n:] if r.soft is not None else None
+        o.fic_bits, o.fic_crc, o.msc = r.fic_bits[n * g:], r.fic_crc[n * g:], r.msc
+        return o
+
+    @staticmethod
+    def concat_results(a, b):
+        o = DecodeOut()
+        o.nframes, o.consumed, o.info = a.nframes + b.nframes, a.consumed + b.consumed, list(a.info) + list(b.info)
+        o.soft = np.concatenate([a.soft, b.soft]) if a.soft is not None and b.soft is not None else None
+        o.fic_bits, o.fic_crc = np.concatenate([a.fic_bits, b.fic_bits]), np.concatenate([a.fic_crc, b.fic_crc])
+        o.msc = [np.concatenate([x, y]) for x, y in zip(a.msc, b.msc)]
+        return o
+
     def state_get(self):
         s = StreamState()
         self._check(self.lib.dabgpu_state_get(self.h, C.byref(s)))
@@ -288,6 +336,10 @@ class DabGpu:
 
     def state_set(self, s):
         self._check(self.lib.dabgpu_state_set(self.h, C.byref(s)))
+
+    def state_predict(self, s, nframes):
+        """closed-form tracking state `nframes` frames after the locked state s (dabgpu_host_state_predict)"""
+        return state_predict(self.mode, s, nframes)
 
     def export_state(self):
         """-> uint8 ndarray: the whole stream state (sync, sample tail, de-interleaver halo)"""

@@ -638,6 +638,23 @@ extern "C" int dabgpu_state_set (dabgpu_t *h, const dabgpu_stream_state *s) {
 	return DABGPU_OK;
 }
 
+extern "C" int dabgpu_host_state_predict (int32_t mode, const dabgpu_stream_state *in, int64_t nframes, dabgpu_stream_state *out) {
+	DabParams p;
+	if (!in || !out || nframes < 0 || dab_mode_params (mode, &p)) return DABGPU_ERR_ARG;
+	if (!in -> synced || in -> f2Correction) return DABGPU_ERR_STATE;
+	*out = *in;
+	long long phi = ((long long) in -> coarse + in -> fine) % DAB_INPUT_RATE;
+	if (phi < 0) phi += DAB_INPUT_RATE;
+	const long long adv = (long long) ((__int128) nframes * p. T_F % DAB_INPUT_RATE);
+	long long lp = ((long long) in -> localPhase - adv * phi % DAB_INPUT_RATE) % DAB_INPUT_RATE;
+	if (lp < 0) lp += DAB_INPUT_RATE;
+	out -> localPhase = (int32_t) lp;
+	out -> abs_pos = in -> abs_pos + nframes * p. T_F;
+	out -> frames = in -> frames + nframes;
+	out -> cifs = in -> cifs + nframes * p. cifsPerFrame;
+	return DABGPU_OK;
+}
+
 static int ensure_frame_capacity (dabgpu *h, long long frames);
 
 // ---- whole stream state as one blob (the multi-GPU hand-over: sync/AFC state + unconsumed samples + the

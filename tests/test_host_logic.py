@@ -96,3 +96,25 @@ def test_prbs(lib, port):
     out = np.zeros(9216, np.uint8)
     assert lib.dabgpu_host_prbs(9216, out.ctypes.data_as(C.POINTER(C.c_uint8))) == 0
     assert np.array_equal(out, port.prbs(9216))
+
+
+def test_state_predict_follows_the_oracle_trajectory(lib, port):
+    """dabgpu_host_state_predict (what parallel.decode_sharded starts its shards from) against the oracle's own
+    frame-by-frame replay of ofdmProcessor::run on a locked Mode II stream: position and NCO phase of frame k + n
+    follow from frame k in closed form."""
+    pkg = engine_pkg()
+    mod = dabmod.Modulator(port, 2, [(0, 64, 1, 0o102)], 5)
+    tr = mod.generate(14, cfo_hz=2.0, snr_db=25.0, lead=700, tail=3000)
+    _, info = port.ofdm_run(2, tr["iq"], 20)
+    assert len(info) >= 12
+    k = 6                                                     # well past the coarse search
+    assert info[k].coarse == info[-1].coarse and info[k].fine == info[-1].fine
+    s = pkg.binding.StreamState(synced=1, coarse=info[k].coarse, fine=info[k].fine, f2Correction=0, previous_1=0, previous_2=0,
+                                localPhase=info[k].phase0, abs_pos=info[k].pos, frames=k, cifs=k)
+    for n in (0, 1, 3, len(info) - 1 - k):
+        p = pkg.binding.state_predict(2, s, n)
+        assert (p.abs_pos, p.localPhase, p.coarse, p.fine) == (info[k + n].pos, info[k + n].phase0, info[k].coarse, info[k].fine)
+        assert (p.frames, p.cifs) == (k + n, k + n)
+    s.f2Correction = 1
+    with pytest.raises(pkg.DabGpuError):
+        pkg.binding.state_predict(2, s, 1)

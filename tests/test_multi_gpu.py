@@ -84,3 +84,58 @@ def test_split_recording_two_gpus_nccl(port):
     for i in range(len(SUB)):
         assert np.array_equal(np.concatenate([got[0][3][i], got[1][3][i]]), want.msc[i])
     one.close()
+
+
+# ---- one recording, shards decoded in parallel from the predicted tracking state (parallel.decode_sharded) ----
+def _sharded_worker(rank, world, port_no, iq, q, backend, lead):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    gpu = rank if backend == "nccl" else 0                    # gloo: all ranks share GPU 0 (the plumbing runs on CPU tensors)
+    torch.cuda.set_device(gpu)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", gpu))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = engine_pkg()
+    par = __import__("importlib").import_module("sdr-j-dab_b200.parallel")
+    e = pkg.DabGpu(mode=1, device=gpu); e.set_subchannels(SUB)
+    dev = torch.device("cuda", gpu) if backend == "nccl" else "cpu"
+    r, first, mode = par.decode_sharded(e, iq, lambda n: e.alloc_result(n), rank, world, dist, dev, lead_frames=lead)
+    q.put((rank, mode, r.nframes, r.soft.copy(), r.fic_bits.copy(), [m.copy() for m in r.msc], [(i.pos, i.fine, i.phase0) for i in r.info]))
+    dist.barrier()
+    dist.destroy_process_group()
+    e.close()
+
+
+@pytest.mark.parametrize("world,cfo,want_mode", [(2, 8.0, "parallel"), (3, 8.0, "parallel"), (2, -1220.0, "chain")])
+def test_sharded_recording_equals_one_shot(port, world, cfo, want_mode):
+    """cfo 8 Hz: inside the fine corrector's dead zone, the receiver is locked right after the coarse search -> the
+    shards run in parallel; cfo -1220 Hz: the integrator is still moving after a 16-frame lead-in -> the boundary
+    check fails and the serial chain takes over.  Either way the output equals the one-GPU decode."""
+    import torch
+    import torch.multiprocessing as mp
+    backend = "nccl" if torch.cuda.device_count() >= world else "gloo"
+    pkg = engine_pkg()
+    mod = dabmod.Modulator(port, 1, [(0, 128, 1, 0o103), (100, 32, 0, 5)], 57)
+    iq = mod.generate(46, cfo_hz=cfo, snr_db=20.0, lead=3000, tail=6000)["iq"]
+    one = pkg.DabGpu(mode=1); one.set_subchannels(SUB)
+    want = one.decode(iq, one.alloc_result(60))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port_no = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port_no, iq, q, backend, 16)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert [g[1] for g in got] == [want_mode] * world
+    assert sum(g[2] for g in got) == want.nframes and all(g[2] > 0 for g in got)
+    assert np.array_equal(np.concatenate([g[3] for g in got]), want.soft)
+    assert np.array_equal(np.concatenate([g[4] for g in got]), want.fic_bits)
+    for i in range(len(SUB)):
+        assert np.array_equal(np.concatenate([g[5][i] for g in got]), want.msc[i])
+    assert sum((g[6] for g in got), []) == [(i.pos, i.fine, i.phase0) for i in want.info]
+    one.close()
