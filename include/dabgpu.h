@@ -105,6 +105,16 @@ int dabgpu_protect_decode (dabgpu_t *h, int32_t bitRate, int32_t uepFlag, int32_
  * soft[ngroups][2304] -> bits[ngroups][768], crc_ok[ngroups][3] (crc_ok may be NULL) */
 int dabgpu_fic_decode (dabgpu_t *h, const int16_t *soft, int32_t ngroups, uint8_t *bits, uint8_t *crc_ok);
 
+/* fib_processor::process_FIB restricted to what the MSC decoder needs: FIG 0/1, the sub-channel organisation
+ * (fib-processor.cpp:123-158 process_FIB, 163-177 process_FIG0, 278-347 FIG0Extension1 / HandleFIG0Extension1),
+ * applied to every FIB whose CRC holds (fic-handler.cpp:309-319), in order; table[SubChId] = the ficList entry
+ * (fib-processor.h:78-87).  uepFlag / protLevel use the reference's encoding, so an entry can be handed to
+ * dabgpu_set_subchannels as it is.  fic_bits[ngroups][768], crc_ok[ngroups][3] as dabgpu_fic_decode returns them. */
+typedef struct { int32_t defined, startAddr, length, uepFlag, protLevel, bitRate; } dabgpu_subch_info;
+int dabgpu_fig01_scan (dabgpu_t *h, const uint8_t *fic_bits, const uint8_t *crc_ok, int32_t ngroups, dabgpu_subch_info table [64]);
+/* the running table of the stream engine: every FIB a dabgpu_decode call decodes is scanned on the device */
+int dabgpu_get_subch_table (dabgpu_t *h, dabgpu_subch_info table [64]);
+
 /* dabConcurrent::run (dab-concurrent.cpp:144-193) for one sub-channel over ncif consecutive CIF fragments:
  * 16-CIF time de-interleaving, 16-CIF warm-up skip, eep/uep depuncture + Viterbi, energy dispersal.
  * A backend object carries the de-interleaver history across calls like the reference object does.

@@ -264,6 +264,75 @@ int orc_fic_frames (int mode, const int16_t *sym, int nframes, uint8_t *bits, ui
 	return ngroups;
 }
 
+/* ---- FIG 0/1 sub-channel organisation: fib_processor::process_FIB -> process_FIG0 -> FIG0Extension1 ->
+ * HandleFIG0Extension1 (fib-processor.cpp:123-158, 163-177, 278-347), called for every FIB whose CRC holds
+ * (fic-handler.cpp:309-319).  Only the ficList fields are kept (fib-processor.h:78-87).  The reference reads bits
+ * through unchecked pointers; a FIG whose length field runs past the FIB reads on into the rest of the 768-bit
+ * group (defined) or past it (undefined): here bits past the group read as 0. ---- */
+static const int16_t fig_prot_level [64][3] = {                              /* fib-processor.cpp:32-95 */
+	{16,5,32}, {21,4,32}, {24,3,32}, {29,2,32}, {35,1,32}, {24,5,48}, {29,4,48}, {35,3,48}, {42,2,48}, {52,1,48},
+	{29,5,56}, {35,4,56}, {42,3,56}, {52,2,56}, {32,5,64}, {42,4,64}, {48,3,64}, {58,2,64}, {70,1,64}, {40,5,80},
+	{52,4,80}, {58,3,80}, {70,2,80}, {84,1,80}, {48,5,96}, {58,4,96}, {70,3,96}, {84,2,96}, {104,1,96}, {58,5,112},
+	{70,4,112}, {84,3,112}, {104,2,112}, {64,5,128}, {84,4,128}, {96,3,128}, {116,2,128}, {140,1,128}, {80,5,160},
+	{104,4,160}, {116,3,160}, {140,2,160}, {168,1,160}, {96,5,192}, {116,4,192}, {140,3,192}, {168,2,192}, {208,1,192},
+	{116,5,224}, {140,4,224}, {168,3,224}, {208,2,224}, {232,1,224}, {128,5,256}, {168,4,256}, {192,3,256}, {232,2,256},
+	{280,1,256}, {160,5,320}, {208,4,320}, {280,2,320}, {192,5,384}, {280,3,384}, {416,1,384} };
+
+typedef struct { const uint8_t *g; int lim; } fig_bits;                      /* g = the 768-bit group, reads relative to it */
+static int fig_get (const fig_bits *b, int off, int n) {                     /* getBits, dab-constants.h:182-191 */
+	int r = 0;
+	for (int i = 0; i < n; i ++) r = (r << 1) | (off + i < b -> lim ? (b -> g [off + i] & 1) : 0);
+	return r;
+}
+
+static int fig0_ext1_entry (const fig_bits *b, int d, int offset, orc_subch_info *list) {       /* :289-347 */
+	int bitOffset = offset * 8;
+	const int SubChId = fig_get (b, d + bitOffset, 6), StartAdr = fig_get (b, d + bitOffset + 6, 10);
+	orc_subch_info *e = &list [SubChId];
+	e -> defined = 1;
+	e -> startAddr = StartAdr;
+	if (fig_get (b, d + bitOffset + 16, 1) == 0) {                           /* short form */
+		const int ti = fig_get (b, d + bitOffset + 18, 6);
+		e -> length = fig_prot_level [ti][0]; e -> uepFlag = 0;
+		e -> protLevel = fig_prot_level [ti][1]; e -> bitRate = fig_prot_level [ti][2];
+		bitOffset += 24;
+	} else {                                                                 /* EEP long form */
+		e -> uepFlag = 1;
+		const int option = fig_get (b, d + bitOffset + 17, 3);
+		if (option == 0 || option == 1) {
+			static const int divA [5] = { 0, 12, 8, 6, 4 }, divB [5] = { 0, 27, 21, 18, 15 };
+			const int protLevel = fig_get (b, d + bitOffset + 20, 2) + 1, size = fig_get (b, d + bitOffset + 22, 10);
+			e -> protLevel = protLevel + (option == 0 ? 0100 : 0200);
+			e -> length = size;
+			e -> bitRate = option == 0 ? size / divA [protLevel] * 8 : size / divB [protLevel] * 32;
+		}
+		bitOffset += 32;
+	}
+	return bitOffset / 8;
+}
+
+int orc_fig01_scan (const uint8_t *bits, const uint8_t *crc_ok, int ngroups, orc_subch_info *list /* [64], updated */) {
+	for (int gidx = 0; gidx < ngroups; gidx ++)
+		for (int j = 0; j < 3; j ++) {
+			if (!crc_ok [3 * gidx + j]) continue;                            /* fic-handler.cpp:311-314 */
+			const fig_bits b = { bits + (size_t) gidx * 768, 768 };
+			const int p = 256 * j;
+			int processedBytes = 0, d = p;                                   /* process_FIB, :123-158 */
+			while (processedBytes < 30) {
+				const int FIGtype = fig_get (&b, d, 3);
+				if (FIGtype == 7) break;
+				if (FIGtype == 0 && fig_get (&b, d + 8 + 3, 5) == 1) {       /* process_FIG0 -> FIG0Extension1, :278-287 */
+					const int Length = fig_get (&b, d + 3, 5);
+					int used = 2;
+					while (used < Length - 1) used = fig0_ext1_entry (&b, d, used, list);
+				}
+				processedBytes += fig_get (&b, d + 3, 5) + 1;
+				d = p + processedBytes * 8;
+			}
+		}
+	return 0;
+}
+
 /* ---- CIF assembly + sub-channel slice: msc-handler.cpp:125-193 ---- */
 int orc_msc_slice (int mode, const int16_t *sym, int nframes, int startAddr, int Length, int16_t *frag) {
 	orc_params p;

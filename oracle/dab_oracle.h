@@ -66,6 +66,10 @@ void orc_time_deinterleave (const int16_t *in, int ncif, int fragmentSize, int16
 /* ---- frame level regrouping ---- */
 /* soft bits of nframes frames: sym[frame][L-1][2K] (symbols 1..L-1) */
 /* ficHandler::run regroup (fic-handler.cpp:192-230) + process_ficInput per group */
+/* ficList entry (fib-processor.h:78-87), the fields FIG 0/1 fills */
+typedef struct { int32_t defined, startAddr, length, uepFlag, protLevel, bitRate; } orc_subch_info;
+/* FIG 0/1 of every CRC-clean FIB of ngroups FIC groups, in order, into list[64] (fib-processor.cpp:123-158, 278-347) */
+int orc_fig01_scan (const uint8_t *bits, const uint8_t *crc_ok, int ngroups, orc_subch_info *list);
 int orc_fic_frames (int mode, const int16_t *sym, int nframes, uint8_t *bits /* [nframes*groups][768] */,
                     uint8_t *crc_ok /* [nframes*groups][3] */);
 /* mscHandler::process_mscBlock (msc-handler.cpp:125-193): CIF assembly and sub-channel slice

@@ -86,6 +86,8 @@ def load_library():
     L.dabgpu_reset.argtypes = [C.c_void_p]
     L.dabgpu_state_get.argtypes = [C.c_void_p, C.POINTER(StreamState)]
     L.dabgpu_state_set.argtypes = [C.c_void_p, C.POINTER(StreamState)]
+    L.dabgpu_fig01_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.dabgpu_get_subch_table.argtypes = [C.c_void_p, C.c_void_p]
     L.dabgpu_host_state_predict.argtypes = [C.c_int32, C.POINTER(StreamState), C.c_int64, C.POINTER(StreamState)]
     L.dabgpu_state_export.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.dabgpu_state_import.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -198,6 +200,21 @@ class DabGpu:
         self._check(self.lib.dabgpu_fic_decode(self.h, soft.ctypes.data, soft.shape[0], bits.ctypes.data,
                                                crc.ctypes.data))
         return bits, crc
+
+    def fig01_scan(self, fic_bits, crc_ok):
+        """FIG 0/1 sub-channel table of the given FIC groups -> (64, 6) int32: defined, startAddr, length, uepFlag, protLevel, bitRate"""
+        bits = np.ascontiguousarray(fic_bits, np.uint8).reshape(-1, 768)
+        crc = np.ascontiguousarray(crc_ok, np.uint8).reshape(-1, 3)
+        assert bits.shape[0] == crc.shape[0]
+        table = np.zeros((64, 6), np.int32)
+        self._check(self.lib.dabgpu_fig01_scan(self.h, bits.ctypes.data, crc.ctypes.data, bits.shape[0], table.ctypes.data))
+        return table
+
+    def subch_table(self):
+        """the stream engine's running FIG 0/1 table (same layout as fig01_scan)"""
+        table = np.zeros((64, 6), np.int32)
+        self._check(self.lib.dabgpu_get_subch_table(self.h, table.ctypes.data))
+        return table
 
     # ---- OFDM group, per-call ----
     def fft(self, v, inverse=False):

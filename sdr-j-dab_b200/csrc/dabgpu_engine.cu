@@ -567,6 +567,8 @@ int dab_engine_init (dabgpu *h) {
 	memset (&E -> ctl, 0, sizeof (StreamCtl));
 	E -> ctl. f2 = 1; E -> ctl. prev1 = 1000; E -> ctl. prev2 = 999;     // ofdm-processor.cpp:258-259, 73
 	E -> groups = h -> p. L > 100 ? 8 : 5;
+	CUDA_TRY (h, E -> d_figkeys. ensure (128 * sizeof (unsigned long long)));
+	CUDA_TRY (h, cudaMemsetAsync (E -> d_figkeys. p, 0, 128 * sizeof (unsigned long long), h -> stream));
 	CUDA_TRY (h, cudaStreamCreateWithFlags (&E -> copy_st, cudaStreamNonBlocking));
 	const int big = 100 * 1024;
 	CUDA_TRY (h, cudaFuncSetAttribute (front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -586,7 +588,7 @@ void dab_engine_free (dabgpu *h) {
 	E -> tail. release (); E -> tail_spare. release (); E -> d_ctl. release (); E -> h_ctl. release ();
 	E -> d_frameout. release (); E -> d_framein. release (); E -> d_fcpart. release (); E -> d_spec0. release (); E -> d_info. release ();
 	E -> d_fic. release (); E -> d_msc. release (); E -> d_histtmp. release (); E -> d_fic8. release (); E -> d_msc8. release ();
-	E -> d_ficbits. release (); E -> d_ficcrc. release ();
+	E -> d_ficbits. release (); E -> d_ficcrc. release (); E -> d_figkeys. release ();
 	for (auto &b : E -> d_mscbits) b. release ();
 	delete E;
 	h -> engine = nullptr;
@@ -615,6 +617,13 @@ extern "C" int dabgpu_set_subchannels (dabgpu_t *h, const dabgpu_subch *sc, int3
 	for (auto &b : E -> d_mscbits) b. release ();
 	E -> d_mscbits. assign (nsub, DevBuf ());
 	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_get_subch_table (dabgpu_t *h, dabgpu_subch_info *table) {
+	if (!h || !table) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_get_subch_table: bad argument");
+	CUDA_TRY (h, cudaSetDevice (h -> device));
+	for (int i = 1; i < 4; i ++) CUDA_TRY (h, cudaStreamSynchronize (h -> vctx [i]. st));
+	return fig01_table (h, (const unsigned long long *) h -> engine -> d_figkeys. p, table, h -> stream);
 }
 
 extern "C" int dabgpu_state_get (dabgpu_t *h, dabgpu_stream_state *s) {
@@ -783,6 +792,11 @@ static int channel_chunk (dabgpu *h, int f0, int nv, dabgpu_result *out, std::ve
 		if (simd) {
 			if ((rc = dab_vit_simd_run (h, jobs))) break;
 			if (ngroups > 0) { cudaError_t e = fib_crc_launch (h, ficbits, 3 * ngroups, ficcrc); if (e != cudaSuccess) { rc = dab_fail (h, DABGPU_ERR_CUDA, "crc launch: %s", cudaGetErrorString (e)); break; } }
+		}
+		if (ngroups > 0) {                                   // FIG 0/1 of the FIBs just checked (fib-processor.cpp:278-347)
+			cudaError_t fe = fig01_launch (h, ficbits, ficcrc, 3 * ngroups, (unsigned long long) (E -> frames_total * p. ficGroups + g0) * 3ull,
+			                               (unsigned long long *) E -> d_figkeys. p, st);
+			if (fe != cudaSuccess) { rc = dab_fail (h, DABGPU_ERR_CUDA, "fig scan launch: %s", cudaGetErrorString (fe)); break; }
 		}
 		cudaError_t e = cudaSuccess;
 		if (ngroups > 0 && out -> fic_bits) e = cudaMemcpyAsync (out -> fic_bits + (size_t) g0 * 768, ficbits, (size_t) ngroups * 768, cudaMemcpyDeviceToHost, st);

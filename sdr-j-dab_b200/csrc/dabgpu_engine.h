@@ -54,6 +54,7 @@ struct Engine {
 	DevBuf d_fic8, d_msc8;              // the same as 0..255 Viterbi symbols (viterbi.cpp:229-235), written by the symbol kernels alongside
 	long long cap_frames = 0;
 	DevBuf d_ficbits, d_ficcrc;
+	DevBuf d_figkeys;                   // FIG 0/1 scan: 64 x 2 persistent keys (dabgpu_fig.cu)
 	std::vector<DevBuf> d_mscbits;
 	bool hist_init = false;
 	std::vector<dabgpu_subch> subch;

@@ -1,0 +1,120 @@
+// dabgpu_fig.cu -- FIG 0/1 (sub-channel organisation) extraction on the device: the part of fib_processor the MSC
+// decoder depends on (fib-processor.cpp:123-158 process_FIB, :163-177 process_FIG0, :278-347 FIG0Extension1 /
+// HandleFIG0Extension1; ficList, fib-processor.h:78-87), run on every CRC-clean FIB (fic-handler.cpp:309-319).
+//
+// The reference walks the FIBs one after the other and simply overwrites ficList[SubChId]; the result is "last write
+// wins", per field group: StartAddr / uepFlag are written by every entry, Length / protLevel / BitRate only by the
+// short form and by long-form options 0 and 1.  Here one thread parses one FIB and publishes each entry with an
+// atomicMax on two 64-bit keys per sub-channel, the high bits being the entry's position in the reference's
+// processing order (global FIB number, entry number inside the FIB), the low bits the raw fields.  The keys are
+// persistent in the handle, so batches decoded out of order on different streams still resolve to the reference's
+// result.  The reference reads through unchecked pointers; bits past the 768-bit FIC group read as 0 here
+// (oracle/dab_oracle.c: orc_fig01_scan follows the same rule).
+#include "dabgpu_internal.h"
+
+__constant__ short c_fig_prot [64][3] = {                                    // fib-processor.cpp:32-95
+	{16,5,32}, {21,4,32}, {24,3,32}, {29,2,32}, {35,1,32}, {24,5,48}, {29,4,48}, {35,3,48}, {42,2,48}, {52,1,48},
+	{29,5,56}, {35,4,56}, {42,3,56}, {52,2,56}, {32,5,64}, {42,4,64}, {48,3,64}, {58,2,64}, {70,1,64}, {40,5,80},
+	{52,4,80}, {58,3,80}, {70,2,80}, {84,1,80}, {48,5,96}, {58,4,96}, {70,3,96}, {84,2,96}, {104,1,96}, {58,5,112},
+	{70,4,112}, {84,3,112}, {104,2,112}, {64,5,128}, {84,4,128}, {96,3,128}, {116,2,128}, {140,1,128}, {80,5,160},
+	{104,4,160}, {116,3,160}, {140,2,160}, {168,1,160}, {96,5,192}, {116,4,192}, {140,3,192}, {168,2,192}, {208,1,192},
+	{116,5,224}, {140,4,224}, {168,3,224}, {208,2,224}, {232,1,224}, {128,5,256}, {168,4,256}, {192,3,256}, {232,2,256},
+	{280,1,256}, {160,5,320}, {208,4,320}, {280,2,320}, {192,5,384}, {280,3,384}, {416,1,384} };
+
+struct FigBits { const uint8_t *g; };                                        // g = start of the 768-bit group
+__device__ __forceinline__ int fig_get (const FigBits &b, int off, int n) {   // getBits, dab-constants.h:182-191
+	int r = 0;
+	for (int i = 0; i < n; i ++) r = (r << 1) | (off + i < 768 ? (int) (b. g [off + i] & 1) : 0);
+	return r;
+}
+
+// keys [64][2]: [0] = order << 11 | StartAddr << 1 | uepFlag;  [1] = order << 16 | form << 15 | fields
+//   short form: fields = table index (6 bits); long form (option 0 / 1): option << 12 | (level - 1) << 10 | size
+__global__ void fig01_kernel (const uint8_t *bits, const uint8_t *crc_ok, int nfibs, unsigned long long order0, unsigned long long *keys) {
+	const int f = blockIdx. x * blockDim. x + threadIdx. x;
+	if (f >= nfibs || !crc_ok [f]) return;                                   // fic-handler.cpp:311-314
+	const FigBits b { bits + (size_t) (f / 3) * 768 };
+	const int p = 256 * (f % 3);
+	unsigned long long order = ((order0 + (unsigned long long) f) << 5) + 1; // + entry number; never 0
+	int processedBytes = 0, d = p;
+	while (processedBytes < 30) {                                            // process_FIB
+		const int FIGtype = fig_get (b, d, 3);
+		if (FIGtype == 7) break;
+		if (FIGtype == 0 && fig_get (b, d + 8 + 3, 5) == 1) {                // FIG 0/1
+			const int Length = fig_get (b, d + 3, 5);
+			int used = 2;
+			while (used < Length - 1) {                                      // HandleFIG0Extension1
+				const int o = d + used * 8;
+				const int SubChId = fig_get (b, o, 6), StartAdr = fig_get (b, o + 6, 10);
+				const int lng = fig_get (b, o + 16, 1);
+				atomicMax (&keys [2 * SubChId], (order << 11) | ((unsigned long long) StartAdr << 1) | (unsigned long long) lng);
+				if (!lng) {
+					atomicMax (&keys [2 * SubChId + 1], (order << 16) | (unsigned long long) fig_get (b, o + 18, 6));
+					used += 3;
+				} else {
+					const int option = fig_get (b, o + 17, 3);
+					if (option < 2)
+						atomicMax (&keys [2 * SubChId + 1], (order << 16) | 0x8000ull | ((unsigned long long) option << 12) |
+						           ((unsigned long long) fig_get (b, o + 20, 2) << 10) | (unsigned long long) fig_get (b, o + 22, 10));
+					used += 4;
+				}
+				order ++;
+			}
+		}
+		processedBytes += fig_get (b, d + 3, 5) + 1;
+		d = p + processedBytes * 8;
+	}
+}
+
+// keys -> ficList entries
+__global__ void fig01_table_kernel (const unsigned long long *keys, dabgpu_subch_info *table) {
+	const int id = threadIdx. x;
+	dabgpu_subch_info e = { 0, 0, 0, 0, 0, 0 };
+	const unsigned long long ka = keys [2 * id], kb = keys [2 * id + 1];
+	if (ka) { e. defined = 1; e. startAddr = (int) ((ka >> 1) & 1023); e. uepFlag = (int) (ka & 1); }
+	if (kb) {
+		if (!(kb & 0x8000ull)) {
+			const int ti = (int) (kb & 63);
+			e. length = c_fig_prot [ti][0]; e. protLevel = c_fig_prot [ti][1]; e. bitRate = c_fig_prot [ti][2];
+		} else {
+			const int option = (int) ((kb >> 12) & 1), level = (int) ((kb >> 10) & 3) + 1, size = (int) (kb & 1023);
+			const int divA [5] = { 1, 12, 8, 6, 4 }, divB [5] = { 1, 27, 21, 18, 15 };
+			e. protLevel = level + (option == 0 ? 0100 : 0200);
+			e. length = size;
+			e. bitRate = option == 0 ? size / divA [level] * 8 : size / divB [level] * 32;
+		}
+	}
+	table [id] = e;
+}
+
+cudaError_t fig01_launch (dabgpu *h, const uint8_t *d_bits, const uint8_t *d_crc, int nfibs, unsigned long long order0, unsigned long long *d_keys, cudaStream_t st) {
+	if (nfibs <= 0) return cudaSuccess;
+	fig01_kernel<<<(nfibs + 127) / 128, 128, 0, st>>> (d_bits, d_crc, nfibs, order0, d_keys);
+	h -> launches ++;
+	return cudaGetLastError ();
+}
+
+int fig01_table (dabgpu *h, const unsigned long long *d_keys, dabgpu_subch_info *host_table, cudaStream_t st) {
+	CUDA_TRY (h, h -> d_aux. ensure (64 * sizeof (dabgpu_subch_info)));
+	fig01_table_kernel<<<1, 64, 0, st>>> (d_keys, (dabgpu_subch_info *) h -> d_aux. p);
+	h -> launches ++;
+	CUDA_TRY (h, cudaGetLastError ());
+	CUDA_TRY (h, cudaMemcpyAsync (host_table, h -> d_aux. p, 64 * sizeof (dabgpu_subch_info), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY (h, cudaStreamSynchronize (st));
+	return DABGPU_OK;
+}
+
+// fib_processor::process_FIB restricted to FIG 0/1, stateless parity entry point
+extern "C" int dabgpu_fig01_scan (dabgpu_t *h, const uint8_t *fic_bits, const uint8_t *crc_ok, int32_t ngroups, dabgpu_subch_info *table) {
+	if (!h || !table || ngroups < 0 || (ngroups > 0 && (!fic_bits || !crc_ok))) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_fig01_scan: bad argument");
+	CUDA_TRY (h, cudaSetDevice (h -> device));
+	const size_t nb = (size_t) ngroups * 768, nc = (size_t) ngroups * 3, nk = 128 * sizeof (unsigned long long);
+	CUDA_TRY (h, h -> d_in. ensure (nb + nc + 16 + nk));
+	CUDA_TRY (h, h -> h_in. ensure (nb + nc + 16));
+	if (ngroups) { memcpy (h -> h_in. p, fic_bits, nb); memcpy ((char *) h -> h_in. p + nb, crc_ok, nc); }
+	unsigned long long *d_keys = (unsigned long long *) ((char *) h -> d_in. p + ((nb + nc + 15) & ~(size_t) 15));
+	CUDA_TRY (h, cudaMemcpyAsync (h -> d_in. p, h -> h_in. p, nb + nc, cudaMemcpyHostToDevice, h -> stream));
+	CUDA_TRY (h, cudaMemsetAsync (d_keys, 0, nk, h -> stream));
+	CUDA_TRY (h, fig01_launch (h, (const uint8_t *) h -> d_in. p, (const uint8_t *) h -> d_in. p + nb, 3 * ngroups, 0, d_keys, h -> stream));
+	return fig01_table (h, d_keys, table, h -> stream);
+}

@@ -147,6 +147,14 @@ class Oracle:
         assert n == bits.shape[0]
         return bits, crc
 
+    def fig01_scan(self, bits, crc, table=None):
+        """FIG 0/1 table after the given FIC groups (updates and returns `table`, (64, 6) int32)"""
+        bits = np.ascontiguousarray(bits, np.uint8).reshape(-1, 768)
+        crc = np.ascontiguousarray(crc, np.uint8).reshape(-1, 3)
+        table = np.zeros((64, 6), np.int32) if table is None else table
+        self.lib.orc_fig01_scan(_p(bits, C.c_uint8), _p(crc, C.c_uint8), bits.shape[0], _p(table, C.c_int32))
+        return table
+
     def msc_slice(self, mode, sym, startAddr, Length):
         p = self.mode_params(mode)
         sym = np.ascontiguousarray(sym, np.int16)
