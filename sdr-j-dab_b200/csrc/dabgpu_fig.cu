@@ -9,7 +9,7 @@
 // processing order (global FIB number, entry number inside the FIB), the low bits the raw fields.  The keys are
 // persistent in the handle, so batches decoded out of order on different streams still resolve to the reference's
 // result.  The reference reads through unchecked pointers; bits past the 768-bit FIC group read as 0 here
-// (oracle/dab_oracle.c: orc_fig01_scan follows the same rule).
+// (the test-side restatement follows the same rule).
 #include "dabgpu_internal.h"
 
 __constant__ short c_fig_prot [64][3] = {                                    // fib-processor.cpp:32-95
