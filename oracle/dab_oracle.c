@@ -333,6 +333,106 @@ int orc_fig01_scan (const uint8_t *bits, const uint8_t *crc_ok, int ngroups, orc
 	return 0;
 }
 
+int  orc_firecode_check (const uint8_t *x11) { return k_firecode_check (x11); }
+int  orc_rs_dec (const uint8_t *r120, uint8_t *d110) { return k_rs_dec (r120, d110); }
+void orc_rs_enc (const uint8_t *d110, uint8_t *r120) { k_rs_enc (d110, r120); }
+
+/* ---- DAB+ super-frame layer: mp4Processor::addtoFrame + the Fire code / Reed-Solomon / AU-table part of
+ * processSuperframe (mp4processor.cpp:107-150, 152-275), dabPlus_crc (:40-61).  The AAC decoder behind it is out of
+ * scope; what leaves here is the corrected super frame, the access-unit table and the per-AU CRC verdicts. ---- */
+struct orc_dabplus {
+	int bitRate, RSDims;
+	uint8_t *frameBytes, *outVector;
+	int blockFillIndex, blocksInBuffer;
+	int64_t cifs;
+};
+orc_dabplus *orc_dabplus_new (int bitRate) {
+	orc_dabplus *d = (orc_dabplus *) calloc (1, sizeof (*d));
+	d -> bitRate = bitRate; d -> RSDims = bitRate / 8;
+	d -> frameBytes = (uint8_t *) calloc ((size_t) d -> RSDims * 120, 1);
+	d -> outVector = (uint8_t *) calloc ((size_t) d -> RSDims * 110, 1);
+	return d;
+}
+void orc_dabplus_free (orc_dabplus *d) { if (d) { free (d -> frameBytes); free (d -> outVector); free (d); } }
+
+static int dabplus_crc (const uint8_t *msg, int len) {                      /* :40-61 */
+	unsigned acc = 0xFFFF;
+	for (int i = 0; i < len; i ++) {
+		unsigned data = (unsigned) msg [i] << 8;
+		for (int j = 8; j > 0; j --) {
+			acc = ((data ^ acc) & 0x8000) ? ((acc << 1) ^ 0x1021) & 0xFFFF : (acc << 1) & 0xFFFF;
+			data = (data << 1) & 0xFFFF;
+		}
+	}
+	const unsigned crc = ~(((unsigned) msg [len] << 8) | msg [len + 1]) & 0xFFFF;
+	return (crc ^ acc) == 0;
+}
+
+static int dabplus_superframe (orc_dabplus *d, int base, orc_superframe_info *fi) {     /* processSuperframe, :152-275 */
+	const int R = d -> RSDims;
+	uint8_t rsIn [120], rsOut [110];
+	int nErrors = 0;
+	for (int j = 0; j < R; j ++) {
+		for (int k = 0; k < 120; k ++) rsIn [k] = d -> frameBytes [(base + j + k * R) % (R * 120)];
+		const int ler = k_rs_dec (rsIn, rsOut);
+		if (ler > 0) nErrors += ler;
+		if (ler < 0) return 0;
+		for (int k = 0; k < 110; k ++) d -> outVector [j + k * R] = rsOut [k];
+	}
+	const uint8_t *o = d -> outVector;
+	const int dacRate = (o [2] >> 6) & 1, sbrFlag = (o [2] >> 5) & 1;
+	int au [7], n;
+	switch (2 * dacRate + sbrFlag) {
+	   default:
+	   case 0: n = 4; au [0] = 8;  au [1] = o [3] * 16 + (o [4] >> 4); au [2] = (o [4] & 0xf) * 256 + o [5];
+	           au [3] = o [6] * 16 + (o [7] >> 4); au [4] = 110 * R; break;
+	   case 1: n = 2; au [0] = 5;  au [1] = o [3] * 16 + (o [4] >> 4); au [2] = 110 * R; break;
+	   case 2: n = 6; au [0] = 11; au [1] = o [3] * 16 + (o [4] >> 4); au [2] = (o [4] & 0xf) * 256 + o [5];
+	           au [3] = o [6] * 16 + (o [7] >> 4); au [4] = (o [7] & 0xf) * 256 + o [8];
+	           au [5] = o [9] * 16 + (o [10] >> 4); au [6] = 110 * R; break;
+	   case 3: n = 3; au [0] = 6;  au [1] = o [3] * 16 + (o [4] >> 4); au [2] = (o [4] & 0xf) * 256 + o [5]; au [3] = 110 * R; break;
+	}
+	int crcmask = 0;
+	for (int i = 0; i < n; i ++) {
+		if (au [i + 1] < au [i]) return 0;
+		const int len = au [i + 1] - au [i] - 2;
+		if (len >= 960 || len < 0) return 0;
+		if (dabplus_crc (&o [au [i]], len)) crcmask |= 1 << i;
+	}
+	fi -> corrected = nErrors; fi -> num_aus = n; fi -> au_crc = crcmask;
+	for (int i = 0; i < 7; i ++) fi -> au_start [i] = i <= n ? au [i] : 0;
+	return 1;
+}
+
+int orc_dabplus_process (orc_dabplus *d, const uint8_t *bits, int ncif, uint8_t *superframes, orc_superframe_info *info, int max_sf) {
+	const int nbits = 24 * d -> bitRate, nb = nbits / 8;
+	int nsf = 0;
+	for (int c = 0; c < ncif; c ++) {                                        /* addtoFrame, :107-150 */
+		const uint8_t *V = bits + (size_t) c * nbits;
+		for (int i = 0; i < nb; i ++) {
+			uint8_t temp = 0;
+			for (int j = 0; j < 8; j ++) temp = (uint8_t) ((temp << 1) | (V [i * 8 + j] & 1));
+			d -> frameBytes [d -> blockFillIndex * nb + i] = temp;
+		}
+		d -> blocksInBuffer ++;
+		d -> blockFillIndex = (d -> blockFillIndex + 1) % 5;
+		d -> cifs ++;
+		if (d -> blocksInBuffer >= 5) {
+			orc_superframe_info fi;
+			if (k_firecode_check (&d -> frameBytes [d -> blockFillIndex * nb]) && dabplus_superframe (d, d -> blockFillIndex * nb, &fi)) {
+				d -> blocksInBuffer = 0;
+				if (nsf < max_sf) {
+					fi. first_cif = d -> cifs - 5;
+					info [nsf] = fi;
+					memcpy (superframes + (size_t) nsf * d -> RSDims * 110, d -> outVector, (size_t) d -> RSDims * 110);
+				}
+				nsf ++;
+			} else d -> blocksInBuffer = 4;
+		}
+	}
+	return nsf;
+}
+
 /* ---- CIF assembly + sub-channel slice: msc-handler.cpp:125-193 ---- */
 int orc_msc_slice (int mode, const int16_t *sym, int nframes, int startAddr, int Length, int16_t *frag) {
 	orc_params p;

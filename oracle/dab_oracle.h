@@ -66,6 +66,18 @@ void orc_time_deinterleave (const int16_t *in, int ncif, int fragmentSize, int16
 /* ---- frame level regrouping ---- */
 /* soft bits of nframes frames: sym[frame][L-1][2K] (symbols 1..L-1) */
 /* ficHandler::run regroup (fic-handler.cpp:192-230) + process_ficInput per group */
+/* DAB+ super-frame layer (mp4processor.cpp:107-275): Fire code sync over 5 CIFs, RS(120,110) per column, AU table + CRCs */
+typedef struct orc_dabplus orc_dabplus;
+typedef struct { int64_t first_cif; int32_t corrected, num_aus, au_start [7], au_crc; } orc_superframe_info;
+orc_dabplus *orc_dabplus_new (int bitRate);
+void orc_dabplus_free (orc_dabplus *);
+/* bits[ncif][24*bitRate] (1 bit per byte) -> superframes[n][110*bitRate/8], info[n]; returns n (may exceed max_sf: then truncated) */
+int  orc_dabplus_process (orc_dabplus *, const uint8_t *bits, int ncif, uint8_t *superframes, orc_superframe_info *info, int max_sf);
+/* primitives, exposed for the tests: firecode_checker::check, reedSolomon::dec / enc (cutlen 135) */
+int  orc_firecode_check (const uint8_t *x11);
+int  orc_rs_dec (const uint8_t *r120, uint8_t *d110);
+void orc_rs_enc (const uint8_t *d110, uint8_t *r120);
+
 /* ficList entry (fib-processor.h:78-87), the fields FIG 0/1 fills */
 typedef struct { int32_t defined, startAddr, length, uepFlag, protLevel, bitRate; } orc_subch_info;
 /* FIG 0/1 of every CRC-clean FIB of ngroups FIC groups, in order, into list[64] (fib-processor.cpp:123-158, 278-347) */

@@ -34,6 +34,12 @@ void    k_get_phase_reference (k_ofdm *, float *out);
 void    k_get_ref_table (k_ofdm *, float *out);
 int     k_fft (float *v, int n, int inverse);
 
+
+/* DAB+ super-frame layer: firecode_checker::check on 11 bytes, reedSolomon (8, 0435, 0, 1, 10)::dec / enc with cutlen 135 */
+int  k_firecode_check (const uint8_t *x11);
+int  k_rs_dec (const uint8_t *r120, uint8_t *d110);
+void k_rs_enc (const uint8_t *d110, uint8_t *r120);
+
 #ifdef __cplusplus
 }
 #endif

@@ -355,3 +355,202 @@ void k_token (k_ofdm *o, const float *inv, int16_t *ibits) {   /* ofdm-decoder.c
 
 void k_get_phase_reference (k_ofdm *o, float *out) { memcpy (out, o -> phaseRef, sizeof (float) * 2 * o -> p. T_u); }
 void k_get_ref_table (k_ofdm *o, float *out) { memcpy (out, o -> refTable, sizeof (float) * 2 * o -> p. T_u); }
+
+/* ====================================================================================================
+ * DAB+ super-frame layer primitives: Fire code check and RS(120,110) over GF(2^8).
+ * ==================================================================================================== */
+/* ---- firecode_checker (firecode-checker.cpp:33-95): g(x) = (x^11+1)(x^5+x^3+x^2+x+1), byte-wise by table ---- */
+static uint16_t fire_tab [256];
+static int fire_ready;
+static uint16_t fire_run8 (uint8_t regs [16]) {                         /* :59-75 */
+	static const uint8_t g [16] = { 1, 1, 1, 1, 0, 1, 0, 0, 0, 0, 0, 1, 1, 1, 1, 0 };
+	for (int i = 0; i < 8; i ++) {
+		const uint8_t z = regs [15];
+		for (int j = 15; j > 0; j --) regs [j] = regs [j - 1] ^ (z & g [j]);
+		regs [0] = z;
+	}
+	uint16_t v = 0;
+	for (int i = 15; i >= 0; i --) v = (uint16_t) ((v << 1) | regs [i]);
+	return v;
+}
+static void fire_init (void) {                                           /* :36-54 */
+	uint16_t itab [8];
+	for (int i = 0; i < 8; i ++) {
+		uint8_t regs [16];
+		memset (regs, 0, 16);
+		regs [8 + i] = 1;
+		itab [i] = fire_run8 (regs);
+	}
+	for (int i = 0; i < 256; i ++) {
+		fire_tab [i] = 0;
+		for (int j = 0; j < 8; j ++) if (i & (1 << j)) fire_tab [i] ^= itab [j];
+	}
+	fire_ready = 1;
+}
+void k_firecode_table (uint16_t *tab256) { if (!fire_ready) fire_init (); memcpy (tab256, fire_tab, sizeof (fire_tab)); }
+int k_firecode_check (const uint8_t *x) {                                /* :77-95 */
+	if (!fire_ready) fire_init ();
+	uint16_t state = (uint16_t) ((x [2] << 8) | x [3]), istate;
+	for (int i = 4; i < 11; i ++) {
+		istate = fire_tab [state >> 8];
+		state = (uint16_t) (((istate & 0x00ff) ^ x [i]) | ((istate ^ (state << 8)) & 0xff00));
+	}
+	for (int i = 0; i < 2; i ++) {
+		istate = fire_tab [state >> 8];
+		state = (uint16_t) (((istate & 0x00ff) ^ x [i]) | ((istate ^ (state << 8)) & 0xff00));
+	}
+	return state == 0;
+}
+
+/* ---- galois (galois.cpp:39-127) for symsize 8, gfpoly 0435; reedSolomon (8, 0435, 0, 1, 10) (mp4processor.cpp:75) ---- */
+#define RS_NN 255
+#define RS_NROOTS 10
+static uint16_t gf_alpha_to [256], gf_index_of [256];
+static uint8_t rs_generator [RS_NROOTS + 1];
+static int gf_ready;
+static int gf_modnn (int x) { while (x >= RS_NN) { x -= RS_NN; x = (x >> 8) + (x & RS_NN); } return x; }     /* :64-70 */
+static int gf_mul_power (int a, int b) { return gf_modnn (a + b); }
+static int gf_mul_poly (int a, int b) { return (a == 0 || b == 0) ? 0 : gf_alpha_to [gf_mul_power (gf_index_of [a], gf_index_of [b])]; }
+static int gf_div_power (int a, int b) { return gf_modnn (256 - 1 + a - b); }
+static int gf_div_poly (int a, int b) { return a == 0 ? 0 : gf_alpha_to [gf_div_power (gf_index_of [a], gf_index_of [b])]; }
+static int gf_pow_power (int a, int n) { return a == 0 ? 0 : (a * n) % 255; }
+static void gf_init (void) {
+	int sr = 1;
+	gf_index_of [0] = RS_NN; gf_alpha_to [RS_NN] = 0;
+	for (int i = 0; i < RS_NN; i ++) {
+		gf_index_of [sr] = (uint16_t) i; gf_alpha_to [i] = (uint16_t) sr;
+		sr <<= 1;
+		if (sr & 256) sr ^= 0435;
+		sr &= RS_NN;
+	}
+	/* generator polynomial, reed-solomon.cpp:47-76 (fcr 0, prim 1) */
+	memset (rs_generator, 0, sizeof (rs_generator));
+	rs_generator [0] = 1;
+	for (int i = 0, root = 0; i < RS_NROOTS; i ++, root ++) {
+		rs_generator [i + 1] = 1;
+		for (int j = i; j > 0; j --) {
+			if (rs_generator [j] != 0)
+				rs_generator [j] = (uint8_t) (rs_generator [j - 1] ^ gf_alpha_to [gf_mul_power (gf_index_of [rs_generator [j]], root)]);
+			else
+				rs_generator [j] = rs_generator [j - 1];
+		}
+		rs_generator [0] = (uint8_t) gf_alpha_to [gf_mul_power (root, gf_index_of [rs_generator [0]])];
+	}
+	for (int i = 0; i <= RS_NROOTS; i ++) rs_generator [i] = (uint8_t) gf_index_of [rs_generator [i]];
+	gf_ready = 1;
+}
+void k_gf_tables (uint16_t *alpha_to, uint16_t *index_of) {
+	if (!gf_ready) gf_init ();
+	memcpy (alpha_to, gf_alpha_to, sizeof (gf_alpha_to)); memcpy (index_of, gf_index_of, sizeof (gf_index_of));
+}
+
+/* reedSolomon::decode_rs on a full 255-symbol word (reed-solomon.cpp:145-232 with :236-399) */
+static int rs_decode (uint8_t *data) {
+	uint8_t syn [RS_NROOTS + 1], Lambda [RS_NROOTS + 1], Corrector [RS_NROOTS + 1], omega [RS_NROOTS + 1];
+	uint8_t rootTable [RS_NROOTS], locTable [RS_NROOTS];
+	/* syndromes by Horner, :236-270 (uu1 = root for fcr 0, prim 1) */
+	int any = 0;
+	for (int i = 0; i < RS_NROOTS; i ++) {
+		int s = data [0];
+		for (int j = 1; j < RS_NN; j ++)
+			s = s == 0 ? data [j] : data [j] ^ gf_alpha_to [gf_mul_power (gf_index_of [s], gf_pow_power (gf_mul_power (0, i), 1))];
+		syn [i] = (uint8_t) s; any |= s;
+	}
+	syn [RS_NROOTS] = 0;                                     /* the reference reads one element past its array here; the value is never used */
+	if (!any) return 0;
+	/* Berlekamp-Massey, :275-325 */
+	int K = 1, L = 0, deg_lambda = 0;
+	memset (Lambda, 0, sizeof (Lambda)); memset (Corrector, 0, sizeof (Corrector));
+	int error = syn [0];
+	Lambda [0] = 1; Corrector [1] = 1;
+	while (K <= RS_NROOTS) {
+		uint8_t old [RS_NROOTS + 1];
+		memcpy (old, Lambda, sizeof (old));
+		for (int i = 0; i < RS_NROOTS + 1; i ++) Lambda [i] ^= (uint8_t) gf_mul_poly (error, Corrector [i]);
+		if (2 * L < K && error != 0) {
+			L = K - L;
+			for (int i = 0; i < RS_NROOTS + 1; i ++) Corrector [i] = (uint8_t) gf_div_poly (old [i], error);
+		}
+		for (int i = RS_NROOTS; i >= 1; i --) Corrector [i] = Corrector [i - 1];
+		Corrector [0] = 0;
+		error = syn [K];
+		for (int i = 1; i <= K; i ++) error ^= gf_mul_poly (syn [K - i], Lambda [i]);
+		K ++;
+	}
+	for (int i = 0; i < RS_NROOTS + 1; i ++) {
+		if (Lambda [i] != 0) deg_lambda = i;
+		Lambda [i] = (uint8_t) gf_index_of [Lambda [i]];
+	}
+	/* Chien search, :330-362 (iprim = 1) */
+	int rootCount = 0;
+	{
+		uint8_t reg [RS_NROOTS + 1];
+		memcpy (reg, Lambda, sizeof (reg));
+		for (int i = 1, k = 0; i <= RS_NN; i ++, k ++) {
+			int result = 1;
+			for (int j = deg_lambda; j > 0; j --)
+				if (reg [j] != RS_NN) { reg [j] = (uint8_t) gf_mul_power (reg [j], j); result ^= gf_alpha_to [reg [j]]; }
+			if (result != 0) continue;
+			if (rootCount < RS_NROOTS) { rootTable [rootCount] = (uint8_t) i; locTable [rootCount] = (uint8_t) k; }
+			rootCount ++;
+		}
+		if (rootCount != deg_lambda) return -1;
+	}
+	/* omega = s * lambda mod x^nroots, :372-399 */
+	int deg_omega = 0;
+	for (int i = 0; i < RS_NROOTS; i ++) {
+		int tmp = 0;
+		for (int j = deg_lambda < i ? deg_lambda : i; j >= 0; j --)
+			if (gf_index_of [syn [i - j]] != RS_NN && Lambda [j] != RS_NN)
+				tmp ^= gf_alpha_to [gf_mul_power (gf_index_of [syn [i - j]], Lambda [j])];
+		if (tmp != 0) deg_omega = i;
+		omega [i] = (uint8_t) gf_index_of [tmp];
+	}
+	omega [RS_NROOTS] = RS_NN;
+	/* Forney, :171-231 */
+	for (int j = rootCount - 1; j >= 0; j --) {
+		int num1 = 0, den = 0;
+		for (int i = deg_omega; i >= 0; i --)
+			if (omega [i] != RS_NN) num1 ^= gf_alpha_to [gf_mul_power (omega [i], gf_pow_power (i, rootTable [j]))];
+		const int num2 = gf_alpha_to [gf_mul_power (gf_pow_power (rootTable [j], gf_div_power (0, 1)), RS_NN)];
+		for (int i = (deg_lambda < RS_NROOTS - 1 ? deg_lambda : RS_NROOTS - 1) & ~1; i >= 0; i -= 2)
+			if (Lambda [i + 1] != RS_NN) den ^= gf_alpha_to [gf_mul_power (Lambda [i + 1], gf_pow_power (i, rootTable [j]))];
+		if (den == 0) return -1;
+		if (num1 != 0) {
+			if (locTable [j] >= (uint8_t) (RS_NN - RS_NROOTS)) rootCount --;
+			else {
+				int y = gf_mul_power (gf_index_of [num1], gf_index_of [num2]);
+				y = gf_mul_power (y, RS_NN - gf_index_of [den]);
+				data [locTable [j]] ^= (uint8_t) gf_alpha_to [y];
+			}
+		}
+	}
+	return rootCount;
+}
+
+int k_rs_dec (const uint8_t *r120, uint8_t *d110) {          /* reedSolomon::dec (r, d, 135), reed-solomon.cpp:129-143 */
+	if (!gf_ready) gf_init ();
+	uint8_t rf [RS_NN];
+	memset (rf, 0, 135);
+	memcpy (rf + 135, r120, 120);
+	const int ret = rs_decode (rf);
+	memcpy (d110, rf + 135, 110);
+	return ret;
+}
+
+void k_rs_enc (const uint8_t *d110, uint8_t *r120) {         /* reedSolomon::enc (r, d, 135), :79-127 */
+	if (!gf_ready) gf_init ();
+	uint8_t rf [RS_NN], bb [RS_NROOTS];
+	memset (rf, 0, 135);
+	memcpy (rf + 135, d110, 110);
+	memset (bb, 0, sizeof (bb));
+	for (int i = 0; i < RS_NN - RS_NROOTS; i ++) {
+		const int feedback = gf_index_of [rf [i] ^ bb [0]];
+		if (feedback != RS_NN)
+			for (int j = 1; j < RS_NROOTS; j ++) bb [j] ^= (uint8_t) gf_alpha_to [gf_mul_power (feedback, rs_generator [RS_NROOTS - j])];
+		memmove (&bb [0], &bb [1], RS_NROOTS - 1);
+		bb [RS_NROOTS - 1] = feedback != RS_NN ? (uint8_t) gf_alpha_to [gf_mul_power (feedback, rs_generator [0])] : 0;
+	}
+	memcpy (r120, rf + 135, 110);
+	memcpy (r120 + 110, bb, RS_NROOTS);
+}

@@ -155,6 +155,25 @@ class Oracle:
         self.lib.orc_fig01_scan(_p(bits, C.c_uint8), _p(crc, C.c_uint8), bits.shape[0], _p(table, C.c_int32))
         return table
 
+    # ---- DAB+ super-frame layer ----
+    def firecode_check(self, x11):
+        b = np.ascontiguousarray(x11, np.uint8)
+        return bool(self.lib.orc_firecode_check(_p(b, C.c_uint8)))
+
+    def rs_dec(self, r120):
+        r = np.ascontiguousarray(r120, np.uint8)
+        d = np.zeros(110, np.uint8)
+        return int(self.lib.orc_rs_dec(_p(r, C.c_uint8), _p(d, C.c_uint8))), d
+
+    def rs_enc(self, d110):
+        d = np.ascontiguousarray(d110, np.uint8)
+        r = np.zeros(120, np.uint8)
+        self.lib.orc_rs_enc(_p(d, C.c_uint8), _p(r, C.c_uint8))
+        return r
+
+    def dabplus(self, bitRate):
+        return _DabPlus(self, bitRate)
+
     def msc_slice(self, mode, sym, startAddr, Length):
         p = self.mode_params(mode)
         sym = np.ascontiguousarray(sym, np.int16)
@@ -181,6 +200,39 @@ class Oracle:
         n = self.lib.orc_ofdm_run(mode, threshold, freqSyncMethod, iq.ctypes.data, iq.size // 2, max_frames,
                                   sym.ctypes.data, C.addressof(info))
         return sym[:n], [info[i] for i in range(n)]
+
+
+class SuperframeInfo(C.Structure):
+    _fields_ = [("first_cif", C.c_int64), ("corrected", C.c_int32), ("num_aus", C.c_int32), ("au_start", C.c_int32 * 7),
+                ("au_crc", C.c_int32)]
+
+    def key(self):
+        return (self.first_cif, self.corrected, self.num_aus, tuple(self.au_start), self.au_crc)
+
+
+class _DabPlus:
+    """mp4Processor's super-frame front (stateful, like the reference object)"""
+
+    def __init__(self, orc, bitRate):
+        self.lib, self.bitRate = orc.lib, bitRate
+        self.lib.orc_dabplus_new.restype = C.c_void_p
+        self.lib.orc_dabplus_free.argtypes = [C.c_void_p]
+        self.lib.orc_dabplus_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        self.h = self.lib.orc_dabplus_new(bitRate)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.orc_dabplus_free(self.h)
+            self.h = None
+
+    def process(self, bits):
+        bits = np.ascontiguousarray(bits, np.uint8).reshape(-1, 24 * self.bitRate)
+        cap = bits.shape[0] // 5 + 2
+        sf = np.zeros((cap, 110 * (self.bitRate // 8)), np.uint8)
+        info = (SuperframeInfo * cap)()
+        n = self.lib.orc_dabplus_process(self.h, bits.ctypes.data, bits.shape[0], sf.ctypes.data, C.addressof(info), cap)
+        assert n <= cap
+        return sf[:n], [info[i].key() for i in range(n)]
 
 
 class _Ofdm:
