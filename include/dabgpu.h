@@ -129,6 +129,24 @@ int  dabgpu_backend_process (dabgpu_backend_t *b, const int16_t *frags, int32_t 
 int  dabgpu_backend_get_state (dabgpu_backend_t *b, int16_t *hist, int32_t *cifs_seen);
 int  dabgpu_backend_set_state (dabgpu_backend_t *b, const int16_t *hist, int32_t cifs_seen);
 
+/* DAB+ super-frame layer, the stage right behind the MSC decoder for every DAB+ service: mp4Processor::addtoFrame
+ * and the Fire-code / Reed-Solomon / access-unit-table part of processSuperframe (mp4processor.cpp:107-150,
+ * 152-275; firecode-checker.cpp:77-95; reed-solomon.cpp:129-399 with galois.cpp; dabPlus_crc mp4processor.cpp:40-61).
+ * An object carries the 5-CIF window and the sync counter across calls like the reference object does.
+ * bits[ncif][24*bitRate] = the blocks dabgpu_backend_process / dabgpu_decode return for the sub-channel;
+ * superframes[*nsf][110*bitRate/8] repaired super frames in order (at most max_sf are copied out), info[i] =
+ * first CIF (counted from the object's creation), RS symbol errors corrected, the access-unit table
+ * au_start[0..num_aus] and the per-AU CRC verdicts (bit i = AU i passes).  The AAC decoder is out of scope. */
+typedef struct dabgpu_dabplus dabgpu_dabplus_t;
+typedef struct { int64_t first_cif; int32_t corrected, num_aus, au_start [7], au_crc; } dabgpu_superframe_info;
+int  dabgpu_dabplus_create (dabgpu_t *h, int32_t bitRate, dabgpu_dabplus_t **out);
+void dabgpu_dabplus_destroy (dabgpu_dabplus_t *d);
+int  dabgpu_dabplus_process (dabgpu_dabplus_t *d, const uint8_t *bits, int32_t ncif, uint8_t *superframes,
+                             dabgpu_superframe_info *info, int32_t max_sf, int32_t *nsf);
+/* same with the bits already on the handle's device (e.g. straight from the MSC decoder's output buffer) */
+int  dabgpu_dabplus_process_dev (dabgpu_dabplus_t *d, const uint8_t *d_bits, int32_t ncif, uint8_t *superframes,
+                                 dabgpu_superframe_info *info, int32_t max_sf, int32_t *nsf);
+
 /* ------------------------------------------------------------------------------------------------
  * OFDM front end (FFT + demod group), per-call parity entry points
  * ---------------------------------------------------------------------------------------------- */

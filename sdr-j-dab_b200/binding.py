@@ -108,6 +108,53 @@ def state_predict(mode, s, nframes):
     return out
 
 
+class SuperframeInfo(C.Structure):
+    _fields_ = [("first_cif", C.c_int64), ("corrected", C.c_int32), ("num_aus", C.c_int32), ("au_start", C.c_int32 * 7),
+                ("au_crc", C.c_int32)]
+
+    def key(self):
+        return (self.first_cif, self.corrected, self.num_aus, tuple(self.au_start), self.au_crc)
+
+
+class DabPlus:
+    """DAB+ super-frame layer object (dabgpu_dabplus_*): Fire-code sync, RS(120,110) repair, AU table"""
+
+    def __init__(self, engine, bitRate):
+        self.eng, self.bitRate = engine, bitRate
+        self.lib = engine.lib
+        self.lib.dabgpu_dabplus_create.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        self.lib.dabgpu_dabplus_destroy.argtypes = [C.c_void_p]
+        self.lib.dabgpu_dabplus_destroy.restype = None
+        for f in (self.lib.dabgpu_dabplus_process, self.lib.dabgpu_dabplus_process_dev):
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+        self.d = C.c_void_p()
+        engine._check(self.lib.dabgpu_dabplus_create(engine.h, bitRate, C.byref(self.d)))
+
+    def close(self):
+        if getattr(self, "d", None):
+            self.lib.dabgpu_dabplus_destroy(self.d)
+            self.d = None
+
+    __del__ = close
+
+    def process(self, bits, dev_ptr=None, ncif=None):
+        """bits[ncif][24*bitRate] (host numpy) or a device pointer -> (superframes[n][110*R], [info keys])"""
+        if dev_ptr is None:
+            bits = np.ascontiguousarray(bits, np.uint8).reshape(-1, 24 * self.bitRate)
+            ncif = bits.shape[0]
+        cap = ncif // 5 + 2
+        sf = np.zeros((cap, 110 * (self.bitRate // 8)), np.uint8)
+        info = (SuperframeInfo * cap)()
+        n = C.c_int32(0)
+        if dev_ptr is None:
+            rc = self.lib.dabgpu_dabplus_process(self.d, bits.ctypes.data, ncif, sf.ctypes.data, C.addressof(info), cap, C.byref(n))
+        else:
+            rc = self.lib.dabgpu_dabplus_process_dev(self.d, dev_ptr, ncif, sf.ctypes.data, C.addressof(info), cap, C.byref(n))
+        self.eng._check(rc)
+        assert n.value <= cap
+        return sf[:n.value], [info[i].key() for i in range(n.value)]
+
+
 class DecodeOut:
     """Host-side result buffers of one dabgpu_decode call."""
     pass

@@ -65,11 +65,14 @@ def firecode(data9):
     return acc
 
 
-def make_superframe(bitRate, rng, dac_rate=1, sbr=0):
+def make_superframe(bitRate, rng, dac_rate=1, sbr=0, mangle_table=False):
     """-> (data[110*R] before RS, coded[120*R] as transmitted = 5 CIF blocks of 3*bitRate bytes)"""
     R = bitRate // 8
     size = 110 * R
-    n, first = {(0, 0): (4, 8), (0, 1): (2, 5), (1, 0): (6, 11), (1, 1): (3, 6)}[(dac_rate, sbr)]
+    table = {(0, 0): (4, 8), (0, 1): (2, 5), (1, 0): (6, 11), (1, 1): (3, 6)}
+    if (size - table[(dac_rate, sbr)][1]) // table[(dac_rate, sbr)][0] > 940:      # access units would exceed 960 bytes at this
+        dac_rate, sbr = 1, 0                                                        # bit rate: use the six-AU layout instead
+    n, first = table[(dac_rate, sbr)]
     step = (size - first) // n                                # roughly equal access units with some jitter
     jit = max(0, min(step // 4, (955 - step) // 2))             # an access unit must stay below 960 bytes (mp4processor.cpp:246)
     cuts = [first + k * step + int(rng.integers(-jit, jit + 1)) for k in range(1, n)]
@@ -89,6 +92,8 @@ def make_superframe(bitRate, rng, dac_rate=1, sbr=0):
         c = crc16_ccitt(body)
         sf[a:b - 2] = body
         sf[b - 2], sf[b - 1] = c >> 8, c & 255
+    if mangle_table:                                          # second AU 'starts' before the first: valid Fire code and RS,
+        sf[3], sf[4] = 0, (1 << 4) | (sf[4] & 15)             # but processSuperframe must refuse it (mp4processor.cpp:241-244)
     fc = firecode(sf[2:11])
     sf[0], sf[1] = fc >> 8, fc & 255
     coded = np.zeros(120 * R, np.int64)
