@@ -9,7 +9,7 @@
 static uint32_t lcg (uint32_t &s) { s = s * 1664525u + 1013904223u; return s >> 8; }
 static unsigned long long fnv (const uint8_t *p, size_t n) { unsigned long long h = 1469598103934665603ull; for (size_t i = 0; i < n; i ++) { h ^= p [i]; h *= 1099511628211ull; } return h; }
 
-int main () {
+int main (int argc, char **argv) {
 	try {
 		uint32_t seed = 12345;
 		{	// viterbi (768), as ficHandler does (fic-handler.cpp:84, 293)
@@ -34,6 +34,25 @@ int main () {
 			std::vector<int16_t> frag (12 * 64);
 			for (int t = 0; t < 20; t ++) { for (auto &x : frag) x = (int16_t) (lcg (seed) % 255) - 127; b. process (frag. data (), 12 * 64); }
 			printf ("backend %d %016llx\n", frames, acc);
+		}
+		{	// figSubchannels = fib_processor's FIG 0/1 path on 40 pseudo-random FIC groups (all CRC flags set)
+			figSubchannels f (1);
+			std::vector<uint8_t> bits (40 * 768), crc (40 * 3, 1);
+			for (auto &x : bits) x = (uint8_t) (lcg (seed) & 1);
+			f. process_groups (bits. data (), crc. data (), 40);
+			printf ("fig01 %016llx\n", fnv (reinterpret_cast<const uint8_t *> (f. ficList), sizeof (f. ficList)));
+		}
+		if (argc > 1) {	// mp4SuperframeFront = mp4Processor::addtoFrame, one CIF per call, bit rate 32: CIF blocks from a file
+			FILE *fp = fopen (argv [1], "rb");
+			if (!fp) throw std::runtime_error ("cannot open the CIF file");
+			int count = 0; unsigned long long acc = 0;
+			mp4SuperframeFront m (1, 32, [&] (const uint8_t *sf, int32_t n, const dabgpu_superframe_info &fi) {
+				count ++; acc ^= fnv (sf, n) + (unsigned long long) fi. first_cif * 1315423911ull + fi. corrected;
+			});
+			std::vector<uint8_t> cif (24 * 32);
+			while (fread (cif. data (), 1, cif. size (), fp) == cif. size ()) m. addtoFrame (cif. data (), 24 * 32);
+			fclose (fp);
+			printf ("dabplus %d %016llx\n", count, acc);
 		}
 	} catch (const std::exception &e) { fprintf (stderr, "adapter_demo: %s\n", e. what ()); return 1; }
 	return 0;

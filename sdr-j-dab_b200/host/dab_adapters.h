@@ -20,6 +20,7 @@
 #ifndef DAB_ADAPTERS_H
 #define DAB_ADAPTERS_H
 #include <complex>
+#include <cstring>
 #include <functional>
 #include <stdexcept>
 #include <string>
@@ -179,6 +180,55 @@ private:
 	int BitsperBlock, index = 0, ficno = 0;
 	fibSink sink;
 	int16_t ofdm_input [2304];
+};
+
+/* ---- mscDatagroup::run (data/msc-datagroup.cpp:149-198): the packet-mode / data sub-channel front half is the very
+ * chain dabConcurrent runs (time de-interleave, eep/uep depuncture + Viterbi, dispersal); only the sink differs ---- */
+typedef dabBackend dataBackend;
+
+/* ---- fib_processor's FIG 0/1 path (fib-processor.cpp:123-158, 278-347): feed CRC-clean FIC groups, read ficList.
+ * The other FIG types (labels, service lists) stay with the host's own fib_processor ---- */
+class figSubchannels {
+public:
+	explicit figSubchannels (uint8_t dabMode) : h (dabgpu_host::engine (dabMode)) { memset (ficList, 0, sizeof (ficList)); }
+	/* groups of 768 bits with their three CRC flags, as dabgpu_fic_decode returns them; later calls override earlier ones */
+	void process_groups (const uint8_t *bits768, const uint8_t *crc3, int32_t ngroups) {
+		dabgpu_subch_info t [64];
+		dabgpu_host::check (h, dabgpu_fig01_scan (h, bits768, crc3, ngroups, t));
+		for (int i = 0; i < 64; i ++) {
+			if (!t [i]. defined) continue;
+			ficList [i]. defined = 1; ficList [i]. startAddr = t [i]. startAddr; ficList [i]. uepFlag = t [i]. uepFlag;
+			if (t [i]. bitRate || t [i]. length) { ficList [i]. length = t [i]. length; ficList [i]. protLevel = t [i]. protLevel; ficList [i]. bitRate = t [i]. bitRate; }
+		}
+	}
+	dabgpu_subch_info ficList [64];
+private:
+	dabgpu_t *h;
+};
+
+/* ---- mp4Processor's super-frame front (mp4processor.cpp:107-275): addtoFrame per CIF as the reference calls it; every
+ * repaired super frame goes to a sink together with its access-unit table (the AAC decoder stays on the host) ---- */
+class mp4SuperframeFront {
+public:
+	typedef std::function<void (const uint8_t *, int32_t, const dabgpu_superframe_info &)> superframeSink;
+	mp4SuperframeFront (uint8_t dabMode, int16_t bitRate, superframeSink sink)
+	   : h (dabgpu_host::engine (dabMode)), bitRate (bitRate), sink (sink), out (110 * (bitRate / 8)) {
+		dabgpu_host::check (h, dabgpu_dabplus_create (h, bitRate, &d));
+	}
+	~mp4SuperframeFront (void) { dabgpu_dabplus_destroy (d); }
+	void addtoFrame (uint8_t *V, int16_t nbits) {
+		int32_t n = 0;
+		dabgpu_superframe_info fi;
+		(void) nbits;
+		dabgpu_host::check (h, dabgpu_dabplus_process (d, V, 1, out. data (), &fi, 1, &n));
+		if (n == 1 && sink) sink (out. data (), (int32_t) out. size (), fi);
+	}
+private:
+	dabgpu_t *h;
+	dabgpu_dabplus_t *d = nullptr;
+	int16_t bitRate;
+	superframeSink sink;
+	std::vector<uint8_t> out;
 };
 
 #endif

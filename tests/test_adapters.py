@@ -42,7 +42,19 @@ def _fnv(a):
 @pytest.mark.gpu
 def test_adapter_demo_matches_oracle(port):
     _build()
-    r = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
+    import dabplus
+    rng = np.random.default_rng(4)
+    rows = [rng.integers(0, 2, (3, 768), dtype=np.uint8)]
+    for i in range(6):
+        sf, coded, _ = dabplus.make_superframe(32, rng, dac_rate=i & 1, sbr=(i >> 1) & 1)
+        if i == 2:
+            coded[3 * 4 + 1::4][:3] ^= 0x21                      # three byte errors in column 1
+        rows.append(dabplus.to_cif_bits(coded, 32))
+    cifs = np.concatenate(rows)
+    path = os.path.join(HOST, "adapter_demo_cifs.bin")
+    cifs.tofile(path)
+    r = subprocess.run([EXE, path], capture_output=True, text=True, timeout=120)
+    os.remove(path)
     assert r.returncode == 0, r.stderr
     got = dict(line.split(" ", 1) for line in r.stdout.strip().splitlines())
     g = _lcg_stream(12345)
@@ -58,3 +70,12 @@ def test_adapter_demo_matches_oracle(port):
         acc ^= (_fnv(blk) + i + 1) & 0xFFFFFFFFFFFFFFFF
     frames, h = got["backend"].split()
     assert int(frames) == 4 and int(h, 16) == acc
+    bits = np.array([next(g) & 1 for _ in range(40 * 768)], np.uint8)
+    table = port.fig01_scan(bits, np.ones((40, 3), np.uint8))
+    assert int(got["fig01"], 16) == _fnv(table)
+    sfs, info = port.dabplus(32).process(cifs)
+    acc = 0
+    for sf, k in zip(sfs, info):
+        acc ^= (_fnv(sf) + k[0] * 1315423911 + k[1]) & 0xFFFFFFFFFFFFFFFF
+    count, h = got["dabplus"].split()
+    assert int(count) == len(info) == 6 and int(h, 16) == acc
