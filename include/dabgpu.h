@@ -196,6 +196,12 @@ int dabgpu_set_subchannels (dabgpu_t *h, const dabgpu_subch *sc, int32_t nsub); 
 int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out);
 /* same with the input already resident on the handle's device (result pointers stay host pointers) */
 int dabgpu_decode_dev (dabgpu_t *h, const uint8_t *d_iq_u8, size_t nsamples, dabgpu_result *out);
+/* The same stream engine fed with complex float samples (interleaved re, im at 2.048 MS/s): the form in which
+ * every input device of the reference hands samples to ofdmProcessor (virtualInput::getSamples, virtual-input.h:62-63;
+ * wavfiles.cpp:168-180 for .sdr recordings; the dabstick / sdrplay / airspy handlers).  A stream may switch format
+ * only when no unconsumed samples are pending (DABGPU_ERR_STATE otherwise). */
+int dabgpu_decode_cf32 (dabgpu_t *h, const float *iq, size_t nsamples, dabgpu_result *out);
+int dabgpu_decode_cf32_dev (dabgpu_t *h, const float *d_iq, size_t nsamples, dabgpu_result *out);
 int dabgpu_reset (dabgpu_t *h);                                                   /* ofdmProcessor::reset  */
 
 /* stream state for splitting a recording across calls / GPUs */

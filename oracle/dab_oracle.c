@@ -486,12 +486,14 @@ static const float *oscillator (void) {
 typedef struct {
 	const uint8_t *iq; int64_t n, pos;
 	const float *osc; int32_t localPhase; float sLevel;
+	const float *fq;                                  /* non-NULL: complex float samples as virtualInput::getSamples delivers them */
 } pump_t;
 
 static inline int pump_sample (pump_t *s, int32_t phase, float *re, float *im) {
 	if (s -> pos >= s -> n) return 0;                 /* the reference blocks/throws here (:135-145) */
-	const float a = (float) (s -> iq [2 * s -> pos] - 128) / 128.0f;
-	const float b = (float) (s -> iq [2 * s -> pos + 1] - 128) / 128.0f;
+	/* rawfiles.cpp:113-116 for u8 files; wavfiles.cpp:168-180 and every device handler hand over floats directly */
+	const float a = s -> fq ? s -> fq [2 * s -> pos]     : (float) (s -> iq [2 * s -> pos] - 128) / 128.0f;
+	const float b = s -> fq ? s -> fq [2 * s -> pos + 1] : (float) (s -> iq [2 * s -> pos + 1] - 128) / 128.0f;
 	s -> pos ++;
 	s -> localPhase -= phase;                                           /* :165 */
 	s -> localPhase = (s -> localPhase + INPUT_RATE) % INPUT_RATE;      /* :166 */
@@ -508,13 +510,23 @@ static inline int pump_samples (pump_t *s, float *v, int n, int32_t phase) {
 	return 1;
 }
 
+static int ofdm_run_impl (int mode, int threshold, int freqSyncMethod, const uint8_t *iq, const float *fq, int64_t nsamples,
+                          int max_frames, int16_t *sym, orc_frame_info *info);
 int orc_ofdm_run (int mode, int threshold, int freqSyncMethod, const uint8_t *iq, int64_t nsamples,
                   int max_frames, int16_t *sym, orc_frame_info *info) {
+	return ofdm_run_impl (mode, threshold, freqSyncMethod, iq, NULL, nsamples, max_frames, sym, info);
+}
+int orc_ofdm_run_cf32 (int mode, int threshold, int freqSyncMethod, const float *iq, int64_t nsamples,
+                       int max_frames, int16_t *sym, orc_frame_info *info) {
+	return ofdm_run_impl (mode, threshold, freqSyncMethod, NULL, iq, nsamples, max_frames, sym, info);
+}
+static int ofdm_run_impl (int mode, int threshold, int freqSyncMethod, const uint8_t *iq, const float *fq, int64_t nsamples,
+                          int max_frames, int16_t *sym, orc_frame_info *info) {
 	orc_params p;
 	if (orc_mode_params (mode, &p)) return -1;
 	const int T_u = p. T_u, T_s = p. T_s, T_null = p. T_null, T_F = p. T_F, K = p. K;
 	k_ofdm *dec = k_ofdm_new (&p, threshold, freqSyncMethod);
-	pump_t s = { iq, nsamples, 0, oscillator (), 0, 0 };
+	pump_t s = { iq, nsamples, 0, oscillator (), 0, 0, fq };
 	float *ofdmBuffer = (float *) malloc (sizeof (float) * 2 * 76 * T_s);
 	float *envBuffer = (float *) calloc (32768, sizeof (float));
 	const int syncBufferMask = 32768 - 1;

@@ -118,6 +118,10 @@ typedef struct {
  * bits handed to process_ficBlock / process_mscBlock.  Returns frames decoded. */
 int orc_ofdm_run (int mode, int threshold, int freqSyncMethod, const uint8_t *iq, int64_t nsamples,
                   int max_frames, int16_t *sym, orc_frame_info *info);
+/* the same loop fed with complex float samples (interleaved re, im), the form every input device of the reference
+ * delivers (virtual-input.h:62-63; wavfiles.cpp:168-180 for .sdr files) */
+int orc_ofdm_run_cf32 (int mode, int threshold, int freqSyncMethod, const float *iq, int64_t nsamples,
+                       int max_frames, int16_t *sym, orc_frame_info *info);
 
 const char *orc_build_kind (void);   /* "port" or "reference" */
 

@@ -163,10 +163,11 @@ class DecodeOut:
 class DabGpu:
     """One engine handle (dabgpu_t)."""
 
-    def __init__(self, mode=1, device=0, threshold=3, freqSyncMethod=1, viterbi_path=0, host_batch_frames=0):
+    def __init__(self, mode=1, device=0, threshold=3, freqSyncMethod=1, viterbi_path=0, host_batch_frames=0, generic_symbol_kernel=False):
         self.lib = load_library()
         cfg = Config(device=device, dabMode=mode, threshold=threshold, freqSyncMethod=freqSyncMethod, viterbi_path=viterbi_path)
         cfg.host_batch_frames = host_batch_frames
+        cfg.reserved[0] = 1 if generic_symbol_kernel else 0
         self.h = C.c_void_p()
         rc = self.lib.dabgpu_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:
@@ -326,9 +327,15 @@ class DabGpu:
         return o
 
     def decode(self, iq_u8, out):
-        """iq_u8: numpy uint8 (interleaved I,Q) or an int host address with `nsamples` given via a tuple"""
+        """iq_u8: numpy uint8 (interleaved I,Q; rawfile format) or float32 (interleaved re, im: dabgpu_decode_cf32), or an
+        int host address of u8 samples with `nsamples` given via a tuple"""
         if isinstance(iq_u8, tuple):
             ptr, nsamples = iq_u8
+        elif np.asarray(iq_u8).dtype == np.float32:
+            iq = np.ascontiguousarray(iq_u8, np.float32)
+            self.lib.dabgpu_decode_cf32.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Result)]
+            self._check(self.lib.dabgpu_decode_cf32(self.h, iq.ctypes.data, iq.size // 2, C.byref(out.res)))
+            return self._trim(out)
         else:
             iq = np.ascontiguousarray(iq_u8, np.uint8)
             ptr, nsamples = iq.ctypes.data, iq.size // 2

@@ -13,8 +13,15 @@
 #include <math.h>
 #include "dabgpu_engine.h"
 
-__device__ __forceinline__ uchar2 win_fetch (const SampleWin &w, long long i) {
+__device__ __forceinline__ uchar2 win_fetch (const SampleWin &w, long long i) {      // u8 windows only
 	return i < w. len0 ? __ldg (&w. seg0 [i]) : __ldg (&w. seg1 [i - w. len0]);
+}
+// sample i as the complex float the reference's getSample sees before the NCO (ofdm-processor.cpp:133-183)
+__device__ __forceinline__ float2 win_sample (const SampleWin &w, long long i) {
+	if (w. cf32)
+		return i < w. len0 ? __ldg (reinterpret_cast<const float2 *> (w. seg0) + i) : __ldg (reinterpret_cast<const float2 *> (w. seg1) + (i - w. len0));
+	const uchar2 s = win_fetch (w, i);
+	return make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f));
 }
 
 // dst[i] = sample (first + i) after u8 conversion and NCO, i < n (rawfiles.cpp:113-116; ofdm-processor.cpp:217-226)
@@ -25,9 +32,7 @@ __device__ __forceinline__ void load_win_nco (float2 *dst, const SampleWin &w, l
 	int lp = mod_rate ((long long) lp_before - (long long) (tid + 1) * ph);
 	const int step = mod_rate ((long long) OFDM_THREADS * ph);
 	for (int i = tid; i < n; i += OFDM_THREADS) {
-		const uchar2 s = win_fetch (w, first + i);
-		const float2 v = make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f));
-		dst [i] = cmul (v, nco (T, lp));
+		dst [i] = cmul (win_sample (w, first + i), nco (T, lp));
 		lp -= step;
 		if (lp < 0) lp += DAB_INPUT_RATE;
 	}
@@ -70,8 +75,7 @@ __global__ void __launch_bounds__ (32) acquire_kernel (SampleWin w, OfdmTables T
 			int lp = mod_rate ((long long) s_lp - (long long) (lane + 1) * ph);
 			const int step = mod_rate (32ll * ph);
 			for (int i = lane; i < n; i += 32) {
-				const uchar2 s = win_fetch (w, s_pos + i);
-				const float2 v = cmul (make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f)), nco (T, lp));
+				const float2 v = cmul (win_sample (w, s_pos + i), nco (T, lp));
 				s_ja [i] = fabsf (v. x) + fabsf (v. y);           // jan_abs
 				s_ha [i] = hypotf (v. x, v. y);                   // abs
 				lp -= step; if (lp < 0) lp += DAB_INPUT_RATE;
@@ -669,7 +673,7 @@ static int ensure_frame_capacity (dabgpu *h, long long frames);
 // ---- whole stream state as one blob (the multi-GPU hand-over: sync/AFC state + unconsumed samples + the
 // 15-CIF soft-bit halo of the time de-interleaver + per-sub-channel warm-up counters) ----
 struct StateBlobHeader {
-	uint32_t magic; int32_t mode, nsub, hist_valid;
+	uint32_t magic; int32_t mode, nsub, hist_valid, cf32, pad;
 	StreamCtl ctl; long long abs_base, frames_total, cifs_total, tail_len;
 };
 #define STATE_MAGIC 0x44414247u
@@ -678,19 +682,20 @@ extern "C" int dabgpu_state_export (dabgpu_t *h, void *buf, size_t capacity, siz
 	if (!h || !used) return DABGPU_ERR_ARG;
 	Engine *E = h -> engine;
 	const size_t rowb = (size_t) CIF_BITS * sizeof (int16_t);
-	const size_t need = sizeof (StateBlobHeader) + E -> backends. size () * sizeof (int64_t) + (size_t) E -> tail_len * sizeof (uchar2) + 15 * rowb;
+	const size_t need = sizeof (StateBlobHeader) + E -> backends. size () * sizeof (int64_t) + (size_t) E -> tail_len * E -> sample_bytes () + 15 * rowb;
 	*used = need;
 	if (!buf) return DABGPU_OK;
 	if (capacity < need) return dab_fail (h, DABGPU_ERR_ARG, "state blob needs %zu bytes", need);
 	CUDA_TRY (h, cudaSetDevice (h -> device));
 	StateBlobHeader hd {};
+	hd. cf32 = E -> cf32; hd. pad = 0;
 	hd. magic = STATE_MAGIC; hd. mode = h -> p. dabMode; hd. nsub = (int32_t) E -> backends. size (); hd. hist_valid = E -> hist_init;
 	hd. ctl = E -> ctl; hd. abs_base = E -> abs_base; hd. frames_total = E -> frames_total; hd. cifs_total = E -> cifs_total; hd. tail_len = E -> tail_len;
 	char *q = (char *) buf;
 	memcpy (q, &hd, sizeof (hd)); q += sizeof (hd);
 	for (auto *b : E -> backends) { int64_t c = dab_backend_cifs_seen (b); memcpy (q, &c, sizeof (c)); q += sizeof (c); }
-	if (E -> tail_len) CUDA_TRY (h, cudaMemcpyAsync (q, E -> tail. p, (size_t) E -> tail_len * sizeof (uchar2), cudaMemcpyDeviceToHost, h -> stream));
-	q += (size_t) E -> tail_len * sizeof (uchar2);
+	if (E -> tail_len) CUDA_TRY (h, cudaMemcpyAsync (q, E -> tail. p, (size_t) E -> tail_len * E -> sample_bytes (), cudaMemcpyDeviceToHost, h -> stream));
+	q += (size_t) E -> tail_len * E -> sample_bytes ();
 	if (E -> hist_init) CUDA_TRY (h, cudaMemcpyAsync (q, E -> d_msc. p, 15 * rowb, cudaMemcpyDeviceToHost, h -> stream));
 	else memset (q, 0, 15 * rowb);
 	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
@@ -704,7 +709,7 @@ extern "C" int dabgpu_state_import (dabgpu_t *h, const void *buf, size_t n) {
 	memcpy (&hd, buf, sizeof (hd));
 	const size_t rowb = (size_t) CIF_BITS * sizeof (int16_t);
 	if (hd. magic != STATE_MAGIC || hd. mode != h -> p. dabMode || hd. nsub != (int32_t) E -> backends. size () || hd. tail_len < 0 ||
-	    n != sizeof (hd) + (size_t) hd. nsub * sizeof (int64_t) + (size_t) hd. tail_len * sizeof (uchar2) + 15 * rowb)
+	    n != sizeof (hd) + (size_t) hd. nsub * sizeof (int64_t) + (size_t) hd. tail_len * (hd. cf32 ? sizeof (float2) : sizeof (uchar2)) + 15 * rowb)
 		return dab_fail (h, DABGPU_ERR_ARG, "state blob does not match this handle (mode / sub-channel count / size)");
 	CUDA_TRY (h, cudaSetDevice (h -> device));
 	int rc = ensure_frame_capacity (h, 1);
@@ -713,11 +718,12 @@ extern "C" int dabgpu_state_import (dabgpu_t *h, const void *buf, size_t n) {
 	for (auto *b : E -> backends) { int64_t c; memcpy (&c, q, sizeof (c)); q += sizeof (c); dab_backend_set_cifs_seen (b, c); }
 	E -> ctl = hd. ctl; E -> abs_base = hd. abs_base; E -> frames_total = hd. frames_total; E -> cifs_total = hd. cifs_total;
 	E -> tail_len = hd. tail_len;
+	E -> cf32 = hd. cf32 ? 1 : 0;
 	if (hd. tail_len) {
-		CUDA_TRY (h, E -> tail. ensure ((size_t) hd. tail_len * sizeof (uchar2)));
-		CUDA_TRY (h, cudaMemcpyAsync (E -> tail. p, q, (size_t) hd. tail_len * sizeof (uchar2), cudaMemcpyHostToDevice, h -> stream));
+		CUDA_TRY (h, E -> tail. ensure ((size_t) hd. tail_len * E -> sample_bytes ()));
+		CUDA_TRY (h, cudaMemcpyAsync (E -> tail. p, q, (size_t) hd. tail_len * E -> sample_bytes (), cudaMemcpyHostToDevice, h -> stream));
 	}
-	q += (size_t) hd. tail_len * sizeof (uchar2);
+	q += (size_t) hd. tail_len * E -> sample_bytes ();
 	CUDA_TRY (h, cudaMemcpyAsync (E -> d_msc. p, q, 15 * rowb, cudaMemcpyHostToDevice, h -> stream));
 	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
 	E -> hist_init = true;
@@ -816,13 +822,15 @@ static int channel_chunk (dabgpu *h, int f0, int nv, dabgpu_result *out, std::ve
 
 // decode core on a device-resident input segment.  `ready` (optional): events of the piecewise host-to-device copy
 // of the input; piece k covers new-segment samples [k * piece, (k+1) * piece).
-static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_result *out,
+static int decode_core (dabgpu *h, const void *d_new_v, long long nnew, dabgpu_result *out,
                         const std::vector<cudaEvent_t> *ready = nullptr, long long piece = 0, int vit_batch_frames = 0x7fffffff) {
 	Engine *E = h -> engine;
 	const DabParams &p = h -> p;
 	if (p. dabMode == 3)
 		return dab_fail (h, DABGPU_ERR_ARG, "stream decode is not available for Mode III (the reference has no Mode III framing either)");
-	SampleWin w { (const uchar2 *) E -> tail. p, E -> tail_len, d_new, nnew };
+	const uchar2 *d_new = (const uchar2 *) d_new_v;
+	const size_t sb = E -> sample_bytes ();
+	SampleWin w { (const uchar2 *) E -> tail. p, E -> tail_len, d_new, nnew, E -> cf32 };
 	const long long total = E -> tail_len + nnew;
 	const long long frame_need = 2ll * p. T_u + (long long) (p. L - 1) * p. T_s + p. T_null;   // worst case from P
 	const long long max_frames_possible = total / p. T_F + 2;
@@ -895,7 +903,7 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 			{ ProfScope prof (h, KC_FRONT);
 			front_kernel<<<(int) C, OFDM_THREADS, sm_front, h -> stream>>> (w, E -> T, fin, fo, (float2 *) E -> d_spec0. p); }
 			{ ProfScope prof (h, KC_SYMBOL);
-			if (p. T_u == R8_N && p. K == 1536)
+			if (p. T_u == R8_N && p. K == 1536 && !E -> cf32 && !h -> cfg. reserved [0])     // reserved[0] = 1: generic kernel (A/B testing)
 				symbol_kernel_r8<<<(int) C * E -> groups, 256, R8_DYN_SMEM, h -> stream>>> (w, E -> T, fin, nframes, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
 					fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p,
 					(uint8_t *) E -> d_fic8. p, (uint8_t *) E -> d_msc8. p);
@@ -952,12 +960,12 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 	out -> consumed = consumed - E -> tail_len;               // relative to this call's input (may be negative: none of it)
 	if (keep > 0) {
 		DevBuf &nt = E -> tail_spare;                       // ping-pong: no allocation once both buffers are big enough
-		CUDA_TRY (h, nt. ensure ((size_t) keep * sizeof (uchar2)));
+		CUDA_TRY (h, nt. ensure ((size_t) keep * sb));
 		long long from0 = consumed < E -> tail_len ? E -> tail_len - consumed : 0;     // part still in the old tail
 		if (from0 > 0)
-			CUDA_TRY (h, cudaMemcpyAsync (nt. p, (const uchar2 *) E -> tail. p + consumed, (size_t) from0 * sizeof (uchar2), cudaMemcpyDeviceToDevice, h -> stream));
+			CUDA_TRY (h, cudaMemcpyAsync (nt. p, (const char *) E -> tail. p + (size_t) consumed * sb, (size_t) from0 * sb, cudaMemcpyDeviceToDevice, h -> stream));
 		const long long off1 = consumed > E -> tail_len ? consumed - E -> tail_len : 0;
-		CUDA_TRY (h, cudaMemcpyAsync ((uchar2 *) nt. p + from0, d_new + off1, (size_t) (nnew - off1) * sizeof (uchar2), cudaMemcpyDeviceToDevice, h -> stream));
+		CUDA_TRY (h, cudaMemcpyAsync ((char *) nt. p + (size_t) from0 * sb, (const char *) d_new + (size_t) off1 * sb, (size_t) (nnew - off1) * sb, cudaMemcpyDeviceToDevice, h -> stream));
 		CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
 		DevBuf t = E -> tail; E -> tail = E -> tail_spare; E -> tail_spare = t;
 	} else
@@ -969,17 +977,45 @@ static int decode_core (dabgpu *h, const uchar2 *d_new, long long nnew, dabgpu_r
 	return DABGPU_OK;
 }
 
+// the sample format of a stream may only change while no unconsumed samples are pending
+static int set_format (dabgpu *h, int cf32) {
+	Engine *E = h -> engine;
+	if (E -> cf32 != cf32 && E -> tail_len > 0)
+		return dab_fail (h, DABGPU_ERR_STATE, "sample format changed while %lld samples of the other format are pending", E -> tail_len);
+	E -> cf32 = cf32;
+	return DABGPU_OK;
+}
+
+static int decode_host (dabgpu *h, const void *iq, size_t nsamples, int cf32, dabgpu_result *out);
+
 extern "C" int dabgpu_decode_dev (dabgpu_t *h, const uint8_t *d_iq_u8, size_t nsamples, dabgpu_result *out) {
 	if (!h || !out || (nsamples > 0 && !d_iq_u8)) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_decode: bad argument");
 	CUDA_TRY (h, cudaSetDevice (h -> device));
-	return decode_core (h, (const uchar2 *) d_iq_u8, (long long) nsamples, out);
+	int rc = set_format (h, 0);
+	if (rc) return rc;
+	return decode_core (h, d_iq_u8, (long long) nsamples, out);
 }
 
-extern "C" int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out) {
+extern "C" int dabgpu_decode_cf32_dev (dabgpu_t *h, const float *d_iq, size_t nsamples, dabgpu_result *out) {
+	if (!h || !out || (nsamples > 0 && !d_iq)) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_decode_cf32: bad argument");
+	CUDA_TRY (h, cudaSetDevice (h -> device));
+	int rc = set_format (h, 1);
+	if (rc) return rc;
+	return decode_core (h, d_iq, (long long) nsamples, out);
+}
+
+extern "C" int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out) { return decode_host (h, iq_u8, nsamples, 0, out); }
+extern "C" int dabgpu_decode_cf32 (dabgpu_t *h, const float *iq, size_t nsamples, dabgpu_result *out) { return decode_host (h, iq, nsamples, 1, out); }
+
+static int decode_host (dabgpu *h, const void *iq_v, size_t nsamples, int cf32, dabgpu_result *out) {
+	const uint8_t *iq_u8 = (const uint8_t *) iq_v;
 	if (!h || !out || (nsamples > 0 && !iq_u8)) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_decode: bad argument");
 	CUDA_TRY (h, cudaSetDevice (h -> device));
 	Engine *E = h -> engine;
-	const size_t bytes = nsamples * 2;
+	int frc = set_format (h, cf32);
+	if (frc) return frc;
+	const size_t sb = E -> sample_bytes ();
+	const size_t bytes = nsamples * sb;
 	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
 	CUDA_TRY (h, h -> d_in. ensure (bytes + 16));
 	// the input goes up in pieces on its own stream; every chunk of frames waits only for the pieces it reads, so
@@ -1003,7 +1039,7 @@ extern "C" int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples
 			E -> copy_events. push_back (e);
 		}
 		for (size_t k = 0; k < npieces; k ++) {
-			const size_t off = k * (size_t) piece * 2, len = (k + 1 == npieces ? bytes - off : (size_t) piece * 2);
+			const size_t off = k * (size_t) piece * sb, len = (k + 1 == npieces ? bytes - off : (size_t) piece * sb);
 			CUDA_TRY (h, cudaMemcpyAsync ((char *) h -> d_in. p + off, src + off, len, cudaMemcpyHostToDevice, E -> copy_st));
 			CUDA_TRY (h, cudaEventRecord (E -> copy_events [k], E -> copy_st));
 			ready. push_back (E -> copy_events [k]);
@@ -1011,7 +1047,7 @@ extern "C" int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples
 	}
 	// host input: the PCIe copy paces the call and the GPU idles most of the time, so channel decoding follows the
 	// OFDM part in small batches: what is left to do once the last sample has arrived is then short
-	int rc = decode_core (h, (const uchar2 *) h -> d_in. p, (long long) nsamples, out, &ready, piece,
+	int rc = decode_core (h, h -> d_in. p, (long long) nsamples, out, &ready, piece,
 	                      h -> cfg. host_batch_frames > 0 ? h -> cfg. host_batch_frames : E -> vit_batch_frames);
 	cudaStreamSynchronize (E -> copy_st);
 	return rc;

@@ -19,8 +19,9 @@ struct StreamCtl {
 };
 
 struct SampleWin {                      // two-segment sample window: [tail of earlier calls | this call's input]
-	const uchar2 *seg0; long long len0;
+	const uchar2 *seg0; long long len0;     // lengths in samples; with cf32 set the pointers are really const float2 *
 	const uchar2 *seg1; long long len1;
+	int cf32;                               // 0: u8 I,Q pairs (rawfiles.cpp:113-116); 1: complex float samples (virtual-input.h:62-63)
 };
 
 struct FrameIn {                        // per chunk slot: the inputs a frame is (re)computed from
@@ -45,7 +46,9 @@ struct Engine {
 	StreamCtl ctl {};
 	long long abs_base = 0;             // absolute sample index of window position 0
 	long long frames_total = 0, cifs_total = 0;
-	DevBuf tail, tail_spare; long long tail_len = 0;     // unconsumed samples (uchar2), ping-pong
+	DevBuf tail, tail_spare; long long tail_len = 0;     // unconsumed samples, ping-pong
+	int cf32 = 0;                       // sample format of the stream (fixed while a tail is pending)
+	size_t sample_bytes () const { return cf32 ? sizeof (float2) : sizeof (uchar2); }
 	DevBuf d_ctl;                       // StreamCtl on the device
 	PinBuf h_ctl;
 	int chunk = 1, max_chunk = 1024;

@@ -192,13 +192,20 @@ class Oracle:
     def ofdm(self, mode, threshold=3, freqSyncMethod=1):
         return _Ofdm(self, mode, threshold, freqSyncMethod)
 
-    def ofdm_run(self, mode, iq_u8, max_frames, threshold=3, freqSyncMethod=1):
+    def ofdm_run(self, mode, iq, max_frames, threshold=3, freqSyncMethod=1):
+        """iq: uint8 (rawfile format) or float32 (interleaved re, im: what the reference's input devices deliver)"""
         p = self.mode_params(mode)
-        iq = np.ascontiguousarray(iq_u8, np.uint8)
         sym = np.zeros((max_frames, p.L - 1, 2 * p.K), np.int16)
         info = (FrameInfo * max_frames)()
-        n = self.lib.orc_ofdm_run(mode, threshold, freqSyncMethod, iq.ctypes.data, iq.size // 2, max_frames,
-                                  sym.ctypes.data, C.addressof(info))
+        if np.asarray(iq).dtype == np.float32:
+            iq = np.ascontiguousarray(iq, np.float32)
+            self.lib.orc_ofdm_run_cf32.argtypes = self.lib.orc_ofdm_run.argtypes
+            n = self.lib.orc_ofdm_run_cf32(mode, threshold, freqSyncMethod, iq.ctypes.data, iq.size // 2, max_frames,
+                                           sym.ctypes.data, C.addressof(info))
+        else:
+            iq = np.ascontiguousarray(iq, np.uint8)
+            n = self.lib.orc_ofdm_run(mode, threshold, freqSyncMethod, iq.ctypes.data, iq.size // 2, max_frames,
+                                      sym.ctypes.data, C.addressof(info))
         return sym[:n], [info[i] for i in range(n)]
 
 
