@@ -202,6 +202,14 @@ int dabgpu_decode_dev (dabgpu_t *h, const uint8_t *d_iq_u8, size_t nsamples, dab
  * only when no unconsumed samples are pending (DABGPU_ERR_STATE otherwise). */
 int dabgpu_decode_cf32 (dabgpu_t *h, const float *iq, size_t nsamples, dabgpu_result *out);
 int dabgpu_decode_cf32_dev (dabgpu_t *h, const float *d_iq, size_t nsamples, dabgpu_result *out);
+/* airspyHandler's sample-rate conversion (airspy-handler.cpp:138-148, 342-370): int16 I,Q pairs at in_rate samples/s
+ * (a multiple of 1000) -> complex floats at 2 048 000 samples/s by linear interpolation in 1 ms blocks, ready for
+ * dabgpu_decode_cf32.  Block b reads input samples [b R, b R + R], R = in_rate / 1000, and writes 2048 samples; a call
+ * converts the (n_in - 1) / R whole blocks it holds: *n_out = samples written to out (capacity needed:
+ * ((n_in - 1) / R) * 2048 complex floats), *consumed = input samples the caller may drop (it keeps the rest,
+ * including the sample shared with the next block, for its next call). */
+int dabgpu_resample_i16 (dabgpu_t *h, const int16_t *iq, size_t n_in, int32_t in_rate, float *out, size_t *n_out, size_t *consumed);
+int dabgpu_resample_i16_dev (dabgpu_t *h, const int16_t *d_iq, size_t n_in, int32_t in_rate, float *d_out, size_t *n_out, size_t *consumed);
 int dabgpu_reset (dabgpu_t *h);                                                   /* ofdmProcessor::reset  */
 
 /* stream state for splitting a recording across calls / GPUs */

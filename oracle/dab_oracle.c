@@ -433,6 +433,41 @@ int orc_dabplus_process (orc_dabplus *d, const uint8_t *bits, int ncif, uint8_t 
 	return nsf;
 }
 
+/* ---- airspyHandler: sample-rate conversion to 2.048 MS/s by linear interpolation in 1 ms blocks
+ * (airspy-handler.cpp:138-148 tables, 342-370 data_available).  Streaming over the whole input; returns the number
+ * of output samples. ---- */
+int64_t orc_resample_i16 (const int16_t *sbuf, int64_t nSamples, int selectedRate, float *out) {
+	const int convBufferSize = selectedRate / 1000;
+	int16_t mapTable_int [2048]; float mapTable_float [2048];
+	for (int i = 0; i < 2048; i ++) {
+		const float inVal = (float) (selectedRate / 1000);
+		mapTable_int [i] = (int16_t) (int) floor (i * (inVal / 2048.0));
+		mapTable_float [i] = (float) (i * (inVal / 2048.0) - mapTable_int [i]);
+	}
+	float *convBuffer = (float *) malloc (sizeof (float) * 2 * (convBufferSize + 1));
+	int convIndex = 0;
+	int64_t nout = 0;
+	for (int64_t i = 0; i < nSamples; i ++) {
+		convBuffer [2 * convIndex] = sbuf [2 * i] / (float) 2048;
+		convBuffer [2 * convIndex + 1] = sbuf [2 * i + 1] / (float) 2048;
+		convIndex ++;
+		if (convIndex > convBufferSize) {
+			for (int j = 0; j < 2048; j ++) {
+				const int b = mapTable_int [j];
+				const float r = mapTable_float [j], q = 1 - r;
+				/* cmul (complex, float) = component-wise product (dab-constants.h) */
+				out [2 * nout]     = convBuffer [2 * (b + 1)] * r + convBuffer [2 * b] * q;
+				out [2 * nout + 1] = convBuffer [2 * (b + 1) + 1] * r + convBuffer [2 * b + 1] * q;
+				nout ++;
+			}
+			convBuffer [0] = convBuffer [2 * convBufferSize]; convBuffer [1] = convBuffer [2 * convBufferSize + 1];
+			convIndex = 1;
+		}
+	}
+	free (convBuffer);
+	return nout;
+}
+
 /* ---- CIF assembly + sub-channel slice: msc-handler.cpp:125-193 ---- */
 int orc_msc_slice (int mode, const int16_t *sym, int nframes, int startAddr, int Length, int16_t *frag) {
 	orc_params p;

@@ -78,6 +78,9 @@ int  orc_firecode_check (const uint8_t *x11);
 int  orc_rs_dec (const uint8_t *r120, uint8_t *d110);
 void orc_rs_enc (const uint8_t *d110, uint8_t *r120);
 
+/* airspyHandler's rate conversion (airspy-handler.cpp:138-148, 342-370): int16 I,Q at selectedRate -> floats at 2.048 MS/s */
+int64_t orc_resample_i16 (const int16_t *sbuf, int64_t nSamples, int selectedRate, float *out);
+
 /* ficList entry (fib-processor.h:78-87), the fields FIG 0/1 fills */
 typedef struct { int32_t defined, startAddr, length, uepFlag, protLevel, bitRate; } orc_subch_info;
 /* FIG 0/1 of every CRC-clean FIB of ngroups FIC groups, in order, into list[64] (fib-processor.cpp:123-158, 278-347) */

@@ -249,6 +249,16 @@ class DabGpu:
                                                crc.ctypes.data))
         return bits, crc
 
+    def resample_i16(self, iq, rate):
+        """airspy-style rate conversion: int16 I,Q at `rate` -> (float32 interleaved re,im at 2.048 MS/s, consumed input samples)"""
+        iq = np.ascontiguousarray(iq, np.int16)
+        n = iq.size // 2
+        out = np.zeros(2 * 2048 * (max(n - 1, 0) // (rate // 1000)) + 2, np.float32)
+        n_out, consumed = C.c_size_t(0), C.c_size_t(0)
+        self.lib.dabgpu_resample_i16.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        self._check(self.lib.dabgpu_resample_i16(self.h, iq.ctypes.data, n, rate, out.ctypes.data, C.byref(n_out), C.byref(consumed)))
+        return out[:2 * n_out.value], consumed.value
+
     def fig01_scan(self, fic_bits, crc_ok):
         """FIG 0/1 sub-channel table of the given FIC groups -> (64, 6) int32: defined, startAddr, length, uepFlag, protLevel, bitRate"""
         bits = np.ascontiguousarray(fic_bits, np.uint8).reshape(-1, 768)

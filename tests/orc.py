@@ -155,6 +155,15 @@ class Oracle:
         self.lib.orc_fig01_scan(_p(bits, C.c_uint8), _p(crc, C.c_uint8), bits.shape[0], _p(table, C.c_int32))
         return table
 
+    def resample_i16(self, iq, rate):
+        iq = np.ascontiguousarray(iq, np.int16)
+        n = iq.size // 2
+        out = np.zeros(2 * 2048 * (n // (rate // 1000) + 1), np.float32)
+        self.lib.orc_resample_i16.restype = C.c_int64
+        self.lib.orc_resample_i16.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+        k = self.lib.orc_resample_i16(iq.ctypes.data, n, rate, out.ctypes.data)
+        return out[:2 * k]
+
     # ---- DAB+ super-frame layer ----
     def firecode_check(self, x11):
         b = np.ascontiguousarray(x11, np.uint8)
