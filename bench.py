@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dev-batch", type=int, default=0, help="frames per channel-decoding launch on the device-resident path; 0 = one launch per step")
     ap.add_argument("--host-batch", type=int, default=0, help="frames per channel-decoding launch on the host-input (e2e) path; 0 = engine default")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -182,12 +183,13 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout for the one JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     iq, mod, truth = make_workload(args.frames, 1002 + rank, orc_mod, dabmod)
     subs = [(s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel) for s in mod.sub]
-    eng = pkg.DabGpu(mode=MODE, device=local_rank, host_batch_frames=args.host_batch)
+    eng = pkg.DabGpu(mode=MODE, device=local_rank, host_batch_frames=args.host_batch, dev_batch_frames=args.dev_batch)
     eng.set_subchannels(subs)
 
     # lead-in: acquire + lock + fill the de-interleaver, then remember the locked stream state

@@ -46,7 +46,9 @@ typedef struct {
 	int32_t viterbi_path;      /* 0 = auto (by batch size), 1 = warp-per-code-word kernel, 2 = throughput (two threads per code word) kernel */
 	int32_t host_batch_frames; /* dabgpu_decode from HOST memory: frames per channel-decoding launch while the input is
 	                              still arriving over PCIe (0 = default 128)                                           */
-	int32_t reserved [2];
+	int32_t reserved [2];      /* tuning / A-B switches, 0 = default: [0] = 1 forces the generic symbol kernel in Mode I,
+	                              [1] = frames per channel-decoding launch on the device-resident path (default: one
+	                              launch per call, measured fastest) */
 } dabgpu_config;
 
 /* one MSC sub-channel, the fields of audiodata/packetdata the decode path uses (dab-constants.h:151-175;

@@ -163,11 +163,12 @@ class DecodeOut:
 class DabGpu:
     """One engine handle (dabgpu_t)."""
 
-    def __init__(self, mode=1, device=0, threshold=3, freqSyncMethod=1, viterbi_path=0, host_batch_frames=0, generic_symbol_kernel=False):
+    def __init__(self, mode=1, device=0, threshold=3, freqSyncMethod=1, viterbi_path=0, host_batch_frames=0, generic_symbol_kernel=False, dev_batch_frames=0):
         self.lib = load_library()
         cfg = Config(device=device, dabMode=mode, threshold=threshold, freqSyncMethod=freqSyncMethod, viterbi_path=viterbi_path)
         cfg.host_batch_frames = host_batch_frames
         cfg.reserved[0] = 1 if generic_symbol_kernel else 0
+        cfg.reserved[1] = dev_batch_frames
         self.h = C.c_void_p()
         rc = self.lib.dabgpu_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:

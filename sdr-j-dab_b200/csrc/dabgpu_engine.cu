@@ -993,7 +993,7 @@ extern "C" int dabgpu_decode_dev (dabgpu_t *h, const uint8_t *d_iq_u8, size_t ns
 	CUDA_TRY (h, cudaSetDevice (h -> device));
 	int rc = set_format (h, 0);
 	if (rc) return rc;
-	return decode_core (h, d_iq_u8, (long long) nsamples, out);
+	return decode_core (h, d_iq_u8, (long long) nsamples, out, nullptr, 0, h -> cfg. reserved [1] > 0 ? h -> cfg. reserved [1] : 0x7fffffff);
 }
 
 extern "C" int dabgpu_decode_cf32_dev (dabgpu_t *h, const float *d_iq, size_t nsamples, dabgpu_result *out) {
