@@ -7,7 +7,7 @@ keys = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__regis
         'smsp__inst_executed.sum', 'sm__warps_active.avg.pct_of_peak_sustained_active', '_per_issue_active.ratio',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'pipe_fma.avg.pct_of_peak_sustained_active',
         'pipe_alu.avg.pct_of_peak_sustained_active', 'pipe_lsu.avg.pct_of_peak_sustained_active', 'pipe_xu.avg.pct_of_peak_sustained_active',
-        'pipe_fp64', 'dram__bytes_read.sum [', 'dram__bytes_write.sum [', 'gpu__dram_throughput.avg.pct', 'launch__occupancy_limit', 'lts__t_sector_hit_rate.pct',
+        'pipe_fp64', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct', 'launch__occupancy_limit', 'lts__t_sector_hit_rate.pct',
         'sm__throughput.avg.pct', 'l1tex__t_sector_hit_rate']
 for i, n in enumerate(h):
     if any(k in n for k in keys):
