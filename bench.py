@@ -133,6 +133,32 @@ def cpu_reference_run(iq, mod, nthreads, frames_per_piece, steps, warmup, orc_mo
     return O.kind, frames / dt, dt * 1e3, frames
 
 
+def cpu_viterbi_only(nthreads, orc_mod, seconds=3.0):
+    """Viterbi-only leg of the CPU baseline: the reference's time de-interleave + EEP-3A depuncture +
+    viterbi::deconvolve + dispersal on random soft bits, one decoder object per thread, decoded Mbit/s over all threads"""
+    try:
+        O = orc_mod.Oracle("ref")
+    except Exception:
+        O = orc_mod.Oracle("port")
+    rng = np.random.default_rng(7)
+    ncif = 16 + 96
+    frags = rng.integers(-127, 128, (ncif, 96 * 64), dtype=np.int16)
+    done = [0] * nthreads
+    t_end = time.perf_counter() + seconds
+
+    def work(t):
+        while time.perf_counter() < t_end:
+            O.msc_backend(frags, 128, 1, 0o103)
+            done[t] += (ncif - 16) * 3072
+    th = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    t0 = time.perf_counter()
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    return sum(done) / (time.perf_counter() - t0) / 1e6
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -301,6 +327,13 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        traffic = {}
+        try:                                                     # per-launch DRAM bytes of the committed ncu capture (same launch shape only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tj.get("frames_per_launch") == frames_per_step and not args.dev_batch:
+                traffic = {k: v["read"] + v["write"] for k, v in tj.items() if isinstance(v, dict)}
+        except Exception:
+            pass
         ip = eng.int_peak()
         int_peak = max(ip[k] for k in ("add", "min", "add_mad"))
         n_vit, ms_vit = prof["viterbi_msc"]                   # forward (add-compare-select) launches: FIC + all sub-channels per launch
@@ -331,13 +364,13 @@ def main():
             "clocks": clocks,
             # dominant kernel by time: the Viterbi forward pass; integer-ALU bound
             "roofline": {"kernel": "vit_simd_forward (add-compare-select of FIC + 9 sub-channels, one launch per step)", "bound": "alu", "achieved": vit_ops / 1e12, "peak": int_peak / 1e12,
-                         "unit": "Tint-op/s", "frac": vit_ops / int_peak if int_peak else None, "traffic": None,
+                         "unit": "Tint-op/s", "frac": vit_ops / int_peak if int_peak else None, "traffic": traffic.get("vit_simd_forward"),
                          "avg_launch_ms": vit_avg_ms, "launches": n_vit, "share_of_step": shares.get("viterbi_msc"),
                          "peak_source": "measured live by dabgpu_int_peak (add / min / add+mad.lo micro-benchmark): %s" %
                                         {k: round(v / 1e12, 2) for k, v in ip.items()},
                          "algorithmic": "272 int-ops per trellis step (SURVEY.md 8d) x %d steps per launch" % steps_per_launch},
             "roofline_hbm": {"kernel": "symbol_kernel (FFT+demod group)", "bound": "hbm", "achieved": sym_gbs, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": sym_gbs / hbm_peak, "traffic": None, "avg_launch_ms": sym_avg_ms, "launches": n_sym_work,
+                             "frac": sym_gbs / hbm_peak, "traffic": traffic.get("symbol_kernel_r8"), "avg_launch_ms": sym_avg_ms, "launches": n_sym_work,
                              "share_of_step": shares.get("symbol"), "peak_source": peak_src,
                              "algorithmic": "854016 B per Mode I frame (SURVEY.md 8d) x %.1f frames per working launch (+ %d no-op verification launches)" % (sym_frames, n_sym - n_sym_work),
                              "fp32_tflops": 11.9e6 * sym_frames / (sym_avg_ms * 1e-3) / 1e12 if n_sym else None},
@@ -352,6 +385,10 @@ def main():
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": nthreads, "kind": kind,
                                 "sample": "%d threads x (%d lead-in + %d frames) of the same stream, full chain incl. all 9 sub-channels, "
                                           "%d frames per %.2f s pass, passes repeated for >= 10 s; FFT = labelled FFTW stand-in" % (nthreads, LEAD_FRAMES, fpp, frames, ms / 1e3)}
+        # the same chain on ONE thread, and the Viterbi-only rate (bounded samples, a few seconds each)
+        _, fps1, _, _ = cpu_reference_run(iq, mod, 1, fpp, 1, 0, orc_mod, min_seconds=2.0)
+        line["cpu_baseline"]["single_thread_frames_per_s"] = fps1
+        line["cpu_baseline"]["viterbi_only_mbit_per_s"] = {"threads_%d" % nthreads: cpu_viterbi_only(nthreads, orc_mod), "threads_1": cpu_viterbi_only(1, orc_mod, 2.0)}
     if rank == 0:
         print(json.dumps(line))
     eng.close()

@@ -204,6 +204,13 @@ int dabgpu_decode_dev (dabgpu_t *h, const uint8_t *d_iq_u8, size_t nsamples, dab
  * only when no unconsumed samples are pending (DABGPU_ERR_STATE otherwise). */
 int dabgpu_decode_cf32 (dabgpu_t *h, const float *iq, size_t nsamples, dabgpu_result *out);
 int dabgpu_decode_cf32_dev (dabgpu_t *h, const float *d_iq, size_t nsamples, dabgpu_result *out);
+/* 16-bit PCM samples (interleaved I,Q at 2.048 MS/s), the payload of a 16-bit ".sdr" / WAV recording as wavFiles
+ * reads it (wavfiles.cpp:186-197): libsndfile's sf_readf_float delivers x / 32768 (third-party, not vendored by the
+ * reference: README "libsndfile"; the normalisation is libsndfile's documented default for 16-bit PCM).  The division is
+ * exact in float, so the result equals dabgpu_decode_cf32 on the converted samples bit for bit; the conversion happens
+ * in the kernels' sample fetch, no float copy of the recording is made. */
+int dabgpu_decode_i16 (dabgpu_t *h, const int16_t *iq, size_t nsamples, dabgpu_result *out);
+int dabgpu_decode_i16_dev (dabgpu_t *h, const int16_t *d_iq, size_t nsamples, dabgpu_result *out);
 /* airspyHandler's sample-rate conversion (airspy-handler.cpp:138-148, 342-370): int16 I,Q pairs at in_rate samples/s
  * (a multiple of 1000) -> complex floats at 2 048 000 samples/s by linear interpolation in 1 ms blocks, ready for
  * dabgpu_decode_cf32.  Block b reads input samples [b R, b R + R], R = in_rate / 1000, and writes 2048 samples; a call
@@ -255,6 +262,22 @@ int dabgpu_host_depuncture_lut (int32_t fic, int32_t bitRate, int32_t uepFlag, i
                                 int32_t *lut, int32_t lut_capacity, int32_t *lut_len, int32_t *n_punctured);
 /* energy-dispersal sequence (fic-handler.cpp:100-108), one bit per byte */
 int dabgpu_host_prbs (int32_t nbits, uint8_t *out);
+/* ".sdr" recordings are RIFF/WAVE files (wavfiles.cpp:44-75 opens them with libsndfile and rejects everything that is
+ * not 2 channels at 2 048 000 samples/s).  This parses the header of a file image (or of its first bytes: 64 KiB is
+ * plenty) and says where the samples are and which decode call takes them:
+ *   sample_format  1 -> dabgpu_decode_cf32 (32-bit IEEE float),  2 -> dabgpu_decode_i16 (16-bit PCM).
+ * Returns DABGPU_ERR_ARG for anything else (not RIFF/WAVE, other rate / channel count -- "This is not a recorded dab
+ * file", wavfiles.cpp:66-71 -- or a sample type the engine has no fetch for). */
+typedef struct dabgpu_wav_info {
+	int32_t format_tag;      /* 1 = PCM, 3 = IEEE float (WAVE_FORMAT_EXTENSIBLE resolved through its sub-format) */
+	int32_t channels, samplerate, bits;
+	int32_t sample_format;   /* see above */
+	int32_t pad;
+	int64_t data_offset;     /* byte offset of the first sample in the file */
+	int64_t nsamples;        /* complex samples present in the bytes given (the data chunk may run past them) */
+	int64_t nsamples_total;  /* complex samples the data chunk announces */
+} dabgpu_wav_info;
+int dabgpu_host_wav_parse (const void *file_image, size_t nbytes, dabgpu_wav_info *info);
 
 #ifdef __cplusplus
 }

@@ -155,6 +155,21 @@ class DabPlus:
         return sf[:n.value], [info[i].key() for i in range(n.value)]
 
 
+class WavInfo(C.Structure):
+    _fields_ = [("format_tag", C.c_int32), ("channels", C.c_int32), ("samplerate", C.c_int32), ("bits", C.c_int32),
+                ("sample_format", C.c_int32), ("pad", C.c_int32), ("data_offset", C.c_int64), ("nsamples", C.c_int64),
+                ("nsamples_total", C.c_int64)]
+
+
+def wav_parse(lib, image):
+    """dabgpu_host_wav_parse on a bytes-like file image -> WavInfo, or None when the engine does not take the file"""
+    buf = np.frombuffer(image, np.uint8)
+    info = WavInfo()
+    lib.dabgpu_host_wav_parse.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(WavInfo)]
+    rc = lib.dabgpu_host_wav_parse(buf.ctypes.data if buf.size else None, buf.size, C.byref(info))
+    return info if rc == 0 else None
+
+
 class DecodeOut:
     """Host-side result buffers of one dabgpu_decode call."""
     pass
@@ -346,6 +361,11 @@ class DabGpu:
             iq = np.ascontiguousarray(iq_u8, np.float32)
             self.lib.dabgpu_decode_cf32.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Result)]
             self._check(self.lib.dabgpu_decode_cf32(self.h, iq.ctypes.data, iq.size // 2, C.byref(out.res)))
+            return self._trim(out)
+        elif np.asarray(iq_u8).dtype == np.int16:                 # 16-bit .sdr / WAV payload (dabgpu_decode_i16)
+            iq = np.ascontiguousarray(iq_u8, np.int16)
+            self.lib.dabgpu_decode_i16.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Result)]
+            self._check(self.lib.dabgpu_decode_i16(self.h, iq.ctypes.data, iq.size // 2, C.byref(out.res)))
             return self._trim(out)
         else:
             iq = np.ascontiguousarray(iq_u8, np.uint8)

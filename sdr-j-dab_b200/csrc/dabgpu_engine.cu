@@ -18,8 +18,12 @@ __device__ __forceinline__ uchar2 win_fetch (const SampleWin &w, long long i) { 
 }
 // sample i as the complex float the reference's getSample sees before the NCO (ofdm-processor.cpp:133-183)
 __device__ __forceinline__ float2 win_sample (const SampleWin &w, long long i) {
-	if (w. cf32)
+	if (w. cf32 == 1)
 		return i < w. len0 ? __ldg (reinterpret_cast<const float2 *> (w. seg0) + i) : __ldg (reinterpret_cast<const float2 *> (w. seg1) + (i - w. len0));
+	if (w. cf32 == 2) {                                      // 16-bit PCM as sf_readf_float delivers it (wavfiles.cpp:190): x / 32768, exact in float
+		const short2 v = i < w. len0 ? __ldg (reinterpret_cast<const short2 *> (w. seg0) + i) : __ldg (reinterpret_cast<const short2 *> (w. seg1) + (i - w. len0));
+		return make_float2 ((float) v. x * (1.0f / 32768.0f), (float) v. y * (1.0f / 32768.0f));
+	}
 	const uchar2 s = win_fetch (w, i);
 	return make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f));
 }
@@ -709,7 +713,7 @@ extern "C" int dabgpu_state_import (dabgpu_t *h, const void *buf, size_t n) {
 	memcpy (&hd, buf, sizeof (hd));
 	const size_t rowb = (size_t) CIF_BITS * sizeof (int16_t);
 	if (hd. magic != STATE_MAGIC || hd. mode != h -> p. dabMode || hd. nsub != (int32_t) E -> backends. size () || hd. tail_len < 0 ||
-	    n != sizeof (hd) + (size_t) hd. nsub * sizeof (int64_t) + (size_t) hd. tail_len * (hd. cf32 ? sizeof (float2) : sizeof (uchar2)) + 15 * rowb)
+	    n != sizeof (hd) + (size_t) hd. nsub * sizeof (int64_t) + (size_t) hd. tail_len * dab_sample_bytes (hd. cf32) + 15 * rowb || hd. cf32 < 0 || hd. cf32 > 2)
 		return dab_fail (h, DABGPU_ERR_ARG, "state blob does not match this handle (mode / sub-channel count / size)");
 	CUDA_TRY (h, cudaSetDevice (h -> device));
 	int rc = ensure_frame_capacity (h, 1);
@@ -718,7 +722,7 @@ extern "C" int dabgpu_state_import (dabgpu_t *h, const void *buf, size_t n) {
 	for (auto *b : E -> backends) { int64_t c; memcpy (&c, q, sizeof (c)); q += sizeof (c); dab_backend_set_cifs_seen (b, c); }
 	E -> ctl = hd. ctl; E -> abs_base = hd. abs_base; E -> frames_total = hd. frames_total; E -> cifs_total = hd. cifs_total;
 	E -> tail_len = hd. tail_len;
-	E -> cf32 = hd. cf32 ? 1 : 0;
+	E -> cf32 = hd. cf32;
 	if (hd. tail_len) {
 		CUDA_TRY (h, E -> tail. ensure ((size_t) hd. tail_len * E -> sample_bytes ()));
 		CUDA_TRY (h, cudaMemcpyAsync (E -> tail. p, q, (size_t) hd. tail_len * E -> sample_bytes (), cudaMemcpyHostToDevice, h -> stream));
@@ -1004,7 +1008,16 @@ extern "C" int dabgpu_decode_cf32_dev (dabgpu_t *h, const float *d_iq, size_t ns
 	return decode_core (h, d_iq, (long long) nsamples, out);
 }
 
+extern "C" int dabgpu_decode_i16_dev (dabgpu_t *h, const int16_t *d_iq, size_t nsamples, dabgpu_result *out) {
+	if (!h || !out || (nsamples > 0 && !d_iq)) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_decode_i16: bad argument");
+	CUDA_TRY (h, cudaSetDevice (h -> device));
+	int rc = set_format (h, 2);
+	if (rc) return rc;
+	return decode_core (h, d_iq, (long long) nsamples, out);
+}
+
 extern "C" int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out) { return decode_host (h, iq_u8, nsamples, 0, out); }
+extern "C" int dabgpu_decode_i16 (dabgpu_t *h, const int16_t *iq, size_t nsamples, dabgpu_result *out) { return decode_host (h, iq, nsamples, 2, out); }
 extern "C" int dabgpu_decode_cf32 (dabgpu_t *h, const float *iq, size_t nsamples, dabgpu_result *out) { return decode_host (h, iq, nsamples, 1, out); }
 
 static int decode_host (dabgpu *h, const void *iq_v, size_t nsamples, int cf32, dabgpu_result *out) {

@@ -19,9 +19,9 @@ struct StreamCtl {
 };
 
 struct SampleWin {                      // two-segment sample window: [tail of earlier calls | this call's input]
-	const uchar2 *seg0; long long len0;     // lengths in samples; with cf32 set the pointers are really const float2 *
+	const uchar2 *seg0; long long len0;     // lengths in samples; the pointers are really const float2 * (cf32 = 1) / const short2 * (cf32 = 2)
 	const uchar2 *seg1; long long len1;
-	int cf32;                               // 0: u8 I,Q pairs (rawfiles.cpp:113-116); 1: complex float samples (virtual-input.h:62-63)
+	int cf32;                               // sample format: 0 = u8 I,Q pairs (rawfiles.cpp:113-116); 1 = complex float (virtual-input.h:62-63); 2 = int16 I,Q (16-bit .sdr/WAV, wavfiles.cpp:186-197)
 };
 
 struct FrameIn {                        // per chunk slot: the inputs a frame is (re)computed from
@@ -36,6 +36,8 @@ struct FrameOut {                       // per chunk slot, written by the front 
 	int startIndex, correction;
 };
 
+static inline size_t dab_sample_bytes (int fmt) { return fmt == 1 ? sizeof (float2) : fmt == 2 ? sizeof (short2) : sizeof (uchar2); }
+
 struct dabgpu_backend;
 
 struct Engine {
@@ -48,7 +50,7 @@ struct Engine {
 	long long frames_total = 0, cifs_total = 0;
 	DevBuf tail, tail_spare; long long tail_len = 0;     // unconsumed samples, ping-pong
 	int cf32 = 0;                       // sample format of the stream (fixed while a tail is pending)
-	size_t sample_bytes () const { return cf32 ? sizeof (float2) : sizeof (uchar2); }
+	size_t sample_bytes () const { return dab_sample_bytes (cf32); }
 	DevBuf d_ctl;                       // StreamCtl on the device
 	PinBuf h_ctl;
 	int chunk = 1, max_chunk = 1024;

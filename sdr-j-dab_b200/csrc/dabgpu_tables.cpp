@@ -175,3 +175,50 @@ void prbs_packed (int nbits, std::vector<uint32_t> *words) {   // x^9 + x^5 + 1,
 		(*words) [i >> 5] |= b << (i & 31);
 	}
 }
+
+// ".sdr" = RIFF/WAVE (wavfiles.cpp:44-75).  Header walk: "RIFF" size "WAVE", then chunks {id, size, payload padded to even};
+// "fmt " gives the sample type, "data" the samples.  The reference's acceptance test is libsndfile's view of the file:
+// 2 channels at 2 048 000 samples/s (wavfiles.cpp:66-71).
+static uint32_t rd32 (const uint8_t *p) { return (uint32_t) p [0] | ((uint32_t) p [1] << 8) | ((uint32_t) p [2] << 16) | ((uint32_t) p [3] << 24); }
+static uint32_t rd16 (const uint8_t *p) { return (uint32_t) p [0] | ((uint32_t) p [1] << 8); }
+
+extern "C" int dabgpu_host_wav_parse (const void *file_image, size_t nbytes, dabgpu_wav_info *info) {
+	if (!file_image || !info) return DABGPU_ERR_ARG;
+	const uint8_t *b = (const uint8_t *) file_image;
+	memset (info, 0, sizeof (*info));
+	if (nbytes < 12 || memcmp (b, "RIFF", 4) != 0 || memcmp (b + 8, "WAVE", 4) != 0) return DABGPU_ERR_ARG;
+	size_t pos = 12;
+	bool have_fmt = false;
+	while (pos + 8 <= nbytes) {
+		const uint32_t size = rd32 (b + pos + 4);
+		const uint8_t *body = b + pos + 8;
+		if (memcmp (b + pos, "fmt ", 4) == 0) {
+			if (size < 16 || pos + 8 + 16 > nbytes) return DABGPU_ERR_ARG;
+			info -> format_tag = (int32_t) rd16 (body);
+			info -> channels = (int32_t) rd16 (body + 2);
+			info -> samplerate = (int32_t) rd32 (body + 4);
+			info -> bits = (int32_t) rd16 (body + 14);
+			if (info -> format_tag == 0xFFFE) {              // WAVE_FORMAT_EXTENSIBLE: the first two bytes of the sub-format GUID are the tag
+				if (size < 40 || pos + 8 + 26 > nbytes) return DABGPU_ERR_ARG;
+				info -> format_tag = (int32_t) rd16 (body + 24);
+			}
+			have_fmt = true;
+		} else if (memcmp (b + pos, "data", 4) == 0) {
+			if (!have_fmt) return DABGPU_ERR_ARG;
+			if (info -> channels != 2 || info -> samplerate != DAB_INPUT_RATE) return DABGPU_ERR_ARG;   // wavfiles.cpp:66-71
+			if (info -> format_tag == 3 && info -> bits == 32) info -> sample_format = 1;
+			else if (info -> format_tag == 1 && info -> bits == 16) info -> sample_format = 2;
+			else return DABGPU_ERR_ARG;
+			const int64_t bps = info -> bits / 8 * 2;
+			info -> data_offset = (int64_t) (pos + 8);
+			int64_t announced = size;
+			const int64_t present = (int64_t) nbytes - info -> data_offset;
+			if (size == 0xFFFFFFFFu || size == 0) announced = present;        // streamed recordings leave the size open
+			info -> nsamples_total = announced / bps;
+			info -> nsamples = (announced < present ? announced : present) / bps;
+			return DABGPU_OK;
+		}
+		pos += 8 + (size_t) size + (size & 1);
+	}
+	return DABGPU_ERR_ARG;
+}

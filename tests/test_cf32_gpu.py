@@ -73,3 +73,33 @@ def test_format_switch_needs_an_empty_tail(port):
     with pytest.raises(pkg.DabGpuError, match="sample format"):
         eng.decode(np.zeros(1000, np.float32), eng.alloc_result(8))
     eng.close()
+
+
+def test_int16_recording_equals_its_float_form(port):
+    """a 16-bit .sdr / WAV payload (dabgpu_decode_i16): sf_readf_float hands the reference x / 32768 (wavfiles.cpp:186-197);
+    the engine converts in the sample fetch -- same frames, same soft bits, same decoded bits as the float stream, which
+    in turn is checked against the oracle's float run"""
+    pkg = engine_pkg()
+    mod = dabmod.Modulator(port, 1, [(0, 128, 1, 0o103), (96, 64, 0, 3)], 31)
+    tr = mod.generate(22, cfo_hz=-1870.0, snr_db=18.0, lead=6001, tail=5000)
+    i16 = ((tr["iq"].astype(np.int16) - 128) * 200).astype(np.int16)          # an int16 recording of the same signal
+    f32 = (i16.astype(np.float32) / np.float32(32768.0)).astype(np.float32)
+    subs = [(s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel) for s in mod.sub]
+    ea = pkg.DabGpu(mode=1); ea.set_subchannels(subs)
+    eb = pkg.DabGpu(mode=1); eb.set_subchannels(subs)
+    cuts = [0, 2 * 700001, 2 * 2100000, i16.size]
+    a_parts = [ea.decode(i16[x:y], ea.alloc_result(30)) for x, y in zip(cuts[:-1], cuts[1:])]   # ragged pieces: the int16 tail carries over
+    b = eb.decode(f32, eb.alloc_result(30))
+    assert sum(p.nframes for p in a_parts) == b.nframes >= 19
+    assert np.array_equal(np.concatenate([p.soft for p in a_parts]), b.soft)
+    assert np.array_equal(np.concatenate([p.fic_bits for p in a_parts]), b.fic_bits)
+    for k in range(len(subs)):
+        assert np.array_equal(np.concatenate([p.msc[k] for p in a_parts]), b.msc[k])
+    sym, info = port.ofdm_run(1, f32, 30)
+    bits, crc = port.fic_frames(1, sym)
+    assert np.array_equal(b.fic_bits, bits[:b.nframes * 4]) and np.array_equal(b.fic_crc, crc[:b.nframes * 4])
+    assert b.fic_crc[-8:].all()
+    # a state blob of an int16 stream carries its sample tail
+    blob = ea.export_state()
+    ec = pkg.DabGpu(mode=1); ec.set_subchannels(subs); ec.import_state(blob)
+    ea.close(); eb.close(); ec.close()

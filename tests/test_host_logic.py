@@ -118,3 +118,67 @@ def test_state_predict_follows_the_oracle_trajectory(lib, port):
     s.f2Correction = 1
     with pytest.raises(pkg.DabGpuError):
         pkg.binding.state_predict(2, s, 1)
+
+
+# ---- ".sdr" recordings: RIFF/WAVE header parsing (wavfiles.cpp:44-75 opens them with libsndfile) ------------------
+def _wav_bytes(samples, rate=2048000, channels=2, kind="pcm16", extensible=False, extra_chunk=True, open_size=False):
+    """independent little WAVE writer (struct.pack only), optionally with a LIST chunk in front of the data"""
+    import struct
+    if kind == "pcm16":
+        tag, bits, payload = 1, 16, np.asarray(samples, np.int16).tobytes()
+    elif kind == "float":
+        tag, bits, payload = 3, 32, np.asarray(samples, np.float32).tobytes()
+    else:
+        tag, bits, payload = 1, 24, bytes(3 * len(samples))
+    ba = channels * bits // 8
+    if extensible:
+        guid_tail = bytes.fromhex("000000001000800000aa00389b71")
+        fmt = struct.pack("<HHIIHHHHI", 0xFFFE, channels, rate, rate * ba, ba, bits, 22, bits, 3) + struct.pack("<H", tag) + guid_tail
+    else:
+        fmt = struct.pack("<HHIIHH", tag, channels, rate, rate * ba, ba, bits)
+    chunks = b"fmt " + struct.pack("<I", len(fmt)) + fmt
+    if extra_chunk:
+        junk = b"recorded by a test\x00"                           # odd length: exercises the pad byte
+        chunks += b"LIST" + struct.pack("<I", len(junk)) + junk + b"\x00"
+    chunks += b"data" + struct.pack("<I", 0xFFFFFFFF if open_size else len(payload)) + payload
+    return b"RIFF" + struct.pack("<I", 4 + len(chunks)) + b"WAVE" + chunks
+
+
+def test_wav_header_parse(lib, tmp_path):
+    from importlib import import_module
+    binding = import_module("sdr-j-dab_b200.binding")
+    rng = np.random.default_rng(3)
+    x16 = rng.integers(-3000, 3000, 2 * 1000, dtype=np.int16)
+    for ext in (False, True):
+        img = _wav_bytes(x16, extensible=ext)
+        w = binding.wav_parse(lib, img)
+        assert w is not None and (w.format_tag, w.channels, w.samplerate, w.bits, w.sample_format) == (1, 2, 2048000, 16, 2)
+        assert w.nsamples == w.nsamples_total == 1000
+        assert np.array_equal(np.frombuffer(img, np.int16, 2 * w.nsamples, w.data_offset), x16)
+    xf = rng.standard_normal(2 * 777).astype(np.float32)
+    img = _wav_bytes(xf, kind="float", extra_chunk=False)
+    w = binding.wav_parse(lib, img)
+    assert w is not None and (w.format_tag, w.bits, w.sample_format, w.nsamples, w.data_offset) == (3, 32, 1, 777, 44)
+    assert np.array_equal(np.frombuffer(img, np.float32, 2 * w.nsamples, w.data_offset), xf)
+    # only the head of a file: the data chunk runs past the bytes given
+    w = binding.wav_parse(lib, _wav_bytes(x16)[:1000])
+    assert w is not None and w.nsamples_total == 1000 and w.nsamples == (1000 - w.data_offset) // 4
+    # a streamed recording with the size left open
+    w = binding.wav_parse(lib, _wav_bytes(x16, open_size=True))
+    assert w is not None and w.nsamples == w.nsamples_total == 1000
+    # the files Python's own writer produces parse the same way
+    import wave
+    path = str(tmp_path / "t.sdr")
+    with wave.open(path, "wb") as f:
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(2048000); f.writeframes(x16.tobytes())
+    img = open(path, "rb").read()
+    w = binding.wav_parse(lib, img)
+    assert w is not None and w.sample_format == 2 and w.nsamples == 1000
+    assert np.array_equal(np.frombuffer(img, np.int16, 2000, w.data_offset), x16)
+    # what the reference refuses (wavfiles.cpp:66-71) and what the engine has no fetch for
+    assert binding.wav_parse(lib, _wav_bytes(x16, rate=2000000)) is None
+    assert binding.wav_parse(lib, _wav_bytes(x16[:1000], channels=1)) is None
+    assert binding.wav_parse(lib, _wav_bytes(x16, kind="pcm24")) is None
+    assert binding.wav_parse(lib, b"RIFF\x04\x00\x00\x00WAVE") is None
+    assert binding.wav_parse(lib, b"not a wave file at all") is None
+    assert binding.wav_parse(lib, b"") is None
