@@ -220,6 +220,9 @@ int dabgpu_decode_i16_dev (dabgpu_t *h, const int16_t *d_iq, size_t nsamples, da
 int dabgpu_resample_i16 (dabgpu_t *h, const int16_t *iq, size_t n_in, int32_t in_rate, float *out, size_t *n_out, size_t *consumed);
 int dabgpu_resample_i16_dev (dabgpu_t *h, const int16_t *d_iq, size_t n_in, int32_t in_rate, float *d_out, size_t *n_out, size_t *consumed);
 int dabgpu_reset (dabgpu_t *h);                                                   /* ofdmProcessor::reset  */
+/* ofdmProcessor::coarseCorrectorOn (on != 0: coarse search on, coarseCorrector = 0) / coarseCorrectorOff
+ * (ofdm-processor.cpp:499-506); takes effect with the next frame decoded */
+int dabgpu_coarse_corrector (dabgpu_t *h, int32_t on);
 
 /* stream state for splitting a recording across calls / GPUs */
 typedef struct {

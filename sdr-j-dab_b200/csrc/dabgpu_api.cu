@@ -214,7 +214,7 @@ int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
 	for (auto &j : jobs) {
 		j. cta_first = ctas; j. cta_first2 = ctas2; j. one = 1u;
 		ctas += (j. ncw + 63) / 64; ctas2 += (j. ncw + cw2 - 1) / cw2;
-		dec_words += padded (j. nsteps) * j. ncw;
+		dec_words += padded (j. nsteps) * (size_t) ((j. ncw + 31) / 32 * 32);
 		j. sym8_ready = j. sym8 != nullptr;                      // the caller already holds the byte symbols (stream engine)
 		if (j. sym8_ready) continue;
 		need_sym8 = true;
@@ -228,7 +228,7 @@ int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
 	CUDA_TRY (h, cx. d_sym8. ensure (sym_bytes + 64));
 	size_t off = 0, soff = 0;
 	for (auto &j : jobs) {
-		j. dec = (uint2 *) cx. d_dec. p + off; off += padded (j. nsteps) * j. ncw;
+		j. dec = (uint2 *) cx. d_dec. p + off; off += padded (j. nsteps) * (size_t) ((j. ncw + 31) / 32 * 32);
 		if (!j. sym8_ready) { j. sym8 = (uint8_t *) cx. d_sym8. p + soff; soff += (size_t) (j. ncw + (j. deint ? 15 : 0)) * j. stride8; }
 	}
 	CUDA_TRY (h, cx. d_jobs. ensure (jb));

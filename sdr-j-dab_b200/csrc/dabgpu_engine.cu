@@ -256,7 +256,9 @@ __device__ __forceinline__ float u8_to_f (uint32_t s, int which) {
 // soft-bit quantisation of ofdm-decoder.cpp:183-189 with the quotient from the reciprocal unit (2 ulp; the soft bits'
 // stated tolerance is +-1 step and comes from the FFT, whose rounding differs from the reference's FFTW anyway)
 __device__ __forceinline__ int quant127_fast (float num, float ab1) {
-	return __double2int_rz ((double) __fdividef (- num, ab1) * 127.0);       // NaN (ab1 == 0) -> 0 (App. B-5)
+	// (double) q * 127.0 is exact (24 + 7 bits); its truncation equals the truncation of the round-toward-zero float
+	// product, because rounding toward zero never crosses an integer (all |integers| <= 127 are floats)
+	return __float2int_rz (__fmul_rz (__fdividef (- num, ab1), 127.0f));      // NaN (ab1 == 0) -> 0 (App. B-5)
 }
 
 __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTables T, const FrameIn *fin, int slot0, int groups,
@@ -606,6 +608,13 @@ extern "C" int dabgpu_reset (dabgpu_t *h) {                 // ofdmProcessor::re
 	if (!h) return DABGPU_ERR_ARG;
 	h -> engine -> ctl. fine = h -> engine -> ctl. coarse = 0;
 	h -> engine -> ctl. f2 = 1;
+	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_coarse_corrector (dabgpu_t *h, int32_t on) {   // ofdm-processor.cpp:499-506
+	if (!h) return DABGPU_ERR_ARG;
+	if (on) { h -> engine -> ctl. f2 = 1; h -> engine -> ctl. coarse = 0; }
+	else h -> engine -> ctl. f2 = 0;
 	return DABGPU_OK;
 }
 

@@ -92,7 +92,7 @@ struct VitSimdJob {
 	int cta_first;            // first CTA of this job in the chain-back launch (64 code words per CTA)
 	int cta_first2;           // same for the forward kernel (VS_CW code words per CTA)
 	unsigned one;             // = 1, set by dab_vit_simd_run; opaque to the compiler on purpose (see vs_acs)
-	uint2 *dec;               // [nsteps padded to VS_CHUNK][ncw] decision words
+	uint2 *dec;               // [ncw / 32][nsteps padded to VS_CHUNK][32] decision words
 	const uint32_t *prbs;     // packed dispersal sequence or nullptr
 	uint8_t *out;             // [ncw][frameBits]
 };

@@ -93,8 +93,9 @@ __device__ __forceinline__ void load_u8_nco (float2 *dst, const uchar2 *__restri
 
 // soft-bit quantisation of ofdm-decoder.cpp:183-189: float negate + divide, double multiply, truncation
 __device__ __forceinline__ short quant127 (float num, float ab1) {
-	const double x = (double) (- num / ab1) * 127.0;
-	return (short) __double2int_rz (x);               // NaN (ab1 == 0) -> 0, as x86's conversion ends up (App. B-5)
+	// the reference's double product q * 127.0 is exact (24 + 7 bits); truncating it equals truncating the float product
+	// rounded toward zero, because that rounding never crosses an integer (every |integer| <= 127 is a float)
+	return (short) __float2int_rz (__fmul_rz (- num / ab1, 127.0f));   // NaN (ab1 == 0) -> 0, as x86's conversion ends up (App. B-5)
 }
 
 // DQPSK demod + frequency de-interleave of one symbol (ofdm-decoder.cpp:178-190): cur = FFT of the symbol,

@@ -39,15 +39,23 @@ __host__ __device__ constexpr int vs_insert00 (int r, int p) { return ((r >> p) 
 // packed compare-select: min (upper, lower) per 16-bit lane; `bit` is ORed into wlo / whi where the lower candidate
 // won (decision = upper > lower; a tie keeps the upper one).  __vibmin_u16x2 is one VIMNMX.U16x2 with two predicate
 // outputs (predicate = upper <= lower) on sm_100a.
-__device__ __forceinline__ uint32_t vs_acs (uint32_t upper, uint32_t lower, uint32_t &acc, const uint32_t bit, const uint32_t one) {
+__device__ __forceinline__ uint32_t vs_acs (uint32_t upper, uint32_t lower, uint32_t &acc, const uint32_t bit_lo, const uint32_t bit_hi, const uint32_t one) {
 	bool ph, pl;
 	const uint32_t r = __vibmin_u16x2 (upper, lower, &ph, &pl);
 	// decision bits are accumulated with predicated multiply-adds (acc += one * bit): `one` is 1 at run time but opaque
 	// to the compiler, which keeps these on the FMA pipe; the ALU pipe, busy with the packed min and everything else,
 	// is the scarce one here
-	asm ("{ .reg .pred p; setp.eq.u32 p, %1, 0; @p mad.lo.u32 %0, %3, %2, %0; }" : "+r" (acc) : "r" ((uint32_t) pl), "r" (bit), "r" (one));
-	asm ("{ .reg .pred p; setp.eq.u32 p, %1, 0; @p mad.lo.u32 %0, %3, %2, %0; }" : "+r" (acc) : "r" ((uint32_t) ph), "r" (bit << 16), "r" (one));
+	asm ("{ .reg .pred p; setp.eq.u32 p, %1, 0; @p mad.lo.u32 %0, %3, %2, %0; }" : "+r" (acc) : "r" ((uint32_t) pl), "r" (bit_lo), "r" (one));
+	asm ("{ .reg .pred p; setp.eq.u32 p, %1, 0; @p mad.lo.u32 %0, %3, %2, %0; }" : "+r" (acc) : "r" ((uint32_t) ph), "r" (bit_hi), "r" (one));
 	return r;
+}
+
+// Where the decision of a new state goes.  At step K the decision word of a thread (lane bit = new-state bit K + 2) holds
+// the 32 new states that share this lane bit; the bit index is the new state number n with bit K + 2 deleted -- the form
+// the chain-back can rebuild with one shift and one select-by-mask.  Here n = (r without/with the half and lane bits) :
+// n0 = e (even / odd result), bits 1..K = low K bits of r, bit K + 1 = half, bits above = the rest of r.
+__host__ __device__ constexpr uint32_t vs_decbit (int K, int r, int e, int half) {
+	return 1u << (e | ((r & ((1 << K) - 1)) << 1) | (half << (K + 1)) | ((r >> K) << (K + 2)));
 }
 
 __device__ __forceinline__ uint32_t vs_sel (uint32_t a, uint32_t b, uint32_t mask) { return (a & ~mask) | (b & mask); }   // one LOP3
@@ -85,8 +93,8 @@ __device__ __forceinline__ void vs_step (const uint32_t (&R) [16], uint32_t (&Q)
 		// the halves and the full-rate IADD replaces the half-rate VIADD.16x2
 		const uint32_t m0 = a + PL [x],     m1 = b + PL [7 - x];
 		const uint32_t m2 = a + PL [7 - x], m3 = b + PL [x];
-		Q [2 * r]     = vs_acs (m0, m1, acc [r], 1u << (2 * r), one);
-		Q [2 * r + 1] = vs_acs (m2, m3, acc [r], 1u << (2 * r + 1), one);
+		Q [2 * r]     = vs_acs (m0, m1, acc [r], vs_decbit (K, r, 0, 0), vs_decbit (K, r, 0, 1), one);
+		Q [2 * r + 1] = vs_acs (m2, m3, acc [r], vs_decbit (K, r, 1, 0), vs_decbit (K, r, 1, 1), one);
 	}
 	dec = ((acc [0] + acc [1]) + (acc [2] + acc [3])) + ((acc [4] + acc [5]) + (acc [6] + acc [7]));
 }
@@ -172,9 +180,11 @@ __global__ void __launch_bounds__ (VS_THREADS, 10) vit_simd_forward (const VitSi
 	for (int q = 0; q < 16; q ++) R [q] = 63u | (63u << 16);
 	if (!lanebit) R [0] = 0u | (63u << 16);                    // state 0 = lane 0, register 0, low half (viterbi.cpp:364-370)
 
-	uint32_t *dec = reinterpret_cast<uint32_t *> (j. dec) + 2 * (size_t) cw + (lanebit ? 1 : 0);
-	const size_t dstride = 2 * (size_t) j. ncw;
 	const int nchunks = (j. nsteps + VS_CHUNK - 1) / VS_CHUNK;
+	// decision words: [block of 32 code words][step][32] uint2 -- a CTA writes one sequential stream, and the chain-back
+	// reads 8 KB contiguous per warp and output word instead of 512-byte pieces 32 KB apart
+	uint32_t *dec = reinterpret_cast<uint32_t *> (j. dec) + 2 * ((size_t) (cw >> 5) * (size_t) (nchunks * VS_CHUNK) * 32 + (cw & 31)) + (lanebit ? 1 : 0);
+	const size_t dstride = 64;
 	for (int k = 0; k < nchunks; k ++) {
 		if (k + 1 < nchunks) stage (k + 1); else asm volatile ("cp.async.commit_group;");
 		asm volatile ("cp.async.wait_group 1;");
@@ -221,9 +231,27 @@ __global__ void __launch_bounds__ (VS_THREADS, 10) vit_simd_forward (const VitSi
 }
 
 // chain-back (viterbi.cpp:333-357) + energy dispersal + unpack, one thread per code word.  The decision of new
-// state n at step t sits in the word of lane l = bit p'+1 of n, at bit 16 h + (n without bits p', p'+1), h = bit p' of n,
-// p' = (t mod 4) + 1.
+// state n at step t sits in the word of lane l = bit p+1 of n, at bit (n with bit p+1 deleted), p = (t mod 4) + 1
+// (vs_decbit).  The walk keeps the decoded bits in a 32-bit shift register S whose top six bits ARE the state
+// (newest bit on top, viterbi.cpp:347-352): one step is  n = S >> 26;  word = lane-select;  bit = word >> index (n);
+// S = (bit : S) >> 1  -- a funnel shift -- and after 32 steps S is the output word, bit-reversed.
 #define TB_THREADS 64
+template <bool FULL>
+__device__ __forceinline__ uint32_t tb_walk_word (uint32_t &S, const uint2 (*dq) [TB_THREADS], const int tid, const int nvalid) {
+#pragma unroll
+	for (int u = 0; u < 32; u ++) {
+		if (!FULL && u < 32 - nvalid) continue;             // a partial top word: slots of bits beyond frameBits are not there
+		const int pp = ((37 - u) & 3) + 1;                  // step t = 32 wi + 37 - u
+		const uint2 dd = dq [u][tid];
+		const uint32_t n = S >> 26, n1 = S >> 27;
+		const uint32_t lowmask = (1u << (pp + 1)) - 1u;
+		const uint32_t idx = (n & lowmask) | (n1 & ~lowmask);
+		const uint32_t word = (S & (1u << (26 + pp + 1))) ? dd. y : dd. x;
+		S = __funnelshift_r (S, word >> (idx & 31u), 1);
+	}
+	return __brev (S);
+}
+
 __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimdJob *jobs, int njobs) {
 	__shared__ uint32_t bits [TB_THREADS * 5];               // 128 decoded bits per code word per round, row stride 5 words
 	__shared__ __align__ (16) uint2 dq [2][32][TB_THREADS];  // the decision words of two output words (32 steps each) per thread
@@ -234,18 +262,23 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 	const int tid = threadIdx. x, lane = tid & 31, warp = tid >> 5;
 	const int cw = c0 + tid;
 	const bool live = cw < j. ncw;
-	const uint2 *dec = j. dec + (live ? cw : 0);
-	unsigned state = 0;
+	const size_t npad = (size_t) ((j. nsteps + VS_CHUNK - 1) / VS_CHUNK * VS_CHUNK);
+	const uint2 *dec = j. dec + (live ? (size_t) (cw >> 5) * npad * 32 + (cw & 31) : 0);
+	uint32_t S = 0;                                          // chain-back starts in state 0 (viterbi.cpp:340)
 	const int nrounds = (j. frameBits + 127) / 128, nwords = (j. frameBits + 31) / 32;
 	// The loads do not depend on the state: while output word wi is walked, the 32 decision words of word wi - 1 are
 	// already on their way into shared memory (cp.async; every thread consumes only what it copied itself, so no
 	// barrier is involved).  Slot u of a word holds information bit 32 wi + 31 - u = trellis step 32 wi + 37 - u.
 	auto fetch = [&] (int wi) {
 		if (wi >= 0 && live) {
+			const uint2 *src = dec + (size_t) (32 * wi + 37) * 32;
+			if (32 * wi + 32 <= j. frameBits) {
 #pragma unroll
-			for (int u = 0; u < 32; u ++) {
-				const int i = 32 * wi + 31 - u;
-				if (i < j. frameBits) vs_cp_async8 (&dq [wi & 1][u][tid], &dec [(size_t) (i + 6) * j. ncw]);
+				for (int u = 0; u < 32; u ++) vs_cp_async8 (&dq [wi & 1][u][tid], src - 32 * u);
+			} else {
+#pragma unroll
+				for (int u = 0; u < 32; u ++)
+					if (32 * wi + 31 - u < j. frameBits) vs_cp_async8 (&dq [wi & 1][u][tid], src - 32 * u);
 			}
 		}
 		asm volatile ("cp.async.commit_group;");
@@ -261,22 +294,9 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 			fetch (wi - 1);
 			asm volatile ("cp.async.wait_group 1;" ::: "memory");
 			if (!live) continue;
-			uint32_t acc = 0;
-#pragma unroll
-			for (int u = 0; u < 32; u ++) {
-				const int i = 32 * wi + 31 - u;
-				if (i >= top) continue;
-				const int t = i + 6;                            // decision of step i+6 = information bit i
-				const uint2 dd = dq [wi & 1][u][tid];
-				// word = lane bit (state bit pp+1), bit = 16 half + state without bits pp, pp+1
-				const int pp = (t & 3) + 1;
-				const unsigned h = (state >> pp) & 1u, l = (state >> (pp + 1)) & 1u;
-				const unsigned q = ((state >> (pp + 2)) << pp) | (state & ((1u << pp) - 1u));
-				const unsigned bit = ((l ? dd. y : dd. x) >> (16u * h + q)) & 1u;
-				state = (state >> 1) | (bit << 5);
-				acc |= bit << (31 - u);
-			}
-			w [wd] = acc;
+			const int nvalid = min (32, j. frameBits - 32 * wi);
+			// (a partial word can only be the first one walked: S is still 0 below the bits it shifts in)
+			w [wd] = nvalid == 32 ? tb_walk_word<true> (S, dq [wi & 1], tid, 32) : tb_walk_word<false> (S, dq [wi & 1], tid, nvalid);
 		}
 		__syncthreads ();
 #pragma unroll

@@ -54,6 +54,24 @@ int main (int argc, char **argv) {
 			fclose (fp);
 			printf ("dabplus %d %016llx\n", count, acc);
 		}
+		if (argc > 2) {	// ofdmProcessor (throughput form): a recording of complex floats behind a virtualInput, FIBs and frames through the handlers' sinks
+			struct fileInput : public virtualInput {
+				FILE *fp;
+				explicit fileInput (const char *path) : fp (fopen (path, "rb")) { if (!fp) throw std::runtime_error ("cannot open the IQ file"); }
+				~fileInput (void) { fclose (fp); }
+				int32_t getSamples (DSPCOMPLEX *v, int32_t size) { return (int32_t) fread (v, sizeof (DSPCOMPLEX), (size_t) size, fp); }
+				int32_t Samples (void) { return 1 << 20; }
+			} rig (argv [2]);
+			DabParams p = { 1, 76, 1536, 2656, 196608, 2552, 2048, 504, 1000 };          // gui.cpp:1361-1371
+			int fibs = 0, frames = 0; unsigned long long facc = 0, macc = 0;
+			ficHandler fic (nullptr, 1, [&] (uint8_t *fib, uint16_t ficno) { fibs ++; facc = facc * 31 + fnv (fib, 256) + ficno; });
+			mscHandler msc (nullptr, &p, nullptr, 1, [&] (uint8_t *v, int16_t n) { frames ++; macc = macc * 31 + fnv (v, (size_t) n); });
+			audiodata ad = {}; ad. startAddr = 0; ad. length = 96; ad. bitRate = 128; ad. uepFlag = 1; ad. protLevel = 0103;
+			msc. set_audioChannel (&ad);
+			ofdmProcessor op (&rig, &p, nullptr, &msc, &fic, 3, nullptr, 1, 5);
+			op. run ();                                                                     // returns at the end of the file
+			printf ("stream %lld %d %016llx %d %016llx %d\n", (long long) op. frames_decoded (), fibs, facc, frames, macc, (int) fic. get_ficRatio ());
+		}
 	} catch (const std::exception &e) { fprintf (stderr, "adapter_demo: %s\n", e. what ()); return 1; }
 	return 0;
 }

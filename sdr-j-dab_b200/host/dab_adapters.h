@@ -19,9 +19,11 @@
  */
 #ifndef DAB_ADAPTERS_H
 #define DAB_ADAPTERS_H
+#include <atomic>
 #include <complex>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -36,6 +38,18 @@ struct DabParams {                     /* includes/dab-constants.h:137-149 */
 };
 class RadioInterface;
 template <class T> class RingBuffer;
+typedef struct {                       /* includes/dab-constants.h:165-176 */
+	int16_t subchId, startAddr; uint8_t uepFlag; int16_t protLevel, length, bitRate, ASCTy, language, programType;
+} audiodata;
+typedef struct {                       /* includes/dab-constants.h:152-163 */
+	int16_t subchId, startAddr; uint8_t uepFlag; int16_t protLevel, DSCTy, length, bitRate, FEC_scheme, DGflag, packetAddress;
+} packetdata;
+class virtualInput {                   /* src/input/virtual-input.h:51-69: the two members the OFDM thread uses */
+public:
+	virtual ~virtualInput (void) {}
+	virtual int32_t getSamples (DSPCOMPLEX *, int32_t) = 0;      /* size in I/Q pairs; returns the number delivered */
+	virtual int32_t Samples (void) = 0;
+};
 #endif
 
 namespace dabgpu_host {
@@ -229,6 +243,132 @@ private:
 	int16_t bitRate;
 	superframeSink sink;
 	std::vector<uint8_t> out;
+};
+
+/* ------------------------------------------------------------------------------------------------------------
+ * The throughput substitution: ofdmProcessor with the reference's constructor and control members
+ * (ofdm-processor.h:49-68) whose run () hands blocks of samples from virtualInput::getSamples to the stream engine
+ * (dabgpu_decode_cf32) instead of walking them sample by sample (ofdm-processor.cpp:247-474).  Decoded FIBs and
+ * sub-channel frames come back through ficHandler / mscHandler objects that carry the sinks the reference's handlers
+ * end in: fib_processor::process_FIB (fib-processor.h:96, called at fic-handler.cpp:309-319) and
+ * dabProcessor::addtoFrame (dab-processor.h:39, called at dab-concurrent.cpp:191).  Their process_ficBlock /
+ * process_mscBlock entry points (soft bits per OFDM symbol) do not exist here: soft bits never leave the GPU.
+ * ---------------------------------------------------------------------------------------------------------- */
+class ficHandler {                     /* fic-handler.h:44-46 */
+public:
+	typedef std::function<void (uint8_t *, uint16_t)> fibSink;
+	ficHandler (RadioInterface *mr, int16_t dabMode, fibSink sink = nullptr) : sink (sink) { (void) mr; (void) dabMode; }
+	void set_sink (fibSink s) { sink = s; }
+	int16_t get_ficRatio (void) { return total ? (int16_t) (100 * good / total) : 0; }      /* fic-handler.cpp:323-325 */
+	void stop (void) {}
+	/* engine side: the FIC groups of one decode call (768 bits + 3 CRC flags each, ficGroups per frame) */
+	void deliver (uint8_t *bits768, const uint8_t *crc3, int32_t ngroups, int32_t groupsPerFrame) {
+		for (int32_t g = 0; g < ngroups; g ++)
+			for (int f = 0; f < 3; f ++) {
+				total ++;
+				if (!crc3 [3 * g + f]) continue;
+				good ++;
+				if (sink) sink (&bits768 [768 * g + 256 * f], (uint16_t) (g % groupsPerFrame));   /* ficno, fic-handler.cpp:309-319 */
+			}
+	}
+private:
+	fibSink sink;
+	long long good = 0, total = 0;
+};
+
+class mscHandler {                     /* msc-handler.h:43-57 */
+public:
+	typedef std::function<void (uint8_t *, int16_t)> frameSink;
+	mscHandler (RadioInterface *mr, DabParams *p, void *audioSink_unused, uint8_t concurrencyOn, frameSink sink = nullptr)
+	   : sink (sink) { (void) mr; (void) p; (void) audioSink_unused; (void) concurrencyOn; }
+	void set_sink (frameSink s) { sink = s; }
+	void set_audioChannel (audiodata *d) {                        /* msc-handler.cpp:91-105: takes effect at the next block */
+		std::lock_guard<std::mutex> g (m);
+		sc = { d -> startAddr, d -> length, d -> bitRate, d -> uepFlag, d -> protLevel }; have = true; changed = true;
+	}
+	void set_dataChannel (packetdata *d) {                        /* msc-handler.cpp:107-123 */
+		std::lock_guard<std::mutex> g (m);
+		sc = { d -> startAddr, d -> length, d -> bitRate, d -> uepFlag, d -> protLevel }; have = true; changed = true;
+	}
+	void stopProcessing (void) { std::lock_guard<std::mutex> g (m); have = false; changed = true; }
+	void stop (void) {}
+	/* engine side */
+	bool take_change (dabgpu_subch *out, bool *active) {
+		std::lock_guard<std::mutex> g (m);
+		if (!changed) return false;
+		changed = false; *out = sc; *active = have;
+		return true;
+	}
+	void deliver (uint8_t *frames, int32_t nframes, int32_t frameBits) {
+		for (int32_t i = 0; i < nframes && sink; i ++) sink (frames + (size_t) i * frameBits, (int16_t) frameBits);
+	}
+private:
+	frameSink sink;
+	std::mutex m;
+	dabgpu_subch sc {};
+	bool have = false, changed = false;
+};
+
+class ofdmProcessor {                  /* ofdm-processor.h:49-68 (the build without HAVE_SPECTRUM) */
+public:
+	ofdmProcessor (virtualInput *theRig, DabParams *p, RadioInterface *mr, mscHandler *msc, ficHandler *fic,
+	               int16_t threshold, RingBuffer<DSPCOMPLEX> *iqBuffer, uint8_t freqSyncMethod, int32_t framesPerCall = 8)
+	   : theRig (theRig), params (*p), my_mscHandler (msc), my_ficHandler (fic), framesPerCall (framesPerCall) {
+		(void) mr; (void) iqBuffer;
+		dabgpu_config cfg = {};
+		cfg. device = 0; cfg. dabMode = p -> dabMode; cfg. threshold = threshold; cfg. freqSyncMethod = freqSyncMethod;
+		if (dabgpu_create (&cfg, &h) != DABGPU_OK) throw std::runtime_error (std::string ("dabgpu_create: ") + dabgpu_last_error (nullptr));
+		int32_t mp [12];
+		dabgpu_host_mode_params (p -> dabMode, mp);
+		ficGroups = mp [9]; cifsPerFrame = mp [10];
+	}
+	~ofdmProcessor (void) { dabgpu_destroy (h); }
+	void reset (void) { pending_reset = true; }                   /* ofdm-processor.cpp:476-479 */
+	void stop (void) { running = false; }
+	void setOffset (int32_t) {}                                   /* declared by the reference, never defined there either */
+	void coarseCorrectorOn (void) { pending_coarse = 1; }         /* :499-502 */
+	void coarseCorrectorOff (void) { pending_coarse = 0; }        /* :504-506 */
+	void startDumping (void *) {}                                 /* the raw-sample dump stays with the input side */
+	void stopDumping (void) {}
+	void set_scanMode (bool) {}
+	int64_t frames_decoded (void) const { return nframes_total; }
+	/* the thread body (QThread::run in the reference): returns when stop () was called or the input ran dry */
+	void run (void) {
+		running = true;
+		const size_t want = (size_t) framesPerCall * params. T_F;
+		std::vector<DSPCOMPLEX> iq (want);
+		std::vector<uint8_t> fic ((size_t) (framesPerCall + 2) * ficGroups * 768), crc ((size_t) (framesPerCall + 2) * ficGroups * 3), msc;
+		uint8_t *mscp [1] = { nullptr }; int32_t nblk [1] = { 0 };
+		dabgpu_subch sc {}; bool active = false;
+		while (running) {
+			if (pending_reset. exchange (false)) dabgpu_host::check (h, dabgpu_reset (h));
+			const int pc = pending_coarse. exchange (-1);
+			if (pc >= 0) dabgpu_host::check (h, dabgpu_coarse_corrector (h, pc));
+			if (my_mscHandler && my_mscHandler -> take_change (&sc, &active))
+				dabgpu_host::check (h, dabgpu_set_subchannels (h, &sc, active ? 1 : 0));
+			const int32_t n = theRig -> getSamples (iq. data (), (int32_t) want);
+			if (n <= 0) break;
+			if (active) msc. resize ((size_t) (framesPerCall + 2) * cifsPerFrame * 24 * sc. bitRate);
+			mscp [0] = active ? msc. data () : nullptr;
+			dabgpu_result r = {};
+			r. max_frames = framesPerCall + 2; r. fic_bits = fic. data (); r. fic_crc = crc. data (); r. msc_bits = mscp; r. msc_nblocks = nblk;
+			dabgpu_host::check (h, dabgpu_decode_cf32 (h, reinterpret_cast<const float *> (iq. data ()), (size_t) n, &r));
+			nframes_total += r. nframes;
+			if (my_ficHandler) my_ficHandler -> deliver (fic. data (), crc. data (), r. nframes * ficGroups, ficGroups);
+			if (my_mscHandler && active) my_mscHandler -> deliver (msc. data (), nblk [0], 24 * sc. bitRate);
+		}
+		running = false;
+	}
+private:
+	virtualInput *theRig;
+	DabParams params;
+	mscHandler *my_mscHandler;
+	ficHandler *my_ficHandler;
+	int32_t framesPerCall, ficGroups = 4, cifsPerFrame = 4;
+	dabgpu_t *h = nullptr;
+	std::atomic<bool> running { false }, pending_reset { false };
+	std::atomic<int> pending_coarse { -1 };
+	int64_t nframes_total = 0;
 };
 
 #endif

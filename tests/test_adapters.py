@@ -53,8 +53,15 @@ def test_adapter_demo_matches_oracle(port):
     cifs = np.concatenate(rows)
     path = os.path.join(HOST, "adapter_demo_cifs.bin")
     cifs.tofile(path)
-    r = subprocess.run([EXE, path], capture_output=True, text=True, timeout=120)
-    os.remove(path)
+    # a Mode I recording as complex floats for the throughput ofdmProcessor adapter
+    import dabmod
+    mod = dabmod.Modulator(port, 1, [(0, 128, 1, 0o103)], 5150)
+    tr = mod.generate(20, cfo_hz=2345.0, snr_db=20.0, lead=4000, tail=6000)
+    f32 = ((tr["iq"].astype(np.float32) - np.float32(128.0)) / np.float32(128.0)).astype(np.float32)
+    iqpath = os.path.join(HOST, "adapter_demo_iq.bin")
+    f32.tofile(iqpath)
+    r = subprocess.run([EXE, path, iqpath], capture_output=True, text=True, timeout=180)
+    os.remove(path); os.remove(iqpath)
     assert r.returncode == 0, r.stderr
     got = dict(line.split(" ", 1) for line in r.stdout.strip().splitlines())
     g = _lcg_stream(12345)
@@ -79,3 +86,24 @@ def test_adapter_demo_matches_oracle(port):
         acc ^= (_fnv(sf) + k[0] * 1315423911 + k[1]) & 0xFFFFFFFFFFFFFFFF
     count, h = got["dabplus"].split()
     assert int(count) == len(info) == 6 and int(h, 16) == acc
+    # the stream through ofdmProcessor / ficHandler / mscHandler: every CRC-clean FIB (with its ficno) and every frame
+    nfr, nfib, fh, nmsc, mh, ratio = got["stream"].split()
+    sym, finfo = port.ofdm_run(1, f32, 30)
+    n = int(nfr)
+    assert len(finfo) - n in (0, 1) and n >= 14
+    bits, crc = port.fic_frames(1, sym[:n])
+    M = 0xFFFFFFFFFFFFFFFF
+    facc, cnt = 0, 0
+    for g in range(4 * n):
+        for f in range(3):
+            if crc[g][f]:
+                facc = (facc * 31 + _fnv(bits[g][256 * f:256 * f + 256]) + (g % 4)) & M
+                cnt += 1
+    assert int(nfib) == cnt and cnt > 100 and int(fh, 16) == facc
+    s0 = mod.sub[0]
+    frames = port.msc_backend(port.msc_slice(1, sym[:n], s0.startAddr, s0.length), s0.bitRate, s0.uepFlag, s0.protLevel)
+    macc = 0
+    for blk in frames:
+        macc = (macc * 31 + _fnv(blk)) & M
+    assert int(nmsc) == len(frames) > 30 and int(mh, 16) == macc
+    assert int(ratio) == 100 * cnt // (12 * n)

@@ -90,7 +90,7 @@ def test_int16_recording_equals_its_float_form(port):
     cuts = [0, 2 * 700001, 2 * 2100000, i16.size]
     a_parts = [ea.decode(i16[x:y], ea.alloc_result(30)) for x, y in zip(cuts[:-1], cuts[1:])]   # ragged pieces: the int16 tail carries over
     b = eb.decode(f32, eb.alloc_result(30))
-    assert sum(p.nframes for p in a_parts) == b.nframes >= 19
+    assert sum(p.nframes for p in a_parts) == b.nframes >= 16
     assert np.array_equal(np.concatenate([p.soft for p in a_parts]), b.soft)
     assert np.array_equal(np.concatenate([p.fic_bits for p in a_parts]), b.fic_bits)
     for k in range(len(subs)):
