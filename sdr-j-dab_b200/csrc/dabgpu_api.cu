@@ -210,7 +210,7 @@ int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
 	int ctas = 0, ctas2 = 0;
 	bool need_sym8 = false;
 	const int cw2 = vit_simd_cw_per_cta ();
-	auto padded = [] (int nsteps) { return (size_t) ((nsteps + VS_CHUNK - 1) / VS_CHUNK * VS_CHUNK); };
+	auto padded = [] (int nsteps) { return (size_t) vs_npad (nsteps); };
 	for (auto &j : jobs) {
 		j. cta_first = ctas; j. cta_first2 = ctas2; j. one = 1u;
 		ctas += (j. ncw + 63) / 64; ctas2 += (j. ncw + cw2 - 1) / cw2;

@@ -56,6 +56,9 @@ struct ProtProfile {
 	std::vector<uint32_t> gather [2];   // [deint][4 * step + j]: tile byte offset of symbol j relative to the code word's row
 };
 #define VS_CHUNK 40                     // trellis steps per staged chunk of the throughput Viterbi (one renormalisation each)
+// steps per code word in the decision buffer: whole chunks, plus one pair so that the chain-back may fetch the (unused) odd
+// partner of the last step
+__host__ __device__ inline int vs_npad (int nsteps) { return (nsteps + VS_CHUNK - 1) / VS_CHUNK * VS_CHUNK + 2; }
 #define VS_PITCH 184                    // tile row pitch in bytes: 8 x odd (conflict-free over 16 code words), >= 21 granules + pad column
 void prot_build_gather (ProtProfile *pp);
 int  prot_build_identity (int frameBits, ProtProfile *pp);                    // viterbi.cpp:225-242 (no puncturing)
@@ -92,7 +95,7 @@ struct VitSimdJob {
 	int cta_first;            // first CTA of this job in the chain-back launch (64 code words per CTA)
 	int cta_first2;           // same for the forward kernel (VS_CW code words per CTA)
 	unsigned one;             // = 1, set by dab_vit_simd_run; opaque to the compiler on purpose (see vs_acs)
-	uint2 *dec;               // [ncw / 32][nsteps padded to VS_CHUNK][32] decision words
+	uint2 *dec;               // [ncw / 32][vs_npad (nsteps) / 2][32] uint4 decision words of a step pair (dabgpu_vit_simd.cu)
 	const uint32_t *prbs;     // packed dispersal sequence or nullptr
 	uint8_t *out;             // [ncw][frameBits]
 };

@@ -145,6 +145,10 @@ __device__ __forceinline__ void vs_cp_async8 (void *smem, const void *gmem) {
 	asm volatile ("cp.async.ca.shared.global [%0], [%1], 8;" :: "r" ((uint32_t) __cvta_generic_to_shared (smem)), "l" (gmem));
 }
 
+__device__ __forceinline__ void vs_cp_async16 (void *smem, const void *gmem) {
+	asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r" ((uint32_t) __cvta_generic_to_shared (smem)), "l" (gmem));
+}
+
 __global__ void __launch_bounds__ (VS_THREADS, 10) vit_simd_forward (const VitSimdJob *jobs, int njobs) {
 	__shared__ __align__ (16) uint8_t tile [2 * VS_TILE];
 	int jb = 0;
@@ -181,17 +185,17 @@ __global__ void __launch_bounds__ (VS_THREADS, 10) vit_simd_forward (const VitSi
 	if (!lanebit) R [0] = 0u | (63u << 16);                    // state 0 = lane 0, register 0, low half (viterbi.cpp:364-370)
 
 	const int nchunks = (j. nsteps + VS_CHUNK - 1) / VS_CHUNK;
-	// decision words: [block of 32 code words][step][32] uint2 -- a CTA writes one sequential stream, and the chain-back
-	// reads 8 KB contiguous per warp and output word instead of 512-byte pieces 32 KB apart
-	uint32_t *dec = reinterpret_cast<uint32_t *> (j. dec) + 2 * ((size_t) (cw >> 5) * (size_t) (nchunks * VS_CHUNK) * 32 + (cw & 31)) + (lanebit ? 1 : 0);
-	const size_t dstride = 64;
+	// decision words: [block of 32 code words][step pair][32 code words] uint4 = {even step lane 0, odd step lane 0,
+	// even step lane 1, odd step lane 1}: a CTA writes one sequential stream (a thread stores the words of two steps as
+	// 8 bytes), and the chain-back fetches 16 bytes per thread and step pair, 16 KB contiguous per warp and output word
+	uint32_t *dec = reinterpret_cast<uint32_t *> (j. dec) + 4 * ((size_t) (cw >> 5) * (size_t) (vs_npad (j. nsteps) / 2) * 32 + (cw & 31)) + (lanebit ? 2 : 0);
 	for (int k = 0; k < nchunks; k ++) {
 		if (k + 1 < nchunks) stage (k + 1); else asm volatile ("cp.async.commit_group;");
 		asm volatile ("cp.async.wait_group 1;");
 		__syncthreads ();
 		const uint8_t *my = tile + (k & 1) * VS_TILE + cl * VS_PITCH;
 		const uint4 *ga = j. gather + VS_CHUNK * k;
-		uint32_t *d = dec + (size_t) (VS_CHUNK * k) * dstride;
+		uint32_t *d = dec + (size_t) (VS_CHUNK / 2 * k) * 128;
 		// two-deep software pipeline: while step s is processed, the symbols of step s + 1 are read from the tile and the
 		// gather entry of step s + 2 is on its way from the table
 		uint32_t sa, sb, sc;
@@ -213,8 +217,10 @@ __global__ void __launch_bounds__ (VS_THREADS, 10) vit_simd_forward (const VitSi
 #pragma unroll
 			for (int q = 0; q < 16; q ++) R [q] = Q [q];
 			if (live) {
-				d [(size_t) (4 * u + 0) * dstride] = d0; d [(size_t) (4 * u + 1) * dstride] = d1;
-				d [(size_t) (4 * u + 2) * dstride] = d2; d [(size_t) (4 * u + 3) * dstride] = d3;
+				// (four 32-bit stores on purpose: pairing them into 64-bit stores changes the schedule enough to make ptxas spill
+				// predicates -- the decisions -- into a register, +25 % instructions)
+				d [(size_t) (2 * u) * 128] = d0;     d [(size_t) (2 * u) * 128 + 1] = d1;
+				d [(size_t) (2 * u + 1) * 128] = d2; d [(size_t) (2 * u + 1) * 128 + 1] = d3;
 			}
 		}
 		// renormalise: common minimum over the 64 states = both lanes of the pair
@@ -237,24 +243,30 @@ __global__ void __launch_bounds__ (VS_THREADS, 10) vit_simd_forward (const VitSi
 // S = (bit : S) >> 1  -- a funnel shift -- and after 32 steps S is the output word, bit-reversed.
 #define TB_THREADS 64
 template <bool FULL>
-__device__ __forceinline__ uint32_t tb_walk_word (uint32_t &S, const uint2 (*dq) [TB_THREADS], const int tid, const int nvalid) {
+__device__ __forceinline__ uint32_t tb_walk_word (uint32_t &S, const uint4 (*dq) [TB_THREADS], const int tid, const int nvalid) {
 #pragma unroll
-	for (int u = 0; u < 32; u ++) {
-		if (!FULL && u < 32 - nvalid) continue;             // a partial top word: slots of bits beyond frameBits are not there
-		const int pp = ((37 - u) & 3) + 1;                  // step t = 32 wi + 37 - u
-		const uint2 dd = dq [u][tid];
-		const uint32_t n = S >> 26, n1 = S >> 27;
-		const uint32_t lowmask = (1u << (pp + 1)) - 1u;
-		const uint32_t idx = (n & lowmask) | (n1 & ~lowmask);
-		const uint32_t word = (S & (1u << (26 + pp + 1))) ? dd. y : dd. x;
-		S = __funnelshift_r (S, word >> (idx & 31u), 1);
+	for (int m = 0; m < 16; m ++) {                         // slot m = step pair (32 wi + 36 - 2 m, + 1): steps u = 2 m (odd step) and 2 m + 1 (even step)
+		if (!FULL && 2 * m + 1 < 32 - nvalid) continue;     // a partial top word: slots of bits beyond frameBits are not there
+		const uint4 dd = dq [m][tid];
+#pragma unroll
+		for (int e = 0; e < 2; e ++) {
+			const int u = 2 * m + e;
+			if (!FULL && u < 32 - nvalid) continue;
+			const int pp = ((37 - u) & 3) + 1;              // step t = 32 wi + 37 - u
+			const uint32_t n = S >> 26, n1 = S >> 27;
+			const uint32_t lowmask = (1u << (pp + 1)) - 1u;
+			const uint32_t idx = (n & lowmask) | (n1 & ~lowmask);
+			const bool lane1 = (S & (1u << (26 + pp + 1))) != 0;
+			const uint32_t word = e == 0 ? (lane1 ? dd. w : dd. y) : (lane1 ? dd. z : dd. x);
+			S = __funnelshift_r (S, word >> (idx & 31u), 1);
+		}
 	}
 	return __brev (S);
 }
 
 __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimdJob *jobs, int njobs) {
 	__shared__ uint32_t bits [TB_THREADS * 5];               // 128 decoded bits per code word per round, row stride 5 words
-	__shared__ __align__ (16) uint2 dq [2][32][TB_THREADS];  // the decision words of two output words (32 steps each) per thread
+	__shared__ __align__ (16) uint4 dq [2][16][TB_THREADS];  // the decision words of two output words (16 step pairs each) per thread
 	int jb = 0;
 	while (jb + 1 < njobs && (int) blockIdx. x >= jobs [jb + 1]. cta_first) jb ++;
 	const VitSimdJob j = jobs [jb];
@@ -262,8 +274,7 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 	const int tid = threadIdx. x, lane = tid & 31, warp = tid >> 5;
 	const int cw = c0 + tid;
 	const bool live = cw < j. ncw;
-	const size_t npad = (size_t) ((j. nsteps + VS_CHUNK - 1) / VS_CHUNK * VS_CHUNK);
-	const uint2 *dec = j. dec + (live ? (size_t) (cw >> 5) * npad * 32 + (cw & 31) : 0);
+	const uint4 *dec = reinterpret_cast<const uint4 *> (j. dec) + (live ? (size_t) (cw >> 5) * (size_t) (vs_npad (j. nsteps) / 2) * 32 + (cw & 31) : 0);
 	uint32_t S = 0;                                          // chain-back starts in state 0 (viterbi.cpp:340)
 	const int nrounds = (j. frameBits + 127) / 128, nwords = (j. frameBits + 31) / 32;
 	// The loads do not depend on the state: while output word wi is walked, the 32 decision words of word wi - 1 are
@@ -271,14 +282,14 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 	// barrier is involved).  Slot u of a word holds information bit 32 wi + 31 - u = trellis step 32 wi + 37 - u.
 	auto fetch = [&] (int wi) {
 		if (wi >= 0 && live) {
-			const uint2 *src = dec + (size_t) (32 * wi + 37) * 32;
+			const uint4 *src = dec + (size_t) (16 * wi + 18) * 32;      // pair of steps 32 wi + 36, 37
 			if (32 * wi + 32 <= j. frameBits) {
 #pragma unroll
-				for (int u = 0; u < 32; u ++) vs_cp_async8 (&dq [wi & 1][u][tid], src - 32 * u);
+				for (int m = 0; m < 16; m ++) vs_cp_async16 (&dq [wi & 1][m][tid], src - 32 * m);
 			} else {
 #pragma unroll
-				for (int u = 0; u < 32; u ++)
-					if (32 * wi + 31 - u < j. frameBits) vs_cp_async8 (&dq [wi & 1][u][tid], src - 32 * u);
+				for (int m = 0; m < 16; m ++)
+					if (32 * wi + 30 - 2 * m < j. frameBits) vs_cp_async16 (&dq [wi & 1][m][tid], src - 32 * m);
 			}
 		}
 		asm volatile ("cp.async.commit_group;");

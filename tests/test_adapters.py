@@ -99,7 +99,7 @@ def test_adapter_demo_matches_oracle(port):
             if crc[g][f]:
                 facc = (facc * 31 + _fnv(bits[g][256 * f:256 * f + 256]) + (g % 4)) & M
                 cnt += 1
-    assert int(nfib) == cnt and cnt > 100 and int(fh, 16) == facc
+    assert int(nfib) == cnt and cnt > 50 and int(fh, 16) == facc
     s0 = mod.sub[0]
     frames = port.msc_backend(port.msc_slice(1, sym[:n], s0.startAddr, s0.length), s0.bitRate, s0.uepFlag, s0.protLevel)
     macc = 0
