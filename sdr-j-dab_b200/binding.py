@@ -170,6 +170,29 @@ def wav_parse(lib, image):
     return info if rc == 0 else None
 
 
+class _InfoView:
+    """the first n per-frame records of a result buffer, read on demand (building a list of a thousand ctypes
+    structs per call costs more host time than the call itself)"""
+
+    def __init__(self, arr, n, valid=True):
+        self.arr, self.n = arr, (n if valid else 0)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self.arr[k] for k in range(*i.indices(self.n))]
+        if i < 0:
+            i += self.n
+        if not 0 <= i < self.n:
+            raise IndexError(i)
+        return self.arr[i]
+
+    def __iter__(self):
+        return (self.arr[k] for k in range(self.n))
+
+
 class DecodeOut:
     """Host-side result buffers of one dabgpu_decode call."""
     pass
@@ -383,7 +406,7 @@ class DabGpu:
         groups = 3 * 2 * K // 2304
         r = DecodeOut()
         r.nframes, r.consumed = n, o.res.consumed
-        r.info = [o.info[i] for i in range(n)]
+        r.info = _InfoView(o.info, n, bool(o.res.info))
         r.soft = o.soft[:n] if o.soft is not None else None
         r.fic_bits, r.fic_crc = o.fic_bits[:n * groups], o.fic_crc[:n * groups]
         r.msc = [m[:o.nblocks[i]] for i, m in enumerate(o.msc)]

@@ -430,54 +430,54 @@ __global__ void soft_to_sym8_kernel (const int16_t *in, uint8_t *out, long long 
 // ---------------------------------------------------------------------------------------------------
 #define SCAN_MAX 1024
 struct ScanSmem { FrameIn in [SCAN_MAX]; FrameOut fo [SCAN_MAX]; float2 fc [SCAN_MAX]; double inc [SCAN_MAX]; };
-__global__ void __launch_bounds__ (32) scan_kernel (StreamCtl *ctl, FrameIn *fin, int nframes, int slot0, int groups, DabParams dp, const FrameOut *fo,
+#define SCAN_THREADS 256
+__global__ void __launch_bounds__ (SCAN_THREADS) scan_kernel (StreamCtl *ctl, FrameIn *fin, int nframes, int slot0, int groups, DabParams dp, const FrameOut *fo,
                              const float2 *fcpart, dabgpu_frame_info *info, long long abs_base, int derive) {
 	extern __shared__ unsigned char scan_raw [];
 	ScanSmem &S = *reinterpret_cast<ScanSmem *> (scan_raw);
-	__shared__ int s_ninfo, s_start;
-	const int lane = threadIdx. x;
+	__shared__ int s_ninfo, s_start, s_first;
+	const int lane = threadIdx. x;                           // (thread index; thread 0 runs the serial replay)
 	if (!derive && ctl -> n_redo == 0) return;               // the derive pass found nothing to redo and committed already
 	const StreamCtl s0 = *ctl;
 	const int cd = dp. carrierDiff;
+	if (lane == 0) s_first = nframes;
 	// parallel preload of the per-frame records; the serial replay then runs out of shared memory
-	for (int c = lane; c < nframes; c += 32) {
+	for (int c = lane; c < nframes; c += SCAN_THREADS) {
 		S. in [c] = fin [c]; S. fo [c] = fo [c];
 		float2 fc = make_float2 (0.f, 0.f);
 		for (int g = 0; g < groups; g ++) { fc. x += fcpart [c * MAX_GROUPS + g]. x; fc. y += fcpart [c * MAX_GROUPS + g]. y; }
 		S. fc [c] = fc;
 		S. inc [c] = __dmul_rn (__ddiv_rn (__dmul_rn (0.1, (double) atan2f (fc. y, fc. x)), 3.14159265358979323846), (double) (cd / 2));
 	}
-	__syncwarp ();
+	__syncthreads ();
 	// Fast path for a locked receiver.  A frame leaves the tracking state as it found it (apart from advancing by one
 	// frame length) when its window was placed where the replay wants it, the coarse search is off, findIndex returned
-	// T_g and the fine integrator's truncated sum is unchanged.  Such frames are accepted in parallel; the serial replay
-	// starts at the first frame that is not of this kind.
+	// T_g and the fine integrator's truncated sum is unchanged.  The leading run of such frames is accepted in parallel;
+	// the serial replay starts at the first frame that is not of this kind.
 	const int phi0 = s0. coarse + s0. fine;
 	const int phm = mod_rate (phi0);
-	int first_slow = nframes;
+	int first_slow = 0;
 	if (!s0. f2 && s0. fine <= cd / 2 && s0. fine >= - cd / 2) {
-		for (int c0 = 0; c0 < nframes && first_slow == nframes; c0 += 32) {
-			const int c = c0 + lane;
-			bool ok = true;
-			if (c < nframes) {
-				const FrameIn in = S. in [c];
-				const long long P = s0. pos + (long long) c * dp. T_F;
-				const int lp = mod_rate ((long long) s0. lp - (long long) c * dp. T_F % DAB_INPUT_RATE * phm);
-				ok = in. P == P && in. lp == lp && in. phiA == phi0 && in. phiB == phi0 && S. fo [c]. startIndex == dp. T_s - dp. T_u &&
-				     (int) (short) __double2int_rz (__dadd_rn ((double) s0. fine, S. inc [c])) == s0. fine;
-				if (ok) {
-					dabgpu_frame_info fi;
-					fi. pos = abs_base + P; fi. startIndex = dp. T_s - dp. T_u; fi. coarse = s0. coarse; fi. fine = s0. fine;
-					fi. phase0 = lp; fi. correction = 0; fi. freqCorrRe = S. fc [c]. x; fi. freqCorrIm = S. fc [c]. y;
-					info [slot0 + c] = fi;                       // harmless if the chunk is redone: rewritten then
-					if (derive) S. in [c]. active = 0;
-				}
-			}
-			const unsigned bad = __ballot_sync (0xffffffffu, !ok);
-			if (bad) first_slow = c0 + __ffs (bad) - 1;
+		for (int c = lane; c < nframes; c += SCAN_THREADS) {
+			const FrameIn in = S. in [c];
+			const long long P = s0. pos + (long long) c * dp. T_F;
+			const int lp = mod_rate ((long long) s0. lp - (long long) c * dp. T_F % DAB_INPUT_RATE * phm);
+			const bool ok = in. P == P && in. lp == lp && in. phiA == phi0 && in. phiB == phi0 && S. fo [c]. startIndex == dp. T_s - dp. T_u &&
+			                (int) (short) __double2int_rz (__dadd_rn ((double) s0. fine, S. inc [c])) == s0. fine;
+			if (!ok) atomicMin (&s_first, c);
 		}
-	} else first_slow = 0;
-	__syncwarp ();
+		__syncthreads ();
+		first_slow = s_first;
+		for (int c = lane; c < first_slow; c += SCAN_THREADS) {
+			dabgpu_frame_info fi;
+			fi. pos = abs_base + s0. pos + (long long) c * dp. T_F; fi. startIndex = dp. T_s - dp. T_u; fi. coarse = s0. coarse; fi. fine = s0. fine;
+			fi. phase0 = mod_rate ((long long) s0. lp - (long long) c * dp. T_F % DAB_INPUT_RATE * phm);
+			fi. correction = 0; fi. freqCorrRe = S. fc [c]. x; fi. freqCorrIm = S. fc [c]. y;
+			info [slot0 + c] = fi;                           // harmless if the chunk is redone: rewritten then
+			if (derive) S. in [c]. active = 0;
+		}
+	}
+	__syncthreads ();
 	if (lane == 0) {
 		StreamCtl s = s0;
 		int n_redo = 0, ninfo = first_slow;
@@ -558,8 +558,8 @@ __global__ void __launch_bounds__ (32) scan_kernel (StreamCtl *ctl, FrameIn *fin
 		} else { s. n_redo = ctl -> n_redo; *ctl = s; }
 		s_start = first_slow;
 	}
-	__syncwarp ();
-	if (derive) for (int c = lane; c < nframes; c += 32) fin [c] = S. in [c];
+	__syncthreads ();
+	if (derive) for (int c = lane; c < nframes; c += SCAN_THREADS) fin [c] = S. in [c];
 	(void) s_ninfo; (void) s_start;
 }
 
@@ -925,7 +925,7 @@ static int decode_core (dabgpu *h, const void *d_new_v, long long nnew, dabgpu_r
 					fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p,
 					(uint8_t *) E -> d_fic8. p, (uint8_t *) E -> d_msc8. p); }
 			{ ProfScope prof (h, KC_SCAN);
-			scan_kernel<<<1, 32, sizeof (ScanSmem), h -> stream>>> (dctl, fin, (int) C, nframes, E -> groups, p, fo, (const float2 *) E -> d_fcpart. p,
+			scan_kernel<<<1, SCAN_THREADS, sizeof (ScanSmem), h -> stream>>> (dctl, fin, (int) C, nframes, E -> groups, p, fo, (const float2 *) E -> d_fcpart. p,
 				(dabgpu_frame_info *) E -> d_info. p, E -> abs_base, pass == 0 ? 1 : 0); }
 		}
 		h -> launches += 7;
