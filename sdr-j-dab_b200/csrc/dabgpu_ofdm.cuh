@@ -280,13 +280,15 @@ __device__ __forceinline__ void dft8 (float2 (&a) [8]) {
 
 // x[k] = sample t + 256 k on entry; A = R8_SMEM float2 of shared memory.  Twiddles: tw1[2 g + ...] = the thread's own six
 // stage-1 factors W_2048^(n q), n = t + 256 g, q = 1..3 (registers, loaded once per CTA by r8_load_tw1); tw2[j] = W_512^j
-// (512 entries) and tw3[j] = W_64^j (64 entries) in shared memory (r8_fill_tables) -- with most of the SM's on-chip
+// and tw3[j] = W_64^j, stored per output index q (r8_fill_tables), in shared memory -- with most of the SM's on-chip
 // memory carved out as shared memory the L1 is too small to keep a global twiddle table resident.
 #define R8_TW2 512
 #define R8_TW3 64
 __device__ __forceinline__ void r8_fill_tables (float2 *tw2, float2 *tw3, const float2 *__restrict__ tw) {
-	for (int j = threadIdx. x; j < R8_TW2; j += 256) tw2 [j] = __ldg (&tw [4 * j]);
-	if (threadIdx. x < R8_TW3) tw3 [threadIdx. x] = __ldg (&tw [32 * threadIdx. x]);
+	// one run per output index q, so that the lanes of a warp read consecutive entries (tw2 [n q] for even q is a
+	// 2- or 4-way bank conflict): tw2 [64 (q - 1) + n] = W_512^(n q), tw3 [8 (q - 1) + n] = W_64^(n q), q = 1..7
+	for (int j = threadIdx. x; j < 7 * 64; j += 256) tw2 [j] = __ldg (&tw [4 * (((j & 63) * ((j >> 6) + 1)) & 511)]);
+	if (threadIdx. x < 7 * 8) tw3 [threadIdx. x] = __ldg (&tw [32 * ((((int) threadIdx. x & 7) * (((int) threadIdx. x >> 3) + 1)) & 63)]);
 }
 __device__ __forceinline__ void r8_load_tw1 (float2 (&tw1) [6], const float2 *__restrict__ tw) {
 #pragma unroll
@@ -335,9 +337,16 @@ __device__ __forceinline__ void fft2048_r8 (float2 (&x) [8], float2 *A, const fl
 		dft8 (a);
 		R8_ST (be, a [0]);
 #pragma unroll
-		for (int q = 1; q < 8; q ++) R8_ST (((q & 1) ? bo : be) + 8 * 64 * q, cmul (a [q], tw2 [(n * q) & 511]));
+		for (int q = 1; q < 8; q ++) R8_ST (((q & 1) ? bo : be) + 8 * 64 * q, cmul (a [q], tw2 [64 * (q - 1) + n]));
 	}
-	__syncthreads ();
+	// the 512-point block of stage 2 is produced and consumed by the same 64 threads (two warps): a named barrier for
+	// them instead of the whole CTA
+	switch (t >> 6) {                                        // (literal ids: a register id makes ptxas reserve all 16 barriers)
+	case 0:  asm volatile ("bar.sync 1, 64;" ::: "memory"); break;
+	case 1:  asm volatile ("bar.sync 2, 64;" ::: "memory"); break;
+	case 2:  asm volatile ("bar.sync 3, 64;" ::: "memory"); break;
+	default: asm volatile ("bar.sync 4, 64;" ::: "memory"); break;
+	}
 	// stage 3: radix 8 inside blocks of 64: n = t & 7, twiddle W_64^(n q).  element 64 b + n + 8 m: bits 3 | 4,5 = m,
 	// bit 6 = b & 1, so the address is base ^ K(m) with K(m) = 8 ((m >> 1) & 3) + 64 (m & 1) + 128 (m >> 1)
 	{
@@ -349,9 +358,9 @@ __device__ __forceinline__ void fft2048_r8 (float2 (&x) [8], float2 *A, const fl
 		dft8 (a);
 		R8_ST (base, a [0]);
 #pragma unroll
-		for (int q = 1; q < 8; q ++) R8_ST (base ^ (8 * ((q >> 1) & 3) + 64 * (q & 1) + 128 * (q >> 1)), cmul (a [q], tw3 [n * q]));
+		for (int q = 1; q < 8; q ++) R8_ST (base ^ (8 * ((q >> 1) & 3) + 64 * (q & 1) + 128 * (q >> 1)), cmul (a [q], tw3 [8 * (q - 1) + n]));
 	}
-	__syncthreads ();
+	__syncwarp ();                                           // a 64-point block lives in 8 consecutive threads
 	// stage 4: radix 8 on 8 consecutive points, no twiddles.  element 8 t + m: address = base ^ 8 m
 	{
 		const uint32_t base = Ab + r8_swz (8 * t) * 8;
