@@ -903,10 +903,6 @@ static int decode_core (dabgpu *h, const void *d_new_v, long long nnew, dabgpu_r
 		long long C = E -> chunk < chunk_cap ? E -> chunk : chunk_cap;
 		if (C > avail) C = avail;
 		if (C > want - nframes) C = want - nframes;
-		// host input: what is still to do once the LAST sample has arrived is pure latency (OFDM of the last chunk, its
-		// channel decoding, the result copy), so the chunks taper towards the end of the input: ... 128, 64, 32, 32
-		const bool tail_zone = ready && !ready -> empty () && avail <= 160;
-		if (tail_zone && C > 32) { const long long half = avail / 2; C = C < (half > 32 ? half : 32) ? C : (half > 32 ? half : 32); }
 		CUDA_TRY (h, need_input (E -> ctl. pos + (C - 1) * p. T_F + frame_need));
 		*hctl = E -> ctl;
 		CUDA_TRY (h, cudaMemcpyAsync (E -> d_ctl. p, hctl, sizeof (StreamCtl), cudaMemcpyHostToDevice, h -> stream));
@@ -940,7 +936,7 @@ static int decode_core (dabgpu *h, const void *d_new_v, long long nnew, dabgpu_r
 		nframes += E -> ctl. n_valid;
 		// the accepted frames' soft bits are final: once enough of them have piled up to fill the GPU, decode them on a
 		// side stream while the OFDM part (and the input copy) of the following frames goes on
-		if (nframes - decoded_upto >= vit_batch_frames || (tail_zone && nframes - decoded_upto >= 16)) {
+		if (nframes - decoded_upto >= vit_batch_frames) {
 			if ((rc = channel_chunk (h, decoded_upto, nframes - decoded_upto, out, nblk))) return rc;
 			decoded_upto = nframes;
 		}
