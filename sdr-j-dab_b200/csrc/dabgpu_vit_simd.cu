@@ -58,6 +58,28 @@ __host__ __device__ constexpr uint32_t vs_decbit (int K, int r, int e, int half)
 	return 1u << (e | ((r & ((1 << K) - 1)) << 1) | (half << (K + 1)) | ((r >> K) << (K + 2)));
 }
 
+__host__ __device__ constexpr int vs_decidx (int K, int r, int e, int half) {
+	return e | ((r & ((1 << K) - 1)) << 1) | (half << (K + 1)) | ((r >> K) << (K + 2));
+}
+// The same decisions collected in FLOAT accumulators: acc += 2^(index mod 16) under the predicate, one accumulator group
+// for the bit positions below 16 and one for those above; every accumulator receives four distinct powers of two inside a
+// 16-bit window, so the sums are exact, and two float-to-int conversions per step turn them back into the decision word.
+// Unlike the integer multiply-adds, which ptxas partly rewrites into select + three-input add on the (half-rate, busy)
+// ALU pipe, predicated FFMAs stay on the FMA pipe.
+#ifndef VS_FDEC
+#define VS_FDEC 0
+#endif
+#ifndef VS_PL2
+#define VS_PL2 0
+#endif
+__device__ __forceinline__ uint32_t vs_acs_f (uint32_t upper, uint32_t lower, float &acc_l, float &acc_h, const float c_l, const float c_h, const float onef) {
+	bool ph, pl;
+	const uint32_t r = __vibmin_u16x2 (upper, lower, &ph, &pl);
+	asm ("{ .reg .pred p; setp.eq.u32 p, %1, 0; @p fma.rn.f32 %0, %3, %2, %0; }" : "+f" (acc_l) : "r" ((uint32_t) pl), "f" (c_l), "f" (onef));
+	asm ("{ .reg .pred p; setp.eq.u32 p, %1, 0; @p fma.rn.f32 %0, %3, %2, %0; }" : "+f" (acc_h) : "r" ((uint32_t) ph), "f" (c_h), "f" (onef));
+	return r;
+}
+
 __device__ __forceinline__ uint32_t vs_sel (uint32_t a, uint32_t b, uint32_t mask) { return (a & ~mask) | (b & mask); }   // one LOP3
 
 // One trellis step.  a0 = sym0 + sym3 (both use polynomial 0155), s1, s2 = the other two symbols.  The branch metric
@@ -81,9 +103,40 @@ __device__ __forceinline__ void vs_step (const uint32_t (&R) [16], uint32_t (&Q)
 		else               { c [j][0] = c0; c [j][1] = c1; }
 	}
 	uint32_t PL [8];
+#if VS_PL2
+	// two levels of two-input adds (12 instead of 8 three-input ones): two-input adds can go to the FMA pipe as IMAD.IADD
+	uint32_t c01 [4];
+#pragma unroll
+	for (int x = 0; x < 4; x ++) c01 [x] = c [0][x & 1] + c [1][x >> 1];
+#pragma unroll
+	for (int x = 0; x < 8; x ++) PL [x] = c01 [x & 3] + c [2][x >> 2];
+#else
 #pragma unroll
 	for (int x = 0; x < 8; x ++)                                // one three-input add each (kept from being split into shared partial sums)
 		asm ("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r" (PL [x]) : "r" (c [0][x & 1]), "r" (c [1][(x >> 1) & 1]), "r" (c [2][(x >> 2) & 1]));
+#endif
+#if VS_FDEC
+	const float onef = __uint_as_float (one * 0x3f800000u);     // 1.0f, opaque like `one`
+	float g [8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };      // [0..3]: bit positions 0..15, [4..7]: positions 16..31
+#pragma unroll
+	for (int r = 0; r < 8; r ++) {
+		const int x = vs_pat (vs_insert00 (r, K));
+		const uint32_t a = R [r], b = R [r + 8];
+		const uint32_t m0 = a + PL [x],     m1 = b + PL [7 - x];
+		const uint32_t m2 = a + PL [7 - x], m3 = b + PL [x];
+		const int slot = K < 3 ? (r & 3) : (r >> 1);                // every accumulator ends up with four decisions
+#pragma unroll
+		for (int e = 0; e < 2; e ++) {
+			const int il = vs_decidx (K, r, e, 0), ih = vs_decidx (K, r, e, 1);
+			Q [2 * r + e] = vs_acs_f (e ? m2 : m0, e ? m3 : m1, g [4 * (il >> 4) + slot], g [4 * (ih >> 4) + slot],
+			                          (float) (1u << (il & 15)), (float) (1u << (ih & 15)), onef);
+		}
+	}
+	dec = __float2uint_rz ((g [0] + g [1]) + (g [2] + g [3])) + (__float2uint_rz ((g [4] + g [5]) + (g [6] + g [7])) << 16);
+#else
+#ifndef VS_NACC
+#define VS_NACC 2                               // accumulators of decision bits per step (A/B on B200: 8 -> 1.428, 4 -> 1.413, 2 -> 1.386 ms per 1024 frames; 1 makes ptxas spill predicates)
+#endif
 	uint32_t acc [8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 #pragma unroll
 	for (int r = 0; r < 8; r ++) {
@@ -93,10 +146,11 @@ __device__ __forceinline__ void vs_step (const uint32_t (&R) [16], uint32_t (&Q)
 		// the halves and the full-rate IADD replaces the half-rate VIADD.16x2
 		const uint32_t m0 = a + PL [x],     m1 = b + PL [7 - x];
 		const uint32_t m2 = a + PL [7 - x], m3 = b + PL [x];
-		Q [2 * r]     = vs_acs (m0, m1, acc [r], vs_decbit (K, r, 0, 0), vs_decbit (K, r, 0, 1), one);
-		Q [2 * r + 1] = vs_acs (m2, m3, acc [r], vs_decbit (K, r, 1, 0), vs_decbit (K, r, 1, 1), one);
+		Q [2 * r]     = vs_acs (m0, m1, acc [r % VS_NACC], vs_decbit (K, r, 0, 0), vs_decbit (K, r, 0, 1), one);
+		Q [2 * r + 1] = vs_acs (m2, m3, acc [r % VS_NACC], vs_decbit (K, r, 1, 0), vs_decbit (K, r, 1, 1), one);
 	}
 	dec = ((acc [0] + acc [1]) + (acc [2] + acc [3])) + ((acc [4] + acc [5]) + (acc [6] + acc [7]));
+#endif
 }
 
 // lane = s5, half = s4, q = (s3 s2 s1 s0)  ->  lane = s1, half = s0, q = (s5 s4 s3 s2)
