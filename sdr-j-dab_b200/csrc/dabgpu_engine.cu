@@ -11,6 +11,7 @@
 // true state.  Accepted frames are therefore computed from exactly the inputs the reference would have used.
 // Acquisition (null-symbol search) is a sample-serial scan done once per (re)synchronisation.
 #include <math.h>
+#include <stdlib.h>
 #include "dabgpu_engine.h"
 
 __device__ __forceinline__ uchar2 win_fetch (const SampleWin &w, long long i) {      // u8 windows only
@@ -577,6 +578,7 @@ int dab_engine_init (dabgpu *h) {
 	memset (&E -> ctl, 0, sizeof (StreamCtl));
 	E -> ctl. f2 = 1; E -> ctl. prev1 = 1000; E -> ctl. prev2 = 999;     // ofdm-processor.cpp:258-259, 73
 	E -> groups = h -> p. L > 100 ? 8 : 5;
+	if (const char *g = getenv ("DABGPU_GROUPS")) { const int v = atoi (g); if (v >= 1 && v <= MAX_GROUPS) { E -> groups = v; E -> groups_fixed = true; } }   // tuning knob (A/B runs)
 	CUDA_TRY (h, E -> d_figkeys. ensure (128 * sizeof (unsigned long long)));
 	CUDA_TRY (h, cudaMemsetAsync (E -> d_figkeys. p, 0, 128 * sizeof (unsigned long long), h -> stream));
 	CUDA_TRY (h, cudaStreamCreateWithFlags (&E -> copy_st, cudaStreamNonBlocking));
@@ -911,21 +913,25 @@ static int decode_core (dabgpu *h, const void *d_new_v, long long nnew, dabgpu_r
 		FrameOut *fo = (FrameOut *) E -> d_frameout. p;
 		{ ProfScope prof (h, KC_SCAN);
 		predict_kernel<<<((int) C + 127) / 128, 128, 0, h -> stream>>> (dctl, fin, p. T_F, (int) C); }
+		// symbol groups (CTAs) per frame: every group first recomputes the spectrum of the symbol before its own as phase
+		// reference, so few groups mean less redundant work and many groups more CTAs.  A big chunk fills the GPU anyway
+		// (A/B on B200, 1024 frames: 5 groups 0.849 ms, 3 groups 0.828 ms, 1-2 groups the same)
+		const int groups = !E -> groups_fixed && C >= 128 && E -> groups > 3 ? 3 : E -> groups;
 		for (int pass = 0; pass < 2; pass ++) {
 			// pass 0: speculative inputs, then the optimistic replay (derive); pass 1: recompute what changed, then verify
 			{ ProfScope prof (h, KC_FRONT);
 			front_kernel<<<(int) C, OFDM_THREADS, sm_front, h -> stream>>> (w, E -> T, fin, fo, (float2 *) E -> d_spec0. p); }
 			{ ProfScope prof (h, KC_SYMBOL);
 			if (p. T_u == R8_N && p. K == 1536 && !E -> cf32 && !h -> cfg. reserved [0])     // reserved[0] = 1: generic kernel (A/B testing)
-				symbol_kernel_r8<<<(int) C * E -> groups, 256, R8_DYN_SMEM, h -> stream>>> (w, E -> T, fin, nframes, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
+				symbol_kernel_r8<<<(int) C * groups, 256, R8_DYN_SMEM, h -> stream>>> (w, E -> T, fin, nframes, groups, p. blocksPerCIF, p. cifsPerFrame,
 					fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p,
 					(uint8_t *) E -> d_fic8. p, (uint8_t *) E -> d_msc8. p);
 			else
-				symbol_kernel<<<(int) C * E -> groups, OFDM_THREADS, sm_sym, h -> stream>>> (w, E -> T, fin, nframes, E -> groups, p. blocksPerCIF, p. cifsPerFrame,
+				symbol_kernel<<<(int) C * groups, OFDM_THREADS, sm_sym, h -> stream>>> (w, E -> T, fin, nframes, groups, p. blocksPerCIF, p. cifsPerFrame,
 					fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p,
 					(uint8_t *) E -> d_fic8. p, (uint8_t *) E -> d_msc8. p); }
 			{ ProfScope prof (h, KC_SCAN);
-			scan_kernel<<<1, SCAN_THREADS, sizeof (ScanSmem), h -> stream>>> (dctl, fin, (int) C, nframes, E -> groups, p, fo, (const float2 *) E -> d_fcpart. p,
+			scan_kernel<<<1, SCAN_THREADS, sizeof (ScanSmem), h -> stream>>> (dctl, fin, (int) C, nframes, groups, p, fo, (const float2 *) E -> d_fcpart. p,
 				(dabgpu_frame_info *) E -> d_info. p, E -> abs_base, pass == 0 ? 1 : 0); }
 		}
 		h -> launches += 7;

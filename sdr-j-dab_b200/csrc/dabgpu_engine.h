@@ -64,7 +64,8 @@ struct Engine {
 	bool hist_init = false;
 	std::vector<dabgpu_subch> subch;
 	std::vector<dabgpu_backend *> backends;
-	int groups = 5;
+	int groups = 5;                     // symbol groups (CTAs) per frame for small chunks; big chunks use 3
+	bool groups_fixed = false;          // DABGPU_GROUPS given: use it for every chunk
 	cudaStream_t copy_st = nullptr;     // piecewise host-to-device input copies
 	std::vector<cudaEvent_t> copy_events;
 	int vit_batch_frames = 128;         // host-input path: frames per channel-decoding launch (cfg.host_batch_frames overrides)
