@@ -415,6 +415,11 @@ class DabGpu:
     def reset(self):
         self._check(self.lib.dabgpu_reset(self.h))
 
+    def coarse_corrector(self, on):
+        """ofdmProcessor::coarseCorrectorOn / coarseCorrectorOff"""
+        self.lib.dabgpu_coarse_corrector.argtypes = [C.c_void_p, C.c_int32]
+        self._check(self.lib.dabgpu_coarse_corrector(self.h, 1 if on else 0))
+
     # ---- geometry and result helpers used by parallel.decode_sharded
     @property
     def frame_len(self):

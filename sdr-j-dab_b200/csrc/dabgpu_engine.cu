@@ -414,6 +414,100 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Mode I front kernel on the register FFT: same work as front_kernel (SyncOnPhase + OFDM_PRS, ofdm-processor.cpp:344-406).
+// The spectrum of a transform stays in the FFT's digit-reversed shared layout; the correlator's product with the PRS
+// reference reads it through the position map, the magnitude scan walks the storage order and maps every slot back to
+// its bin (first maximum = smallest bin among equals, as the reference's ascending loop finds it).
+// ---------------------------------------------------------------------------------------------------
+#define FRONT_R8_SMEM ((2 * R8_SMEM + R8_TW2 + R8_TW3) * (int) sizeof (float2))
+__host__ __device__ __forceinline__ int r8_pos_inv (int p) { return (p >> 9) | (((p >> 6) & 7) << 2) | (((p >> 3) & 7) << 5) | ((p & 7) << 8); }
+
+__global__ void __launch_bounds__ (256) front_kernel_r8 (SampleWin w, OfdmTables T, const FrameIn *fin, FrameOut *fo, float2 *spec0) {
+	extern __shared__ __align__ (1024) unsigned char fr8_dyn [];
+	float2 *A = reinterpret_cast<float2 *> (fr8_dyn), *B = A + R8_SMEM, *tw2 = B + R8_SMEM, *tw3 = tw2 + R8_TW2;
+	__shared__ float cv [96];
+	__shared__ float s_red [8], s_max [8];
+	__shared__ int s_idx [8], s_result;
+	const int N = R8_N, c = blockIdx. x, t = threadIdx. x;
+	const FrameIn in = fin [c];
+	if (!in. active) return;
+	float2 x [8], tw1 [6];
+	r8_fill_tables (tw2, tw3, T. tw);
+	r8_load_tw1 (tw1, T. tw);
+	const int phA = mod_rate (in. phiA), step256 = mod_rate (256ll * phA);
+	// x [k] = sample (first + t + 256 k) after u8 conversion and NCO (rawfiles.cpp:113-116; ofdm-processor.cpp:217-226)
+	auto load = [&] (long long first, int lp_before) {
+		int lp = mod_rate ((long long) lp_before - (long long) (t + 1) * phA);
+#pragma unroll
+		for (int k = 0; k < 8; k ++) {
+			x [k] = cmul (u8_to_c (win_fetch (w, first + t + 256 * k)), nco (T, lp));
+			lp -= step256; if (lp < 0) lp += DAB_INPUT_RATE;
+		}
+	};
+	load (in. P, in. lp);                                              // :347-348
+	__syncthreads ();                                                  // twiddle tables in place
+	fft2048_r8 (x, A, tw1, tw2, tw3);
+	// res = conj (fft * conj (ref)): the backward transform is conj (forward (conj (x))) (phasereference.cpp:66-73)
+#pragma unroll
+	for (int k = 0; k < 8; k ++) {
+		const int kk = t + 256 * k;
+		const float2 r = cmulc (A [r8_swz (r8_pos (kk))], __ldg (&T. ref [kk]));
+		x [k] = make_float2 (r. x, - r. y);
+	}
+	__syncthreads ();                                                  // everybody has read A
+	fft2048_r8 (x, A, tw1, tw2, tw3);
+	const float factor = (float) (1.0 / (float) N);                    // fft.cpp:114-121
+	float sum = 0.f, mx = -10000.f;
+	int mi = -1;
+#pragma unroll
+	for (int m = 0; m < 8; m ++) {
+		const int slot = t + 256 * m, k = r8_pos_inv (r8_swz (slot));  // the swizzle is an involution
+		const float2 v = A [slot];
+		const float a = hypotf (v. x * factor, (- v. y) * factor);
+		sum += a;
+		if (a > mx || (a == mx && k < mi)) { mx = a; mi = k; }
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		sum += __shfl_xor_sync (0xffffffffu, sum, o);
+		const float om = __shfl_xor_sync (0xffffffffu, mx, o);
+		const int   oi = __shfl_xor_sync (0xffffffffu, mi, o);
+		if (om > mx || (om == mx && oi >= 0 && (mi < 0 || oi < mi))) { mx = om; mi = oi; }
+	}
+	if ((t & 31) == 0) { s_red [t >> 5] = sum; s_max [t >> 5] = mx; s_idx [t >> 5] = mi; }
+	__syncthreads ();
+	if (t == 0) {
+		float tsum = 0.f, tmx = -10000.f;
+		int tmi = -1;
+		for (int q = 0; q < 8; q ++) {
+			tsum += s_red [q];
+			if (s_max [q] > tmx || (s_max [q] == tmx && s_idx [q] >= 0 && (tmi < 0 || s_idx [q] < tmi))) { tmx = s_max [q]; tmi = s_idx [q]; }
+		}
+		if (tmx < (float) T. level * tsum / (float) N)                 // phasereference.cpp:84-85
+			s_result = (int) (- fabsf (tmx / (tsum / (float) N)) - 1.0f);
+		else
+			s_result = tmi;
+	}
+	__syncthreads ();
+	const int s = s_result;                                            // :352
+	int corr = 0;
+	if (s >= 0) {
+		// block 0 = the T_u samples from P + s on (:362-388), same NCO run
+		load (in. P + s, mod_rate ((long long) in. lp - (long long) s * phA));
+		fft2048_r8 (x, A, tw1, tw2, tw3);
+		float2 *g = spec0 + (size_t) c * N;
+#pragma unroll
+		for (int m = 0; m < 8; m ++) {                                 // phaseReference (ofdm-decoder.cpp:91), natural order
+			const int k = t + 256 * m;
+			const float2 v = A [r8_swz (r8_pos (k))];
+			g [k] = v; B [k] = v;
+		}
+		__syncthreads ();
+		corr = coarse_offset_warp0 (B, T, cv);                         // always computed; the scan applies the flag
+	}
+	if (t == 0) { fo [c]. startIndex = s; fo [c]. correction = corr; }
+}
+
 // int16 soft bits -> byte symbols for n elements (the 15 history rows of the time de-interleaver at the start of a call)
 __global__ void soft_to_sym8_kernel (const int16_t *in, uint8_t *out, long long n) {
 	for (long long i = (long long) blockIdx. x * blockDim. x + threadIdx. x; i < n; i += (long long) gridDim. x * blockDim. x)
@@ -587,6 +681,7 @@ int dab_engine_init (dabgpu *h) {
 	CUDA_TRY (h, cudaFuncSetAttribute (symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 	CUDA_TRY (h, cudaFuncSetAttribute (scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (ScanSmem)));
 	CUDA_TRY (h, cudaFuncSetAttribute (symbol_kernel_r8, cudaFuncAttributeMaxDynamicSharedMemorySize, R8_DYN_SMEM));
+	CUDA_TRY (h, cudaFuncSetAttribute (front_kernel_r8, cudaFuncAttributeMaxDynamicSharedMemorySize, FRONT_R8_SMEM));
 	return DABGPU_OK;
 }
 
@@ -920,7 +1015,10 @@ static int decode_core (dabgpu *h, const void *d_new_v, long long nnew, dabgpu_r
 		for (int pass = 0; pass < 2; pass ++) {
 			// pass 0: speculative inputs, then the optimistic replay (derive); pass 1: recompute what changed, then verify
 			{ ProfScope prof (h, KC_FRONT);
-			front_kernel<<<(int) C, OFDM_THREADS, sm_front, h -> stream>>> (w, E -> T, fin, fo, (float2 *) E -> d_spec0. p); }
+			if (p. T_u == R8_N && p. K == 1536 && !E -> cf32 && !h -> cfg. reserved [0])
+				front_kernel_r8<<<(int) C, 256, FRONT_R8_SMEM, h -> stream>>> (w, E -> T, fin, fo, (float2 *) E -> d_spec0. p);
+			else
+				front_kernel<<<(int) C, OFDM_THREADS, sm_front, h -> stream>>> (w, E -> T, fin, fo, (float2 *) E -> d_spec0. p); }
 			{ ProfScope prof (h, KC_SYMBOL);
 			if (p. T_u == R8_N && p. K == 1536 && !E -> cf32 && !h -> cfg. reserved [0])     // reserved[0] = 1: generic kernel (A/B testing)
 				symbol_kernel_r8<<<(int) C * groups, 256, R8_DYN_SMEM, h -> stream>>> (w, E -> T, fin, nframes, groups, p. blocksPerCIF, p. cifsPerFrame,

@@ -96,3 +96,32 @@ def test_noise_only_never_syncs(port):
     sym, info = port.ofdm_run(1, iq, 8)
     assert res.nframes == len(info) == 0
     eng.close()
+
+
+def test_reset_and_coarse_corrector_controls(port):
+    """ofdmProcessor::reset / coarseCorrectorOn / coarseCorrectorOff (ofdm-processor.cpp:476-479, 499-506) act on the
+    tracking state exactly as the reference's members do, without touching the pending samples; a stream whose
+    coarse search was switched back on re-converges to the same offset and keeps decoding"""
+    pkg = engine_pkg()
+    mod = dabmod.Modulator(port, 1, SUBS[:1], 99)
+    tr = mod.generate(36, cfo_hz=137.0, snr_db=25.0, lead=3000, tail=6000)
+    iq = tr["iq"]
+    half = 2 * (iq.size // 4)
+    eng = pkg.DabGpu(mode=1); eng.set_subchannels([(0, 96, 128, 1, 0o103)])
+    a = eng.decode(iq[:half], eng.alloc_result(40))
+    s = eng.state_get()
+    assert s.synced == 1 and a.fic_crc[-8:].all(), (s.synced, s.coarse, s.fine, s.f2Correction)
+    eng.coarse_corrector(False)
+    t = eng.state_get()
+    assert (t.f2Correction, t.coarse, t.fine, t.abs_pos, t.localPhase) == (0, s.coarse, s.fine, s.abs_pos, s.localPhase)
+    eng.coarse_corrector(True)
+    t = eng.state_get()
+    assert (t.f2Correction, t.coarse, t.fine, t.abs_pos, t.localPhase) == (1, 0, s.fine, s.abs_pos, s.localPhase)
+    b = eng.decode(iq[half:], eng.alloc_result(40))                      # the pending samples were kept: the stream goes on
+    u = eng.state_get()
+    assert u.coarse == s.coarse and b.fic_crc[-8:].all(), (u.coarse, s.coarse)
+    assert a.nframes + b.nframes >= 30
+    eng.reset()
+    v = eng.state_get()
+    assert (v.f2Correction, v.coarse, v.fine) == (1, 0, 0)
+    eng.close()
