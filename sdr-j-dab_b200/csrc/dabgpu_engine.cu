@@ -337,6 +337,12 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 	uint32_t pidx [3];                                                     // this thread's six carriers: the pairs 2t, 2t+1 (+ 512 m), packed
 #pragma unroll
 	for (int m = 0; m < 3; m ++) pidx [m] = (uint32_t) __ldg (&T. permpos [2 * t + 512 * m]) | ((uint32_t) __ldg (&T. permpos [2 * t + 1 + 512 * m]) << 16);
+	// the phase reference of a carrier is the value this very thread read for it one symbol earlier: it stays in registers,
+	// and only the first symbol of the group fetches it from the (pseudo-randomly scattered, bank-conflicting) spectrum
+	float2 pv [6];
+	__syncthreads ();
+#pragma unroll
+	for (int m = 0; m < 3; m ++) { pv [2 * m] = prev [pidx [m] & 0xffffu]; pv [2 * m + 1] = prev [pidx [m] >> 16]; }
 	int lpb = mod_rate ((long long) lpD - ((long long) (l0 - 1) * Ts) % DAB_INPUT_RATE * phB);   // localPhase before the symbol's first sample
 	const float sc = 1.0f / 128.0f;
 	// the two NCO phasors of a symbol (guard sample gs, useful sample t) are looked up one symbol ahead
@@ -389,7 +395,9 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 #pragma unroll
 			for (int q = 0; q < 2; q ++) {
 				const int idx = (int) (q ? pidx [m] >> 16 : pidx [m] & 0xffffu);
-				const float2 r1 = cmulc (cur [idx], prev [idx]);
+				const float2 cc = cur [idx];
+				const float2 r1 = cmulc (cc, pv [2 * m + q]);
+				pv [2 * m + q] = cc;
 				const float ab1 = fabsf (r1. x) + fabsf (r1. y);
 				re [q] = quant127_fast (r1. x, ab1); im [q] = quant127_fast (r1. y, ab1);
 			}
@@ -398,7 +406,6 @@ __global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTa
 			*reinterpret_cast<unsigned short *> (out8 + i)        = (unsigned short) ((re [0] + 127) | ((re [1] + 127) << 8));
 			*reinterpret_cast<unsigned short *> (out8 + T. K + i) = (unsigned short) ((im [0] + 127) | ((im [1] + 127) << 8));
 		}
-		float2 *tmp = cur; cur = prev; prev = tmp;
 		off_cur = off_next;
 	}
 	for (int o = 16; o > 0; o >>= 1) {

@@ -24,7 +24,12 @@
 // back to s1 / s0.  All indices are compile-time, the code is unrolled over the four-step cycle.
 #include "dabgpu_internal.h"
 
+#ifndef VS_CW
 #define VS_CW      32          // code words per forward CTA (two threads each)
+#endif
+#ifndef VS_MINB
+#define VS_MINB    (320 / VS_CW)   // resident CTAs per SM the register budget is cut for
+#endif
 #define VS_THREADS (2 * VS_CW)
 #define VS_ROWS    (VS_CW + 15)
 #define VS_TILE    (VS_ROWS * VS_PITCH)
@@ -203,7 +208,7 @@ __device__ __forceinline__ void vs_cp_async16 (void *smem, const void *gmem) {
 	asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r" ((uint32_t) __cvta_generic_to_shared (smem)), "l" (gmem));
 }
 
-__global__ void __launch_bounds__ (VS_THREADS, 10) vit_simd_forward (const VitSimdJob *jobs, int njobs) {
+__global__ void __launch_bounds__ (VS_THREADS, VS_MINB) vit_simd_forward (const VitSimdJob *jobs, int njobs) {
 	__shared__ __align__ (16) uint8_t tile [2 * VS_TILE];
 	int jb = 0;
 	while (jb + 1 < njobs && (int) blockIdx. x >= jobs [jb + 1]. cta_first2) jb ++;
