@@ -537,7 +537,7 @@ __global__ void __launch_bounds__ (SCAN_THREADS) scan_kernel (StreamCtl *ctl, Fr
                              const float2 *fcpart, dabgpu_frame_info *info, long long abs_base, int derive) {
 	extern __shared__ unsigned char scan_raw [];
 	ScanSmem &S = *reinterpret_cast<ScanSmem *> (scan_raw);
-	__shared__ int s_ninfo, s_start, s_first;
+	__shared__ int s_first;
 	const int lane = threadIdx. x;                           // (thread index; thread 0 runs the serial replay)
 	if (!derive && ctl -> n_redo == 0) return;               // the derive pass found nothing to redo and committed already
 	const StreamCtl s0 = *ctl;
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__ (SCAN_THREADS) scan_kernel (StreamCtl *ctl, Fr
 	__syncthreads ();
 	if (lane == 0) {
 		StreamCtl s = s0;
-		int n_redo = 0, ninfo = first_slow;
+		int n_redo = 0;
 		int k_a = 0x7fffffff, k_b = 0, k_c = 0, k_si = -1, k_delta = 0;
 		s. n_valid = first_slow; s. lost = 0;
 		s. pos = s0. pos + (long long) first_slow * dp. T_F;
@@ -635,7 +635,7 @@ __global__ void __launch_bounds__ (SCAN_THREADS) scan_kernel (StreamCtl *ctl, Fr
 			dabgpu_frame_info fi;
 			fi. pos = abs_base + s. pos; fi. startIndex = si; fi. coarse = s. coarse; fi. fine = s. fine;
 			fi. phase0 = s. lp; fi. correction = correction; fi. freqCorrRe = fc. x; fi. freqCorrIm = fc. y;
-			info [slot0 + c] = fi; ninfo = c + 1;
+			info [slot0 + c] = fi;
 			// fineCorrector (int16) += 0.1 * arg (FreqCorr) / M_PI * (carrierDiff / 2)
 			s. fine = (int) (short) __double2int_rz (__dadd_rn ((double) s. fine, inc));
 			const int phiC = s. coarse + s. fine;
@@ -653,16 +653,13 @@ __global__ void __launch_bounds__ (SCAN_THREADS) scan_kernel (StreamCtl *ctl, Fr
 			else if (s. fine < - cd / 2) { s. coarse -= cd; s. fine += cd; }
 			s. n_valid = c + 1;
 		}
-		(void) ninfo;
 		if (derive) {
 			ctl -> n_redo = n_redo;
 			if (n_redo == 0) { s. n_redo = 0; *ctl = s; }    // nothing changes: this replay IS the verification
 		} else { s. n_redo = ctl -> n_redo; *ctl = s; }
-		s_start = first_slow;
 	}
 	__syncthreads ();
 	if (derive) for (int c = lane; c < nframes; c += SCAN_THREADS) fin [c] = S. in [c];
-	(void) s_ninfo; (void) s_start;
 }
 
 // ---------------------------------------------------------------------------------------------------

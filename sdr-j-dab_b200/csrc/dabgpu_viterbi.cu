@@ -154,26 +154,53 @@ cudaError_t vit_launch (dabgpu *h, int cls, const VitJob &job) {
 }
 
 // FIB CRC (dab-constants.h:310-340): CRC-16-CCITT, all-ones start, last 16 bits complemented, over 256
-// one-bit-per-byte values; one thread per FIB.
-__global__ void fib_crc_kernel (const uint8_t *bits, int nfibs, uint8_t *ok) {
-	const int f = blockIdx. x * blockDim. x + threadIdx. x;
-	if (f >= nfibs) return;
-	const uint8_t *p = bits + (size_t) f * 256;
-	unsigned reg = 0xffffu;
-	for (int i = 0; i < 256; i ++) {
-		unsigned in = p [i] & 1u;
-		if (i >= 240) in ^= 1u;
-		const unsigned top = (reg >> 15) & 1u;
-		reg = (reg << 1) & 0xffffu;
-		if (top ^ in) reg ^= 0x1021u;
+// one-bit-per-byte values.  Eight lanes per FIB: lane j runs the shift register over its own 32 bits (lane 0 starts from
+// all ones, the others from zero) and the result is advanced over the 32 (7 - j) bits that follow by a precomputed linear
+// map (the register is linear over GF(2): crc (A | B) = advance (crc (A), |B|) ^ crc_0 (B)); an XOR across the eight
+// lanes gives the reference's register.
+__host__ __device__ constexpr unsigned crc_advance_bits (unsigned reg, int n) {
+	for (int i = 0; i < n; i ++) { const unsigned top = (reg >> 15) & 1u; reg = (reg << 1) & 0xffffu; if (top) reg ^= 0x1021u; }
+	return reg;
+}
+struct CrcAdvance { unsigned short m [8][16]; };
+constexpr CrcAdvance make_crc_advance () {
+	CrcAdvance t {};
+	for (int k = 0; k < 8; k ++) for (int b = 0; b < 16; b ++) t. m [k][b] = (unsigned short) crc_advance_bits (1u << b, 32 * k);
+	return t;
+}
+__constant__ CrcAdvance c_crc_adv = make_crc_advance ();
+
+__global__ void __launch_bounds__ (128) fib_crc_kernel (const uint8_t *bits, int nfibs, uint8_t *ok) {
+	const int g = blockIdx. x * blockDim. x + threadIdx. x, f = g >> 3, j = g & 7;
+	unsigned reg = 0;
+	if (f < nfibs) {
+		const uint4 *p = reinterpret_cast<const uint4 *> (bits + (size_t) f * 256 + 32 * j);
+		const uint4 v0 = __ldg (p), v1 = __ldg (p + 1);
+		const uint32_t w [8] = { v0. x, v0. y, v0. z, v0. w, v1. x, v1. y, v1. z, v1. w };
+		reg = j == 0 ? 0xffffu : 0u;
+#pragma unroll
+		for (int i = 0; i < 32; i ++) {
+			unsigned in = (w [i >> 2] >> (8 * (i & 3))) & 1u;
+			if (j == 7 && i >= 16) in ^= 1u;                               // bits 240..255
+			const unsigned top = (reg >> 15) & 1u;
+			reg = (reg << 1) & 0xffffu;
+			if (top ^ in) reg ^= 0x1021u;
+		}
+		unsigned adv = 0;
+#pragma unroll
+		for (int b = 0; b < 16; b ++) if ((reg >> b) & 1u) adv ^= c_crc_adv. m [7 - j][b];
+		reg = adv;
 	}
-	ok [f] = reg == 0;
+	reg ^= __shfl_xor_sync (0xffffffffu, reg, 1);
+	reg ^= __shfl_xor_sync (0xffffffffu, reg, 2);
+	reg ^= __shfl_xor_sync (0xffffffffu, reg, 4);
+	if (f < nfibs && j == 0) ok [f] = reg == 0;
 }
 
 cudaError_t fib_crc_launch (dabgpu *h, const uint8_t *bits, int nfibs, uint8_t *ok) {
 	if (nfibs <= 0) return cudaSuccess;
 	ProfScope prof (h, KC_CRC, h -> vst ());
-	fib_crc_kernel<<<(nfibs + 127) / 128, 128, 0, h -> vst ()>>> (bits, nfibs, ok);
+	fib_crc_kernel<<<(8 * nfibs + 127) / 128, 128, 0, h -> vst ()>>> (bits, nfibs, ok);
 	h -> launches ++;
 	return cudaGetLastError ();
 }
