@@ -262,7 +262,10 @@ __device__ __forceinline__ int quant127_fast (float num, float ab1) {
 	return __float2int_rz (__fmul_rz (__fdividef (- num, ab1), 127.0f));      // NaN (ab1 == 0) -> 0 (App. B-5)
 }
 
-__global__ void __launch_bounds__ (256, 4) symbol_kernel_r8 (SampleWin w, OfdmTables T, const FrameIn *fin, int slot0, int groups,
+#ifndef R8_MINB
+#define R8_MINB 4
+#endif
+__global__ void __launch_bounds__ (256, R8_MINB) symbol_kernel_r8 (SampleWin w, OfdmTables T, const FrameIn *fin, int slot0, int groups,
                                                           int blocksPerCIF, int cifsPerFrame, const FrameOut *fo,
                                                           const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc,
                                                           uint8_t *fic8, uint8_t *msc8) {

@@ -282,6 +282,9 @@ __device__ __forceinline__ void dft8 (float2 (&a) [8]) {
 // stage-1 factors W_2048^(n q), n = t + 256 g, q = 1..3 (registers, loaded once per CTA by r8_load_tw1); tw2[j] = W_512^j
 // and tw3[j] = W_64^j, stored per output index q (r8_fill_tables), in shared memory -- with most of the SM's on-chip
 // memory carved out as shared memory the L1 is too small to keep a global twiddle table resident.
+#ifndef R8_TWPOW
+#define R8_TWPOW 0                     // 1: stage-2/3 twiddles as powers of one loaded value (A/B switch)
+#endif
 #define R8_TW2 512
 #define R8_TW3 64
 __device__ __forceinline__ void r8_fill_tables (float2 *tw2, float2 *tw3, const float2 *__restrict__ tw) {
@@ -336,8 +339,18 @@ __device__ __forceinline__ void fft2048_r8 (float2 (&x) [8], float2 *A, const fl
 		for (int m = 0; m < 8; m ++) a [m] = R8_LD (((m & 1) ? bo : be) + 8 * 64 * m);
 		dft8 (a);
 		R8_ST (be, a [0]);
+#if R8_TWPOW
+		{	// powers of one loaded twiddle instead of seven loads: shared memory is the stressed resource, the FP pipe has room
+			const float2 w1 = tw2 [n], w2 = cmul (w1, w1), w3 = cmul (w2, w1), w4 = cmul (w2, w2);
+			const float2 w5 = cmul (w4, w1), w6 = cmul (w3, w3), w7 = cmul (w4, w3);
+			const float2 wq [8] = { w1, w1, w2, w3, w4, w5, w6, w7 };
+#pragma unroll
+			for (int q = 1; q < 8; q ++) R8_ST (((q & 1) ? bo : be) + 8 * 64 * q, cmul (a [q], wq [q]));
+		}
+#else
 #pragma unroll
 		for (int q = 1; q < 8; q ++) R8_ST (((q & 1) ? bo : be) + 8 * 64 * q, cmul (a [q], tw2 [64 * (q - 1) + n]));
+#endif
 	}
 	// the 512-point block of stage 2 is produced and consumed by the same 64 threads (two warps): a named barrier for
 	// them instead of the whole CTA
@@ -357,8 +370,18 @@ __device__ __forceinline__ void fft2048_r8 (float2 (&x) [8], float2 *A, const fl
 		for (int m = 0; m < 8; m ++) a [m] = R8_LD (base ^ (8 * ((m >> 1) & 3) + 64 * (m & 1) + 128 * (m >> 1)));
 		dft8 (a);
 		R8_ST (base, a [0]);
+#if R8_TWPOW
+		{
+			const float2 w1 = tw3 [n], w2 = cmul (w1, w1), w3 = cmul (w2, w1), w4 = cmul (w2, w2);
+			const float2 w5 = cmul (w4, w1), w6 = cmul (w3, w3), w7 = cmul (w4, w3);
+			const float2 wq [8] = { w1, w1, w2, w3, w4, w5, w6, w7 };
+#pragma unroll
+			for (int q = 1; q < 8; q ++) R8_ST (base ^ (8 * ((q >> 1) & 3) + 64 * (q & 1) + 128 * (q >> 1)), cmul (a [q], wq [q]));
+		}
+#else
 #pragma unroll
 		for (int q = 1; q < 8; q ++) R8_ST (base ^ (8 * ((q >> 1) & 3) + 64 * (q & 1) + 128 * (q >> 1)), cmul (a [q], tw3 [8 * (q - 1) + n]));
+#endif
 	}
 	__syncwarp ();                                           // a 64-point block lives in 8 consecutive threads
 	// stage 4: radix 8 on 8 consecutive points, no twiddles.  element 8 t + m: address = base ^ 8 m
