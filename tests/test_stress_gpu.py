@@ -40,7 +40,7 @@ def test_cfo_awgn_stress_matches_oracle(port, mode, snr, carriers, frac):
     nframes = 24 if mode == 1 else 48
     tr = mod.generate(nframes, cfo_hz=cfo, snr_db=snr, lead=7777 + 131 * mode, tail=5000)
     sym, info, bits, crc, msc = _oracle_chain(port, mode, tr["iq"], nframes + 4, mod.sub)
-    eng = pkg.DabGpu(mode=mode, viterbi_path=2 if mode == 1 else 0)
+    eng = pkg.DabGpu(mode=mode, viterbi_path=2)                  # the throughput Viterbi in every mode (Modes II / IV: one CIF per frame)
     eng.set_subchannels([(s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel) for s in mod.sub])
     res = eng.decode(tr["iq"], eng.alloc_result(nframes + 4))
     n = res.nframes
