@@ -884,7 +884,11 @@ static int channel_chunk (dabgpu *h, int f0, int nv, dabgpu_result *out, std::ve
 	h -> cur = 1 + (E -> vrr ++ % 3);
 	cudaStream_t st = h -> vst ();
 	int rc = DABGPU_OK;
-	const bool simd = dab_use_simd (h, (long long) ngroups + (long long) ncif * (long long) E -> backends. size ());
+	// the throughput kernels take every job of the chunk in ONE launch pair; the warp-cooperative kernel is launched once per
+	// sub-channel, 0.3 ms each however few code words there are -- so with two or more sub-channels the throughput path wins
+	// even for a single frame (measured: 9 sub-channels, 1-32 frames per call: 2.9 ms against 0.6 ms)
+	const bool simd = dab_use_simd (h, (long long) ngroups + (long long) ncif * (long long) E -> backends. size ()) ||
+	                  (h -> cfg. viterbi_path == 0 && E -> backends. size () >= 2 && ncif > 0);
 	std::vector<VitSimdJob> jobs;
 	uint8_t *ficbits = (uint8_t *) E -> d_ficbits. p + (size_t) g0 * 768, *ficcrc = (uint8_t *) E -> d_ficcrc. p + (size_t) g0 * 3;
 	do {
