@@ -149,3 +149,32 @@ def test_generic_and_register_fft_kernels_agree(port):
     assert np.array_equal(a.fic_bits, b.fic_bits) and np.array_equal(a.fic_crc, b.fic_crc)
     for x, y in zip(a.msc, b.msc):
         assert np.array_equal(x, y)
+
+
+def test_stream_api_edges(port):
+    """empty input, a result buffer smaller than the input holds (the rest waits in the handle and comes out of the next
+    calls, even without new input), Mode III has no stream decode (as the reference)"""
+    pkg = engine_pkg()
+    mod = dabmod.Modulator(port, 1, SUBS[:1], 31337)
+    tr = mod.generate(22, cfo_hz=610.0, snr_db=22.0, lead=2000, tail=7000)
+    sub = [(0, 96, 128, 1, 0o103)]
+    e1 = pkg.DabGpu(mode=1); e1.set_subchannels(sub)
+    empty = e1.decode(np.zeros(0, np.uint8), e1.alloc_result(4))
+    assert empty.nframes == 0 and empty.fic_bits.shape[0] == 0
+    one = e1.decode(tr["iq"], e1.alloc_result(30))
+    assert one.nframes >= 18
+    e2 = pkg.DabGpu(mode=1); e2.set_subchannels(sub)
+    parts = [e2.decode(tr["iq"], e2.alloc_result(5))]
+    assert parts[0].nframes == 5
+    for _ in range(10):
+        parts.append(e2.decode(np.zeros(0, np.uint8), e2.alloc_result(5)))
+        if parts[-1].nframes == 0:
+            break
+    assert sum(p.nframes for p in parts) == one.nframes
+    assert np.array_equal(np.concatenate([p.soft for p in parts]), one.soft)
+    assert np.array_equal(np.concatenate([p.fic_bits for p in parts]), one.fic_bits)
+    assert np.array_equal(np.concatenate([p.msc[0] for p in parts]), one.msc[0])
+    e3 = pkg.DabGpu(mode=3)
+    with pytest.raises(pkg.DabGpuError, match="Mode III"):
+        e3.decode(tr["iq"][:200000], e3.alloc_result(4))
+    e1.close(); e2.close(); e3.close()
