@@ -45,82 +45,114 @@ __device__ __forceinline__ void load_win_nco (float2 *dst, const SampleWin &w, l
 
 // ---------------------------------------------------------------------------------------------------
 // acquisition: notSynced -> SyncOnNull -> SyncOnEndNull (ofdm-processor.cpp:275-338), one warp.
-// Lanes convert / mix a chunk of samples in parallel, lane 0 runs the sample-serial recurrences
-// (signal level IIR, 50-sample envelope window, thresholds) exactly in the reference's order.
+// The reference walks the samples one by one through two recurrences -- the signal level IIR
+// (sLevel = 0.00001 * jan_abs (v) + (1 - 0.00001) * sLevel, in double, rounded to float, :168) and the running sum of a
+// 50-sample envelope window -- and tests a threshold before every sample.  Only the two recurrences are serial.  Per chunk:
+//   1. all lanes convert / mix the samples and prepare everything that does not depend on the recurrences: the
+//      envelope value e_i (|re| + |im|, or the true magnitude in SyncOnEndNull), the double product 0.00001 * jan_abs,
+//      the window difference e_i - e_(i-50);
+//   2. lane 0 runs the two recurrences (one double multiply-add-round chain, one float add chain) and records the
+//      values BEFORE every sample;
+//   3. all lanes evaluate the reference's threshold tests on the recorded values and the first sample that leaves the
+//      state is found by a warp reduction; the state is committed up to there.
+// Same operations in the same order on every value as the reference's loop, hence the same result bit for bit.
 // ---------------------------------------------------------------------------------------------------
-#define ACQ_CHUNK 256
+#define ACQ_CHUNK 512
 __global__ void __launch_bounds__ (32) acquire_kernel (SampleWin w, OfdmTables T, int T_F, int T_null, StreamCtl *ctl) {
-	__shared__ float s_ja [ACQ_CHUNK], s_ha [ACQ_CHUNK];
-	__shared__ int s_n, s_phase, s_lp, s_done;
-	__shared__ long long s_pos;
+	__shared__ float s_e [ACQ_CHUNK], s_d [ACQ_CHUNK], s_sl [ACQ_CHUNK], s_csb [ACQ_CHUNK], s_ring [64];
+	__shared__ double s_ax [ACQ_CHUNK];
 	const int lane = threadIdx. x;
 	const long long total = w. len0 + w. len1;
-	// lane-0 state
-	int stage = 0, cnt = 0, counter = 0, idx = 0;
-	float sLevel = 0.f, cs = 0.f, env [64];
-	long long attempt_pos = ctl -> pos; int attempt_lp = ctl -> lp;
+	// scalar state, identical in every lane (updated from lane 0's results by shuffles)
+	int stage = 0, cnt = 0, counter = 0, idx = 0, done = 0;
+	float sLevel = 0.f, cs = 0.f;
+	long long pos = ctl -> pos, attempt_pos = pos;
+	int lp = ctl -> lp, attempt_lp = lp;
 	const int phi = ctl -> coarse + ctl -> fine;
-	if (lane == 0) { s_pos = attempt_pos; s_lp = attempt_lp; s_done = 0; }
-	__syncwarp ();
 	while (true) {
-		if (lane == 0) {
-			int n;                                        // samples until the NCO frequency can change
-			if (stage == 0) n = 20 * T. T_s - cnt + 50;
-			else if (stage == 1) n = 50 - cnt;
-			else if (stage == 2) n = T_F + 1 - counter;
-			else n = T_null + 51 - counter;
-			if (n > ACQ_CHUNK) n = ACQ_CHUNK;
-			if (s_pos + n > total) { s_done = 2; n = 0; }          // out of data: rewind to the attempt start
-			s_n = n; s_phase = stage < 2 ? 0 : phi;
-		}
-		__syncwarp ();
-		if (s_done) break;
-		const int n = s_n, ph = mod_rate (s_phase);
-		{
-			int lp = mod_rate ((long long) s_lp - (long long) (lane + 1) * ph);
+		int n;                                                       // samples until the stage can change by COUNT
+		if (stage == 0) n = 20 * T. T_s - cnt;                       // :278-280
+		else if (stage == 1) n = 50 - cnt;                           // :284-290
+		else if (stage == 2) n = T_F + 1 - counter;                  // :314-315: the (T_F + 1)-th sample is still consumed
+		else n = T_null + 51 - counter;                              // :336-337
+		if (n > ACQ_CHUNK) n = ACQ_CHUNK;
+		if (pos + n > total) { done = 2; break; }                    // out of data: rewind to the attempt start
+		const int ph = stage < 2 ? 0 : mod_rate (phi);               // getSample (0) while looking for a signal at all (:279, 285)
+		{	// 1. per-sample values
+			int l = mod_rate ((long long) lp - (long long) (lane + 1) * ph);
 			const int step = mod_rate (32ll * ph);
 			for (int i = lane; i < n; i += 32) {
-				const float2 v = cmul (win_sample (w, s_pos + i), nco (T, lp));
-				s_ja [i] = fabsf (v. x) + fabsf (v. y);           // jan_abs
-				s_ha [i] = hypotf (v. x, v. y);                   // abs
-				lp -= step; if (lp < 0) lp += DAB_INPUT_RATE;
+				const float2 v = cmul (win_sample (w, pos + i), nco (T, l));
+				const float ja = fabsf (v. x) + fabsf (v. y);            // jan_abs
+				s_ax [i] = __dmul_rn (0.00001, (double) ja);
+				s_e [i] = stage == 3 ? hypotf (v. x, v. y) : ja;           // abs () in SyncOnEndNull (:329)
+				l -= step; if (l < 0) l += DAB_INPUT_RATE;
 			}
+			__syncwarp ();
+			if (stage >= 1)
+				for (int i = lane; i < n; i += 32)
+					s_d [i] = stage == 1 ? s_e [i] : __fsub_rn (s_e [i], i >= 50 ? s_e [i - 50] : s_ring [(idx + i - 50) & 63]);
+			__syncwarp ();
 		}
-		__syncwarp ();
-		if (lane == 0) {
-			int used = n, restart = 0;
-			for (int i = 0; i < n; i ++) {
-				if (stage == 2 && !((double) (cs / 50.0f) > 0.40 * (double) sLevel)) { stage = 3; counter = 0; }   // :301
-				if (stage == 3 && !((double) (cs / 50.0f) < 0.75 * (double) sLevel)) { s_done = 1; used = i; break; }   // :323
-				const float ja = s_ja [i];
-				sLevel = (float) __dadd_rn (__dmul_rn (0.00001, (double) ja), __dmul_rn (1 - 0.00001, (double) sLevel));   // :168
-				if (stage == 0) {
-					if (++ cnt == 20 * T. T_s) { stage = 1; cnt = 0; idx = 0; cs = 0.f; }
-				} else if (stage == 1) {
-					env [idx & 63] = ja; cs = __fadd_rn (cs, ja); idx ++;
-					if (++ cnt == 50) { stage = 2; counter = 0; }
-				} else {
-					const float e = stage == 2 ? ja : s_ha [i];
-					env [idx & 63] = e;
-					cs = __fadd_rn (cs, __fsub_rn (e, env [(idx - 50) & 63]));
-					idx ++;
-					counter ++;
-					if ((stage == 2 && counter > T_F) || (stage == 3 && counter > T_null + 50)) { restart = 1; used = i + 1; break; }
+		float sl_end = sLevel, cs_end = cs;
+		if (lane == 0) {                                             // 2. the two recurrences
+			float a = sLevel, c = cs;
+			if (stage == 0) {
+#pragma unroll 4
+				for (int i = 0; i < n; i ++)
+					a = __double2float_rn (__dadd_rn (s_ax [i], __dmul_rn (1 - 0.00001, (double) a)));
+			} else {
+#pragma unroll 4
+				for (int i = 0; i < n; i ++) {
+					s_sl [i] = a; s_csb [i] = c;
+					a = __double2float_rn (__dadd_rn (s_ax [i], __dmul_rn (1 - 0.00001, (double) a)));
+					c = __fadd_rn (c, s_d [i]);
 				}
 			}
-			s_pos += used;
-			s_lp = mod_rate ((long long) s_lp - (long long) used * ph);
-			if (restart) {                                   // goto notSynced (:315, :337)
-				stage = 0; cnt = 0; counter = 0; idx = 0; cs = 0.f; sLevel = 0.f;
-				attempt_pos = s_pos; attempt_lp = s_lp;
-			}
+			sl_end = a; cs_end = c;
 		}
 		__syncwarp ();
-		if (s_done) break;
+		int used = n;
+		if (stage >= 2) {                                            // 3. the threshold tests (:301, :323), in parallel
+			int first = n;
+			for (int i = lane; i < n && first == n; i += 32) {
+				const double lhs = (double) (s_csb [i] / 50.0f), lv = (double) s_sl [i];
+				const bool leave = stage == 2 ? !(lhs > 0.40 * lv) : !(lhs < 0.75 * lv);
+				if (leave) first = i;
+			}
+			for (int o = 16; o > 0; o >>= 1) first = min (first, __shfl_xor_sync (0xffffffffu, first, o));
+			used = first;
+		}
+		// commit the state after `used` samples
+		if (used < n) { sLevel = s_sl [used]; cs = s_csb [used]; }
+		else { sLevel = __shfl_sync (0xffffffffu, sl_end, 0); cs = __shfl_sync (0xffffffffu, cs_end, 0); }
+		if (stage >= 1) {
+			for (int i = lane; i < used; i += 32) if (i >= used - 64) s_ring [(idx + i) & 63] = s_e [i];
+			idx += used;
+		}
+		__syncwarp ();
+		pos += used;
+		lp = mod_rate ((long long) lp - (long long) used * ph);
+		bool restart = false;
+		if (stage == 0) { cnt += used; if (cnt == 20 * T. T_s) { stage = 1; cnt = 0; idx = 0; cs = 0.f; } }
+		else if (stage == 1) { cnt += used; if (cnt == 50) { stage = 2; counter = 0; } }
+		else if (stage == 2) {
+			counter += used;
+			if (used < n) { stage = 3; counter = 0; }                // :301 fails before sample `used`: on to SyncOnEndNull
+			else if (counter > T_F) restart = true;                  // :314-315
+		} else {
+			counter += used;
+			if (used < n) { done = 1; break; }                       // :323 fails: the null symbol has ended, sample `used` is the next to read
+			if (counter > T_null + 50) restart = true;               // :336-337
+		}
+		if (restart) {                                               // goto notSynced
+			stage = 0; cnt = 0; counter = 0; idx = 0; cs = 0.f; sLevel = 0.f;
+			attempt_pos = pos; attempt_lp = lp;
+		}
 	}
 	if (lane == 0) {
-		if (s_done == 1) { ctl -> synced = 1; ctl -> pos = s_pos; ctl -> lp = s_lp; ctl -> acq_done = 1; }
-		else             { ctl -> synced = 0; ctl -> pos = attempt_pos; ctl -> lp = attempt_lp; ctl -> acq_done = 0; }
+		if (done == 1) { ctl -> synced = 1; ctl -> pos = pos; ctl -> lp = lp; ctl -> acq_done = 1; }
+		else           { ctl -> synced = 0; ctl -> pos = attempt_pos; ctl -> lp = attempt_lp; ctl -> acq_done = 0; }
 	}
 }
 
