@@ -58,8 +58,9 @@ extern "C" void dabgpu_destroy (dabgpu_t *h) {
 	if (!h) return;
 	cudaSetDevice (h -> device);
 	if (h -> stream) cudaStreamSynchronize (h -> stream);
+	for (int i = 1; i < 4; i ++) if (h -> vctx [i]. st) cudaStreamSynchronize (h -> vctx [i]. st);   // released buffers go to the process-wide cache: nothing may still use them
 	dab_engine_free (h);
-	for (auto &kv : h -> d_tables) cudaFree (kv. second);
+	for (auto &b : h -> d_table_bufs) b. release ();
 	h -> d_in. release (); h -> d_out. release (); h -> d_aux. release ();
 	for (int i = 0; i < 4; i ++) {
 		dabgpu::VitCtx &c = h -> vctx [i];
@@ -146,11 +147,13 @@ extern "C" int64_t dabgpu_launch_count (const dabgpu_t *h) { return h ? h -> lau
 int dab_device_table (dabgpu *h, long long key, const void *host, size_t bytes, void **dev) {
 	auto it = h -> d_tables. find (key);
 	if (it != h -> d_tables. end ()) { *dev = it -> second; return DABGPU_OK; }
-	void *d = nullptr;
-	CUDA_TRY (h, cudaMalloc (&d, bytes));
+	DevBuf b;
+	CUDA_TRY (h, b. ensure (bytes));
+	void *d = b. p;
 	cudaError_t e = cudaMemcpyAsync (d, host, bytes, cudaMemcpyHostToDevice, h -> stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize (h -> stream);     // `host` may be a temporary
-	if (e != cudaSuccess) { cudaFree (d); return dab_fail (h, DABGPU_ERR_CUDA, "table upload: %s", cudaGetErrorString (e)); }
+	if (e != cudaSuccess) { b. release (); return dab_fail (h, DABGPU_ERR_CUDA, "table upload: %s", cudaGetErrorString (e)); }
+	h -> d_table_bufs. push_back (b);
 	h -> d_tables [key] = d;
 	*dev = d;
 	return DABGPU_OK;

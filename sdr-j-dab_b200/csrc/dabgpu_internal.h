@@ -18,19 +18,55 @@ struct DabParams {                      // gui.cpp:1328-1372 + derived geometry
 };
 int dab_mode_params (int mode, DabParams *p);
 
-// growable device / pinned-host buffers
+// growable device / pinned-host buffers.  Buffers released by a handle go to a process-wide cache instead of back to the
+// driver, and a new handle takes them from there: cudaMalloc / cudaFree / cudaMallocHost take milliseconds each and wait for
+// every kernel running on the device -- with many short-lived handles (one per short stream, several host threads) they
+// were what the threads queued on.  release () may only be called while none of the handle's streams still uses the
+// buffer (the API is synchronous: every entry point returns with its streams idle); growing a live buffer frees the old
+// block to the driver, which synchronises by itself.
+#include <mutex>
+struct BufCache {
+	std::mutex m;
+	std::multimap<size_t, void *> dev [16], pin;
+	size_t dev_bytes [16] = {}, pin_bytes = 0;
+	static constexpr size_t DEV_LIMIT = 8ull << 30, PIN_LIMIT = 2ull << 30;
+	void *take (std::multimap<size_t, void *> &pool, size_t &total, size_t want, size_t *got) {
+		std::lock_guard<std::mutex> g (m);
+		auto it = pool. lower_bound (want);
+		if (it == pool. end () || it -> first > 2 * want + (1u << 20)) return nullptr;
+		void *p = it -> second; *got = it -> first; total -= it -> first;
+		pool. erase (it);
+		return p;
+	}
+	bool give (std::multimap<size_t, void *> &pool, size_t &total, size_t limit, size_t cap, void *p) {
+		std::lock_guard<std::mutex> g (m);
+		if (total + cap > limit) return false;
+		pool. emplace (cap, p); total += cap;
+		return true;
+	}
+};
+inline BufCache &buf_cache () { static BufCache c; return c; }
+
 struct DevBuf {
-	void *p = nullptr; size_t cap = 0;
+	void *p = nullptr; size_t cap = 0; int dev = 0;
 	cudaError_t ensure (size_t bytes) {
 		if (bytes <= cap) return cudaSuccess;
 		if (p) cudaFree (p);
 		p = nullptr; cap = 0;
 		size_t want = bytes + bytes / 4 + 256;
+		cudaGetDevice (&dev);
+		if (dev < 0 || dev >= 16) dev = 0;
+		BufCache &c = buf_cache ();
+		if ((p = c. take (c. dev [dev], c. dev_bytes [dev], want, &cap))) return cudaSuccess;
 		cudaError_t e = cudaMalloc (&p, want);
 		if (e == cudaSuccess) cap = want;
 		return e;
 	}
-	void release () { if (p) cudaFree (p); p = nullptr; cap = 0; }
+	void release () {
+		BufCache &c = buf_cache ();
+		if (p && !c. give (c. dev [dev], c. dev_bytes [dev], BufCache::DEV_LIMIT, cap, p)) cudaFree (p);
+		p = nullptr; cap = 0;
+	}
 };
 struct PinBuf {
 	void *p = nullptr; size_t cap = 0;
@@ -39,11 +75,17 @@ struct PinBuf {
 		if (p) cudaFreeHost (p);
 		p = nullptr; cap = 0;
 		size_t want = bytes + bytes / 4 + 256;
+		BufCache &c = buf_cache ();
+		if ((p = c. take (c. pin, c. pin_bytes, want, &cap))) return cudaSuccess;
 		cudaError_t e = cudaMallocHost (&p, want);
 		if (e == cudaSuccess) cap = want;
 		return e;
 	}
-	void release () { if (p) cudaFreeHost (p); p = nullptr; cap = 0; }
+	void release () {
+		BufCache &c = buf_cache ();
+		if (p && !c. give (c. pin, c. pin_bytes, BufCache::PIN_LIMIT, cap, p)) cudaFreeHost (p);
+		p = nullptr; cap = 0;
+	}
 };
 
 // ---- puncturing / protection profiles (host side, dabgpu_tables.cpp) ----
@@ -137,6 +179,7 @@ struct dabgpu {
 	PinBuf h_in, h_out;
 	// cached device tables
 	std::map<long long, void *> d_tables;          // key -> device pointer (LUTs, PRBS)
+	std::vector<DevBuf> d_table_bufs;              // their storage
 	std::map<long long, ProtProfile> profiles;
 };
 
