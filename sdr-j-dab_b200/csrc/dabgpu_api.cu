@@ -75,6 +75,23 @@ extern "C" void dabgpu_destroy (dabgpu_t *h) {
 	delete h;
 }
 
+extern "C" int dabgpu_release_cached_memory (void) {
+	BufCache &c = buf_cache ();
+	std::vector<std::pair<int, void *>> dev; std::vector<void *> pin;
+	{	std::lock_guard<std::mutex> g (c. m);
+		for (int d = 0; d < 16; d ++) { for (auto &kv : c. dev [d]) dev. emplace_back (d, kv. second); c. dev [d]. clear (); c. dev_bytes [d] = 0; }
+		for (auto &kv : c. pin) pin. push_back (kv. second);
+		c. pin. clear (); c. pin_bytes = 0;
+	}
+	if (dev. empty () && pin. empty ()) return DABGPU_OK;
+	int cur = 0;
+	cudaGetDevice (&cur);
+	for (auto &dp : dev) { cudaSetDevice (dp. first); cudaFree (dp. second); }
+	for (void *p : pin) cudaFreeHost (p);
+	cudaSetDevice (cur);
+	return DABGPU_OK;
+}
+
 extern "C" int dabgpu_sync (dabgpu_t *h) {
 	if (!h) return DABGPU_ERR_ARG;
 	CUDA_TRY (h, cudaSetDevice (h -> device));

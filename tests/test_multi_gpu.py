@@ -139,3 +139,24 @@ def test_sharded_recording_equals_one_shot(port, world, cfo, want_mode):
         assert np.array_equal(np.concatenate([g[5][i] for g in got]), want.msc[i])
     assert sum((g[6] for g in got), []) == [(i.pos, i.fine, i.phase0) for i in want.info]
     one.close()
+
+
+def test_buffer_cache_release(port):
+    """buffers of closed handles are reused by the next handle and can be handed back to the driver at any time"""
+    import torch
+    pkg = engine_pkg()
+    lib = pkg.load_library()
+    mod = dabmod.Modulator(port, 1, [(0, 128, 1, 0o103)], 8)
+    iq = mod.generate(12, cfo_hz=300.0, snr_db=25.0, lead=2500, tail=6000)["iq"]
+    outs = []
+    for k in range(3):
+        e = pkg.DabGpu(mode=1); e.set_subchannels([(0, 96, 128, 1, 0o103)])
+        r = e.decode(iq, e.alloc_result(16))
+        outs.append((r.nframes, r.soft.copy(), r.fic_bits.copy(), r.msc[0].copy()))
+        e.close()
+        if k == 1:
+            free0 = torch.cuda.mem_get_info()[0]
+            assert lib.dabgpu_release_cached_memory() == 0
+            assert torch.cuda.mem_get_info()[0] > free0            # the cache held device memory and gave it back
+    for o in outs[1:]:
+        assert o[0] == outs[0][0] and all(np.array_equal(a, b) for a, b in zip(o[1:], outs[0][1:]))
