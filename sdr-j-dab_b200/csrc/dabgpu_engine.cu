@@ -266,7 +266,7 @@ __global__ void __launch_bounds__ (OFDM_THREADS) symbol_kernel (SampleWin w, Ofd
 
 // ---------------------------------------------------------------------------------------------------
 // Mode I symbol kernel: same work as symbol_kernel, built on the 8-points-per-thread register FFT.
-//   * the raw u8 IQ of symbol l+1 streams into shared memory (16-byte cp.async, double buffered) while symbol l
+//   * the raw u8 IQ of symbol l+1 streams into shared memory (one TMA bulk copy + mbarrier, double buffered) while symbol l
 //     is transformed, so no thread ever waits on HBM;
 //   * samples go shared (raw) -> registers (u8 convert + NCO by a per-thread phasor recurrence, the 1/128 of
 //     rawfiles.cpp:113-116 folded into the phasor: an exact power-of-two scaling) -> first butterflies;
@@ -297,6 +297,9 @@ __device__ __forceinline__ int quant127_fast (float num, float ab1) {
 #ifndef R8_MINB
 #define R8_MINB 4
 #endif
+#ifndef R8_TMA
+#define R8_TMA 1                                                           // raw symbols staged by TMA bulk copies + mbarrier (0: per-thread cp.async)
+#endif
 __global__ void __launch_bounds__ (256, R8_MINB) symbol_kernel_r8 (SampleWin w, OfdmTables T, const FrameIn *fin, int slot0, int groups,
                                                           int blocksPerCIF, int cifsPerFrame, const FrameOut *fo,
                                                           const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc,
@@ -326,6 +329,16 @@ __global__ void __launch_bounds__ (256, R8_MINB) symbol_kernel_r8 (SampleWin w, 
 	if (((uint32_t) __cvta_generic_to_shared (bufA) & 511u) != 0) __trap ();   // layout contract of fft2048_r8
 	r8_fill_tables (tw2, tw3, T. tw);
 	r8_load_tw1 (tw1, T. tw);
+#if R8_TMA
+	// one mbarrier per raw buffer: the TMA engine's bulk copy of a symbol signals it (complete_tx), every thread waits on it
+	__shared__ __align__ (8) unsigned long long s_mbar [2];
+	const uint32_t mbar0 = (uint32_t) __cvta_generic_to_shared (&s_mbar [0]);
+	if (t == 0) {
+		asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r" (mbar0));
+		asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r" (mbar0 + 8));
+		asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+#endif
 	__syncthreads ();
 
 	// raw u8 IQ of symbol l (guard + useful part, T_s samples from `first`) -> raw buffer b; returns the byte offset of
@@ -343,17 +356,42 @@ __global__ void __launch_bounds__ (256, R8_MINB) symbol_kernel_r8 (SampleWin w, 
 			off = (int) (p - pa);
 			const int n16 = (off + 2 * Ts + 15) >> 4;
 			fast = pa >= (unsigned long long) seg && pa + 16ull * n16 <= (unsigned long long) (seg + seglen);
+#if R8_TMA
+			if (fast && t == 0) {                                          // one bulk copy by the TMA engine, 16-byte aligned on both sides
+				const uint32_t bytes = 16u * (uint32_t) n16, mb = mbar0 + 8u * (uint32_t) b;
+				asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer's last readers (generic proxy) are past a CTA barrier
+				asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r" (mb), "r" (bytes) : "memory");
+				asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				              :: "r" ((uint32_t) __cvta_generic_to_shared (dst)), "l" (pa), "r" (bytes), "r" (mb) : "memory");
+			}
+#else
 			if (fast)
 				for (int i = t; i < n16; i += 256)
 					asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r" ((uint32_t) __cvta_generic_to_shared (dst + 16 * i)), "l" (pa + 16ull * i));
+#endif
 		}
 		if (!fast) {                                                       // symbol straddles the tail | input seam or touches a buffer end
 			off = 0;
 			for (int i = t; i < Ts; i += 256) reinterpret_cast<uchar2 *> (dst) [i] = win_fetch (w, first + i);
+#if R8_TMA
+			if (t == 0) asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r" (mbar0 + 8u * (uint32_t) b) : "memory");   // nothing in flight: the CTA barrier below orders the stores
+#endif
 		}
+#if !R8_TMA
 		asm volatile ("cp.async.commit_group;");
+#endif
 		return off;
 	};
+#if R8_TMA
+	auto wait_raw = [&] (int b, int use) {                                 // use = how often buffer b has been waited for before
+		const uint32_t mb = mbar0 + 8u * (uint32_t) b, parity = (uint32_t) use & 1u;
+		uint32_t ok = 0;
+		for (int spin = 0; !ok; spin ++) {
+			asm volatile ("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r" (ok) : "r" (mb), "r" (parity) : "memory");
+			if (spin > (1 << 16)) __trap ();                               // a lost copy must not hang the GPU
+		}
+	};
+#endif
 
 	int off_cur = stage (l0, 0);
 	if (l0 == 1) {
@@ -391,11 +429,19 @@ __global__ void __launch_bounds__ (256, R8_MINB) symbol_kernel_r8 (SampleWin w, 
 	for (int l = l0; l < l1; l ++) {
 		const int b = (l - l0) & 1;
 		int off_next = 0;
+#if R8_TMA
+		if (l + 1 < l1) off_next = stage (l + 1, b ^ 1);
+#else
 		if (l + 1 < l1) off_next = stage (l + 1, b ^ 1); else asm volatile ("cp.async.commit_group;");
+#endif
 		float2 phg = make_float2 (phg_n. x * sc, phg_n. y * sc), ph = make_float2 (ph_n. x * sc, ph_n. y * sc);
 		lpb -= dTs; if (lpb < 0) lpb += DAB_INPUT_RATE;
 		phasors (lpb, phg_n, ph_n);
+#if R8_TMA
+		wait_raw (b, (l - l0) >> 1);
+#else
 		asm volatile ("cp.async.wait_group 1;" ::: "memory");
+#endif
 		__syncthreads ();                                                  // raw buffer b complete; last symbol's demod reads done
 		const unsigned short *rs = reinterpret_cast<const unsigned short *> (raw + b * R8_RAW + off_cur);
 		// guard samples gs and gs + 256 (the ones x[6] and x[7] are correlated with), mixed like every other sample
