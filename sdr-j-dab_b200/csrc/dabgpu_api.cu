@@ -229,11 +229,11 @@ int dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs) {
 	size_t dec_words = 0, sym_bytes = 0;
 	int ctas = 0, ctas2 = 0;
 	bool need_sym8 = false;
-	const int cw2 = vit_simd_cw_per_cta ();
+	const int cw2 = vit_simd_cw_per_cta (), cw1 = vit_simd_tb_cw_per_cta ();
 	auto padded = [] (int nsteps) { return (size_t) vs_npad (nsteps); };
 	for (auto &j : jobs) {
 		j. cta_first = ctas; j. cta_first2 = ctas2; j. one = 1u;
-		ctas += (j. ncw + 63) / 64; ctas2 += (j. ncw + cw2 - 1) / cw2;
+		ctas += (j. ncw + cw1 - 1) / cw1; ctas2 += (j. ncw + cw2 - 1) / cw2;
 		dec_words += padded (j. nsteps) * (size_t) ((j. ncw + 31) / 32 * 32);
 		j. sym8_ready = j. sym8 != nullptr;                      // the caller already holds the byte symbols (stream engine)
 		if (j. sym8_ready) continue;

@@ -143,6 +143,7 @@ struct VitSimdJob {
 };
 cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas, int total_ctas2, bool convert);
 int vit_simd_cw_per_cta ();
+int vit_simd_tb_cw_per_cta ();
 cudaError_t fib_crc_launch (dabgpu *h, const uint8_t *bits, int nfibs, uint8_t *ok);
 // FIG 0/1 scan (dabgpu_fig.cu): keys = 128 persistent 64-bit words per stream, order0 = global number of the first FIB
 cudaError_t fig01_launch (dabgpu *h, const uint8_t *d_bits, const uint8_t *d_crc, int nfibs, unsigned long long order0, unsigned long long *d_keys, cudaStream_t st);

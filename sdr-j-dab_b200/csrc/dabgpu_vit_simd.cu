@@ -300,7 +300,19 @@ __global__ void __launch_bounds__ (VS_THREADS, VS_MINB) vit_simd_forward (const 
 // (vs_decbit).  The walk keeps the decoded bits in a 32-bit shift register S whose top six bits ARE the state
 // (newest bit on top, viterbi.cpp:347-352): one step is  n = S >> 26;  word = lane-select;  bit = word >> index (n);
 // S = (bit : S) >> 1  -- a funnel shift -- and after 32 steps S is the output word, bit-reversed.
+#ifndef TB_THREADS
 #define TB_THREADS 64
+#endif
+#ifndef TB_NBUF
+#define TB_NBUF 2                      // output words whose decision words are resident or in flight per thread (A/B: 3 and 4 are slower, as are 32-thread CTAs: 0.188 / 0.195 / 0.201 ms)
+#endif
+#if TB_NBUF == 2
+#define TB_WAIT "1"
+#elif TB_NBUF == 3
+#define TB_WAIT "2"
+#else
+#define TB_WAIT "3"
+#endif
 template <bool FULL>
 __device__ __forceinline__ uint32_t tb_walk_word (uint32_t &S, const uint4 (*dq) [TB_THREADS], const int tid, const int nvalid) {
 #pragma unroll
@@ -325,7 +337,7 @@ __device__ __forceinline__ uint32_t tb_walk_word (uint32_t &S, const uint4 (*dq)
 
 __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimdJob *jobs, int njobs) {
 	__shared__ uint32_t bits [TB_THREADS * 5];               // 128 decoded bits per code word per round, row stride 5 words
-	__shared__ __align__ (16) uint4 dq [2][16][TB_THREADS];  // the decision words of two output words (16 step pairs each) per thread
+	__shared__ __align__ (16) uint4 dq [TB_NBUF][16][TB_THREADS];  // the decision words of TB_NBUF output words (16 step pairs each) per thread
 	int jb = 0;
 	while (jb + 1 < njobs && (int) blockIdx. x >= jobs [jb + 1]. cta_first) jb ++;
 	const VitSimdJob j = jobs [jb];
@@ -344,16 +356,17 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 			const uint4 *src = dec + (size_t) (16 * wi + 18) * 32;      // pair of steps 32 wi + 36, 37
 			if (32 * wi + 32 <= j. frameBits) {
 #pragma unroll
-				for (int m = 0; m < 16; m ++) vs_cp_async16 (&dq [wi & 1][m][tid], src - 32 * m);
+				for (int m = 0; m < 16; m ++) vs_cp_async16 (&dq [wi % TB_NBUF][m][tid], src - 32 * m);
 			} else {
 #pragma unroll
 				for (int m = 0; m < 16; m ++)
-					if (32 * wi + 30 - 2 * m < j. frameBits) vs_cp_async16 (&dq [wi & 1][m][tid], src - 32 * m);
+					if (32 * wi + 30 - 2 * m < j. frameBits) vs_cp_async16 (&dq [wi % TB_NBUF][m][tid], src - 32 * m);
 			}
 		}
 		asm volatile ("cp.async.commit_group;");
 	};
-	fetch (nwords - 1);
+#pragma unroll
+	for (int k = 1; k < TB_NBUF; k ++) fetch (nwords - k);
 	for (int rd = nrounds - 1; rd >= 0; rd --) {
 		const int base = 128 * rd, top = min (j. frameBits, base + 128);
 		uint32_t w [4] = { 0, 0, 0, 0 };
@@ -361,12 +374,12 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 		for (int wd = 3; wd >= 0; wd --) {
 			const int wi = 4 * rd + wd;
 			if (wi >= nwords) continue;
-			fetch (wi - 1);
-			asm volatile ("cp.async.wait_group 1;" ::: "memory");
+			fetch (wi - (TB_NBUF - 1));
+			asm volatile ("cp.async.wait_group " TB_WAIT ";" ::: "memory");
 			if (!live) continue;
 			const int nvalid = min (32, j. frameBits - 32 * wi);
 			// (a partial word can only be the first one walked: S is still 0 below the bits it shifts in)
-			w [wd] = nvalid == 32 ? tb_walk_word<true> (S, dq [wi & 1], tid, 32) : tb_walk_word<false> (S, dq [wi & 1], tid, nvalid);
+			w [wd] = nvalid == 32 ? tb_walk_word<true> (S, dq [wi % TB_NBUF], tid, 32) : tb_walk_word<false> (S, dq [wi % TB_NBUF], tid, nvalid);
 		}
 		__syncthreads ();
 #pragma unroll
@@ -407,6 +420,7 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 }
 
 int vit_simd_cw_per_cta () { return VS_CW; }
+int vit_simd_tb_cw_per_cta () { return TB_THREADS; }
 
 cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas, int total_ctas2, bool convert) {
 	if (njobs <= 0 || total_ctas <= 0) return cudaSuccess;
