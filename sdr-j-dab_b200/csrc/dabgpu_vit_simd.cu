@@ -91,8 +91,8 @@ __device__ __forceinline__ uint32_t vs_sel (uint32_t a, uint32_t b, uint32_t mas
 // of pattern x is B[x] = sum_j (x_j ? C_j - v_j : v_j) with (v, C) = (a0, 510), (s1, 255), (s2, 255); a register needs
 // it for the low-half state and, 16 bits up, for the high-half state (pattern x ^ dh); the odd lane of a pair sees
 // pattern x ^ dl (lm = all ones in the odd lane, 0 in the even one).  Built per component, so that PL[x] is a sum of
-// three terms.  The 32 decisions of the step are disjoint bits spread over four accumulators (short dependency chains:
-// the predicates of the packed min are consumed as fast as they are produced).
+// three terms.  The 32 decisions of the step are disjoint bits spread over VS_NACC accumulators (the predicates of the
+// packed min are consumed about as fast as they are produced; see VS_NACC for the count).
 template <int K>
 __device__ __forceinline__ void vs_step (const uint32_t (&R) [16], uint32_t (&Q) [16], const uint32_t a0, const uint32_t s1, const uint32_t s2,
                                          const uint32_t lm, uint32_t &dec, const uint32_t one) {
