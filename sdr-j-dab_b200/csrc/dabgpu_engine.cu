@@ -1055,7 +1055,10 @@ static int decode_core (dabgpu *h, const void *d_new_v, long long nnew, dabgpu_r
 	StreamCtl *hctl = (StreamCtl *) E -> h_ctl. p;
 	int nframes = 0, decoded_upto = 0;
 	// host input arrives piecewise: smaller chunks let the first frames start before the last samples are up
-	const int chunk_cap = ready && !ready -> empty () ? (E -> max_chunk < 128 ? E -> max_chunk : 128) : E -> max_chunk;
+	// device-resident input with a channel-decoding batch given (dabgpu_config.reserved[1]): chunks no larger than the batch, so
+	// that the OFDM part of the next chunk overlaps the channel decoding of this one on the side streams
+	const int dev_cap = !ready && vit_batch_frames < E -> max_chunk ? (vit_batch_frames > 16 ? vit_batch_frames : 16) : E -> max_chunk;
+	const int chunk_cap = ready && !ready -> empty () ? (E -> max_chunk < 128 ? E -> max_chunk : 128) : dev_cap;
 	long long waited = -1;                                   // input pieces [0, waited] are known to have arrived on the main stream
 	auto need_input = [&] (long long upto_window_pos) -> cudaError_t {      // samples before this window position must be resident
 		if (!ready || ready -> empty ()) return cudaSuccess;
