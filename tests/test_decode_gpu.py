@@ -178,3 +178,27 @@ def test_stream_api_edges(port):
     with pytest.raises(pkg.DabGpuError, match="Mode III"):
         e3.decode(tr["iq"][:200000], e3.alloc_result(4))
     e1.close(); e2.close(); e3.close()
+
+
+def test_device_resident_input_and_pipelined_batches(port):
+    """dabgpu_decode_dev (samples already in HBM) equals dabgpu_decode, also when the call is cut into pipelined
+    chunk / channel-decoding batches (dabgpu_config.reserved[1]) and when the device pointer is not 16-byte aligned
+    (the TMA staging then falls back to per-thread loads where it must)"""
+    import torch
+    pkg = engine_pkg()
+    mod = dabmod.Modulator(port, 1, SUBS, 606)
+    tr = mod.generate(40, cfo_hz=1444.0, snr_db=20.0, lead=5003, tail=6000)
+    subs = [(s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel) for s in mod.sub]
+    ref = pkg.DabGpu(mode=1); ref.set_subchannels(subs)
+    want = ref.decode(tr["iq"], ref.alloc_result(44))
+    ref.close()
+    d = torch.zeros(tr["iq"].size + 64, dtype=torch.uint8, device="cuda")
+    for batch, shift in ((0, 0), (16, 0), (16, 6), (0, 2)):
+        d[shift:shift + tr["iq"].size] = torch.from_numpy(tr["iq"]).cuda()
+        eng = pkg.DabGpu(mode=1, dev_batch_frames=batch); eng.set_subchannels(subs)
+        got = eng.decode_dev(d.data_ptr() + shift, tr["iq"].size // 2, eng.alloc_result(44))
+        assert got.nframes == want.nframes
+        assert np.array_equal(got.soft, want.soft) and np.array_equal(got.fic_bits, want.fic_bits) and np.array_equal(got.fic_crc, want.fic_crc)
+        for a, b in zip(got.msc, want.msc):
+            assert np.array_equal(a, b)
+        eng.close()
