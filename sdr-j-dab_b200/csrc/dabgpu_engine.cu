@@ -386,9 +386,14 @@ __global__ void __launch_bounds__ (256, R8_MINB) symbol_kernel_r8 (SampleWin w, 
 	auto wait_raw = [&] (int b, int use) {                                 // use = how often buffer b has been waited for before
 		const uint32_t mb = mbar0 + 8u * (uint32_t) b, parity = (uint32_t) use & 1u;
 		uint32_t ok = 0;
+		unsigned long long t0 = 0;
 		for (int spin = 0; !ok; spin ++) {
 			asm volatile ("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r" (ok) : "r" (mb), "r" (parity) : "memory");
-			if (spin > (1 << 16)) __trap ();                               // a lost copy must not hang the GPU
+			if (!ok && (spin & 1023) == 1023) {                            // a lost copy must not hang the GPU: give up after 2 s of waiting
+				unsigned long long now;
+				asm volatile ("mov.u64 %0, %%globaltimer;" : "=l" (now));
+				if (t0 == 0) t0 = now; else if (now - t0 > 2000000000ull) __trap ();
+			}
 		}
 	};
 #endif
