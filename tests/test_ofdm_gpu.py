@@ -71,10 +71,10 @@ def test_find_index(eng, port):
         assert g == w or (g < 0 and w < 0 and abs(g - w) <= 1), (got, want)
 
 
-@pytest.mark.parametrize("method", [1, 2])
+@pytest.mark.parametrize("method", [0, 1, 2])
 def test_block0_coarse_offset(port, method, eng):
-    if eng.mode == 3:
-        pytest.skip("the reference has no Mode III PRS table (SURVEY.md §8c)")
+    # Mode III: the reference has no PRS table of its own and falls through to Mode I's (phasetable.cpp:123-139); engine
+    # and oracle do the same, so processBlock_0 is comparable there too.  Method 0 = getMiddle with its bug (:252-255).
     e = engine_pkg().DabGpu(mode=eng.mode, freqSyncMethod=method)
     o = port.ofdm(eng.mode, freqSyncMethod=method)
     for shift in (-20, -5, 0, 3, 17):
@@ -82,7 +82,7 @@ def test_block0_coarse_offset(port, method, eng):
         prs = x[p.T_g:p.T_g + p.T_u]
         want = o.block0(prs, True)
         assert e.block0(prs, True) == want
-        if eng.mode == 1:
+        if eng.mode == 1 and method != 0:
             assert want == shift
         assert _rel(e.phase_reference(), o.phase_reference()) < FFT_RTOL
     assert e.block0(prs, False) == 0
