@@ -211,6 +211,22 @@ int dabgpu_decode_cf32_dev (dabgpu_t *h, const float *d_iq, size_t nsamples, dab
  * in the kernels' sample fetch, no float copy of the recording is made. */
 int dabgpu_decode_i16 (dabgpu_t *h, const int16_t *iq, size_t nsamples, dabgpu_result *out);
 int dabgpu_decode_i16_dev (dabgpu_t *h, const int16_t *d_iq, size_t nsamples, dabgpu_result *out);
+/* Many independent streams in one call (BASELINE configs[3]: short recordings of different ensembles).  The reference
+ * runs one ofdmProcessor / ficHandler / mscHandler chain per stream (gui.cpp:160-179); its sample-serial acquisition
+ * (ofdm-processor.cpp:275-338) and the frame-by-frame AFC convergence (:390-405, 445-466) are independent across streams,
+ * so the engine walks all streams in lockstep through the same kernel launches: n acquisitions cost the time of one.
+ * Stream i is decoded exactly as a FRESH handle with this handle's configuration and sub-channels would decode it with
+ * one dabgpu_decode call (acquisition from the first sample, coarse search on, empty de-interleaver): jobs[i].out is
+ * filled like dabgpu_decode fills it (out->consumed = samples of the stream consumed).  The handle's own stream state
+ * is not touched.  sample_format: 0 = u8 I,Q (rawfiles.cpp:113-116), 1 = complex float, 2 = int16 I,Q.
+ * _dev: jobs[i].iq are device pointers on the handle's device (result pointers stay host pointers). */
+typedef struct {
+	const void *iq;            /* nsamples complex samples of the given format                                     */
+	size_t nsamples;
+	dabgpu_result *out;
+} dabgpu_stream_job;
+int dabgpu_decode_multi (dabgpu_t *h, const dabgpu_stream_job *jobs, int32_t nstreams, int32_t sample_format);
+int dabgpu_decode_multi_dev (dabgpu_t *h, const dabgpu_stream_job *jobs, int32_t nstreams, int32_t sample_format);
 /* airspyHandler's sample-rate conversion (airspy-handler.cpp:138-148, 342-370): int16 I,Q pairs at in_rate samples/s
  * (a multiple of 1000) -> complex floats at 2 048 000 samples/s by linear interpolation in 1 ms blocks, ready for
  * dabgpu_decode_cf32.  Block b reads input samples [b R, b R + R], R = in_rate / 1000, and writes 2048 samples; a call

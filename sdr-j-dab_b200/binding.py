@@ -35,6 +35,10 @@ class Result(C.Structure):
                 ("consumed", C.c_int64)]
 
 
+class StreamJob(C.Structure):
+    _fields_ = [("iq", C.c_void_p), ("nsamples", C.c_size_t), ("out", C.POINTER(Result))]
+
+
 class StreamState(C.Structure):
     _fields_ = [("synced", C.c_int32), ("coarse", C.c_int32), ("fine", C.c_int32), ("f2Correction", C.c_int32),
                 ("previous_1", C.c_int32), ("previous_2", C.c_int32), ("localPhase", C.c_int32),
@@ -399,6 +403,31 @@ class DabGpu:
     def decode_dev(self, d_ptr, nsamples, out):
         self._check(self.lib.dabgpu_decode_dev(self.h, d_ptr, nsamples, C.byref(out.res)))
         return self._trim(out)
+
+    def decode_multi(self, streams, outs, dev_ptrs=None):
+        """dabgpu_decode_multi: `streams` = list of numpy arrays (all uint8, float32 or int16, interleaved I,Q), one per
+        independent stream; outs = one alloc_result buffer per stream.  dev_ptrs: [(device pointer, nsamples)] instead of
+        host arrays (dabgpu_decode_multi_dev, sample format u8).  -> list of trimmed results"""
+        n = len(outs)
+        jobs = (StreamJob * max(n, 1))()
+        keep = []
+        fmt = 0
+        if dev_ptrs is None:
+            dt = np.asarray(streams[0]).dtype if n else np.dtype(np.uint8)
+            fmt = 1 if dt == np.float32 else 2 if dt == np.int16 else 0
+            for i, x in enumerate(streams):
+                a = np.ascontiguousarray(x, dt)
+                keep.append(a)
+                jobs[i].iq, jobs[i].nsamples = a.ctypes.data, a.size // 2
+        else:
+            for i, (ptr, ns) in enumerate(dev_ptrs):
+                jobs[i].iq, jobs[i].nsamples = ptr, ns
+        for i, o in enumerate(outs):
+            jobs[i].out = C.pointer(o.res)
+        f = self.lib.dabgpu_decode_multi if dev_ptrs is None else self.lib.dabgpu_decode_multi_dev
+        f.argtypes = [C.c_void_p, C.POINTER(StreamJob), C.c_int32, C.c_int32]
+        self._check(f(self.h, jobs, n, fmt))
+        return [self._trim(o) for o in outs]
 
     def _trim(self, o):
         L, K, _, _, _, _, cpf = MODE_PARAMS[self.mode]

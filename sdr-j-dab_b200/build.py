@@ -13,7 +13,8 @@ FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-li
 
 def sources():
     src = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")) + glob.glob(os.path.join(HERE, "csrc", "*.cpp")))
-    hdr = sorted(glob.glob(os.path.join(HERE, "csrc", "*.h")) + glob.glob(os.path.join(HERE, "..", "include", "*.h")))
+    hdr = sorted(glob.glob(os.path.join(HERE, "csrc", "*.h")) + glob.glob(os.path.join(HERE, "csrc", "*.cuh")) +
+                 glob.glob(os.path.join(HERE, "..", "include", "*.h")))
     return src, hdr
 
 

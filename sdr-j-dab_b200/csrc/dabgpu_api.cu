@@ -65,7 +65,7 @@ extern "C" void dabgpu_destroy (dabgpu_t *h) {
 	for (int i = 0; i < 4; i ++) {
 		dabgpu::VitCtx &c = h -> vctx [i];
 		if (i > 0 && c. st) { cudaStreamSynchronize (c. st); cudaStreamDestroy (c. st); }
-		c. d_dec. release (); c. d_jobs. release (); c. h_jobs. release ();
+		c. d_dec. release (); c. d_jobs. release (); c. d_sym8. release (); c. h_jobs. release ();
 	}
 	h -> h_in. release (); h -> h_out. release ();
 	if (h -> ev0) { cudaEventDestroy (h -> ev0); cudaEventDestroy (h -> ev1); }
@@ -367,18 +367,19 @@ int dab_fic_simd_job (dabgpu *h, const int16_t *d_soft, long long stride, int ng
 	return DABGPU_OK;
 }
 
-int dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, uint8_t *d_crc) {
+int dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, const uint8_t *d_soft8, long long stride, int ngroups, uint8_t *d_bits, uint8_t *d_crc) {
 	const ProtProfile *pp; const uint16_t *d_lut; const uint32_t *d_prbs;
 	int rc = dab_get_profile (h, 0, 0, 1, 0, &pp, &d_lut);
 	if (rc) return rc;
 	if ((rc = dab_get_prbs (h, 768, &d_prbs))) return rc;
 	VitJob j {};
-	j. in = d_soft; j. in_stride = stride; j. lut = d_lut;
+	j. in = d_soft; j. in8 = d_soft8; j. in_stride = stride; j. lut = d_lut;
 	j. frameBits = 768; j. nsteps = 774; j. nblocks = ngroups;
 	j. prbs = d_prbs; j. out = d_bits;
 	if (dab_use_simd (h, ngroups)) {
 		std::vector<VitSimdJob> jobs (1);
 		if ((rc = dab_fic_simd_job (h, d_soft, stride, ngroups, d_bits, &jobs [0]))) return rc;
+		if (d_soft8) { jobs [0]. sym8 = const_cast<uint8_t *> (d_soft8); jobs [0]. stride8 = stride; }
 		if ((rc = dab_vit_simd_run (h, jobs))) return rc;
 	} else
 		CUDA_TRY (h, vit_launch (h, KC_VITERBI_FIC, j));
@@ -395,7 +396,7 @@ extern "C" int dabgpu_fic_decode (dabgpu_t *h, const int16_t *soft, int32_t ngro
 	const size_t obytes = (size_t) ngroups * 768, cbytes = (size_t) ngroups * 3;
 	CUDA_TRY (h, h -> d_out. ensure (obytes + cbytes));
 	uint8_t *d_bits = (uint8_t *) h -> d_out. p, *d_crc = d_bits + obytes;
-	if ((rc = dab_fic_decode_dev (h, (const int16_t *) d_in, 2304, ngroups, d_bits, d_crc))) return rc;
+	if ((rc = dab_fic_decode_dev (h, (const int16_t *) d_in, nullptr, 2304, ngroups, d_bits, d_crc))) return rc;
 	CUDA_TRY (h, h -> h_out. ensure (obytes + cbytes));
 	CUDA_TRY (h, cudaMemcpyAsync (h -> h_out. p, d_bits, obytes + cbytes, cudaMemcpyDeviceToHost, h -> stream));
 	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
@@ -446,16 +447,17 @@ extern "C" void dabgpu_backend_destroy (dabgpu_backend_t *b) {
 }
 
 // device-side core: rows = [15 history][ncif new] fragments; decodes the CIFs past the warm-up
-int dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row_stride, int row0, int ncif,
-                         uint8_t *d_out, int *nout, VitSimdJob *simd_job) {
+int dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, const uint8_t *d_rows8, long long row_stride, int row0, int ncif,
+                         uint8_t *d_out, int *nout, VitSimdJob *simd_job, int64_t cifs_seen) {
 	dabgpu *h = b -> h;
-	// dab-concurrent.cpp:172-175: the first 16 CIFs only fill the de-interleaver
-	int64_t skip = 16 - b -> cifs_seen;
+	// dab-concurrent.cpp:172-175: the first 16 CIFs only fill the de-interleaver (cifs_seen >= 0: the caller keeps the
+	// counter itself -- one backend object serving many independent streams)
+	int64_t skip = 16 - (cifs_seen >= 0 ? cifs_seen : b -> cifs_seen);
 	if (skip < 0) skip = 0;
 	if (skip > ncif) skip = ncif;
 	const int n = ncif - (int) skip;
 	VitJob j {};
-	j. in = d_rows; j. in_stride = row_stride; j. first_row = 15 + row0 + (int) skip; j. lut = b -> d_lut;
+	j. in = d_rows; j. in8 = d_rows8; j. in_stride = row_stride; j. first_row = 15 + row0 + (int) skip; j. lut = b -> d_lut;
 	j. frameBits = b -> pp -> frameBits; j. nsteps = j. frameBits + 6; j. nblocks = n;
 	j. deint = 1; j. prbs = b -> d_prbs; j. out = d_out;
 	*nout = n;
@@ -494,9 +496,9 @@ extern "C" int dabgpu_backend_process (dabgpu_backend_t *b, const int16_t *frags
 	int rc;
 	if (dab_use_simd (h, ncif)) {
 		std::vector<VitSimdJob> jobs (1);
-		if ((rc = dab_backend_run_dev (b, d_rows, (long long) fs, 0, ncif, (uint8_t *) h -> d_out. p, &n, &jobs [0]))) return rc;
+		if ((rc = dab_backend_run_dev (b, d_rows, nullptr, (long long) fs, 0, ncif, (uint8_t *) h -> d_out. p, &n, &jobs [0]))) return rc;
 		if (n > 0 && (rc = dab_vit_simd_run (h, jobs))) return rc;
-	} else if ((rc = dab_backend_run_dev (b, d_rows, (long long) fs, 0, ncif, (uint8_t *) h -> d_out. p, &n, nullptr))) return rc;
+	} else if ((rc = dab_backend_run_dev (b, d_rows, nullptr, (long long) fs, 0, ncif, (uint8_t *) h -> d_out. p, &n, nullptr))) return rc;
 	// new history = last 15 rows of [history | new]
 	CUDA_TRY (h, cudaMemcpyAsync (b -> hist. p, d_rows + (size_t) ncif * fs, 15 * rowb, cudaMemcpyDeviceToDevice, h -> stream));
 	b -> cifs_seen += ncif;

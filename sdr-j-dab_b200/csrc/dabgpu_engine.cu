@@ -1,777 +1,47 @@
-// dabgpu_engine.cu -- the stream engine: ofdmProcessor::run (ofdm-processor.cpp:247-474) re-designed for a
+// dabgpu_engine.cu -- host side of the stream engine: ofdmProcessor::run (ofdm-processor.cpp:247-474) re-designed for a
 // frame-parallel GPU, feeding the FIC and MSC decoders (fic-handler.cpp, msc-handler.cpp, dab-concurrent.cpp).
 //
 // The reference loop is sequential through three couplings: the frame position (findIndex of frame n fixes
 // where frame n+1 is read), the NCO phase/frequency (coarse/fine correctors updated once per frame) and the
-// 16-CIF time de-interleaver.  The engine speculates: a pass decodes a chunk of frames in parallel assuming
+// 16-CIF time de-interleaver.  The engine speculates: a round decodes a chunk of frames in parallel assuming
 // the tracking state stays what it is at the chunk start (start index T_g, correctors unchanged -- the steady
-// state of a locked receiver), then a single-thread scan kernel replays the reference's scalar state machine
-// over the per-frame results (findIndex, coarse correction, cyclic-prefix correlation) and accepts frames up
-// to the first one whose assumed inputs differ from the replayed truth; the next pass restarts there with the
-// true state.  Accepted frames are therefore computed from exactly the inputs the reference would have used.
+// state of a locked receiver), then a scan kernel replays the reference's scalar state machine over the per-frame
+// results (findIndex, coarse correction, cyclic-prefix correlation), recomputes what the replay wants differently and
+// accepts frames up to the first one whose inputs differ from the replayed truth; the next round restarts there with
+// the true state.  Accepted frames are therefore computed from exactly the inputs the reference would have used.
 // Acquisition (null-symbol search) is a sample-serial scan done once per (re)synchronisation.
+//
+// A round works on an ARRAY of streams (StreamDev): dabgpu_decode runs one stream per handle, dabgpu_decode_multi
+// any number of independent streams in lockstep through the same kernels (one warp / CTA per stream in the
+// sequential kernels, one CTA per frame in the parallel ones), so n acquisitions or AFC convergences cost the time
+// of one.  Kernels: dabgpu_sync.cu (acquire, predict, scan), dabgpu_symbol.cu (front, symbol).
 #include <math.h>
 #include <stdlib.h>
+#include <algorithm>
 #include "dabgpu_engine.h"
 
-__device__ __forceinline__ uchar2 win_fetch (const SampleWin &w, long long i) {      // u8 windows only
-	return i < w. len0 ? __ldg (&w. seg0 [i]) : __ldg (&w. seg1 [i - w. len0]);
-}
-// sample i as the complex float the reference's getSample sees before the NCO (ofdm-processor.cpp:133-183)
-__device__ __forceinline__ float2 win_sample (const SampleWin &w, long long i) {
-	if (w. cf32 == 1)
-		return i < w. len0 ? __ldg (reinterpret_cast<const float2 *> (w. seg0) + i) : __ldg (reinterpret_cast<const float2 *> (w. seg1) + (i - w. len0));
-	if (w. cf32 == 2) {                                      // 16-bit PCM as sf_readf_float delivers it (wavfiles.cpp:190): x / 32768, exact in float
-		const short2 v = i < w. len0 ? __ldg (reinterpret_cast<const short2 *> (w. seg0) + i) : __ldg (reinterpret_cast<const short2 *> (w. seg1) + (i - w. len0));
-		return make_float2 ((float) v. x * (1.0f / 32768.0f), (float) v. y * (1.0f / 32768.0f));
-	}
-	const uchar2 s = win_fetch (w, i);
-	return make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f));
+// ---------------------------------------------------------------------------------------------------
+// handle life cycle, control members
+// ---------------------------------------------------------------------------------------------------
+static void ctl_fresh (StreamCtl *c) {                      // ofdm-processor.cpp:258-259, 73
+	memset (c, 0, sizeof (*c));
+	c -> f2 = 1; c -> prev1 = 1000; c -> prev2 = 999;
 }
 
-// dst[i] = sample (first + i) after u8 conversion and NCO, i < n (rawfiles.cpp:113-116; ofdm-processor.cpp:217-226)
-__device__ __forceinline__ void load_win_nco (float2 *dst, const SampleWin &w, long long first, int n,
-                                              int lp_before, int phase, const OfdmTables &T) {
-	const int tid = threadIdx. x;
-	const int ph = mod_rate (phase);
-	int lp = mod_rate ((long long) lp_before - (long long) (tid + 1) * ph);
-	const int step = mod_rate ((long long) OFDM_THREADS * ph);
-	for (int i = tid; i < n; i += OFDM_THREADS) {
-		dst [i] = cmul (win_sample (w, first + i), nco (T, lp));
-		lp -= step;
-		if (lp < 0) lp += DAB_INPUT_RATE;
-	}
-}
-
-// ---------------------------------------------------------------------------------------------------
-// acquisition: notSynced -> SyncOnNull -> SyncOnEndNull (ofdm-processor.cpp:275-338), one warp.
-// The reference walks the samples one by one through two recurrences -- the signal level IIR
-// (sLevel = 0.00001 * jan_abs (v) + (1 - 0.00001) * sLevel, in double, rounded to float, :168) and the running sum of a
-// 50-sample envelope window -- and tests a threshold before every sample.  Only the two recurrences are serial.  Per chunk:
-//   1. all lanes convert / mix the samples and prepare everything that does not depend on the recurrences: the
-//      envelope value e_i (|re| + |im|, or the true magnitude in SyncOnEndNull), the double product 0.00001 * jan_abs,
-//      the window difference e_i - e_(i-50);
-//   2. lane 0 runs the two recurrences (one double multiply-add-round chain, one float add chain) and records the
-//      values BEFORE every sample;
-//   3. all lanes evaluate the reference's threshold tests on the recorded values and the first sample that leaves the
-//      state is found by a warp reduction; the state is committed up to there.
-// Same operations in the same order on every value as the reference's loop, hence the same result bit for bit.
-// ---------------------------------------------------------------------------------------------------
-#define ACQ_CHUNK 512
-__global__ void __launch_bounds__ (32) acquire_kernel (SampleWin w, OfdmTables T, int T_F, int T_null, StreamCtl *ctl) {
-	__shared__ float s_e [ACQ_CHUNK], s_d [ACQ_CHUNK], s_sl [ACQ_CHUNK], s_csb [ACQ_CHUNK], s_ring [64];
-	__shared__ double s_ax [ACQ_CHUNK];
-	const int lane = threadIdx. x;
-	const long long total = w. len0 + w. len1;
-	// scalar state, identical in every lane (updated from lane 0's results by shuffles)
-	int stage = 0, cnt = 0, counter = 0, idx = 0, done = 0;
-	float sLevel = 0.f, cs = 0.f;
-	long long pos = ctl -> pos, attempt_pos = pos;
-	int lp = ctl -> lp, attempt_lp = lp;
-	const int phi = ctl -> coarse + ctl -> fine;
-	while (true) {
-		int n;                                                       // samples until the stage can change by COUNT
-		if (stage == 0) n = 20 * T. T_s - cnt;                       // :278-280
-		else if (stage == 1) n = 50 - cnt;                           // :284-290
-		else if (stage == 2) n = T_F + 1 - counter;                  // :314-315: the (T_F + 1)-th sample is still consumed
-		else n = T_null + 51 - counter;                              // :336-337
-		if (n > ACQ_CHUNK) n = ACQ_CHUNK;
-		if (pos + n > total) { done = 2; break; }                    // out of data: rewind to the attempt start
-		const int ph = stage < 2 ? 0 : mod_rate (phi);               // getSample (0) while looking for a signal at all (:279, 285)
-		{	// 1. per-sample values
-			int l = mod_rate ((long long) lp - (long long) (lane + 1) * ph);
-			const int step = mod_rate (32ll * ph);
-			for (int i = lane; i < n; i += 32) {
-				const float2 v = cmul (win_sample (w, pos + i), nco (T, l));
-				const float ja = fabsf (v. x) + fabsf (v. y);            // jan_abs
-				s_ax [i] = __dmul_rn (0.00001, (double) ja);
-				s_e [i] = stage == 3 ? hypotf (v. x, v. y) : ja;           // abs () in SyncOnEndNull (:329)
-				l -= step; if (l < 0) l += DAB_INPUT_RATE;
-			}
-			__syncwarp ();
-			if (stage >= 1)
-				for (int i = lane; i < n; i += 32)
-					s_d [i] = stage == 1 ? s_e [i] : __fsub_rn (s_e [i], i >= 50 ? s_e [i - 50] : s_ring [(idx + i - 50) & 63]);
-			__syncwarp ();
-		}
-		float sl_end = sLevel, cs_end = cs;
-		if (lane == 0) {                                             // 2. the two recurrences
-			float a = sLevel, c = cs;
-			if (stage == 0) {
-#pragma unroll 4
-				for (int i = 0; i < n; i ++)
-					a = __double2float_rn (__dadd_rn (s_ax [i], __dmul_rn (1 - 0.00001, (double) a)));
-			} else {
-#pragma unroll 4
-				for (int i = 0; i < n; i ++) {
-					s_sl [i] = a; s_csb [i] = c;
-					a = __double2float_rn (__dadd_rn (s_ax [i], __dmul_rn (1 - 0.00001, (double) a)));
-					c = __fadd_rn (c, s_d [i]);
-				}
-			}
-			sl_end = a; cs_end = c;
-		}
-		__syncwarp ();
-		int used = n;
-		if (stage >= 2) {                                            // 3. the threshold tests (:301, :323), in parallel
-			int first = n;
-			for (int i = lane; i < n && first == n; i += 32) {
-				const double lhs = (double) (s_csb [i] / 50.0f), lv = (double) s_sl [i];
-				const bool leave = stage == 2 ? !(lhs > 0.40 * lv) : !(lhs < 0.75 * lv);
-				if (leave) first = i;
-			}
-			for (int o = 16; o > 0; o >>= 1) first = min (first, __shfl_xor_sync (0xffffffffu, first, o));
-			used = first;
-		}
-		// commit the state after `used` samples
-		if (used < n) { sLevel = s_sl [used]; cs = s_csb [used]; }
-		else { sLevel = __shfl_sync (0xffffffffu, sl_end, 0); cs = __shfl_sync (0xffffffffu, cs_end, 0); }
-		if (stage >= 1) {
-			for (int i = lane; i < used; i += 32) if (i >= used - 64) s_ring [(idx + i) & 63] = s_e [i];
-			idx += used;
-		}
-		__syncwarp ();
-		pos += used;
-		lp = mod_rate ((long long) lp - (long long) used * ph);
-		bool restart = false;
-		if (stage == 0) { cnt += used; if (cnt == 20 * T. T_s) { stage = 1; cnt = 0; idx = 0; cs = 0.f; } }
-		else if (stage == 1) { cnt += used; if (cnt == 50) { stage = 2; counter = 0; } }
-		else if (stage == 2) {
-			counter += used;
-			if (used < n) { stage = 3; counter = 0; }                // :301 fails before sample `used`: on to SyncOnEndNull
-			else if (counter > T_F) restart = true;                  // :314-315
-		} else {
-			counter += used;
-			if (used < n) { done = 1; break; }                       // :323 fails: the null symbol has ended, sample `used` is the next to read
-			if (counter > T_null + 50) restart = true;               // :336-337
-		}
-		if (restart) {                                               // goto notSynced
-			stage = 0; cnt = 0; counter = 0; idx = 0; cs = 0.f; sLevel = 0.f;
-			attempt_pos = pos; attempt_lp = lp;
-		}
-	}
-	if (lane == 0) {
-		if (done == 1) { ctl -> synced = 1; ctl -> pos = pos; ctl -> lp = lp; ctl -> acq_done = 1; }
-		else           { ctl -> synced = 0; ctl -> pos = attempt_pos; ctl -> lp = attempt_lp; ctl -> acq_done = 0; }
-	}
-}
-
-// ---------------------------------------------------------------------------------------------------
-// predict kernel: frame c of the chunk is assumed to start T_F after frame c-1 with unchanged correctors
-// ---------------------------------------------------------------------------------------------------
-__global__ void predict_kernel (const StreamCtl *ctl, FrameIn *fin, int T_F, int nframes) {
-	const int c = blockIdx. x * blockDim. x + threadIdx. x;
-	if (c >= nframes) return;
-	const int phi = ctl -> coarse + ctl -> fine;
-	FrameIn f;
-	f. P = ctl -> pos + (long long) c * T_F;
-	f. lp = mod_rate ((long long) ctl -> lp - (long long) c * T_F % DAB_INPUT_RATE * mod_rate (phi));
-	f. phiA = f. phiB = phi; f. active = 1; f. pad = 0;
-	fin [c] = f;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// front kernel, one CTA per frame of the chunk: SyncOnPhase + OFDM_PRS (ofdm-processor.cpp:344-406)
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__ (OFDM_THREADS) front_kernel (SampleWin w, OfdmTables T, const FrameIn *fin,
-                                                               FrameOut *fo, float2 *spec0) {
-	extern __shared__ float2 sm [];
-	__shared__ float cv [96];
-	const int N = T. T_u, c = blockIdx. x;
-	const FrameIn in = fin [c];
-	if (!in. active) return;
-	float2 *a = sm, *b = sm + N;
-	load_win_nco (a, w, in. P, N, in. lp, in. phiA, T);                // :347-348
-	const int s = find_index_block (a, b, T);                          // :352
-	int corr = 0;
-	if (s >= 0) {
-		// block 0 = the T_u samples from P + s on (:362-388), same NCO run
-		const int lp0 = mod_rate ((long long) in. lp - (long long) s * mod_rate (in. phiA));
-		__syncthreads ();
-		load_win_nco (a, w, in. P + s, N, lp0, in. phiA, T);
-		float2 *f = block_fft (a, b, N, T. tw);
-		float2 *g = spec0 + (size_t) c * N;
-		for (int i = threadIdx. x; i < N; i += OFDM_THREADS) g [i] = f [i];   // phaseReference (ofdm-decoder.cpp:91)
-		corr = coarse_offset_warp0 (f, T, cv);                         // always computed; the scan applies the flag
-	}
-	if (threadIdx. x == 0) { fo [c]. startIndex = s; fo [c]. correction = corr; }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// symbol kernel, CTA (c, g) = frame c of the chunk, symbol group g: OFDM_SYMBOLS (ofdm-processor.cpp:414-442)
-// with processToken (ofdm-decoder.cpp:167-190) and the cyclic-prefix correlation (:424-425) fused.
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__ (OFDM_THREADS) symbol_kernel (SampleWin w, OfdmTables T, const FrameIn *fin, int slot0, int groups,
-                                                                int blocksPerCIF, int cifsPerFrame, const FrameOut *fo,
-                                                                const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc,
-                                                                uint8_t *fic8, uint8_t *msc8) {
-	extern __shared__ float2 sm [];
-	__shared__ float2 s_fc [OFDM_THREADS / 32];
-	const int N = T. T_u, Ts = T. T_s, Tg = T. T_g, c = blockIdx. x / groups, g = blockIdx. x % groups;
-	const FrameIn in = fin [c];
-	if (!in. active) return;
-	const int s = fo [c]. startIndex;
-	if (s < 0) { if (threadIdx. x == 0) fcpart [c * MAX_GROUPS + g] = make_float2 (0.f, 0.f); return; }
-	float2 *symbuf = sm, *scratch = sm + Ts, *prev = sm + Ts + N;
-	const int nsym = T. L - 1, per = (nsym + groups - 1) / groups;
-	const int l0 = 1 + g * per, l1 = min (nsym + 1, l0 + per);             // symbols [l0, l1)
-	const int phA = mod_rate (in. phiA), phiB = in. phiB, phB = mod_rate (phiB);
-	const long long F = in. P + s;                                         // first sample of the PRS
-	const int lpD = mod_rate ((long long) in. lp - (long long) (s + N) * phA);  // localPhase after the PRS
-	// symbol l (>= 1) occupies samples [F + N + (l-1) Ts, + Ts): guard first, then the useful part
-	if (l0 == 1) {
-		const float2 *p0 = spec0 + (size_t) c * N;
-		for (int i = threadIdx. x; i < N; i += OFDM_THREADS) prev [i] = p0 [i];
-	} else {
-		const long long first = F + N + (long long) (l0 - 2) * Ts + Tg;
-		const int lpb = mod_rate ((long long) lpD - ((long long) (l0 - 2) * Ts + Tg) % DAB_INPUT_RATE * phB);
-		load_win_nco (symbuf, w, first, N, lpb, phiB, T);
-		float2 *f = block_fft (symbuf, scratch, N, T. tw);
-		for (int i = threadIdx. x; i < N; i += OFDM_THREADS) prev [i] = f [i];
-	}
-	float2 acc = make_float2 (0.f, 0.f);
-	const int slot = slot0 + c;
-	for (int l = l0; l < l1; l ++) {
-		const long long first = F + N + (long long) (l - 1) * Ts;
-		const int lpb = mod_rate ((long long) lpD - ((long long) (l - 1) * Ts) % DAB_INPUT_RATE * phB);
-		__syncthreads ();
-		load_win_nco (symbuf, w, first, Ts, lpb, phiB, T);
-		__syncthreads ();
-		for (int i = N + threadIdx. x; i < Ts; i += OFDM_THREADS) {        // FreqCorr += x[i] * conj (x[i - T_u])
-			const float2 r = cmulc (symbuf [i], symbuf [i - N]);
-			acc. x += r. x; acc. y += r. y;
-		}
-		float2 *f = block_fft (symbuf + Tg, scratch, N, T. tw);
-		size_t o; int16_t *out; uint8_t *out8;
-		if (l < 4) { o = ((size_t) slot * 3 + (l - 1)) * 2 * T. K; out = fic + o; out8 = fic8 + o; }
-		else {
-			const int m = l - 4;
-			o = ((size_t) 15 + (size_t) slot * cifsPerFrame + m / blocksPerCIF) * CIF_BITS + (size_t) (m % blocksPerCIF) * 2 * T. K;
-			out = msc + o; out8 = msc8 + o;
-		}
-		demod_symbol (f, prev, T, out, out8);
-	}
-	for (int o = 16; o > 0; o >>= 1) {
-		acc. x += __shfl_xor_sync (0xffffffffu, acc. x, o);
-		acc. y += __shfl_xor_sync (0xffffffffu, acc. y, o);
-	}
-	if ((threadIdx. x & 31) == 0) s_fc [threadIdx. x >> 5] = acc;
-	__syncthreads ();
-	if (threadIdx. x == 0) {
-		float2 t = make_float2 (0.f, 0.f);
-		for (int k = 0; k < OFDM_THREADS / 32; k ++) { t. x += s_fc [k]. x; t. y += s_fc [k]. y; }
-		fcpart [c * MAX_GROUPS + g] = t;
-	}
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Mode I symbol kernel: same work as symbol_kernel, built on the 8-points-per-thread register FFT.
-//   * the raw u8 IQ of symbol l+1 streams into shared memory (one TMA bulk copy + mbarrier, double buffered) while symbol l
-//     is transformed, so no thread ever waits on HBM;
-//   * samples go shared (raw) -> registers (u8 convert + NCO by a per-thread phasor recurrence, the 1/128 of
-//     rawfiles.cpp:113-116 folded into the phasor: an exact power-of-two scaling) -> first butterflies;
-//   * the spectrum stays in shared memory in the FFT's own digit-reversed order (the carrier table is
-//     pre-permuted), the previous symbol's spectrum is simply the other buffer (pointer swap instead of a copy);
-//   * NCO phase indices advance by 32-bit adds (one 64-bit modulo per thread and CTA instead of three per symbol);
-//   * a thread demodulates carrier PAIRS, so soft bits leave as 32-bit stores and the Viterbi's byte symbols
-//     (viterbi.cpp:229-235) as 16-bit stores.
-// ---------------------------------------------------------------------------------------------------
-#define R8_RAW 5152                                                        // bytes per raw buffer: 2 T_s + alignment slack, multiple of 16
-#define R8_DYN_SMEM ((2 * R8_SMEM + R8_TW2 + R8_TW3) * (int) sizeof (float2) + 2 * R8_RAW)
-
-__device__ __forceinline__ float2 u8_to_c (uchar2 s) {
-	return make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f));
-}
-// (b - 128) as float, exactly, b = byte `which` of s: 0x4B0000bb is 2^23 + b
-__device__ __forceinline__ float u8_to_f (uint32_t s, int which) {
-	return __uint_as_float (__byte_perm (s, 0x4B000000u, which ? 0x7441 : 0x7440)) - 8388736.0f;
-}
-// soft-bit quantisation of ofdm-decoder.cpp:183-189 with the quotient from the reciprocal unit (2 ulp; the soft bits'
-// stated tolerance is +-1 step and comes from the FFT, whose rounding differs from the reference's FFTW anyway)
-__device__ __forceinline__ int quant127_fast (float num, float ab1) {
-	// (double) q * 127.0 is exact (24 + 7 bits); its truncation equals the truncation of the round-toward-zero float
-	// product, because rounding toward zero never crosses an integer (all |integers| <= 127 are floats)
-	return __float2int_rz (__fmul_rz (__fdividef (- num, ab1), 127.0f));      // NaN (ab1 == 0) -> 0 (App. B-5)
-}
-
-#ifndef R8_MINB
-#define R8_MINB 4
-#endif
-#ifndef R8_TMA
-#define R8_TMA 1                                                           // raw symbols staged by TMA bulk copies + mbarrier (0: per-thread cp.async)
-#endif
-__global__ void __launch_bounds__ (256, R8_MINB) symbol_kernel_r8 (SampleWin w, OfdmTables T, const FrameIn *fin, int slot0, int groups,
-                                                          int blocksPerCIF, int cifsPerFrame, const FrameOut *fo,
-                                                          const float2 *spec0, float2 *fcpart, int16_t *fic, int16_t *msc,
-                                                          uint8_t *fic8, uint8_t *msc8) {
-	extern __shared__ __align__ (1024) unsigned char r8_dyn [];     // the FFT buffers must be 512-byte aligned (fft2048_r8)
-	float2 *bufA = reinterpret_cast<float2 *> (r8_dyn), *bufB = bufA + R8_SMEM, *tw2 = bufB + R8_SMEM, *tw3 = tw2 + R8_TW2;
-	unsigned char *raw = reinterpret_cast<unsigned char *> (tw3 + R8_TW3);
-	__shared__ float2 s_fc [8];
-	const int N = R8_N, Ts = T. T_s, Tg = T. T_g, t = threadIdx. x;
-	const int c = blockIdx. x / groups, g = blockIdx. x % groups;
-	const FrameIn in = fin [c];
-	if (!in. active) return;
-	const int s = fo [c]. startIndex;
-	if (s < 0) { if (t == 0) fcpart [c * MAX_GROUPS + g] = make_float2 (0.f, 0.f); return; }
-	const int nsym = T. L - 1, per = (nsym + groups - 1) / groups;
-	const int l0 = 1 + g * per, l1 = min (nsym + 1, l0 + per);             // symbols [l0, l1)
-	const int phA = mod_rate (in. phiA), phB = mod_rate (in. phiB);
-	const long long F = in. P + s;                                         // first sample of the PRS
-	const int lpD = mod_rate ((long long) in. lp - (long long) (s + N) * phA);  // localPhase after the PRS
-	const float2 rot256 = nco (T, mod_rate (- 256ll * phB));               // 256 samples further: phase index - 256 f
-	// guard samples this thread correlates with its own useful samples 1536 + t and 1792 + t: gs and gs + 256
-	const int gs = t + 1536 - (N - Tg);                                    // = t - 8 (T_u - T_g = 1544); negative: x[6] has no partner
-	const int offT = mod_rate ((long long) (gs + 1) * phB), offU = mod_rate ((long long) (Tg + t + 1) * phB);
-	const int dTs = mod_rate ((long long) Ts * phB);
-	float2 *cur = bufA, *prev = bufB;
-	float2 x [8], tw1 [6];
-	if (((uint32_t) __cvta_generic_to_shared (bufA) & 511u) != 0) __trap ();   // layout contract of fft2048_r8
-	r8_fill_tables (tw2, tw3, T. tw);
-	r8_load_tw1 (tw1, T. tw);
-#if R8_TMA
-	// one mbarrier per raw buffer: the TMA engine's bulk copy of a symbol signals it (complete_tx), every thread waits on it
-	__shared__ __align__ (8) unsigned long long s_mbar [2];
-	const uint32_t mbar0 = (uint32_t) __cvta_generic_to_shared (&s_mbar [0]);
-	if (t == 0) {
-		asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r" (mbar0));
-		asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r" (mbar0 + 8));
-		asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-#endif
-	__syncthreads ();
-
-	// raw u8 IQ of symbol l (guard + useful part, T_s samples from `first`) -> raw buffer b; returns the byte offset of
-	// sample 0 inside the buffer.  Fast path: 16-byte cp.async from the 16-byte-aligned address below the first sample.
-	auto stage = [&] (int l, int b) -> int {
-		const long long first = F + N + (long long) (l - 1) * Ts;
-		unsigned char *dst = raw + b * R8_RAW;
-		const uchar2 *seg = nullptr; long long rel = 0, seglen = 0;
-		if (first + Ts <= w. len0) { seg = w. seg0; rel = first; seglen = w. len0; }
-		else if (first >= w. len0) { seg = w. seg1; rel = first - w. len0; seglen = w. len1; }
-		int off = 0;
-		bool fast = seg != nullptr;
-		if (fast) {
-			const unsigned long long p = (unsigned long long) (seg + rel), pa = p & ~15ull;
-			off = (int) (p - pa);
-			const int n16 = (off + 2 * Ts + 15) >> 4;
-			fast = pa >= (unsigned long long) seg && pa + 16ull * n16 <= (unsigned long long) (seg + seglen);
-#if R8_TMA
-			if (fast && t == 0) {                                          // one bulk copy by the TMA engine, 16-byte aligned on both sides
-				const uint32_t bytes = 16u * (uint32_t) n16, mb = mbar0 + 8u * (uint32_t) b;
-				asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer's last readers (generic proxy) are past a CTA barrier
-				asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r" (mb), "r" (bytes) : "memory");
-				asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-				              :: "r" ((uint32_t) __cvta_generic_to_shared (dst)), "l" (pa), "r" (bytes), "r" (mb) : "memory");
-			}
-#else
-			if (fast)
-				for (int i = t; i < n16; i += 256)
-					asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r" ((uint32_t) __cvta_generic_to_shared (dst + 16 * i)), "l" (pa + 16ull * i));
-#endif
-		}
-		if (!fast) {                                                       // symbol straddles the tail | input seam or touches a buffer end
-			off = 0;
-			for (int i = t; i < Ts; i += 256) reinterpret_cast<uchar2 *> (dst) [i] = win_fetch (w, first + i);
-#if R8_TMA
-			if (t == 0) asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r" (mbar0 + 8u * (uint32_t) b) : "memory");   // nothing in flight: the CTA barrier below orders the stores
-#endif
-		}
-#if !R8_TMA
-		asm volatile ("cp.async.commit_group;");
-#endif
-		return off;
-	};
-#if R8_TMA
-	auto wait_raw = [&] (int b, int use) {                                 // use = how often buffer b has been waited for before
-		const uint32_t mb = mbar0 + 8u * (uint32_t) b, parity = (uint32_t) use & 1u;
-		uint32_t ok = 0;
-		unsigned long long t0 = 0;
-		for (int spin = 0; !ok; spin ++) {
-			asm volatile ("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r" (ok) : "r" (mb), "r" (parity) : "memory");
-			if (!ok && (spin & 1023) == 1023) {                            // a lost copy must not hang the GPU: give up after 2 s of waiting
-				unsigned long long now;
-				asm volatile ("mov.u64 %0, %%globaltimer;" : "=l" (now));
-				if (t0 == 0) t0 = now; else if (now - t0 > 2000000000ull) __trap ();
-			}
-		}
-	};
-#endif
-
-	int off_cur = stage (l0, 0);
-	if (l0 == 1) {
-		const float2 *p0 = spec0 + (size_t) c * N;
-		for (int k = t; k < N; k += 256) prev [r8_swz (r8_pos (k))] = p0 [k];
-	} else {                                                               // spectrum of symbol l0-1 as reference
-		const long long first = F + N + (long long) (l0 - 2) * Ts + Tg;
-		const int lpb = mod_rate ((long long) lpD - ((long long) (l0 - 2) * Ts + Tg) % DAB_INPUT_RATE * phB);
-		float2 ph = nco (T, mod_rate ((long long) lpb - (long long) (t + 1) * phB));
-#pragma unroll
-		for (int k = 0; k < 8; k ++) { x [k] = cmul (u8_to_c (win_fetch (w, first + t + 256 * k)), ph); ph = cmul (ph, rot256); }
-		fft2048_r8 (x, prev, tw1, tw2, tw3);
-	}
-	float2 acc = make_float2 (0.f, 0.f);
-	const int slot = slot0 + c;
-	uint32_t pidx [3];                                                     // this thread's six carriers: the pairs 2t, 2t+1 (+ 512 m), packed
-#pragma unroll
-	for (int m = 0; m < 3; m ++) pidx [m] = (uint32_t) __ldg (&T. permpos [2 * t + 512 * m]) | ((uint32_t) __ldg (&T. permpos [2 * t + 1 + 512 * m]) << 16);
-	// the phase reference of a carrier is the value this very thread read for it one symbol earlier: it stays in registers,
-	// and only the first symbol of the group fetches it from the (pseudo-randomly scattered, bank-conflicting) spectrum
-	float2 pv [6];
-	__syncthreads ();
-#pragma unroll
-	for (int m = 0; m < 3; m ++) { pv [2 * m] = prev [pidx [m] & 0xffffu]; pv [2 * m + 1] = prev [pidx [m] >> 16]; }
-	int lpb = mod_rate ((long long) lpD - ((long long) (l0 - 1) * Ts) % DAB_INPUT_RATE * phB);   // localPhase before the symbol's first sample
-	const float sc = 1.0f / 128.0f;
-	// the two NCO phasors of a symbol (guard sample gs, useful sample t) are looked up one symbol ahead
-	auto phasors = [&] (int lp, float2 &pg, float2 &pu) {
-		int ig = lp - offT; if (ig < 0) ig += DAB_INPUT_RATE;
-		int iu = lp - offU; if (iu < 0) iu += DAB_INPUT_RATE;
-		pg = nco (T, ig); pu = nco (T, iu);
-	};
-	float2 phg_n, ph_n;
-	phasors (lpb, phg_n, ph_n);
-	for (int l = l0; l < l1; l ++) {
-		const int b = (l - l0) & 1;
-		int off_next = 0;
-#if R8_TMA
-		if (l + 1 < l1) off_next = stage (l + 1, b ^ 1);
-#else
-		if (l + 1 < l1) off_next = stage (l + 1, b ^ 1); else asm volatile ("cp.async.commit_group;");
-#endif
-		float2 phg = make_float2 (phg_n. x * sc, phg_n. y * sc), ph = make_float2 (ph_n. x * sc, ph_n. y * sc);
-		lpb -= dTs; if (lpb < 0) lpb += DAB_INPUT_RATE;
-		phasors (lpb, phg_n, ph_n);
-#if R8_TMA
-		wait_raw (b, (l - l0) >> 1);
-#else
-		asm volatile ("cp.async.wait_group 1;" ::: "memory");
-#endif
-		__syncthreads ();                                                  // raw buffer b complete; last symbol's demod reads done
-		const unsigned short *rs = reinterpret_cast<const unsigned short *> (raw + b * R8_RAW + off_cur);
-		// guard samples gs and gs + 256 (the ones x[6] and x[7] are correlated with), mixed like every other sample
-		float2 g6 = make_float2 (0.f, 0.f), g7;
-		{
-			const uint32_t r7 = rs [gs + 256];
-			g7 = cmul (make_float2 (u8_to_f (r7, 0), u8_to_f (r7, 1)), cmul (phg, rot256));
-			if (gs >= 0) { const uint32_t r6 = rs [gs]; g6 = cmul (make_float2 (u8_to_f (r6, 0), u8_to_f (r6, 1)), phg); }
-		}
-#pragma unroll
-		for (int k = 0; k < 8; k ++) {
-			const uint32_t v = rs [Tg + t + 256 * k];
-			x [k] = cmul (make_float2 (u8_to_f (v, 0), u8_to_f (v, 1)), ph);
-			ph = cmul (ph, rot256);
-		}
-		// FreqCorr += x[i] * conj (x[i - T_u]), i in [T_u, T_s): useful sample e = i - T_g pairs with guard sample e - (T_u - T_g)
-		if (gs >= 0) { const float2 r = cmulc (x [6], g6); acc. x += r. x; acc. y += r. y; }
-		{ const float2 r = cmulc (x [7], g7); acc. x += r. x; acc. y += r. y; }
-		fft2048_r8 (x, cur, tw1, tw2, tw3);
-		size_t o;
-		if (l < 4) o = ((size_t) slot * 3 + (l - 1)) * 2 * T. K;
-		else {
-			const int m = l - 4;
-			o = ((size_t) 15 + (size_t) slot * cifsPerFrame + m / blocksPerCIF) * CIF_BITS + (size_t) (m % blocksPerCIF) * 2 * T. K;
-		}
-		int16_t *out = (l < 4 ? fic : msc) + o;
-		uint8_t *out8 = (l < 4 ? fic8 : msc8) + o;
-#pragma unroll
-		for (int m = 0; m < 3; m ++) {                                      // K = 1536 = 3 x 256 carrier pairs
-			const int i = 2 * t + 512 * m;
-			int re [2], im [2];
-#pragma unroll
-			for (int q = 0; q < 2; q ++) {
-				const int idx = (int) (q ? pidx [m] >> 16 : pidx [m] & 0xffffu);
-				const float2 cc = cur [idx];
-				const float2 r1 = cmulc (cc, pv [2 * m + q]);
-				pv [2 * m + q] = cc;
-				const float ab1 = fabsf (r1. x) + fabsf (r1. y);
-				re [q] = quant127_fast (r1. x, ab1); im [q] = quant127_fast (r1. y, ab1);
-			}
-			*reinterpret_cast<uint32_t *> (out + i)        = (uint32_t) (re [0] & 0xffff) | ((uint32_t) re [1] << 16);
-			*reinterpret_cast<uint32_t *> (out + T. K + i) = (uint32_t) (im [0] & 0xffff) | ((uint32_t) im [1] << 16);
-			*reinterpret_cast<unsigned short *> (out8 + i)        = (unsigned short) ((re [0] + 127) | ((re [1] + 127) << 8));
-			*reinterpret_cast<unsigned short *> (out8 + T. K + i) = (unsigned short) ((im [0] + 127) | ((im [1] + 127) << 8));
-		}
-		off_cur = off_next;
-	}
-	for (int o = 16; o > 0; o >>= 1) {
-		acc. x += __shfl_xor_sync (0xffffffffu, acc. x, o);
-		acc. y += __shfl_xor_sync (0xffffffffu, acc. y, o);
-	}
-	if ((t & 31) == 0) s_fc [t >> 5] = acc;
-	__syncthreads ();
-	if (t == 0) {
-		float2 sum = make_float2 (0.f, 0.f);
-		for (int k = 0; k < 8; k ++) { sum. x += s_fc [k]. x; sum. y += s_fc [k]. y; }
-		fcpart [c * MAX_GROUPS + g] = sum;
-	}
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Mode I front kernel on the register FFT: same work as front_kernel (SyncOnPhase + OFDM_PRS, ofdm-processor.cpp:344-406).
-// The spectrum of a transform stays in the FFT's digit-reversed shared layout; the correlator's product with the PRS
-// reference reads it through the position map, the magnitude scan walks the storage order and maps every slot back to
-// its bin (first maximum = smallest bin among equals, as the reference's ascending loop finds it).
-// ---------------------------------------------------------------------------------------------------
-#define FRONT_R8_SMEM ((2 * R8_SMEM + R8_TW2 + R8_TW3) * (int) sizeof (float2))
-__host__ __device__ __forceinline__ int r8_pos_inv (int p) { return (p >> 9) | (((p >> 6) & 7) << 2) | (((p >> 3) & 7) << 5) | ((p & 7) << 8); }
-
-__global__ void __launch_bounds__ (256) front_kernel_r8 (SampleWin w, OfdmTables T, const FrameIn *fin, FrameOut *fo, float2 *spec0) {
-	extern __shared__ __align__ (1024) unsigned char fr8_dyn [];
-	float2 *A = reinterpret_cast<float2 *> (fr8_dyn), *B = A + R8_SMEM, *tw2 = B + R8_SMEM, *tw3 = tw2 + R8_TW2;
-	__shared__ float cv [96];
-	__shared__ float s_red [8], s_max [8];
-	__shared__ int s_idx [8], s_result;
-	const int N = R8_N, c = blockIdx. x, t = threadIdx. x;
-	const FrameIn in = fin [c];
-	if (!in. active) return;
-	float2 x [8], tw1 [6];
-	r8_fill_tables (tw2, tw3, T. tw);
-	r8_load_tw1 (tw1, T. tw);
-	const int phA = mod_rate (in. phiA), step256 = mod_rate (256ll * phA);
-	// x [k] = sample (first + t + 256 k) after u8 conversion and NCO (rawfiles.cpp:113-116; ofdm-processor.cpp:217-226)
-	auto load = [&] (long long first, int lp_before) {
-		int lp = mod_rate ((long long) lp_before - (long long) (t + 1) * phA);
-#pragma unroll
-		for (int k = 0; k < 8; k ++) {
-			x [k] = cmul (u8_to_c (win_fetch (w, first + t + 256 * k)), nco (T, lp));
-			lp -= step256; if (lp < 0) lp += DAB_INPUT_RATE;
-		}
-	};
-	load (in. P, in. lp);                                              // :347-348
-	__syncthreads ();                                                  // twiddle tables in place
-	fft2048_r8 (x, A, tw1, tw2, tw3);
-	// res = conj (fft * conj (ref)): the backward transform is conj (forward (conj (x))) (phasereference.cpp:66-73)
-#pragma unroll
-	for (int k = 0; k < 8; k ++) {
-		const int kk = t + 256 * k;
-		const float2 r = cmulc (A [r8_swz (r8_pos (kk))], __ldg (&T. ref [kk]));
-		x [k] = make_float2 (r. x, - r. y);
-	}
-	__syncthreads ();                                                  // everybody has read A
-	fft2048_r8 (x, A, tw1, tw2, tw3);
-	const float factor = (float) (1.0 / (float) N);                    // fft.cpp:114-121
-	float sum = 0.f, mx = -10000.f;
-	int mi = -1;
-#pragma unroll
-	for (int m = 0; m < 8; m ++) {
-		const int slot = t + 256 * m, k = r8_pos_inv (r8_swz (slot));  // the swizzle is an involution
-		const float2 v = A [slot];
-		const float a = hypotf (v. x * factor, (- v. y) * factor);
-		sum += a;
-		if (a > mx || (a == mx && k < mi)) { mx = a; mi = k; }
-	}
-	for (int o = 16; o > 0; o >>= 1) {
-		sum += __shfl_xor_sync (0xffffffffu, sum, o);
-		const float om = __shfl_xor_sync (0xffffffffu, mx, o);
-		const int   oi = __shfl_xor_sync (0xffffffffu, mi, o);
-		if (om > mx || (om == mx && oi >= 0 && (mi < 0 || oi < mi))) { mx = om; mi = oi; }
-	}
-	if ((t & 31) == 0) { s_red [t >> 5] = sum; s_max [t >> 5] = mx; s_idx [t >> 5] = mi; }
-	__syncthreads ();
-	if (t == 0) {
-		float tsum = 0.f, tmx = -10000.f;
-		int tmi = -1;
-		for (int q = 0; q < 8; q ++) {
-			tsum += s_red [q];
-			if (s_max [q] > tmx || (s_max [q] == tmx && s_idx [q] >= 0 && (tmi < 0 || s_idx [q] < tmi))) { tmx = s_max [q]; tmi = s_idx [q]; }
-		}
-		if (tmx < (float) T. level * tsum / (float) N)                 // phasereference.cpp:84-85
-			s_result = (int) (- fabsf (tmx / (tsum / (float) N)) - 1.0f);
-		else
-			s_result = tmi;
-	}
-	__syncthreads ();
-	const int s = s_result;                                            // :352
-	int corr = 0;
-	if (s >= 0) {
-		// block 0 = the T_u samples from P + s on (:362-388), same NCO run
-		load (in. P + s, mod_rate ((long long) in. lp - (long long) s * phA));
-		fft2048_r8 (x, A, tw1, tw2, tw3);
-		float2 *g = spec0 + (size_t) c * N;
-#pragma unroll
-		for (int m = 0; m < 8; m ++) {                                 // phaseReference (ofdm-decoder.cpp:91), natural order
-			const int k = t + 256 * m;
-			const float2 v = A [r8_swz (r8_pos (k))];
-			g [k] = v; B [k] = v;
-		}
-		__syncthreads ();
-		corr = coarse_offset_warp0 (B, T, cv);                         // always computed; the scan applies the flag
-	}
-	if (t == 0) { fo [c]. startIndex = s; fo [c]. correction = corr; }
-}
-
-// int16 soft bits -> byte symbols for n elements (the 15 history rows of the time de-interleaver at the start of a call)
-__global__ void soft_to_sym8_kernel (const int16_t *in, uint8_t *out, long long n) {
-	for (long long i = (long long) blockIdx. x * blockDim. x + threadIdx. x; i < n; i += (long long) gridDim. x * blockDim. x)
-		out [i] = (uint8_t) min (max ((int) in [i] + 127, 0), 255);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// scan kernel (one thread): the scalar state machine of ofdmProcessor::run replayed over the chunk.
-//   derive = 1: optimistic pass.  Walks ALL frames, replacing fin[c] by the inputs the replayed state asks
-//     for and marking the frames whose inputs changed for recomputation.  Where the data symbols were mixed
-//     with another frequency than the replay wants, the cyclic-prefix correlation is corrected by the exact
-//     identity  FreqCorr(f') = FreqCorr(f) * exp (-j 2 pi (f' - f) T_u / 2048000).  Nothing is committed.
-//   derive = 0: verification pass.  Accepts frames only while the inputs they were actually computed from
-//     equal the replayed state, commits the stream state and the per-frame records.
-// ---------------------------------------------------------------------------------------------------
-#define SCAN_MAX 1024
-struct ScanSmem { FrameIn in [SCAN_MAX]; FrameOut fo [SCAN_MAX]; float2 fc [SCAN_MAX]; double inc [SCAN_MAX]; };
-#define SCAN_THREADS 256
-__global__ void __launch_bounds__ (SCAN_THREADS) scan_kernel (StreamCtl *ctl, FrameIn *fin, int nframes, int slot0, int groups, DabParams dp, const FrameOut *fo,
-                             const float2 *fcpart, dabgpu_frame_info *info, long long abs_base, int derive) {
-	extern __shared__ unsigned char scan_raw [];
-	ScanSmem &S = *reinterpret_cast<ScanSmem *> (scan_raw);
-	__shared__ int s_first;
-	const int lane = threadIdx. x;                           // (thread index; thread 0 runs the serial replay)
-	if (!derive && ctl -> n_redo == 0) return;               // the derive pass found nothing to redo and committed already
-	const StreamCtl s0 = *ctl;
-	const int cd = dp. carrierDiff;
-	if (lane == 0) s_first = nframes;
-	// parallel preload of the per-frame records; the serial replay then runs out of shared memory
-	for (int c = lane; c < nframes; c += SCAN_THREADS) {
-		S. in [c] = fin [c]; S. fo [c] = fo [c];
-		float2 fc = make_float2 (0.f, 0.f);
-		for (int g = 0; g < groups; g ++) { fc. x += fcpart [c * MAX_GROUPS + g]. x; fc. y += fcpart [c * MAX_GROUPS + g]. y; }
-		S. fc [c] = fc;
-		S. inc [c] = __dmul_rn (__ddiv_rn (__dmul_rn (0.1, (double) atan2f (fc. y, fc. x)), 3.14159265358979323846), (double) (cd / 2));
-	}
-	__syncthreads ();
-	// Fast path for a locked receiver.  A frame leaves the tracking state as it found it (apart from advancing by one
-	// frame length) when its window was placed where the replay wants it, the coarse search is off, findIndex returned
-	// T_g and the fine integrator's truncated sum is unchanged.  The leading run of such frames is accepted in parallel;
-	// the serial replay starts at the first frame that is not of this kind.
-	const int phi0 = s0. coarse + s0. fine;
-	const int phm = mod_rate (phi0);
-	int first_slow = 0;
-	if (!s0. f2 && s0. fine <= cd / 2 && s0. fine >= - cd / 2) {
-		for (int c = lane; c < nframes; c += SCAN_THREADS) {
-			const FrameIn in = S. in [c];
-			const long long P = s0. pos + (long long) c * dp. T_F;
-			const int lp = mod_rate ((long long) s0. lp - (long long) c * dp. T_F % DAB_INPUT_RATE * phm);
-			const bool ok = in. P == P && in. lp == lp && in. phiA == phi0 && in. phiB == phi0 && S. fo [c]. startIndex == dp. T_s - dp. T_u &&
-			                (int) (short) __double2int_rz (__dadd_rn ((double) s0. fine, S. inc [c])) == s0. fine;
-			if (!ok) atomicMin (&s_first, c);
-		}
-		__syncthreads ();
-		first_slow = s_first;
-		for (int c = lane; c < first_slow; c += SCAN_THREADS) {
-			dabgpu_frame_info fi;
-			fi. pos = abs_base + s0. pos + (long long) c * dp. T_F; fi. startIndex = dp. T_s - dp. T_u; fi. coarse = s0. coarse; fi. fine = s0. fine;
-			fi. phase0 = mod_rate ((long long) s0. lp - (long long) c * dp. T_F % DAB_INPUT_RATE * phm);
-			fi. correction = 0; fi. freqCorrRe = S. fc [c]. x; fi. freqCorrIm = S. fc [c]. y;
-			info [slot0 + c] = fi;                           // harmless if the chunk is redone: rewritten then
-			if (derive) S. in [c]. active = 0;
-		}
-	}
-	__syncthreads ();
-	if (lane == 0) {
-		StreamCtl s = s0;
-		int n_redo = 0;
-		int k_a = 0x7fffffff, k_b = 0, k_c = 0, k_si = -1, k_delta = 0;
-		s. n_valid = first_slow; s. lost = 0;
-		s. pos = s0. pos + (long long) first_slow * dp. T_F;
-		s. lp = mod_rate ((long long) s0. lp - (long long) first_slow * dp. T_F % DAB_INPUT_RATE * phm);
-		for (int c = first_slow; c < nframes; c ++) {
-			FrameIn in = S. in [c];
-			const int phiA = s. coarse + s. fine;
-			bool changed = in. P != s. pos || in. lp != s. lp || in. phiA != phiA;
-			if (derive) { in. P = s. pos; in. lp = s. lp; in. phiA = phiA; }
-			else if (changed) break;                             // computed from other inputs than the replay wants
-			const int si = S. fo [c]. startIndex;                // (derive: from the old window if `changed`; verified later)
-			if (si < 0) {                                        // :353-356 -> notSynced; T_u samples were consumed
-				if (derive && changed) {
-					in. phiB = phiA; in. active = 1; S. in [c] = in; n_redo ++;
-					for (int k = c + 1; k < nframes; k ++) S. in [k]. active = 0;
-					nframes = c + 1;
-					break;
-				}
-				if (derive) for (int k = c; k < nframes; k ++) S. in [k]. active = 0;
-				s. pos += dp. T_u;
-				s. lp = mod_rate ((long long) s. lp - (long long) dp. T_u * mod_rate (phiA));
-				s. synced = 0; s. lost = 1;
-				break;
-			}
-			int correction = 0;
-			const StreamCtl before = s;
-			if (s. f2) {                                         // :390-405
-				correction = S. fo [c]. correction;
-				if (correction == 0 && s. prev1 == 0 && s. prev2 == 0) s. f2 = 0;
-				else if (correction != 100) {
-					s. coarse += correction * cd;
-					if (abs (s. coarse) > 35000) s. coarse = 0;
-					s. prev2 = s. prev1; s. prev1 = correction;
-				}
-			}
-			const int phiB = s. coarse + s. fine;
-			const int usedB = in. phiB;
-			if (derive) {
-				changed = changed || usedB != phiB;
-				in. phiB = phiB; in. active = changed; S. in [c] = in; n_redo += changed;
-			} else if (usedB != phiB) { s = before; break; }
-			const float2 fc = S. fc [c];
-			double inc = S. inc [c];                             // :445-446
-			if (derive && usedB != phiB) {                       // the symbols were mixed with another frequency: rotate
-				double ang = (double) atan2f (fc. y, fc. x);
-				ang -= 2.0 * 3.14159265358979323846 * (double) (phiB - usedB) * (double) dp. T_u / (double) DAB_INPUT_RATE;
-				ang = remainder (ang, 2.0 * 3.14159265358979323846);
-				inc = __dmul_rn (__ddiv_rn (__dmul_rn (0.1, ang), 3.14159265358979323846), (double) (cd / 2));
-			}
-			dabgpu_frame_info fi;
-			fi. pos = abs_base + s. pos; fi. startIndex = si; fi. coarse = s. coarse; fi. fine = s. fine;
-			fi. phase0 = s. lp; fi. correction = correction; fi. freqCorrRe = fc. x; fi. freqCorrIm = fc. y;
-			info [slot0 + c] = fi;
-			// fineCorrector (int16) += 0.1 * arg (FreqCorr) / M_PI * (carrierDiff / 2)
-			s. fine = (int) (short) __double2int_rz (__dadd_rn ((double) s. fine, inc));
-			const int phiC = s. coarse + s. fine;
-			// localPhase after the whole frame: -(si + T_u) fA - (L-1) T_s fB - T_null fC (mod rate); cached while nothing moves
-			if (phiA != k_a || phiB != k_b || phiC != k_c || si != k_si) {
-				long long d = (long long) (si + dp. T_u) * mod_rate (phiA);
-				d += ((long long) (dp. L - 1) * dp. T_s) % DAB_INPUT_RATE * mod_rate (phiB);
-				d += (long long) dp. T_null * mod_rate (phiC);                // :453
-				k_delta = mod_rate (d); k_a = phiA; k_b = phiB; k_c = phiC; k_si = si;
-			}
-			s. lp -= k_delta;
-			if (s. lp < 0) s. lp += DAB_INPUT_RATE;
-			s. pos += si + dp. T_u + (long long) (dp. L - 1) * dp. T_s + dp. T_null;
-			if (s. fine > cd / 2) { s. coarse += cd; s. fine -= cd; }      // :458-465
-			else if (s. fine < - cd / 2) { s. coarse -= cd; s. fine += cd; }
-			s. n_valid = c + 1;
-		}
-		if (derive) {
-			ctl -> n_redo = n_redo;
-			if (n_redo == 0) { s. n_redo = 0; *ctl = s; }    // nothing changes: this replay IS the verification
-		} else { s. n_redo = ctl -> n_redo; *ctl = s; }
-	}
-	__syncthreads ();
-	if (derive) for (int c = lane; c < nframes; c += SCAN_THREADS) fin [c] = S. in [c];
-}
-
-// ---------------------------------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------------------------------
 int dab_engine_init (dabgpu *h) {
 	Engine *E = new Engine ();
 	h -> engine = E;
 	int rc = ofdm_tables_init (h, &E -> T);
 	if (rc) return rc;
 	CUDA_TRY (h, cudaMalloc ((void **) &E -> d_phaseRef, (size_t) h -> p. T_u * sizeof (float2)));
-	CUDA_TRY (h, E -> d_ctl. ensure (sizeof (StreamCtl)));
-	CUDA_TRY (h, E -> h_ctl. ensure (sizeof (StreamCtl)));
-	memset (&E -> ctl, 0, sizeof (StreamCtl));
-	E -> ctl. f2 = 1; E -> ctl. prev1 = 1000; E -> ctl. prev2 = 999;     // ofdm-processor.cpp:258-259, 73
+	ctl_fresh (&E -> ctl);
 	E -> groups = h -> p. L > 100 ? 8 : 5;
 	if (const char *g = getenv ("DABGPU_GROUPS")) { const int v = atoi (g); if (v >= 1 && v <= MAX_GROUPS) { E -> groups = v; E -> groups_fixed = true; } }   // tuning knob (A/B runs)
 	CUDA_TRY (h, E -> d_figkeys. ensure (128 * sizeof (unsigned long long)));
 	CUDA_TRY (h, cudaMemsetAsync (E -> d_figkeys. p, 0, 128 * sizeof (unsigned long long), h -> stream));
 	CUDA_TRY (h, cudaStreamCreateWithFlags (&E -> copy_st, cudaStreamNonBlocking));
-	const int big = 100 * 1024;
-	CUDA_TRY (h, cudaFuncSetAttribute (front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-	CUDA_TRY (h, cudaFuncSetAttribute (symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-	CUDA_TRY (h, cudaFuncSetAttribute (scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (ScanSmem)));
-	CUDA_TRY (h, cudaFuncSetAttribute (symbol_kernel_r8, cudaFuncAttributeMaxDynamicSharedMemorySize, R8_DYN_SMEM));
-	CUDA_TRY (h, cudaFuncSetAttribute (front_kernel_r8, cudaFuncAttributeMaxDynamicSharedMemorySize, FRONT_R8_SMEM));
+	if ((rc = sync_init (h))) return rc;
+	if ((rc = symbol_init (h))) return rc;
 	return DABGPU_OK;
 }
 
@@ -782,11 +52,14 @@ void dab_engine_free (dabgpu *h) {
 	if (E -> d_phaseRef) cudaFree (E -> d_phaseRef);
 	if (E -> copy_st) { cudaStreamSynchronize (E -> copy_st); cudaStreamDestroy (E -> copy_st); }
 	for (auto e : E -> copy_events) cudaEventDestroy (e);
-	E -> tail. release (); E -> tail_spare. release (); E -> d_ctl. release (); E -> h_ctl. release ();
+	E -> tail. release (); E -> tail_spare. release (); E -> d_sd. release (); E -> h_sd. release ();
 	E -> d_frameout. release (); E -> d_framein. release (); E -> d_fcpart. release (); E -> d_spec0. release (); E -> d_info. release ();
-	E -> d_fic. release (); E -> d_msc. release (); E -> d_histtmp. release (); E -> d_fic8. release (); E -> d_msc8. release ();
+	E -> d_soft16. release (); E -> d_hist8. release (); E -> d_fic8. release (); E -> d_msc8. release ();
 	E -> d_ficbits. release (); E -> d_ficcrc. release (); E -> d_figkeys. release ();
 	for (auto &b : E -> d_mscbits) b. release ();
+	E -> m_in. release (); E -> m_fic8. release (); E -> m_msc8. release (); E -> m_info. release ();
+	E -> m_ficbits. release (); E -> m_ficcrc. release (); E -> m_mscbits. release ();
+	E -> mh_in. release (); E -> mh_out. release ();
 	delete E;
 	h -> engine = nullptr;
 }
@@ -845,9 +118,10 @@ extern "C" int dabgpu_state_set (dabgpu_t *h, const dabgpu_stream_state *s) {
 	Engine *E = h -> engine;
 	E -> ctl. synced = s -> synced; E -> ctl. coarse = s -> coarse; E -> ctl. fine = s -> fine;
 	E -> ctl. f2 = s -> f2Correction; E -> ctl. prev1 = s -> previous_1; E -> ctl. prev2 = s -> previous_2;
-	E -> ctl. lp = s -> localPhase;
+	E -> ctl. lp = s -> localPhase; E -> ctl. fault = 0;
 	E -> tail_len = 0; E -> ctl. pos = 0; E -> abs_base = s -> abs_pos;      // the next input starts at abs_pos
 	E -> frames_total = s -> frames; E -> cifs_total = s -> cifs;
+	E -> needs_reset = false;
 	return DABGPU_OK;
 }
 
@@ -868,7 +142,15 @@ extern "C" int dabgpu_host_state_predict (int32_t mode, const dabgpu_stream_stat
 	return DABGPU_OK;
 }
 
-static int ensure_frame_capacity (dabgpu *h, long long frames);
+// the time de-interleaver's 15 history rows (dab-concurrent.cpp:70-74: zero soft bits = erasures = byte symbol 127)
+static int ensure_history (dabgpu *h) {
+	Engine *E = h -> engine;
+	if (E -> hist_init && E -> d_hist8. p) return DABGPU_OK;
+	CUDA_TRY (h, E -> d_hist8. ensure ((size_t) 15 * CIF_BITS));
+	CUDA_TRY (h, cudaMemsetAsync (E -> d_hist8. p, 127, (size_t) 15 * CIF_BITS, h -> stream));
+	E -> hist_init = true;
+	return DABGPU_OK;
+}
 
 // ---- whole stream state as one blob (the multi-GPU hand-over: sync/AFC state + unconsumed samples + the
 // 15-CIF soft-bit halo of the time de-interleaver + per-sub-channel warm-up counters) ----
@@ -876,12 +158,12 @@ struct StateBlobHeader {
 	uint32_t magic; int32_t mode, nsub, hist_valid, cf32, pad;
 	StreamCtl ctl; long long abs_base, frames_total, cifs_total, tail_len;
 };
-#define STATE_MAGIC 0x44414247u
+#define STATE_MAGIC 0x44414238u                              // "DAB8": the halo travels as byte symbols
 
 extern "C" int dabgpu_state_export (dabgpu_t *h, void *buf, size_t capacity, size_t *used) {
 	if (!h || !used) return DABGPU_ERR_ARG;
 	Engine *E = h -> engine;
-	const size_t rowb = (size_t) CIF_BITS * sizeof (int16_t);
+	const size_t rowb = (size_t) CIF_BITS;
 	const size_t need = sizeof (StateBlobHeader) + E -> backends. size () * sizeof (int64_t) + (size_t) E -> tail_len * E -> sample_bytes () + 15 * rowb;
 	*used = need;
 	if (!buf) return DABGPU_OK;
@@ -896,8 +178,8 @@ extern "C" int dabgpu_state_export (dabgpu_t *h, void *buf, size_t capacity, siz
 	for (auto *b : E -> backends) { int64_t c = dab_backend_cifs_seen (b); memcpy (q, &c, sizeof (c)); q += sizeof (c); }
 	if (E -> tail_len) CUDA_TRY (h, cudaMemcpyAsync (q, E -> tail. p, (size_t) E -> tail_len * E -> sample_bytes (), cudaMemcpyDeviceToHost, h -> stream));
 	q += (size_t) E -> tail_len * E -> sample_bytes ();
-	if (E -> hist_init) CUDA_TRY (h, cudaMemcpyAsync (q, E -> d_msc. p, 15 * rowb, cudaMemcpyDeviceToHost, h -> stream));
-	else memset (q, 0, 15 * rowb);
+	if (E -> hist_init) CUDA_TRY (h, cudaMemcpyAsync (q, E -> d_hist8. p, 15 * rowb, cudaMemcpyDeviceToHost, h -> stream));
+	else memset (q, 127, 15 * rowb);
 	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
 	return DABGPU_OK;
 }
@@ -907,16 +189,15 @@ extern "C" int dabgpu_state_import (dabgpu_t *h, const void *buf, size_t n) {
 	Engine *E = h -> engine;
 	StateBlobHeader hd;
 	memcpy (&hd, buf, sizeof (hd));
-	const size_t rowb = (size_t) CIF_BITS * sizeof (int16_t);
-	if (hd. magic != STATE_MAGIC || hd. mode != h -> p. dabMode || hd. nsub != (int32_t) E -> backends. size () || hd. tail_len < 0 ||
-	    n != sizeof (hd) + (size_t) hd. nsub * sizeof (int64_t) + (size_t) hd. tail_len * dab_sample_bytes (hd. cf32) + 15 * rowb || hd. cf32 < 0 || hd. cf32 > 2)
+	const size_t rowb = (size_t) CIF_BITS;
+	if (hd. magic != STATE_MAGIC || hd. mode != h -> p. dabMode || hd. nsub != (int32_t) E -> backends. size () || hd. tail_len < 0 || hd. cf32 < 0 || hd. cf32 > 2 ||
+	    n != sizeof (hd) + (size_t) hd. nsub * sizeof (int64_t) + (size_t) hd. tail_len * dab_sample_bytes (hd. cf32) + 15 * rowb)
 		return dab_fail (h, DABGPU_ERR_ARG, "state blob does not match this handle (mode / sub-channel count / size)");
 	CUDA_TRY (h, cudaSetDevice (h -> device));
-	int rc = ensure_frame_capacity (h, 1);
-	if (rc) return rc;
 	const char *q = (const char *) buf + sizeof (hd);
 	for (auto *b : E -> backends) { int64_t c; memcpy (&c, q, sizeof (c)); q += sizeof (c); dab_backend_set_cifs_seen (b, c); }
-	E -> ctl = hd. ctl; E -> abs_base = hd. abs_base; E -> frames_total = hd. frames_total; E -> cifs_total = hd. cifs_total;
+	E -> ctl = hd. ctl; E -> ctl. fault = 0;
+	E -> abs_base = hd. abs_base; E -> frames_total = hd. frames_total; E -> cifs_total = hd. cifs_total;
 	E -> tail_len = hd. tail_len;
 	E -> cf32 = hd. cf32;
 	if (hd. tail_len) {
@@ -924,99 +205,173 @@ extern "C" int dabgpu_state_import (dabgpu_t *h, const void *buf, size_t n) {
 		CUDA_TRY (h, cudaMemcpyAsync (E -> tail. p, q, (size_t) hd. tail_len * E -> sample_bytes (), cudaMemcpyHostToDevice, h -> stream));
 	}
 	q += (size_t) hd. tail_len * E -> sample_bytes ();
-	CUDA_TRY (h, cudaMemcpyAsync (E -> d_msc. p, q, 15 * rowb, cudaMemcpyHostToDevice, h -> stream));
+	CUDA_TRY (h, E -> d_hist8. ensure (15 * rowb));
+	CUDA_TRY (h, cudaMemcpyAsync (E -> d_hist8. p, q, 15 * rowb, cudaMemcpyHostToDevice, h -> stream));
 	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
 	E -> hist_init = true;
+	E -> needs_reset = false;
 	return DABGPU_OK;
 }
 
 static int ensure_frame_capacity (dabgpu *h, long long frames) {
 	Engine *E = h -> engine;
 	const DabParams &p = h -> p;
+	if (frames < 1) frames = 1;
 	if (frames <= E -> cap_frames) return DABGPU_OK;
 	const long long cap = frames + frames / 8 + 4;
-	// the MSC row buffer carries 15 CIFs of history in front: preserve them across a re-allocation
-	DevBuf nmsc;
-	const size_t rowb = (size_t) CIF_BITS * sizeof (int16_t);
-	CUDA_TRY (h, nmsc. ensure ((15 + (size_t) cap * p. cifsPerFrame) * rowb));
-	if (E -> d_msc. p && E -> hist_init)
-		CUDA_TRY (h, cudaMemcpyAsync (nmsc. p, E -> d_msc. p, 15 * rowb, cudaMemcpyDeviceToDevice, h -> stream));
-	else
-		CUDA_TRY (h, cudaMemsetAsync (nmsc. p, 0, 15 * rowb, h -> stream));
-	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
-	E -> d_msc. release ();
-	E -> d_msc = nmsc;
-	E -> hist_init = true;
-	CUDA_TRY (h, E -> d_fic. ensure ((size_t) cap * 3 * 2 * p. K * sizeof (int16_t)));
 	CUDA_TRY (h, E -> d_fic8. ensure ((size_t) cap * 3 * 2 * p. K + 16));
 	CUDA_TRY (h, E -> d_msc8. ensure ((15 + (size_t) cap * p. cifsPerFrame) * CIF_BITS + 16));
 	CUDA_TRY (h, E -> d_info. ensure ((size_t) cap * sizeof (dabgpu_frame_info)));
-	CUDA_TRY (h, E -> d_histtmp. ensure (15 * rowb));
 	E -> cap_frames = cap;
 	return DABGPU_OK;
 }
 
-// channel decoding (FIC + every configured sub-channel) of the frames [f0, f0 + nv) just accepted by the OFDM part,
-// queued on a side stream so that it overlaps the OFDM work of the next chunk; results are copied to the caller's
-// buffers on the same stream
-static int channel_chunk (dabgpu *h, int f0, int nv, dabgpu_result *out, std::vector<int> &nblk) {
+// ---------------------------------------------------------------------------------------------------
+// one round of the OFDM part over an array of streams
+// ---------------------------------------------------------------------------------------------------
+static int ensure_round_bufs (dabgpu *h, int nstreams, int nslots, ChunkBufs *cb) {
 	Engine *E = h -> engine;
 	const DabParams &p = h -> p;
-	const int ngroups = nv * p. ficGroups, g0 = f0 * p. ficGroups, ncif = nv * p. cifsPerFrame, r0 = f0 * p. cifsPerFrame;
-	if (nv <= 0) return DABGPU_OK;
+	if (nslots < 1) nslots = 1;
+	CUDA_TRY (h, E -> d_frameout. ensure ((size_t) nslots * sizeof (FrameOut)));
+	CUDA_TRY (h, E -> d_framein. ensure ((size_t) nslots * sizeof (FrameIn)));
+	CUDA_TRY (h, E -> d_fcpart. ensure ((size_t) nslots * MAX_GROUPS * sizeof (float2)));
+	CUDA_TRY (h, E -> d_spec0. ensure ((size_t) nslots * p. T_u * sizeof (float2)));
+	CUDA_TRY (h, E -> d_sd. ensure ((size_t) nstreams * sizeof (StreamDev)));
+	CUDA_TRY (h, E -> h_sd. ensure ((size_t) nstreams * sizeof (StreamDev)));
+	cb -> fin = (FrameIn *) E -> d_framein. p; cb -> fo = (FrameOut *) E -> d_frameout. p;
+	cb -> spec0 = (float2 *) E -> d_spec0. p; cb -> fcpart = (float2 *) E -> d_fcpart. p;
+	return DABGPU_OK;
+}
+
+// Runs the streams in the pinned table h_sd through one round on the handle's main stream and brings the table back:
+// [acquire] -> predict -> front, symbol, scan (derive) -> front, symbol, scan (verify).  On return every StreamDev::ctl holds
+// the committed state (ctl.n_valid frames accepted from the stream's chunk, ctl.n_redo of them after a recomputation) and
+// StreamDev::nframes the frames the round actually attempted.
+static int run_round (dabgpu *h, int nstreams, int nslots, int max_budget, bool any_acquire, int fmt, const ChunkBufs &cb) {
+	Engine *E = h -> engine;
+	cudaStream_t st = h -> stream;
+	StreamDev *hsd = (StreamDev *) E -> h_sd. p, *dsd = (StreamDev *) E -> d_sd. p;
+	CUDA_TRY (h, cudaMemcpyAsync (dsd, hsd, (size_t) nstreams * sizeof (StreamDev), cudaMemcpyHostToDevice, st));
+	if (any_acquire) acquire_launch (h, dsd, nstreams, st);
+	predict_launch (h, dsd, nstreams, cb, st);
+	// symbol groups (CTAs) per frame: every group first recomputes the spectrum of the symbol before its own as phase
+	// reference, so few groups mean less redundant work and many groups more CTAs.  A big round fills the GPU anyway
+	// (A/B on B200, 1024 frames: 5 groups 0.849 ms, 3 groups 0.828 ms, 1-2 groups the same)
+	const int groups = !E -> groups_fixed && nslots >= 128 && E -> groups > 3 ? 3 : E -> groups;
+	const int which = h -> cfg. reserved [0] ? 1 : 0;        // reserved[0] = 1: generic kernels (A/B testing)
+	for (int pass = 0; pass < 2; pass ++) {
+		// pass 0: speculative inputs, then the optimistic replay (derive); pass 1: recompute what changed, then verify
+		front_launch (h, dsd, nslots, cb, which, st);
+		symbol_launch (h, dsd, nslots, groups, cb, which, fmt, st);
+		scan_launch (h, dsd, nstreams, max_budget, groups, cb, pass == 0 ? 1 : 0, st);
+	}
+	CUDA_TRY (h, cudaGetLastError ());
+	CUDA_TRY (h, cudaMemcpyAsync (hsd, dsd, (size_t) nstreams * sizeof (StreamDev), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY (h, cudaStreamSynchronize (st));
+	for (int i = 0; i < nstreams; i ++)
+		if (hsd [i]. ctl. fault)
+			return dab_fail (h, DABGPU_ERR_CUDA, "symbol kernel gave up on stream %d (%s)", i,
+			                 hsd [i]. ctl. fault & 2 ? "a bulk copy of raw samples never arrived" : "shared-memory layout contract violated");
+	return DABGPU_OK;
+}
+
+// chunk policy: grow while the speculation holds outright; a chunk that needed recomputation (correctors still
+// moving) or was cut short shrinks, so a converging loop costs little and a locked one runs in one pass
+static int next_chunk (int chunk, int attempted, const StreamCtl &c, int cap) {
+	if (c. n_valid == attempted && c. n_redo == 0) chunk *= 2;
+	else if (c. n_valid == attempted) chunk = chunk > 16 ? chunk / 2 : (chunk < 8 ? chunk * 2 : chunk);
+	else chunk = chunk > 2 ? chunk / 2 : 1;
+	return chunk > cap ? cap : (chunk < 1 ? 1 : chunk);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// channel decoding (FIC + every configured sub-channel) of frames just accepted by the OFDM part
+// ---------------------------------------------------------------------------------------------------
+struct ChanPart {                                           // frames [f0, f0 + nv) of one stream
+	const uint8_t *fic8, *msc8;                             // the stream's soft-bit planes (frame slot 0 / history row 0)
+	int f0, nv;
+	int64_t cifs_before;                                    // CIFs of the stream decoded before frame f0 (warm-up, dab-concurrent.cpp:172-175)
+	uint8_t *ficbits, *ficcrc;                              // device outputs of the stream: [groups][768], [groups][3]
+	uint8_t **mscbits;                                      // [nsub] device outputs of the stream
+	int *nblk;                                              // [nsub] blocks written so far per sub-channel (updated)
+	dabgpu_result *out;                                     // host result buffers of the stream
+	unsigned long long fib0;                                // global number of the stream's first FIB in this part (FIG scan order), ~0 = no scan
+};
+
+// queued on a side stream so that it overlaps the OFDM work of the next chunk; results are copied to the callers'
+// buffers on the same stream.  All parts go through ONE launch pair of the throughput kernels when that path is taken.
+static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts) {
+	Engine *E = h -> engine;
+	const DabParams &p = h -> p;
+	const size_t nsub = E -> backends. size ();
+	long long ncw = 0, ncif_all = 0;
+	for (auto &q : parts) { ncw += (long long) q. nv * p. ficGroups + (long long) q. nv * p. cifsPerFrame * (long long) nsub; ncif_all += (long long) q. nv * p. cifsPerFrame; }
+	if (ncw == 0) return DABGPU_OK;
 	h -> cur = 1 + (E -> vrr ++ % 3);
 	cudaStream_t st = h -> vst ();
 	int rc = DABGPU_OK;
 	// the throughput kernels take every job of the chunk in ONE launch pair; the warp-cooperative kernel is launched once per
 	// sub-channel, 0.3 ms each however few code words there are -- so with two or more sub-channels the throughput path wins
 	// even for a single frame (measured: 9 sub-channels, 1-32 frames per call: 2.9 ms against 0.6 ms)
-	const bool simd = dab_use_simd (h, (long long) ngroups + (long long) ncif * (long long) E -> backends. size ()) ||
-	                  (h -> cfg. viterbi_path == 0 && E -> backends. size () >= 2 && ncif > 0);
+	const bool simd = dab_use_simd (h, ncw) || (h -> cfg. viterbi_path == 0 && (nsub >= 2 || parts. size () >= 2) && ncif_all > 0);
 	std::vector<VitSimdJob> jobs;
-	uint8_t *ficbits = (uint8_t *) E -> d_ficbits. p + (size_t) g0 * 768, *ficcrc = (uint8_t *) E -> d_ficcrc. p + (size_t) g0 * 3;
+	std::vector<std::vector<int>> n_here (parts. size (), std::vector<int> (nsub, 0));
 	do {
-		if (ngroups > 0) {
-			const int16_t *soft = (const int16_t *) E -> d_fic. p + (size_t) f0 * 3 * 2 * p. K;
-			if (simd) {
-				jobs. emplace_back ();
-				if ((rc = dab_fic_simd_job (h, soft, 2304, ngroups, ficbits, &jobs. back ()))) break;
-				jobs. back (). sym8 = (uint8_t *) E -> d_fic8. p + (size_t) f0 * 3 * 2 * p. K;   // written by the symbol kernel
-				jobs. back (). stride8 = 2304;
-			} else if ((rc = dab_fic_decode_dev (h, soft, 2304, ngroups, ficbits, ficcrc))) break;
-		}
-		std::vector<int> n_here (E -> backends. size (), 0);
-		for (size_t i = 0; i < E -> backends. size () && ncif > 0; i ++) {
-			const dabgpu_subch &sc = E -> subch [i];
-			VitSimdJob job;
-			uint8_t *dst = (uint8_t *) E -> d_mscbits [i]. p + (size_t) nblk [i] * 24 * sc. bitRate;
-			if ((rc = dab_backend_run_dev (E -> backends [i], (const int16_t *) E -> d_msc. p + (size_t) sc. startAddr * 64, CIF_BITS, r0, ncif,
-			                               dst, &n_here [i], simd ? &job : nullptr))) break;
-			if (simd && n_here [i] > 0) {
-				job. sym8 = (uint8_t *) E -> d_msc8. p + (size_t) (job. first_row - 15) * CIF_BITS + (size_t) sc. startAddr * 64;
-				job. stride8 = CIF_BITS;
-				jobs. push_back (job);
+		for (size_t k = 0; k < parts. size () && !rc; k ++) {
+			ChanPart &q = parts [k];
+			const int ngroups = q. nv * p. ficGroups, g0 = q. f0 * p. ficGroups, ncif = q. nv * p. cifsPerFrame, r0 = q. f0 * p. cifsPerFrame;
+			if (ngroups > 0) {
+				const uint8_t *soft8 = q. fic8 + (size_t) q. f0 * 3 * 2 * p. K;
+				if (simd) {
+					jobs. emplace_back ();
+					if ((rc = dab_fic_simd_job (h, nullptr, 2304, ngroups, q. ficbits + (size_t) g0 * 768, &jobs. back ()))) break;
+					jobs. back (). sym8 = const_cast<uint8_t *> (soft8);      // written by the symbol kernel
+					jobs. back (). stride8 = 2304;
+				} else if ((rc = dab_fic_decode_dev (h, nullptr, soft8, 2304, ngroups, q. ficbits + (size_t) g0 * 768, q. ficcrc + (size_t) g0 * 3))) break;
 			}
-			dab_backend_note_cifs (E -> backends [i], ncif);
+			for (size_t i = 0; i < nsub && ncif > 0; i ++) {
+				const dabgpu_subch &sc = E -> subch [i];
+				VitSimdJob job;
+				uint8_t *dst = q. mscbits [i] + (size_t) q. nblk [i] * 24 * sc. bitRate;
+				if ((rc = dab_backend_run_dev (E -> backends [i], nullptr, q. msc8 + (size_t) sc. startAddr * 64, CIF_BITS, r0, ncif,
+				                               dst, &n_here [k] [i], simd ? &job : nullptr, q. cifs_before))) break;
+				if (simd && n_here [k] [i] > 0) {
+					job. sym8 = const_cast<uint8_t *> (q. msc8) + (size_t) (job. first_row - 15) * CIF_BITS + (size_t) sc. startAddr * 64;
+					job. stride8 = CIF_BITS;
+					jobs. push_back (job);
+				}
+			}
 		}
 		if (rc) break;
 		if (simd) {
 			if ((rc = dab_vit_simd_run (h, jobs))) break;
-			if (ngroups > 0) { cudaError_t e = fib_crc_launch (h, ficbits, 3 * ngroups, ficcrc); if (e != cudaSuccess) { rc = dab_fail (h, DABGPU_ERR_CUDA, "crc launch: %s", cudaGetErrorString (e)); break; } }
-		}
-		if (ngroups > 0) {                                   // FIG 0/1 of the FIBs just checked (fib-processor.cpp:278-347)
-			cudaError_t fe = fig01_launch (h, ficbits, ficcrc, 3 * ngroups, (unsigned long long) (E -> frames_total * p. ficGroups + g0) * 3ull,
-			                               (unsigned long long *) E -> d_figkeys. p, st);
-			if (fe != cudaSuccess) { rc = dab_fail (h, DABGPU_ERR_CUDA, "fig scan launch: %s", cudaGetErrorString (fe)); break; }
+			for (auto &q : parts) {
+				const int ngroups = q. nv * p. ficGroups, g0 = q. f0 * p. ficGroups;
+				if (ngroups <= 0) continue;
+				cudaError_t e = fib_crc_launch (h, q. ficbits + (size_t) g0 * 768, 3 * ngroups, q. ficcrc + (size_t) g0 * 3);
+				if (e != cudaSuccess) { rc = dab_fail (h, DABGPU_ERR_CUDA, "crc launch: %s", cudaGetErrorString (e)); break; }
+			}
+			if (rc) break;
 		}
 		cudaError_t e = cudaSuccess;
-		if (ngroups > 0 && out -> fic_bits) e = cudaMemcpyAsync (out -> fic_bits + (size_t) g0 * 768, ficbits, (size_t) ngroups * 768, cudaMemcpyDeviceToHost, st);
-		if (e == cudaSuccess && ngroups > 0 && out -> fic_crc) e = cudaMemcpyAsync (out -> fic_crc + (size_t) g0 * 3, ficcrc, (size_t) ngroups * 3, cudaMemcpyDeviceToHost, st);
-		for (size_t i = 0; i < E -> backends. size () && e == cudaSuccess; i ++) {
-			const size_t fb = (size_t) 24 * E -> subch [i]. bitRate;
-			if (out -> msc_bits && out -> msc_bits [i] && n_here [i] > 0)
-				e = cudaMemcpyAsync (out -> msc_bits [i] + (size_t) nblk [i] * fb, (uint8_t *) E -> d_mscbits [i]. p + (size_t) nblk [i] * fb,
-				                     (size_t) n_here [i] * fb, cudaMemcpyDeviceToHost, st);
-			nblk [i] += n_here [i];
+		for (size_t k = 0; k < parts. size () && e == cudaSuccess; k ++) {
+			ChanPart &q = parts [k];
+			const int ngroups = q. nv * p. ficGroups, g0 = q. f0 * p. ficGroups;
+			uint8_t *fb = q. ficbits + (size_t) g0 * 768, *fc = q. ficcrc + (size_t) g0 * 3;
+			if (ngroups > 0 && q. fib0 != ~0ull) {                  // FIG 0/1 of the FIBs just checked (fib-processor.cpp:278-347)
+				e = fig01_launch (h, fb, fc, 3 * ngroups, q. fib0, (unsigned long long *) E -> d_figkeys. p, st);
+				if (e != cudaSuccess) break;
+			}
+			if (ngroups > 0 && q. out -> fic_bits) e = cudaMemcpyAsync (q. out -> fic_bits + (size_t) g0 * 768, fb, (size_t) ngroups * 768, cudaMemcpyDeviceToHost, st);
+			if (e == cudaSuccess && ngroups > 0 && q. out -> fic_crc) e = cudaMemcpyAsync (q. out -> fic_crc + (size_t) g0 * 3, fc, (size_t) ngroups * 3, cudaMemcpyDeviceToHost, st);
+			for (size_t i = 0; i < nsub && e == cudaSuccess; i ++) {
+				const size_t fbytes = (size_t) 24 * E -> subch [i]. bitRate;
+				if (q. out -> msc_bits && q. out -> msc_bits [i] && n_here [k] [i] > 0)
+					e = cudaMemcpyAsync (q. out -> msc_bits [i] + (size_t) q. nblk [i] * fbytes, q. mscbits [i] + (size_t) q. nblk [i] * fbytes,
+					                     (size_t) n_here [k] [i] * fbytes, cudaMemcpyDeviceToHost, st);
+				q. nblk [i] += n_here [k] [i];
+			}
 		}
 		if (e != cudaSuccess) rc = dab_fail (h, DABGPU_ERR_CUDA, "result copy: %s", cudaGetErrorString (e));
 	} while (0);
@@ -1024,17 +379,17 @@ static int channel_chunk (dabgpu *h, int f0, int nv, dabgpu_result *out, std::ve
 	return rc;
 }
 
+// ---------------------------------------------------------------------------------------------------
 // decode core on a device-resident input segment.  `ready` (optional): events of the piecewise host-to-device copy
 // of the input; piece k covers new-segment samples [k * piece, (k+1) * piece).
-static int decode_core (dabgpu *h, const void *d_new_v, long long nnew, dabgpu_result *out,
-                        const std::vector<cudaEvent_t> *ready = nullptr, long long piece = 0, int vit_batch_frames = 0x7fffffff) {
+// ---------------------------------------------------------------------------------------------------
+static int decode_core_inner (dabgpu *h, const void *d_new_v, long long nnew, dabgpu_result *out,
+                              const std::vector<cudaEvent_t> *ready, long long piece, int vit_batch_frames) {
 	Engine *E = h -> engine;
 	const DabParams &p = h -> p;
-	if (p. dabMode == 3)
-		return dab_fail (h, DABGPU_ERR_ARG, "stream decode is not available for Mode III (the reference has no Mode III framing either)");
 	const uchar2 *d_new = (const uchar2 *) d_new_v;
 	const size_t sb = E -> sample_bytes ();
-	SampleWin w { (const uchar2 *) E -> tail. p, E -> tail_len, d_new, nnew, E -> cf32 };
+	const SampleWin w { (const uchar2 *) E -> tail. p, E -> tail_len, d_new, nnew, E -> cf32 };
 	const long long total = E -> tail_len + nnew;
 	const long long frame_need = 2ll * p. T_u + (long long) (p. L - 1) * p. T_s + p. T_null;   // worst case from P
 	const long long max_frames_possible = total / p. T_F + 2;
@@ -1042,130 +397,104 @@ static int decode_core (dabgpu *h, const void *d_new_v, long long nnew, dabgpu_r
 	if (want < 0) want = 0;
 	int rc = ensure_frame_capacity (h, want);
 	if (rc) return rc;
-	CUDA_TRY (h, E -> d_frameout. ensure ((size_t) E -> max_chunk * sizeof (FrameOut)));
-	CUDA_TRY (h, E -> d_framein. ensure ((size_t) E -> max_chunk * sizeof (FrameIn)));
-	CUDA_TRY (h, E -> d_fcpart. ensure ((size_t) E -> max_chunk * MAX_GROUPS * sizeof (float2)));
-	CUDA_TRY (h, E -> d_spec0. ensure ((size_t) E -> max_chunk * p. T_u * sizeof (float2)));
+	if ((rc = ensure_history (h))) return rc;
+	ChunkBufs cb;
+	if ((rc = ensure_round_bufs (h, 1, E -> max_chunk, &cb))) return rc;
 	// result buffers on the device for the whole call (side streams write into them chunk by chunk)
 	for (int i = 1; i < 4; i ++) CUDA_TRY (h, cudaStreamSynchronize (h -> vctx [i]. st));
 	CUDA_TRY (h, E -> d_ficbits. ensure ((size_t) (want * p. ficGroups + 1) * 768));
 	CUDA_TRY (h, E -> d_ficcrc. ensure ((size_t) (want * p. ficGroups + 1) * 3));
-	for (size_t i = 0; i < E -> backends. size (); i ++)
+	std::vector<uint8_t *> mscbits (E -> backends. size ());
+	for (size_t i = 0; i < E -> backends. size (); i ++) {
 		CUDA_TRY (h, E -> d_mscbits [i]. ensure ((size_t) (want * p. cifsPerFrame + 1) * 24 * E -> subch [i]. bitRate));
-	// the 15 history rows of the time de-interleaver as byte symbols (whatever put them there: the previous call, a state
-	// import, a re-allocation)
-	soft_to_sym8_kernel<<<296, 256, 0, h -> stream>>> ((const int16_t *) E -> d_msc. p, (uint8_t *) E -> d_msc8. p, 15ll * CIF_BITS);
-	h -> launches ++;
+		mscbits [i] = (uint8_t *) E -> d_mscbits [i]. p;
+	}
+	// the 15 history rows of the time de-interleaver in front of this call's CIF rows
+	CUDA_TRY (h, cudaMemcpyAsync (E -> d_msc8. p, E -> d_hist8. p, (size_t) 15 * CIF_BITS, cudaMemcpyDeviceToDevice, h -> stream));
 	std::vector<int> nblk (E -> backends. size (), 0);
-	StreamCtl *hctl = (StreamCtl *) E -> h_ctl. p;
+	StreamDev *hsd = (StreamDev *) E -> h_sd. p;
 	int nframes = 0, decoded_upto = 0;
 	// host input arrives piecewise: smaller chunks let the first frames start before the last samples are up
 	// device-resident input with a channel-decoding batch given (dabgpu_config.reserved[1]): chunks no larger than the batch, so
 	// that the OFDM part of the next chunk overlaps the channel decoding of this one on the side streams
+	const bool piecewise = ready && !ready -> empty ();
 	const int dev_cap = !ready && vit_batch_frames < E -> max_chunk ? (vit_batch_frames > 16 ? vit_batch_frames : 16) : E -> max_chunk;
-	const int chunk_cap = ready && !ready -> empty () ? (E -> max_chunk < 128 ? E -> max_chunk : 128) : dev_cap;
+	const int chunk_cap = piecewise ? (E -> max_chunk < 128 ? E -> max_chunk : 128) : dev_cap;
 	long long waited = -1;                                   // input pieces [0, waited] are known to have arrived on the main stream
+	long long limit = piecewise ? E -> tail_len : total;     // window samples known to be resident
 	auto need_input = [&] (long long upto_window_pos) -> cudaError_t {      // samples before this window position must be resident
-		if (!ready || ready -> empty ()) return cudaSuccess;
+		if (!piecewise) return cudaSuccess;
 		long long rel = upto_window_pos - E -> tail_len;
 		if (rel <= 0) return cudaSuccess;
 		long long k = (rel - 1) / piece;
 		if (k >= (long long) ready -> size ()) k = (long long) ready -> size () - 1;
 		cudaError_t e = cudaSuccess;
 		if (k > waited) { e = cudaStreamWaitEvent (h -> stream, (*ready) [k], 0); waited = k; }    // copies are in order on one stream
+		limit = std::min (total, E -> tail_len + (waited + 1) * piece);
 		return e;
 	};
-	const size_t sm_front = 2 * (size_t) p. T_u * sizeof (float2), sm_sym = ((size_t) p. T_s + 2 * p. T_u) * sizeof (float2);
+	const int64_t cifs_seen0 = E -> backends. empty () ? 0 : dab_backend_cifs_seen (E -> backends [0]);
+	auto channel = [&] (int f0, int nv) -> int {
+		if (nv <= 0) return DABGPU_OK;
+		std::vector<ChanPart> parts (1);
+		ChanPart &q = parts [0];
+		q. fic8 = (const uint8_t *) E -> d_fic8. p; q. msc8 = (const uint8_t *) E -> d_msc8. p;
+		q. f0 = f0; q. nv = nv; q. cifs_before = cifs_seen0 + (int64_t) f0 * p. cifsPerFrame;
+		q. ficbits = (uint8_t *) E -> d_ficbits. p; q. ficcrc = (uint8_t *) E -> d_ficcrc. p;
+		q. mscbits = mscbits. data (); q. nblk = nblk. data (); q. out = out;
+		q. fib0 = (unsigned long long) ((E -> frames_total + f0) * p. ficGroups) * 3ull;
+		return channel_parts (h, parts);
+	};
 	while (nframes < want) {
-		if (!E -> ctl. synced) {
+		const bool acquiring = !E -> ctl. synced;
+		long long C;
+		if (acquiring) {
 			CUDA_TRY (h, need_input (total));                // the null search reads until it finds one
-			*hctl = E -> ctl;
-			CUDA_TRY (h, cudaMemcpyAsync (E -> d_ctl. p, hctl, sizeof (StreamCtl), cudaMemcpyHostToDevice, h -> stream));
-			{ ProfScope prof (h, KC_ACQUIRE);
-			acquire_kernel<<<1, 32, 0, h -> stream>>> (w, E -> T, p. T_F, p. T_null, (StreamCtl *) E -> d_ctl. p); }
-			h -> launches ++;
-			CUDA_TRY (h, cudaGetLastError ());
-			CUDA_TRY (h, cudaMemcpyAsync (hctl, E -> d_ctl. p, sizeof (StreamCtl), cudaMemcpyDeviceToHost, h -> stream));
-			CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
-			E -> ctl = *hctl;
-			if (!E -> ctl. synced) break;                   // ran out of samples inside the attempt
-			E -> chunk = 1;
+			E -> chunk = 1; C = 1;
+		} else {
+			if (total - E -> ctl. pos < frame_need) break;
+			const long long avail = (total - E -> ctl. pos - frame_need) / p. T_F + 1;
+			C = E -> chunk < chunk_cap ? E -> chunk : chunk_cap;
+			if (C > avail) C = avail;
+			if (C > want - nframes) C = want - nframes;
+			CUDA_TRY (h, need_input (E -> ctl. pos + (C - 1) * p. T_F + frame_need));
 		}
-		long long avail = (total - E -> ctl. pos - frame_need) / p. T_F + 1;
-		if (total - E -> ctl. pos < frame_need) avail = 0;
-		if (avail <= 0) break;
-		long long C = E -> chunk < chunk_cap ? E -> chunk : chunk_cap;
-		if (C > avail) C = avail;
-		if (C > want - nframes) C = want - nframes;
-		CUDA_TRY (h, need_input (E -> ctl. pos + (C - 1) * p. T_F + frame_need));
-		*hctl = E -> ctl;
-		CUDA_TRY (h, cudaMemcpyAsync (E -> d_ctl. p, hctl, sizeof (StreamCtl), cudaMemcpyHostToDevice, h -> stream));
-		StreamCtl *dctl = (StreamCtl *) E -> d_ctl. p;
-		FrameIn *fin = (FrameIn *) E -> d_framein. p;
-		FrameOut *fo = (FrameOut *) E -> d_frameout. p;
-		{ ProfScope prof (h, KC_SCAN);
-		predict_kernel<<<((int) C + 127) / 128, 128, 0, h -> stream>>> (dctl, fin, p. T_F, (int) C); }
-		// symbol groups (CTAs) per frame: every group first recomputes the spectrum of the symbol before its own as phase
-		// reference, so few groups mean less redundant work and many groups more CTAs.  A big chunk fills the GPU anyway
-		// (A/B on B200, 1024 frames: 5 groups 0.849 ms, 3 groups 0.828 ms, 1-2 groups the same)
-		const int groups = !E -> groups_fixed && C >= 128 && E -> groups > 3 ? 3 : E -> groups;
-		for (int pass = 0; pass < 2; pass ++) {
-			// pass 0: speculative inputs, then the optimistic replay (derive); pass 1: recompute what changed, then verify
-			{ ProfScope prof (h, KC_FRONT);
-			if (p. T_u == R8_N && p. K == 1536 && !E -> cf32 && !h -> cfg. reserved [0])
-				front_kernel_r8<<<(int) C, 256, FRONT_R8_SMEM, h -> stream>>> (w, E -> T, fin, fo, (float2 *) E -> d_spec0. p);
-			else
-				front_kernel<<<(int) C, OFDM_THREADS, sm_front, h -> stream>>> (w, E -> T, fin, fo, (float2 *) E -> d_spec0. p); }
-			{ ProfScope prof (h, KC_SYMBOL);
-			if (p. T_u == R8_N && p. K == 1536 && !E -> cf32 && !h -> cfg. reserved [0])     // reserved[0] = 1: generic kernel (A/B testing)
-				symbol_kernel_r8<<<(int) C * groups, 256, R8_DYN_SMEM, h -> stream>>> (w, E -> T, fin, nframes, groups, p. blocksPerCIF, p. cifsPerFrame,
-					fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p,
-					(uint8_t *) E -> d_fic8. p, (uint8_t *) E -> d_msc8. p);
-			else
-				symbol_kernel<<<(int) C * groups, OFDM_THREADS, sm_sym, h -> stream>>> (w, E -> T, fin, nframes, groups, p. blocksPerCIF, p. cifsPerFrame,
-					fo, (const float2 *) E -> d_spec0. p, (float2 *) E -> d_fcpart. p, (int16_t *) E -> d_fic. p, (int16_t *) E -> d_msc. p,
-					(uint8_t *) E -> d_fic8. p, (uint8_t *) E -> d_msc8. p); }
-			{ ProfScope prof (h, KC_SCAN);
-			scan_kernel<<<1, SCAN_THREADS, sizeof (ScanSmem), h -> stream>>> (dctl, fin, (int) C, nframes, groups, p, fo, (const float2 *) E -> d_fcpart. p,
-				(dabgpu_frame_info *) E -> d_info. p, E -> abs_base, pass == 0 ? 1 : 0); }
-		}
-		h -> launches += 7;
-		CUDA_TRY (h, cudaGetLastError ());
-		CUDA_TRY (h, cudaMemcpyAsync (hctl, E -> d_ctl. p, sizeof (StreamCtl), cudaMemcpyDeviceToHost, h -> stream));
-		CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
-		E -> ctl = *hctl;
+		StreamDev &S = hsd [0];
+		memset (&S, 0, sizeof (S));
+		S. w = w; S. ctl = E -> ctl; S. ctl. fault = 0;
+		S. fic8 = (uint8_t *) E -> d_fic8. p; S. msc8 = (uint8_t *) E -> d_msc8. p; S. info = (dabgpu_frame_info *) E -> d_info. p;
+		S. abs_base = E -> abs_base; S. limit = limit;
+		S. first = 0; S. budget = (int) C; S. nframes = 0; S. slot0 = nframes; S. do_acquire = acquiring;
+		if ((rc = run_round (h, 1, (int) C, (int) C, acquiring, E -> cf32, cb))) return rc;
+		E -> ctl = S. ctl;
+		if (acquiring && !E -> ctl. synced) break;           // ran out of samples inside the attempt
 		nframes += E -> ctl. n_valid;
 		// the accepted frames' soft bits are final: once enough of them have piled up to fill the GPU, decode them on a
 		// side stream while the OFDM part (and the input copy) of the following frames goes on
 		if (nframes - decoded_upto >= vit_batch_frames) {
-			if ((rc = channel_chunk (h, decoded_upto, nframes - decoded_upto, out, nblk))) return rc;
+			if ((rc = channel (decoded_upto, nframes - decoded_upto))) return rc;
 			decoded_upto = nframes;
 		}
-		// chunk policy: grow while the speculation holds outright; a chunk that needed recomputation (correctors still
-		// moving) or was cut short shrinks, so a converging loop costs little and a locked one runs in one pass
-		if (E -> ctl. n_valid == C && E -> ctl. n_redo == 0) { E -> chunk *= 2; if (E -> chunk > chunk_cap) E -> chunk = chunk_cap; }
-		else if (E -> ctl. n_valid == C) { E -> chunk = E -> chunk > 16 ? E -> chunk / 2 : (E -> chunk < 8 ? E -> chunk * 2 : E -> chunk); }
-		else { E -> chunk = E -> chunk > 2 ? E -> chunk / 2 : 1; }
+		if (S. nframes > 0) E -> chunk = next_chunk (E -> chunk, S. nframes, E -> ctl, chunk_cap);
+		else if (!acquiring) break;                          // nothing attempted: not enough resident samples for another frame
 	}
 	out -> nframes = nframes;
 	const int ncif = nframes * p. cifsPerFrame;
-	if ((rc = channel_chunk (h, decoded_upto, nframes - decoded_upto, out, nblk))) return rc;
+	if ((rc = channel (decoded_upto, nframes - decoded_upto))) return rc;
+	for (auto *b : E -> backends) dab_backend_note_cifs (b, ncif);
 	for (int i = 1; i < 4; i ++) CUDA_TRY (h, cudaStreamSynchronize (h -> vctx [i]. st));
 	for (size_t i = 0; i < E -> backends. size (); i ++)
 		if (out -> msc_nblocks) out -> msc_nblocks [i] = nblk [i];
 	if (nframes > 0) {
 		if (out -> info) CUDA_TRY (h, cudaMemcpyAsync (out -> info, E -> d_info. p, (size_t) nframes * sizeof (dabgpu_frame_info), cudaMemcpyDeviceToHost, h -> stream));
-		if (out -> soft) {
-			const size_t dpitch = (size_t) (p. L - 1) * 2 * p. K * sizeof (int16_t), fw = (size_t) 3 * 2 * p. K * sizeof (int16_t);
-			const size_t mw = (size_t) p. cifsPerFrame * CIF_BITS * sizeof (int16_t);
-			CUDA_TRY (h, cudaMemcpy2DAsync (out -> soft, dpitch, E -> d_fic. p, fw, fw, nframes, cudaMemcpyDeviceToHost, h -> stream));
-			CUDA_TRY (h, cudaMemcpy2DAsync ((char *) out -> soft + fw, dpitch, (const int16_t *) E -> d_msc. p + (size_t) 15 * CIF_BITS, mw, mw, nframes,
-			                                cudaMemcpyDeviceToHost, h -> stream));
+		if (out -> soft) {                                   // the int16 form of process_ficBlock / process_mscBlock, on demand
+			const size_t bytes = (size_t) nframes * (p. L - 1) * 2 * p. K * sizeof (int16_t);
+			CUDA_TRY (h, E -> d_soft16. ensure (bytes));
+			soft16_launch (h, (const uint8_t *) E -> d_fic8. p, (const uint8_t *) E -> d_msc8. p, (int16_t *) E -> d_soft16. p, nframes, h -> stream);
+			CUDA_TRY (h, cudaMemcpyAsync (out -> soft, E -> d_soft16. p, bytes, cudaMemcpyDeviceToHost, h -> stream));
 		}
-		// time de-interleaver history for the next call: the last 15 CIF rows move to the front
-		const size_t rowb = (size_t) CIF_BITS * sizeof (int16_t);
-		CUDA_TRY (h, cudaMemcpyAsync (E -> d_histtmp. p, (const char *) E -> d_msc. p + (size_t) ncif * rowb, 15 * rowb, cudaMemcpyDeviceToDevice, h -> stream));
-		CUDA_TRY (h, cudaMemcpyAsync (E -> d_msc. p, E -> d_histtmp. p, 15 * rowb, cudaMemcpyDeviceToDevice, h -> stream));
+		// time de-interleaver history for the next call: the last 15 CIF rows
+		CUDA_TRY (h, cudaMemcpyAsync (E -> d_hist8. p, (const char *) E -> d_msc8. p + (size_t) ncif * CIF_BITS, (size_t) 15 * CIF_BITS, cudaMemcpyDeviceToDevice, h -> stream));
 	}
 	// ---- keep the unconsumed samples for the next call ----
 	CUDA_TRY (h, need_input (total));
@@ -1189,6 +518,30 @@ static int decode_core (dabgpu *h, const void *d_new_v, long long nnew, dabgpu_r
 	E -> ctl. pos = 0;
 	E -> frames_total += nframes; E -> cifs_total += ncif;
 	return DABGPU_OK;
+}
+
+static int decode_core (dabgpu *h, const void *d_new, long long nnew, dabgpu_result *out,
+                        const std::vector<cudaEvent_t> *ready = nullptr, long long piece = 0, int vit_batch_frames = 0x7fffffff) {
+	Engine *E = h -> engine;
+	if (h -> p. dabMode == 3)
+		return dab_fail (h, DABGPU_ERR_ARG, "stream decode is not available for Mode III (the reference has no Mode III framing either)");
+	if (E -> needs_reset)
+		return dab_fail (h, DABGPU_ERR_STATE, "an earlier call on this handle failed half way: set the stream state (dabgpu_state_set / dabgpu_state_import) before decoding on");
+	const int rc = decode_core_inner (h, d_new, nnew, out, ready, piece, vit_batch_frames);
+	if (rc) {
+		// a call that fails half way leaves positions, tail and counters inconsistent with each other: quiesce every stream
+		// (nothing of this call may still be reading the caller's buffers) and refuse further decoding until the caller sets a state
+		const std::string msg = h -> err;
+		cudaStreamSynchronize (h -> stream);
+		for (int i = 1; i < 4; i ++) cudaStreamSynchronize (h -> vctx [i]. st);
+		if (E -> copy_st) cudaStreamSynchronize (E -> copy_st);
+		cudaGetLastError ();
+		E -> tail_len = 0; E -> ctl. pos = 0; E -> ctl. synced = 0; E -> ctl. fault = 0;
+		E -> needs_reset = true;
+		h -> cur = 0;
+		h -> err = msg;
+	}
+	return rc;
 }
 
 // the sample format of a stream may only change while no unconsumed samples are pending
@@ -1230,20 +583,15 @@ extern "C" int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples
 extern "C" int dabgpu_decode_i16 (dabgpu_t *h, const int16_t *iq, size_t nsamples, dabgpu_result *out) { return decode_host (h, iq, nsamples, 2, out); }
 extern "C" int dabgpu_decode_cf32 (dabgpu_t *h, const float *iq, size_t nsamples, dabgpu_result *out) { return decode_host (h, iq, nsamples, 1, out); }
 
-static int decode_host (dabgpu *h, const void *iq_v, size_t nsamples, int cf32, dabgpu_result *out) {
-	const uint8_t *iq_u8 = (const uint8_t *) iq_v;
-	if (!h || !out || (nsamples > 0 && !iq_u8)) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_decode: bad argument");
-	CUDA_TRY (h, cudaSetDevice (h -> device));
+static int decode_host_inner (dabgpu *h, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out) {
 	Engine *E = h -> engine;
-	int frc = set_format (h, cf32);
-	if (frc) return frc;
 	const size_t sb = E -> sample_bytes ();
 	const size_t bytes = nsamples * sb;
 	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
 	CUDA_TRY (h, h -> d_in. ensure (bytes + 16));
 	// the input goes up in pieces on its own stream; every chunk of frames waits only for the pieces it reads, so
 	// the host-to-device copy overlaps the decode of the frames already there
-	const long long piece = 8ll << 20;                       // samples per piece (16 MB)
+	const long long piece = 8ll << 20;                       // samples per piece (16 MB of u8 IQ)
 	std::vector<cudaEvent_t> ready;
 	if (bytes) {
 		cudaPointerAttributes attr;
@@ -1270,8 +618,205 @@ static int decode_host (dabgpu *h, const void *iq_v, size_t nsamples, int cf32, 
 	}
 	// host input: the PCIe copy paces the call and the GPU idles most of the time, so channel decoding follows the
 	// OFDM part in small batches: what is left to do once the last sample has arrived is then short
-	int rc = decode_core (h, h -> d_in. p, (long long) nsamples, out, &ready, piece,
-	                      h -> cfg. host_batch_frames > 0 ? h -> cfg. host_batch_frames : E -> vit_batch_frames);
-	cudaStreamSynchronize (E -> copy_st);
+	return decode_core (h, h -> d_in. p, (long long) nsamples, out, &ready, piece,
+	                    h -> cfg. host_batch_frames > 0 ? h -> cfg. host_batch_frames : E -> vit_batch_frames);
+}
+
+static int decode_host (dabgpu *h, const void *iq_v, size_t nsamples, int cf32, dabgpu_result *out) {
+	if (!h || !out || (nsamples > 0 && !iq_v)) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_decode: bad argument");
+	CUDA_TRY (h, cudaSetDevice (h -> device));
+	int rc = set_format (h, cf32);
+	if (rc) return rc;
+	rc = decode_host_inner (h, (const uint8_t *) iq_v, nsamples, out);
+	cudaStreamSynchronize (h -> engine -> copy_st);          // on every path: the caller's buffer and h_in / d_in are free again when the call returns
 	return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dabgpu_decode_multi: n independent streams, each decoded as a fresh handle with this handle's configuration and
+// sub-channels would decode it in one call (acquisition from the first sample, coarse search on), all of them in
+// lockstep through the same kernel launches.  The handle's own stream state is not touched.
+// ---------------------------------------------------------------------------------------------------
+#define MULTI_SLOT_CAP 4096                                  // chunk slots of one round, all streams together
+
+struct MultiStream {
+	long long nsamples, in_off;                              // samples, byte offset of the stream's input in m_in
+	long long want;                                          // frames wanted at most
+	size_t fic_off, msc_off, info_off, ficbits_off, ficcrc_off;   // offsets of the stream's planes / outputs in the handle's multi buffers
+	std::vector<size_t> mscbits_off;
+	StreamCtl ctl;
+	int chunk, nframes, decoded_upto;
+	bool done;
+	std::vector<int> nblk;
+	std::vector<uint8_t *> mscbits;
+};
+
+static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstreams, int fmt, bool dev_input) {
+	Engine *E = h -> engine;
+	const DabParams &p = h -> p;
+	if (p. dabMode == 3)
+		return dab_fail (h, DABGPU_ERR_ARG, "stream decode is not available for Mode III (the reference has no Mode III framing either)");
+	const size_t sb = dab_sample_bytes (fmt), nsub = E -> backends. size ();
+	const long long frame_need = 2ll * p. T_u + (long long) (p. L - 1) * p. T_s + p. T_null;
+	const size_t ficw = (size_t) 3 * 2 * p. K, cifw = (size_t) CIF_BITS;
+	std::vector<MultiStream> ms (nstreams);
+	size_t in_bytes = 0, fic_bytes = 0, msc_bytes = 0, info_n = 0, ficbits_bytes = 0, ficcrc_bytes = 0, mscbits_bytes = 0;
+	auto up = [] (size_t v, size_t a) { return (v + a - 1) / a * a; };
+	for (int i = 0; i < nstreams; i ++) {
+		const dabgpu_stream_job &J = jobs [i];
+		if (!J. out || (J. nsamples > 0 && !J. iq)) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_decode_multi: stream %d: bad argument", i);
+		MultiStream &m = ms [i];
+		m. nsamples = (long long) J. nsamples;
+		const long long possible = m. nsamples / p. T_F + 2;
+		m. want = J. out -> max_frames < possible ? J. out -> max_frames : possible;
+		if (m. want < 0) m. want = 0;
+		const size_t cap = (size_t) (m. want < 1 ? 1 : m. want);
+		m. in_off = (long long) in_bytes;           in_bytes += up ((size_t) m. nsamples * sb + 16, 256);
+		m. fic_off = fic_bytes;                     fic_bytes += up (cap * ficw + 16, 256);
+		m. msc_off = msc_bytes;                     msc_bytes += up ((15 + cap * p. cifsPerFrame) * cifw + 16, 256);
+		m. info_off = info_n;                       info_n += cap;
+		m. ficbits_off = ficbits_bytes;             ficbits_bytes += up ((cap * p. ficGroups + 1) * 768, 256);
+		m. ficcrc_off = ficcrc_bytes;               ficcrc_bytes += up ((cap * p. ficGroups + 1) * 3, 256);
+		m. mscbits_off. resize (nsub);
+		for (size_t s = 0; s < nsub; s ++) { m. mscbits_off [s] = mscbits_bytes; mscbits_bytes += up ((cap * p. cifsPerFrame + 1) * 24 * (size_t) E -> subch [s]. bitRate, 256); }
+		ctl_fresh (&m. ctl);
+		m. chunk = 1; m. nframes = 0; m. decoded_upto = 0; m. done = m. want == 0;
+		m. nblk. assign (nsub, 0);
+		J. out -> nframes = 0; J. out -> consumed = 0;
+	}
+	for (int i = 1; i < 4; i ++) CUDA_TRY (h, cudaStreamSynchronize (h -> vctx [i]. st));
+	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+	if (!dev_input) CUDA_TRY (h, E -> m_in. ensure (in_bytes + 256));
+	CUDA_TRY (h, E -> m_fic8. ensure (fic_bytes + 256));
+	CUDA_TRY (h, E -> m_msc8. ensure (msc_bytes + 256));
+	CUDA_TRY (h, E -> m_info. ensure ((info_n + 1) * sizeof (dabgpu_frame_info)));
+	CUDA_TRY (h, E -> m_ficbits. ensure (ficbits_bytes + 256));
+	CUDA_TRY (h, E -> m_ficcrc. ensure (ficcrc_bytes + 256));
+	CUDA_TRY (h, E -> m_mscbits. ensure (mscbits_bytes + 256));
+	ChunkBufs cb;
+	int rc = ensure_round_bufs (h, nstreams, MULTI_SLOT_CAP, &cb);
+	if (rc) return rc;
+	// inputs: one copy per stream on the copy stream (pinned or pageable, as the caller has them); history rows = erasures
+	std::vector<const void *> d_in (nstreams);
+	for (int i = 0; i < nstreams; i ++) {
+		MultiStream &m = ms [i];
+		if (dev_input) d_in [i] = jobs [i]. iq;
+		else {
+			d_in [i] = (const char *) E -> m_in. p + m. in_off;
+			if (m. nsamples > 0)
+				CUDA_TRY (h, cudaMemcpyAsync ((void *) d_in [i], jobs [i]. iq, (size_t) m. nsamples * sb, cudaMemcpyHostToDevice, h -> stream));
+		}
+		CUDA_TRY (h, cudaMemsetAsync ((char *) E -> m_msc8. p + m. msc_off, 127, 15 * cifw, h -> stream));
+		m. mscbits. resize (nsub);
+		for (size_t s = 0; s < nsub; s ++) m. mscbits [s] = (uint8_t *) E -> m_mscbits. p + m. mscbits_off [s];
+	}
+	StreamDev *hsd = (StreamDev *) E -> h_sd. p;
+	// channel decoding of everything accepted since the last call, all streams in one launch pair
+	auto channel_all = [&] (bool final) -> int {
+		std::vector<ChanPart> parts;
+		long long pending = 0;
+		for (auto &m : ms) pending += m. nframes - m. decoded_upto;
+		if (pending == 0 || (!final && pending < 256)) return DABGPU_OK;
+		for (int i = 0; i < nstreams; i ++) {
+			MultiStream &m = ms [i];
+			if (m. nframes == m. decoded_upto) continue;
+			ChanPart q;
+			q. fic8 = (const uint8_t *) E -> m_fic8. p + m. fic_off; q. msc8 = (const uint8_t *) E -> m_msc8. p + m. msc_off;
+			q. f0 = m. decoded_upto; q. nv = m. nframes - m. decoded_upto; q. cifs_before = (int64_t) m. decoded_upto * p. cifsPerFrame;
+			q. ficbits = (uint8_t *) E -> m_ficbits. p + m. ficbits_off; q. ficcrc = (uint8_t *) E -> m_ficcrc. p + m. ficcrc_off;
+			q. mscbits = m. mscbits. data (); q. nblk = m. nblk. data (); q. out = jobs [i]. out; q. fib0 = ~0ull;
+			parts. push_back (q);
+			m. decoded_upto = m. nframes;
+		}
+		return channel_parts (h, parts);
+	};
+	while (true) {
+		int nslots = 0, max_budget = 0;
+		bool any = false, any_acquire = false;
+		for (int i = 0; i < nstreams; i ++) {
+			MultiStream &m = ms [i];
+			StreamDev &S = hsd [i];
+			memset (&S, 0, sizeof (S));
+			S. w = SampleWin { nullptr, 0, (const uchar2 *) d_in [i], m. nsamples, fmt };
+			S. ctl = m. ctl; S. ctl. fault = 0;
+			S. fic8 = (uint8_t *) E -> m_fic8. p + m. fic_off; S. msc8 = (uint8_t *) E -> m_msc8. p + m. msc_off;
+			S. info = (dabgpu_frame_info *) E -> m_info. p + m. info_off;
+			S. abs_base = 0; S. limit = m. nsamples; S. first = nslots; S. slot0 = m. nframes;
+			int C = 0;
+			if (!m. done) {
+				if (!m. ctl. synced) { S. do_acquire = 1; m. chunk = 1; C = 1; any_acquire = true; }
+				else if (m. nsamples - m. ctl. pos >= frame_need) {
+					const long long avail = (m. nsamples - m. ctl. pos - frame_need) / p. T_F + 1;
+					C = m. chunk < E -> max_chunk ? m. chunk : E -> max_chunk;
+					if (C > avail) C = (int) avail;
+					if (C > m. want - m. nframes) C = (int) (m. want - m. nframes);
+				}
+				if (C > MULTI_SLOT_CAP - nslots) C = MULTI_SLOT_CAP - nslots;    // (a stream left without slots waits a round)
+				if (C <= 0 && !(m. ctl. synced && m. nsamples - m. ctl. pos >= frame_need && m. nframes < m. want)) m. done = true;
+			}
+			S. budget = C > 0 ? C : 0;
+			if (S. budget == 0) S. do_acquire = 0;
+			nslots += S. budget;
+			if (S. budget > max_budget) max_budget = S. budget;
+			any = any || S. budget > 0;
+		}
+		if (!any) break;
+		if ((rc = run_round (h, nstreams, nslots, max_budget, any_acquire, fmt, cb))) return rc;
+		for (int i = 0; i < nstreams; i ++) {
+			MultiStream &m = ms [i];
+			const StreamDev &S = hsd [i];
+			if (S. budget == 0) continue;
+			const bool was_acquiring = S. do_acquire != 0;
+			m. ctl = S. ctl;
+			if (was_acquiring && !m. ctl. synced && m. ctl. n_valid == 0 && !m. ctl. lost) { m. done = true; continue; }    // out of samples inside the attempt
+			m. nframes += m. ctl. n_valid;
+			if (S. nframes > 0) m. chunk = next_chunk (m. chunk, S. nframes, m. ctl, E -> max_chunk);
+			else if (!was_acquiring) m. done = true;
+			if (m. nframes >= m. want) m. done = true;
+		}
+		if ((rc = channel_all (false))) return rc;
+	}
+	if ((rc = channel_all (true))) return rc;
+	for (int i = 1; i < 4; i ++) CUDA_TRY (h, cudaStreamSynchronize (h -> vctx [i]. st));
+	for (int i = 0; i < nstreams; i ++) {
+		MultiStream &m = ms [i];
+		dabgpu_result *out = jobs [i]. out;
+		out -> nframes = m. nframes;
+		out -> consumed = m. ctl. pos;
+		for (size_t s = 0; s < nsub; s ++) if (out -> msc_nblocks) out -> msc_nblocks [s] = m. nblk [s];
+		if (m. nframes > 0 && out -> info)
+			CUDA_TRY (h, cudaMemcpyAsync (out -> info, (dabgpu_frame_info *) E -> m_info. p + m. info_off, (size_t) m. nframes * sizeof (dabgpu_frame_info), cudaMemcpyDeviceToHost, h -> stream));
+		if (m. nframes > 0 && out -> soft) {
+			const size_t bytes = (size_t) m. nframes * (p. L - 1) * 2 * p. K * sizeof (int16_t);
+			CUDA_TRY (h, cudaStreamSynchronize (h -> stream));                  // d_soft16 is reused stream after stream
+			CUDA_TRY (h, E -> d_soft16. ensure (bytes));
+			soft16_launch (h, (const uint8_t *) E -> m_fic8. p + m. fic_off, (const uint8_t *) E -> m_msc8. p + m. msc_off, (int16_t *) E -> d_soft16. p, m. nframes, h -> stream);
+			CUDA_TRY (h, cudaMemcpyAsync (out -> soft, E -> d_soft16. p, bytes, cudaMemcpyDeviceToHost, h -> stream));
+		}
+	}
+	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+	return DABGPU_OK;
+}
+
+static int decode_multi (dabgpu *h, const dabgpu_stream_job *jobs, int32_t nstreams, int32_t fmt, bool dev_input) {
+	if (!h || nstreams < 0 || (nstreams > 0 && !jobs) || fmt < 0 || fmt > 2) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_decode_multi: bad argument");
+	if (nstreams == 0) return DABGPU_OK;
+	CUDA_TRY (h, cudaSetDevice (h -> device));
+	const int rc = decode_multi_core (h, jobs, nstreams, fmt, dev_input);
+	if (rc) {                                                // nothing of a failed call may still be running when it returns
+		const std::string msg = h -> err;
+		cudaStreamSynchronize (h -> stream);
+		for (int i = 1; i < 4; i ++) cudaStreamSynchronize (h -> vctx [i]. st);
+		cudaGetLastError ();
+		h -> cur = 0;
+		h -> err = msg;
+	}
+	return rc;
+}
+
+extern "C" int dabgpu_decode_multi (dabgpu_t *h, const dabgpu_stream_job *jobs, int32_t nstreams, int32_t sample_format) {
+	return decode_multi (h, jobs, nstreams, sample_format, false);
+}
+extern "C" int dabgpu_decode_multi_dev (dabgpu_t *h, const dabgpu_stream_job *jobs, int32_t nstreams, int32_t sample_format) {
+	return decode_multi (h, jobs, nstreams, sample_format, true);
 }

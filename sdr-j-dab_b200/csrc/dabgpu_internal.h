@@ -110,7 +110,8 @@ void prbs_packed (int nbits, std::vector<uint32_t> *words);                   //
 
 // ---- Viterbi group (dabgpu_viterbi.cu) ----
 struct VitJob {
-	const int16_t *in;        // soft-bit source
+	const int16_t *in;        // soft-bit source (int16), or
+	const uint8_t *in8;       // the same as 0..255 Viterbi symbols (exactly one of the two is set)
 	long long in_stride;      // elements between consecutive code words (rows when deint)
 	int first_row;            // deint: buffer row of the CIF decoded by block 0
 	const uint16_t *lut;      // device LUT [4*nsteps] or nullptr (identity); 0xFFFF = erasure
@@ -205,10 +206,11 @@ int  dab_simd_job_profile (dabgpu *h, int kind, int bitRate, int uepFlag, int pr
 // runs a set of jobs on the one-code-word-per-thread kernels (fills cta_first / dec itself)
 int  dab_vit_simd_run (dabgpu *h, std::vector<VitSimdJob> &jobs);
 bool dab_use_simd (const dabgpu *h, long long ncodewords);
-int  dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, uint8_t *d_crc);
+int  dab_fic_decode_dev (dabgpu *h, const int16_t *d_soft, const uint8_t *d_soft8, long long stride, int ngroups, uint8_t *d_bits, uint8_t *d_crc);   // soft bits as int16 or as byte symbols
 struct dabgpu_backend;
-int  dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, long long row_stride, int row0, int ncif, uint8_t *d_out, int *nout, VitSimdJob *simd_job);
+int  dab_backend_run_dev (dabgpu_backend *b, const int16_t *d_rows, const uint8_t *d_rows8, long long row_stride, int row0, int ncif, uint8_t *d_out, int *nout, VitSimdJob *simd_job, int64_t cifs_seen = -1);
 int  dab_fic_simd_job (dabgpu *h, const int16_t *d_soft, long long stride, int ngroups, uint8_t *d_bits, VitSimdJob *s);
+void soft16_launch (dabgpu *h, const uint8_t *fic8, const uint8_t *msc8, int16_t *out, int nframes, cudaStream_t st);
 void dab_backend_note_cifs (dabgpu_backend *b, int ncif);
 int64_t dab_backend_cifs_seen (const dabgpu_backend *b);
 void dab_backend_set_cifs_seen (dabgpu_backend *b, int64_t n);

@@ -4,6 +4,7 @@
 #include <math.h>
 #include "dabgpu_ofdm.cuh"
 #include "dabgpu_engine.h"
+#include "dabgpu_fftp.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // host-side tables
@@ -93,9 +94,12 @@ int ofdm_tables_init (dabgpu *h, OfdmTables *T) {
 	if ((rc = dab_device_table (h, base + 5, hi. data (), 1000 * sizeof (float2), &d))) return rc; T -> osc_hi = (const float2 *) d;
 	if ((rc = dab_device_table (h, base + 6, lo. data (), 2048 * sizeof (float2), &d))) return rc; T -> osc_lo = (const float2 *) d;
 	T -> permpos = nullptr;
-	if (N == R8_N) {
+	if (p. dabMode == 1 || p. dabMode == 2 || p. dabMode == 4) {      // packed register-FFT kernels: carrier -> position in the transform's shared layout
 		std::vector<uint16_t> pp (p. K);
-		for (int i = 0; i < p. K; i ++) pp [i] = (uint16_t) r8_swz (r8_pos (perm [i]));
+		for (int i = 0; i < p. K; i ++) {
+			const int pos = p. dabMode == 1 ? p_pos<1> (0, perm [i]) : p. dabMode == 4 ? p_pos<2> (0, perm [i]) : p_pos<4> (0, perm [i]);
+			pp [i] = (uint16_t) r8_swz (pos);
+		}
 		if ((rc = dab_device_table (h, base + 7, pp. data (), p. K * sizeof (uint16_t), &d))) return rc;
 		T -> permpos = (const uint16_t *) d;
 	}

@@ -22,7 +22,7 @@ __device__ __forceinline__ unsigned soft_to_sym (int v) {
 }
 
 template <bool DEINT>
-__device__ __forceinline__ unsigned load_step_symbols (const VitJob &j, const int16_t *src, int blk, int t) {
+__device__ __forceinline__ unsigned load_step_symbols (const VitJob &j, const int16_t *src, const uint8_t *src8, int blk, int t) {
 	if (t >= j. nsteps) return 0x7f7f7f7fu;
 	int idx [4];
 	if (j. lut) {
@@ -37,9 +37,8 @@ __device__ __forceinline__ unsigned load_step_symbols (const VitJob &j, const in
 	for (int k = 0; k < 4; k ++) {
 		unsigned sym = 127;                           // punctured position = erasure (deconvolve.cpp:185)
 		if (idx [k] >= 0) {
-			const int16_t *p = src + idx [k];
-			if (DEINT) p -= (long long) c_deint_delay [idx [k] & 15] * j. in_stride;
-			sym = soft_to_sym (__ldg (p));
+			const long long o = (long long) idx [k] - (DEINT ? (long long) c_deint_delay [idx [k] & 15] * j. in_stride : 0ll);
+			sym = src8 ? (unsigned) __ldg (src8 + o) : soft_to_sym (__ldg (src + o));     // in8: already 0..255 symbols
 		}
 		s |= sym << (8 * k);
 	}
@@ -55,7 +54,9 @@ __global__ void __launch_bounds__ (128) vit_warp_kernel (const VitJob j, const i
 	uint2    *dec   = reinterpret_cast<uint2 *> (smem + (size_t) warp * smem_words_per_warp);
 	uint32_t *bitsw = reinterpret_cast<uint32_t *> (dec + j. nsteps);
 
-	const int16_t *src = j. in + (long long) (blk + (DEINT ? j. first_row : 0)) * j. in_stride;
+	const long long row = (long long) (blk + (DEINT ? j. first_row : 0)) * j. in_stride;
+	const int16_t *src = j. in ? j. in + row : nullptr;
+	const uint8_t *src8 = j. in8 ? j. in8 + row : nullptr;
 
 	// lane = butterfly i: Branchtab_j[i] = parity ((2i) & poly_j) ? 255 : 0 (viterbi.cpp:159-164)
 	unsigned xmask = 0;
@@ -68,10 +69,10 @@ __global__ void __launch_bounds__ (128) vit_warp_kernel (const VitJob j, const i
 	unsigned a = lane == 0 ? 0u : 63u, b = 63u;       // old[lane], old[lane + 32] (viterbi.cpp:364-370)
 	const int srcA = lane >> 1, srcB = (lane >> 1) + 16, sh = (lane & 1) * 16;
 
-	unsigned nxt = load_step_symbols<DEINT> (j, src, blk, lane);
+	unsigned nxt = load_step_symbols<DEINT> (j, src, src8, blk, lane);
 	for (int t0 = 0; t0 < j. nsteps; t0 += 32) {
 		const unsigned cur = nxt;
-		nxt = load_step_symbols<DEINT> (j, src, blk, t0 + 32 + lane);
+		nxt = load_step_symbols<DEINT> (j, src, src8, blk, t0 + 32 + lane);
 		const int n = min (32, j. nsteps - t0);
 		for (int k = 0; k < n; k ++) {
 			const unsigned S = __shfl_sync (0xffffffffu, cur, k);

@@ -72,6 +72,33 @@ int main (int argc, char **argv) {
 			op. run ();                                                                     // returns at the end of the file
 			printf ("stream %lld %d %016llx %d %016llx %d\n", (long long) op. frames_decoded (), fibs, facc, frames, macc, (int) fic. get_ficRatio ());
 		}
+		if (argc > 3) {	// ficHandler::process_ficBlock / mscHandler::process_mscBlock, symbol by symbol as ofdmProcessor::run calls them
+			// (ofdm-processor.cpp:421-441); soft bits [frames][75][3072] int16 from a file; once with dabConcurrent behind
+			// mscHandler (concurrencyOn = 1, 16-CIF warm-up), once with dabSerial (15-CIF warm-up: one frame more at the start)
+			FILE *fp = fopen (argv [3], "rb");
+			if (!fp) throw std::runtime_error ("cannot open the soft-bit file");
+			std::vector<int16_t> soft;
+			{ int16_t buf [4096]; size_t n; while ((n = fread (buf, sizeof (int16_t), 4096, fp)) > 0) soft. insert (soft. end (), buf, buf + n); }
+			fclose (fp);
+			DabParams p = { 1, 76, 1536, 2656, 196608, 2552, 2048, 504, 1000 };
+			const size_t nfr = soft. size () / (75 * 3072);
+			for (int conc = 1; conc >= 0; conc --) {
+				int fibs = 0, frames = 0; unsigned long long facc = 0, macc = 0, macc_skip1 = 0;
+				ficHandler fic (nullptr, 2 * p. K, [&] (uint8_t *fib, uint16_t ficno) { fibs ++; facc = facc * 31 + fnv (fib, 256) + ficno; });
+				mscHandler msc (nullptr, &p, nullptr, (uint8_t) conc, [&] (uint8_t *v, int16_t n) {
+					frames ++; macc = macc * 31 + fnv (v, (size_t) n);
+					if (frames > 1) macc_skip1 = macc_skip1 * 31 + fnv (v, (size_t) n);
+				});
+				audiodata ad = {}; ad. startAddr = 0; ad. length = 96; ad. bitRate = 128; ad. uepFlag = 1; ad. protLevel = 0103;
+				msc. set_audioChannel (&ad);
+				for (size_t f = 0; f < nfr; f ++)
+					for (int blk = 1; blk < p. L; blk ++) {
+						int16_t *ibits = &soft [(f * 75 + (size_t) (blk - 1)) * 3072];
+						if (blk < 4) fic. process_ficBlock (ibits, (int16_t) blk); else msc. process_mscBlock (ibits, (int16_t) blk);
+					}
+				printf ("%s %d %016llx %d %016llx %016llx %d\n", conc ? "handlers_concurrent" : "handlers_serial", fibs, facc, frames, macc, macc_skip1, (int) fic. get_ficRatio ());
+			}
+		}
 	} catch (const std::exception &e) { fprintf (stderr, "adapter_demo: %s\n", e. what ()); return 1; }
 	return 0;
 }

@@ -10,8 +10,11 @@
  *   phaseReference (DabParams *, int16_t), int32_t findIndex (DSPCOMPLEX *), getTable ()   phasereference.h:37-40
  *   ofdmDecoder (DabParams *, RingBuffer<DSPCOMPLEX> *, DSPCOMPLEX *, RadioInterface *, uint8_t),
  *       int16_t processBlock_0 (DSPCOMPLEX *, bool), void processToken (DSPCOMPLEX *, int16_t *, int32_t)  ofdm-decoder.h:40-47
- *   dabConcurrent::process (int16_t *, int16_t) -> here dabBackend with a frame sink    dab-concurrent.h, dab-virtual.h:40
- *   ficHandler::process_ficBlock (int16_t *, int16_t) -> here ficDecoder with a FIB sink   fic-handler.h:44-46
+ *   dabVirtual / dabConcurrent / dabSerial (ctor as the reference), int32_t process (int16_t *, int16_t)   dab-virtual.h:36-47, dab-concurrent.h:44-53, dab-serial.h:41-50
+ *   ficHandler (RadioInterface *, int16_t), void process_ficBlock (int16_t *, int16_t), get_ficRatio ()   fic-handler.h:44-52
+ *   mscHandler (RadioInterface *, DabParams *, audioSink *, uint8_t), process_mscBlock (int16_t *, int16_t),
+ *       set_audioChannel (audiodata *), set_dataChannel (packetdata *), stop (), stopProcessing ()           msc-handler.h:43-57
+ *   (decoded FIBs / frames leave through sinks where the reference calls fib_processor::process_FIB / dabProcessor::addtoFrame)
  * Errors: the reference's classes cannot fail after construction; these throw std::runtime_error from the
  * constructor when the engine cannot be created (no GPU) and otherwise keep the reference's sentinels
  * (negative findIndex, 100 from processBlock_0).  One engine handle per DAB mode is shared by all adapter
@@ -21,6 +24,7 @@
 #define DAB_ADAPTERS_H
 #include <atomic>
 #include <complex>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -171,6 +175,69 @@ private:
 	std::vector<uint8_t> outV;
 };
 
+/* ---- dabVirtual (dab-virtual.h:36-47) and its two audio back ends with the reference's constructors:
+ * dabConcurrent (dab-concurrent.h:44-53; warm-up 16 CIFs, dab-concurrent.cpp:172-175) and dabSerial (dab-serial.h:41-50;
+ * warm-up 15 CIFs, dab-serial.cpp:126-129).  process () takes one CIF fragment (the slice mscHandler cuts out of the
+ * CIF); the decoded, dispersal-descrambled frame goes to a sink in place of dabProcessor::addtoFrame (dab-processor.h:39;
+ * the MP2 / AAC decoders behind it stay on the host).  `dabModus` is the reference's DAB / DAB_PLUS audio type, which the
+ * channel decoder does not depend on; the FILE and audioSink arguments belong to the audio decoders and are ignored. ---- */
+#ifndef DAB_ADAPTERS_NO_TYPES
+class audioSink;
+#endif
+#ifndef CUSize
+#define CUSize (4 * 16)
+#endif
+class dabVirtual {
+public:
+	typedef std::function<void (uint8_t *, int16_t)> frameSink;
+	dabVirtual (void) {}
+	virtual ~dabVirtual (void) {}
+	virtual int32_t process (int16_t *, int16_t) { return 32768; }
+	virtual void stopRunning (void) {}
+	virtual void stop (void) {}
+	virtual void setFiles (FILE *, FILE *) {}
+	virtual void set_sink (frameSink) {}
+};
+class dabGpuBackend_ : public dabVirtual {
+public:
+	dabGpuBackend_ (int16_t fragmentSize, int16_t bitRate, int16_t uepFlag, int16_t protLevel, int warmup)
+	   : h (dabgpu_host::engine (1)), bitRate (bitRate), outV (24 * bitRate) {
+		dabgpu_subch sc = { 0, fragmentSize / CUSize, bitRate, uepFlag, protLevel };
+		dabgpu_host::check (h, dabgpu_backend_create (h, &sc, &b));
+		if (warmup != 16) {                /* dabSerial starts decoding one CIF earlier: same de-interleaver, counter one ahead */
+			std::vector<int16_t> zero ((size_t) 15 * fragmentSize, 0);
+			dabgpu_host::check (h, dabgpu_backend_set_state (b, zero. data (), 16 - warmup));
+		}
+	}
+	~dabGpuBackend_ (void) { dabgpu_backend_destroy (b); }
+	int32_t process (int16_t *v, int16_t cnt) {
+		int32_t n = 0;
+		(void) cnt;                        /* "sorry" (dab-serial.cpp:114): the reference ignores it as well */
+		dabgpu_host::check (h, dabgpu_backend_process (b, v, 1, outV. data (), &n));
+		if (n == 1 && sink) sink (outV. data (), (int16_t) (24 * bitRate));
+		return 32768;
+	}
+	void set_sink (frameSink s) { sink = s; }
+private:
+	dabgpu_t *h;
+	dabgpu_backend_t *b = nullptr;
+	int16_t bitRate;
+	frameSink sink;
+	std::vector<uint8_t> outV;
+};
+class dabConcurrent : public dabGpuBackend_ {
+public:
+	dabConcurrent (uint8_t dabModus, int16_t fragmentSize, int16_t bitRate, int16_t uepFlag, int16_t protLevel,
+	               RadioInterface *mr, FILE *, FILE *, audioSink *as)
+	   : dabGpuBackend_ (fragmentSize, bitRate, uepFlag, protLevel, 16) { (void) dabModus; (void) mr; (void) as; }
+};
+class dabSerial : public dabGpuBackend_ {
+public:
+	dabSerial (uint8_t dabModus, int16_t fragmentSize, int16_t bitRate, int16_t uepFlag, int16_t protLevel,
+	           RadioInterface *mr, FILE *, FILE *, audioSink *as)
+	   : dabGpuBackend_ (fragmentSize, bitRate, uepFlag, protLevel, 15) { (void) dabModus; (void) mr; (void) as; }
+};
+
 /* ---- ficHandler::process_ficBlock (fic-handler.cpp:143-230): collects 2304-bit code words, decodes them, hands
  * CRC-clean FIBs to a sink in place of fib_processor::process_FIB (fib-processor.h:96) ---- */
 class ficDecoder {
@@ -251,48 +318,105 @@ private:
  * (dabgpu_decode_cf32) instead of walking them sample by sample (ofdm-processor.cpp:247-474).  Decoded FIBs and
  * sub-channel frames come back through ficHandler / mscHandler objects that carry the sinks the reference's handlers
  * end in: fib_processor::process_FIB (fib-processor.h:96, called at fic-handler.cpp:309-319) and
- * dabProcessor::addtoFrame (dab-processor.h:39, called at dab-concurrent.cpp:191).  Their process_ficBlock /
- * process_mscBlock entry points (soft bits per OFDM symbol) do not exist here: soft bits never leave the GPU.
+ * dabProcessor::addtoFrame (dab-processor.h:39, called at dab-concurrent.cpp:191).  The same two classes also carry the
+ * reference's per-symbol members process_ficBlock / process_mscBlock (substitution 1: the reference's own sample-serial
+ * ofdmProcessor keeps calling them); with the throughput ofdmProcessor below soft bits never leave the GPU and the
+ * engine calls deliver () instead.
  * ---------------------------------------------------------------------------------------------------------- */
 class ficHandler {                     /* fic-handler.h:44-46 */
 public:
 	typedef std::function<void (uint8_t *, uint16_t)> fibSink;
-	ficHandler (RadioInterface *mr, int16_t dabMode, fibSink sink = nullptr) : sink (sink) { (void) mr; (void) dabMode; }
+	/* the reference's constructor (fic-handler.cpp:82-83: the second argument is the soft bits per OFDM symbol, 2 K; the
+	 * DAB mode is accepted as well and mapped to it) */
+	ficHandler (RadioInterface *mr, int16_t bitsperBlock_or_mode, fibSink sink = nullptr) : sink (sink) {
+		(void) mr;
+		static const int16_t k2 [5] = { 0, 2 * 1536, 2 * 384, 2 * 192, 2 * 768 };
+		BitsperBlock = bitsperBlock_or_mode >= 1 && bitsperBlock_or_mode <= 4 ? k2 [bitsperBlock_or_mode] : bitsperBlock_or_mode;
+	}
 	void set_sink (fibSink s) { sink = s; }
+	/* fic-handler.cpp:143-153 + run () :192-230: the soft bits of FIC symbol blkno (1, 2 or 3); every completed 2304-bit
+	 * code word is decoded (process_ficInput, :241-321) and its CRC-clean FIBs go to the sink with their ficno */
+	void process_ficBlock (int16_t *data, int16_t blkno) {
+		if (!h) h = dabgpu_host::engine (1);
+		if (blkno == 1) { index = 0; ficno = 0; }
+		for (int i = 0; i < BitsperBlock; i ++) {
+			ofdm_input [index ++] = data [i];
+			if (index >= 2304) {
+				uint8_t bits [768], crc [3];
+				dabgpu_host::check (h, dabgpu_fic_decode (h, ofdm_input, 1, bits, crc));
+				deliver_group (bits, crc, ficno);
+				index = 0; ficno ++;
+			}
+		}
+	}
 	int16_t get_ficRatio (void) { return total ? (int16_t) (100 * good / total) : 0; }      /* fic-handler.cpp:323-325 */
+	void clearEnsemble (void) {}           /* the service directory (fib_processor) stays on the host */
 	void stop (void) {}
 	/* engine side: the FIC groups of one decode call (768 bits + 3 CRC flags each, ficGroups per frame) */
 	void deliver (uint8_t *bits768, const uint8_t *crc3, int32_t ngroups, int32_t groupsPerFrame) {
-		for (int32_t g = 0; g < ngroups; g ++)
-			for (int f = 0; f < 3; f ++) {
-				total ++;
-				if (!crc3 [3 * g + f]) continue;
-				good ++;
-				if (sink) sink (&bits768 [768 * g + 256 * f], (uint16_t) (g % groupsPerFrame));   /* ficno, fic-handler.cpp:309-319 */
-			}
+		for (int32_t g = 0; g < ngroups; g ++) deliver_group (&bits768 [768 * g], &crc3 [3 * g], (uint16_t) (g % groupsPerFrame));
 	}
 private:
+	void deliver_group (uint8_t *bits768, const uint8_t *crc3, uint16_t no) {
+		for (int f = 0; f < 3; f ++) {
+			total ++;
+			if (!crc3 [f]) continue;
+			good ++;
+			if (sink) sink (&bits768 [256 * f], no);                                 /* fic-handler.cpp:309-319 */
+		}
+	}
 	fibSink sink;
+	dabgpu_t *h = nullptr;
+	int16_t BitsperBlock, index = 0, ficno = 0;
+	int16_t ofdm_input [2304];
 	long long good = 0, total = 0;
 };
 
 class mscHandler {                     /* msc-handler.h:43-57 */
 public:
 	typedef std::function<void (uint8_t *, int16_t)> frameSink;
-	mscHandler (RadioInterface *mr, DabParams *p, void *audioSink_unused, uint8_t concurrencyOn, frameSink sink = nullptr)
-	   : sink (sink) { (void) mr; (void) p; (void) audioSink_unused; (void) concurrencyOn; }
-	void set_sink (frameSink s) { sink = s; }
+	mscHandler (RadioInterface *mr, DabParams *p, audioSink *as, uint8_t concurrencyOn, frameSink sink = nullptr)
+	   : sink (sink), concurrencyOn (concurrencyOn), myRadioInterface (mr), our_audioSink (as), cifVector (55296) {
+		BitsperBlock = 2 * p -> K;                                               /* msc-handler.cpp:61-71 */
+		numberofblocksperCIF = p -> dabMode == 4 ? 36 : p -> dabMode == 1 ? 18 : p -> dabMode == 2 ? 72 : 18;
+	}
+	~mscHandler (void) { delete dabHandler; }
+	void set_sink (frameSink s) { sink = s; if (dabHandler) dabHandler -> set_sink (s); }
 	void set_audioChannel (audiodata *d) {                        /* msc-handler.cpp:91-105: takes effect at the next block */
 		std::lock_guard<std::mutex> g (m);
-		sc = { d -> startAddr, d -> length, d -> bitRate, d -> uepFlag, d -> protLevel }; have = true; changed = true;
+		sc = { d -> startAddr, d -> length, d -> bitRate, d -> uepFlag, d -> protLevel }; have = true; changed = true; newChannel = true;
+		new_dabModus = d -> ASCTy == 077 ? 1 : 0;
 	}
 	void set_dataChannel (packetdata *d) {                        /* msc-handler.cpp:107-123 */
 		std::lock_guard<std::mutex> g (m);
-		sc = { d -> startAddr, d -> length, d -> bitRate, d -> uepFlag, d -> protLevel }; have = true; changed = true;
+		sc = { d -> startAddr, d -> length, d -> bitRate, d -> uepFlag, d -> protLevel }; have = true; changed = true; newChannel = true;
+		new_dabModus = 0;
 	}
-	void stopProcessing (void) { std::lock_guard<std::mutex> g (m); have = false; changed = true; }
-	void stop (void) {}
-	/* engine side */
+	/* msc-handler.cpp:125-193: the soft bits of MSC symbol blkno (4 .. L); CIF assembly, sub-channel slice, hand-over to
+	 * the back end (dabConcurrent, or dabSerial when the object was built with concurrencyOn == 0) */
+	void process_mscBlock (int16_t *fbits, int16_t blkno) {
+		if (!work_to_be_done && !newChannel) return;
+		const int16_t currentblk = (blkno - 4) % numberofblocksperCIF;
+		if (newChannel) {
+			std::lock_guard<std::mutex> g (m);
+			newChannel = false;
+			if (dabHandler) dabHandler -> stopRunning ();
+			delete dabHandler;
+			if (concurrencyOn)
+				dabHandler = new dabConcurrent (new_dabModus, sc. length * CUSize, sc. bitRate, sc. uepFlag, sc. protLevel, myRadioInterface, nullptr, nullptr, our_audioSink);
+			else
+				dabHandler = new dabSerial (new_dabModus, sc. length * CUSize, sc. bitRate, sc. uepFlag, sc. protLevel, myRadioInterface, nullptr, nullptr, our_audioSink);
+			dabHandler -> set_sink (sink);
+			startAddr = sc. startAddr; Length = sc. length;
+			work_to_be_done = true;
+		}
+		memcpy (&cifVector [currentblk * BitsperBlock], fbits, BitsperBlock * sizeof (int16_t));
+		if (currentblk < numberofblocksperCIF - 1) return;
+		(void) dabHandler -> process (&cifVector [startAddr * CUSize], Length * CUSize);
+	}
+	void stopProcessing (void) { std::lock_guard<std::mutex> g (m); have = false; changed = true; work_to_be_done = false; }
+	void stop (void) { work_to_be_done = false; if (dabHandler) dabHandler -> stop (); }
+	/* engine side (the throughput ofdmProcessor below) */
 	bool take_change (dabgpu_subch *out, bool *active) {
 		std::lock_guard<std::mutex> g (m);
 		if (!changed) return false;
@@ -304,9 +428,16 @@ public:
 	}
 private:
 	frameSink sink;
+	uint8_t concurrencyOn;
+	RadioInterface *myRadioInterface;
+	audioSink *our_audioSink;
+	std::vector<int16_t> cifVector;
 	std::mutex m;
 	dabgpu_subch sc {};
-	bool have = false, changed = false;
+	dabVirtual *dabHandler = nullptr;
+	bool have = false, changed = false, newChannel = false, work_to_be_done = false;
+	uint8_t new_dabModus = 0;
+	int16_t BitsperBlock, numberofblocksperCIF, startAddr = 0, Length = 0;
 };
 
 class ofdmProcessor {                  /* ofdm-processor.h:49-68 (the build without HAVE_SPECTRUM) */

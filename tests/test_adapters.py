@@ -60,8 +60,12 @@ def test_adapter_demo_matches_oracle(port):
     f32 = ((tr["iq"].astype(np.float32) - np.float32(128.0)) / np.float32(128.0)).astype(np.float32)
     iqpath = os.path.join(HOST, "adapter_demo_iq.bin")
     f32.tofile(iqpath)
-    r = subprocess.run([EXE, path, iqpath], capture_output=True, text=True, timeout=180)
-    os.remove(path); os.remove(iqpath)
+    # the oracle's soft bits of the same recording for the per-symbol handler members (process_ficBlock / process_mscBlock)
+    sym, finfo = port.ofdm_run(1, f32, 30)
+    softpath = os.path.join(HOST, "adapter_demo_soft.bin")
+    np.ascontiguousarray(sym, np.int16).tofile(softpath)
+    r = subprocess.run([EXE, path, iqpath, softpath], capture_output=True, text=True, timeout=180)
+    os.remove(path); os.remove(iqpath); os.remove(softpath)
     assert r.returncode == 0, r.stderr
     got = dict(line.split(" ", 1) for line in r.stdout.strip().splitlines())
     g = _lcg_stream(12345)
@@ -88,7 +92,6 @@ def test_adapter_demo_matches_oracle(port):
     assert int(count) == len(info) == 6 and int(h, 16) == acc
     # the stream through ofdmProcessor / ficHandler / mscHandler: every CRC-clean FIB (with its ficno) and every frame
     nfr, nfib, fh, nmsc, mh, ratio = got["stream"].split()
-    sym, finfo = port.ofdm_run(1, f32, 30)
     n = int(nfr)
     assert len(finfo) - n in (0, 1) and n >= 14
     bits, crc = port.fic_frames(1, sym[:n])
@@ -107,3 +110,24 @@ def test_adapter_demo_matches_oracle(port):
         macc = (macc * 31 + _fnv(blk)) & M
     assert int(nmsc) == len(frames) > 30 and int(mh, 16) == macc
     assert int(ratio) == 100 * cnt // (12 * n)
+    # ficHandler::process_ficBlock / mscHandler::process_mscBlock fed symbol by symbol with the oracle's soft bits of ALL
+    # its frames: the same FIBs (with ficno) and frames as the oracle's FIC / MSC chain; behind mscHandler once
+    # dabConcurrent (16-CIF warm-up) and once dabSerial (15: one frame more at the start, the rest identical)
+    na = len(finfo)
+    bits, crc = port.fic_frames(1, sym)
+    facc, cnt = 0, 0
+    for g in range(4 * na):
+        for f in range(3):
+            if crc[g][f]:
+                facc = (facc * 31 + _fnv(bits[g][256 * f:256 * f + 256]) + (g % 4)) & M
+                cnt += 1
+    frames = port.msc_backend(port.msc_slice(1, sym, s0.startAddr, s0.length), s0.bitRate, s0.uepFlag, s0.protLevel)
+    macc = 0
+    for blk in frames:
+        macc = (macc * 31 + _fnv(blk)) & M
+    for key, extra in (("handlers_concurrent", 0), ("handlers_serial", 1)):
+        nfib, fh, nmsc, mh, mh_skip1, ratio = got[key].split()
+        assert int(nfib) == cnt and int(fh, 16) == facc, key
+        assert int(nmsc) == len(frames) + extra, key
+        assert int(mh_skip1 if extra else mh, 16) == macc, key
+        assert int(ratio) == 100 * cnt // (12 * na), key

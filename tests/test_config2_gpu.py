@@ -56,9 +56,9 @@ def test_config2_full_stream_matches_oracle(port):
     assert r1.nframes == nbatch and r0.nframes >= nlead - 4
     n0 = r0.nframes
     got_info = list(r0.info) + list(r1.info)
-    for a, b in zip(got_info, info):
+    for k, (a, b) in enumerate(zip(got_info, info)):
         assert (a.pos, a.startIndex, a.coarse, a.fine, a.phase0, a.correction) == \
-               (b.pos, b.startIndex, b.coarse, b.fine, b.phase0, b.correction)
+               (b.pos, b.startIndex, b.coarse, b.fine, b.phase0, b.correction), (k, n0, st.abs_pos)
     n = n0 + nbatch
     assert np.array_equal(np.concatenate([r0.fic_bits, r1.fic_bits]), fic[:4 * n])
     assert np.array_equal(np.concatenate([r0.fic_crc, r1.fic_crc]), crc[:4 * n])
