@@ -195,6 +195,12 @@ typedef struct {
 } dabgpu_result;
 
 int dabgpu_set_subchannels (dabgpu_t *h, const dabgpu_subch *sc, int32_t nsub);   /* set_audioChannel x nsub */
+/* packed != 0: the stream engine (dabgpu_decode*, dabgpu_decode_multi, dabgpu_group_*) delivers MSC blocks with EIGHT bits
+ * per byte, first bit in the top bit of byte 0 -- msc_bits[i] then holds [blocks][3*bitRate] bytes.  The reference hands
+ * dabProcessor::addtoFrame one bit per byte (dab-concurrent.cpp:191) and the DAB+ processor packs them exactly this
+ * way as its first step (mp4Processor::addtoFrame, audio/mp4processor.cpp:107-117); packing on the device cuts the device-to-host
+ * traffic of the decoded bits by 8.  FIC bits stay one per byte (fib_processor::process_FIB reads them that way). */
+int dabgpu_set_msc_output (dabgpu_t *h, int32_t packed);
 int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out);
 /* same with the input already resident on the handle's device (result pointers stay host pointers) */
 int dabgpu_decode_dev (dabgpu_t *h, const uint8_t *d_iq_u8, size_t nsamples, dabgpu_result *out);
@@ -227,6 +233,34 @@ typedef struct {
 } dabgpu_stream_job;
 int dabgpu_decode_multi (dabgpu_t *h, const dabgpu_stream_job *jobs, int32_t nstreams, int32_t sample_format);
 int dabgpu_decode_multi_dev (dabgpu_t *h, const dabgpu_stream_job *jobs, int32_t nstreams, int32_t sample_format);
+/* ------------------------------------------------------------------------------------------------
+ * Several GPUs of one box: one process, one engine handle + one host thread per device.  The reference
+ * has no counterpart (one ofdmProcessor thread per receiver, gui.cpp:160-179); what crosses a shard boundary is the
+ * reference's sequential state: the sync / AFC variables of ofdmProcessor::run (ofdm-processor.cpp:445-466) and the 15
+ * CIFs the time de-interleaver remembers (dab-concurrent.cpp:41-43, 162-175).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dabgpu_group dabgpu_group_t;
+/* one handle per entry of devices[] (NULL: devices 0 .. ndev-1; the same device may appear more than once), all with cfg */
+int  dabgpu_group_create (const dabgpu_config *cfg, const int32_t *devices, int32_t ndev, dabgpu_group_t **out);
+void dabgpu_group_destroy (dabgpu_group_t *g);
+const char *dabgpu_group_last_error (const dabgpu_group_t *g);
+int32_t dabgpu_group_size (const dabgpu_group_t *g);
+dabgpu_t *dabgpu_group_handle (dabgpu_group_t *g, int32_t i);             /* member i (owned by the group) */
+int  dabgpu_group_set_subchannels (dabgpu_group_t *g, const dabgpu_subch *sc, int32_t nsub);
+/* independent streams (BASELINE configs[3]): stream i runs on member i mod n through dabgpu_decode_multi, no communication */
+int  dabgpu_group_decode_multi (dabgpu_group_t *g, const dabgpu_stream_job *jobs, int32_t nstreams, int32_t sample_format);
+/* ONE recording (BASELINE configs[4]) decoded from its first sample by all members; `out` is filled exactly as ONE fresh
+ * handle's dabgpu_decode over the whole recording would fill it (bit for bit), out->consumed = samples consumed.
+ * scheme 1 (default choice): GPU 0 decodes lead_frames frames (<= 0: 24) to lock, every member then decodes its
+ * contiguous frame range IN PARALLEL from the closed-form predicted tracking state (dabgpu_host_state_predict),
+ * starting 16 CIFs early instead of receiving a de-interleaver halo; every boundary is verified against the left
+ * neighbour's true final state, and on any disagreement (or an unlocked receiver) the call falls back to
+ * scheme 0: the exact serial chain -- member r decodes its sample range, then the whole stream state (sync / AFC
+ * variables, unconsumed samples, 15-CIF soft-bit halo) moves to member r + 1 device to device (cudaMemcpyPeerAsync).
+ * *scheme_used (may be NULL) reports which one produced the output. */
+int  dabgpu_group_decode (dabgpu_group_t *g, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out,
+                          int32_t lead_frames, int32_t scheme, int32_t *scheme_used);
+
 /* airspyHandler's sample-rate conversion (airspy-handler.cpp:138-148, 342-370): int16 I,Q pairs at in_rate samples/s
  * (a multiple of 1000) -> complex floats at 2 048 000 samples/s by linear interpolation in 1 ms blocks, ready for
  * dabgpu_decode_cf32.  Block b reads input samples [b R, b R + R], R = in_rate / 1000, and writes 2048 samples; a call

@@ -4,4 +4,4 @@ The product is the C-ABI shared library ``libdabgpu.so`` (include/dabgpu.h) buil
 package only holds its build recipe and a thin ctypes binding used by the tests and bench.py.  There is no
 CPU fallback: without the built library, or without a CUDA device, everything here raises.
 """
-from .binding import DabGpu, DabGpuError, Backend, SubCh, load_library, LIB_PATH   # noqa: F401
+from .binding import DabGpu, DabGroup, DabGpuError, Backend, SubCh, load_library, LIB_PATH   # noqa: F401

@@ -369,7 +369,7 @@ class DabGpu:
         groups = 3 * 2 * K // 2304
         o.fic_bits = alloc((max_frames * groups, 768), np.uint8)
         o.fic_crc = alloc((max_frames * groups, 3), np.uint8)
-        o.msc = [alloc((max_frames * cpf, 24 * s.bitRate), np.uint8) for s in subs]
+        o.msc = [alloc((max_frames * cpf, (3 if getattr(self, "_packed", False) else 24) * s.bitRate), np.uint8) for s in subs]
         o.ptrs = (C.POINTER(C.c_uint8) * max(len(subs), 1))(*[m.ctypes.data_as(C.POINTER(C.c_uint8)) for m in o.msc])
         o.nblocks = (C.c_int32 * max(len(subs), 1))()
         o.res = Result(max_frames=max_frames, nframes=0, info=o.info,
@@ -403,6 +403,12 @@ class DabGpu:
     def decode_dev(self, d_ptr, nsamples, out):
         self._check(self.lib.dabgpu_decode_dev(self.h, d_ptr, nsamples, C.byref(out.res)))
         return self._trim(out)
+
+    def set_msc_output(self, packed):
+        """dabgpu_set_msc_output: MSC blocks with 8 bits per byte (first bit on top); affects result buffers allocated afterwards"""
+        self.lib.dabgpu_set_msc_output.argtypes = [C.c_void_p, C.c_int32]
+        self._check(self.lib.dabgpu_set_msc_output(self.h, 1 if packed else 0))
+        self._packed = bool(packed)
 
     def decode_multi(self, streams, outs, dev_ptrs=None):
         """dabgpu_decode_multi: `streams` = list of numpy arrays (all uint8, float32 or int16, interleaved I,Q), one per
@@ -514,6 +520,79 @@ class DabGpu:
 
     def backend(self, startAddr, length, bitRate, uepFlag, protLevel):
         return Backend(self, SubCh(startAddr, length, bitRate, uepFlag, protLevel))
+
+
+class DabGroup:
+    """dabgpu_group_t: several engine handles (one per GPU, or several on one GPU for tests) behind one object"""
+
+    def __init__(self, devices, mode=1, threshold=3, freqSyncMethod=1, viterbi_path=0):
+        self.lib = load_library()
+        L = self.lib
+        L.dabgpu_group_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
+        L.dabgpu_group_destroy.argtypes = [C.c_void_p]
+        L.dabgpu_group_destroy.restype = None
+        L.dabgpu_group_last_error.argtypes = [C.c_void_p]
+        L.dabgpu_group_last_error.restype = C.c_char_p
+        L.dabgpu_group_set_subchannels.argtypes = [C.c_void_p, C.POINTER(SubCh), C.c_int32]
+        L.dabgpu_group_decode_multi.argtypes = [C.c_void_p, C.POINTER(StreamJob), C.c_int32, C.c_int32]
+        L.dabgpu_group_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Result), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+        cfg = Config(device=0, dabMode=mode, threshold=threshold, freqSyncMethod=freqSyncMethod, viterbi_path=viterbi_path)
+        devs = (C.c_int32 * len(devices))(*devices)
+        self.g = C.c_void_p()
+        rc = L.dabgpu_group_create(C.byref(cfg), devs, len(devices), C.byref(self.g))
+        if rc != 0:
+            self.g = None
+            raise DabGpuError("dabgpu_group_create failed (%d): %s" % (rc, L.dabgpu_last_error(None).decode()))
+        self.mode, self.n = mode, len(devices)
+        self._shape = DabGpu.__new__(DabGpu)                 # result-buffer helper (alloc_result / _trim), no handle of its own
+        self._shape.mode, self._shape.h, self._shape.lib = mode, None, L
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.lib.dabgpu_group_destroy(self.g)
+            self.g = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise DabGpuError("dabgpu group error %d: %s" % (rc, self.lib.dabgpu_group_last_error(self.g).decode()))
+
+    def set_subchannels(self, subs):
+        arr = (SubCh * max(len(subs), 1))(*[SubCh(*s) for s in subs])
+        self._check(self.lib.dabgpu_group_set_subchannels(self.g, arr, len(subs)))
+        self._shape._subs = [SubCh(*s) for s in subs]
+
+    def alloc_result(self, max_frames, **kw):
+        return self._shape.alloc_result(max_frames, **kw)
+
+    def decode(self, iq_u8, out, lead_frames=24, scheme=1):
+        """ONE recording over all members -> (trimmed result, scheme used: 1 parallel / 0 chain)"""
+        if isinstance(iq_u8, tuple):
+            ptr, ns = iq_u8
+        else:
+            iq = np.ascontiguousarray(iq_u8, np.uint8)
+            ptr, ns = iq.ctypes.data, iq.size // 2
+        used = C.c_int32(-1)
+        self._check(self.lib.dabgpu_group_decode(self.g, ptr, ns, C.byref(out.res), lead_frames, scheme, C.byref(used)))
+        return self._shape._trim(out), used.value
+
+    def decode_multi(self, streams, outs):
+        n = len(outs)
+        jobs = (StreamJob * max(n, 1))()
+        dt = np.asarray(streams[0]).dtype if n else np.dtype(np.uint8)
+        fmt = 1 if dt == np.float32 else 2 if dt == np.int16 else 0
+        keep = []
+        for i, x in enumerate(streams):
+            if isinstance(x, tuple):
+                jobs[i].iq, jobs[i].nsamples = x
+            else:
+                a = np.ascontiguousarray(x, dt)
+                keep.append(a)
+                jobs[i].iq, jobs[i].nsamples = a.ctypes.data, a.size // 2
+            jobs[i].out = C.pointer(outs[i].res)
+        self._check(self.lib.dabgpu_group_decode_multi(self.g, jobs, n, fmt))
+        return [self._shape._trim(o) for o in outs]
 
 
 class Backend:

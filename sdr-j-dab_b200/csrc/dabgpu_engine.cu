@@ -288,6 +288,15 @@ static int next_chunk (int chunk, int attempted, const StreamCtl &c, int cap) {
 // ---------------------------------------------------------------------------------------------------
 // channel decoding (FIC + every configured sub-channel) of frames just accepted by the OFDM part
 // ---------------------------------------------------------------------------------------------------
+// bytes of one decoded MSC block in the output buffers: 24 * bitRate bits, one per byte (viterbi.cpp:240-241) or packed
+static inline size_t msc_block_bytes (const Engine *E, const dabgpu_subch &sc) { return E -> msc_packed ? (size_t) 3 * sc. bitRate : (size_t) 24 * sc. bitRate; }
+
+extern "C" int dabgpu_set_msc_output (dabgpu_t *h, int32_t packed) {
+	if (!h) return DABGPU_ERR_ARG;
+	h -> engine -> msc_packed = packed != 0;
+	return DABGPU_OK;
+}
+
 struct ChanPart {                                           // frames [f0, f0 + nv) of one stream
 	const uint8_t *fic8, *msc8;                             // the stream's soft-bit planes (frame slot 0 / history row 0)
 	int f0, nv;
@@ -297,24 +306,30 @@ struct ChanPart {                                           // frames [f0, f0 + 
 	int *nblk;                                              // [nsub] blocks written so far per sub-channel (updated)
 	dabgpu_result *out;                                     // host result buffers of the stream
 	unsigned long long fib0;                                // global number of the stream's first FIB in this part (FIG scan order), ~0 = no scan
+	int out_skip = 0;                                       // FIC results of frames below this slot are not delivered; frame f goes to output index f - out_skip
 };
 
 // queued on a side stream so that it overlaps the OFDM work of the next chunk; results are copied to the callers'
 // buffers on the same stream.  All parts go through ONE launch pair of the throughput kernels when that path is taken.
-static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts) {
+// span: one FIB-CRC launch over a whole buffer of FIC groups instead of one per part.  It also covers groups decoded by
+// EARLIER calls, so all calls that share the buffer must then use the same side stream (stream order keeps a group's bits
+// complete before any later launch re-reads them): such callers always get context 1.
+struct CrcSpan { uint8_t *bits, *crc; int ngroups; };
+static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts, const CrcSpan *span = nullptr) {
 	Engine *E = h -> engine;
 	const DabParams &p = h -> p;
 	const size_t nsub = E -> backends. size ();
 	long long ncw = 0, ncif_all = 0;
 	for (auto &q : parts) { ncw += (long long) q. nv * p. ficGroups + (long long) q. nv * p. cifsPerFrame * (long long) nsub; ncif_all += (long long) q. nv * p. cifsPerFrame; }
 	if (ncw == 0) return DABGPU_OK;
-	h -> cur = 1 + (E -> vrr ++ % 3);
+	h -> cur = span ? 1 : 1 + (E -> vrr ++ % 3);
 	cudaStream_t st = h -> vst ();
 	int rc = DABGPU_OK;
 	// the throughput kernels take every job of the chunk in ONE launch pair; the warp-cooperative kernel is launched once per
 	// sub-channel, 0.3 ms each however few code words there are -- so with two or more sub-channels the throughput path wins
 	// even for a single frame (measured: 9 sub-channels, 1-32 frames per call: 2.9 ms against 0.6 ms)
-	const bool simd = dab_use_simd (h, ncw) || (h -> cfg. viterbi_path == 0 && (nsub >= 2 || parts. size () >= 2) && ncif_all > 0);
+	const bool simd = dab_use_simd (h, ncw) || (h -> cfg. viterbi_path == 0 && (nsub >= 2 || parts. size () >= 2) && ncif_all > 0) ||
+	                  (E -> msc_packed && ncif_all > 0 && nsub > 0);      // (packing is done by the throughput kernels' chain-back)
 	std::vector<VitSimdJob> jobs;
 	std::vector<std::vector<int>> n_here (parts. size (), std::vector<int> (nsub, 0));
 	do {
@@ -333,12 +348,13 @@ static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts) {
 			for (size_t i = 0; i < nsub && ncif > 0; i ++) {
 				const dabgpu_subch &sc = E -> subch [i];
 				VitSimdJob job;
-				uint8_t *dst = q. mscbits [i] + (size_t) q. nblk [i] * 24 * sc. bitRate;
+				uint8_t *dst = q. mscbits [i] + (size_t) q. nblk [i] * msc_block_bytes (E, sc);
 				if ((rc = dab_backend_run_dev (E -> backends [i], nullptr, q. msc8 + (size_t) sc. startAddr * 64, CIF_BITS, r0, ncif,
 				                               dst, &n_here [k] [i], simd ? &job : nullptr, q. cifs_before))) break;
 				if (simd && n_here [k] [i] > 0) {
 					job. sym8 = const_cast<uint8_t *> (q. msc8) + (size_t) (job. first_row - 15) * CIF_BITS + (size_t) sc. startAddr * 64;
 					job. stride8 = CIF_BITS;
+					job. packed = E -> msc_packed ? 1 : 0;
 					jobs. push_back (job);
 				}
 			}
@@ -346,7 +362,10 @@ static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts) {
 		if (rc) break;
 		if (simd) {
 			if ((rc = dab_vit_simd_run (h, jobs))) break;
-			for (auto &q : parts) {
+			if (span) {
+				cudaError_t e = fib_crc_launch (h, span -> bits, 3 * span -> ngroups, span -> crc);
+				if (e != cudaSuccess) rc = dab_fail (h, DABGPU_ERR_CUDA, "crc launch: %s", cudaGetErrorString (e));
+			} else for (auto &q : parts) {
 				const int ngroups = q. nv * p. ficGroups, g0 = q. f0 * p. ficGroups;
 				if (ngroups <= 0) continue;
 				cudaError_t e = fib_crc_launch (h, q. ficbits + (size_t) g0 * 768, 3 * ngroups, q. ficcrc + (size_t) g0 * 3);
@@ -363,10 +382,12 @@ static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts) {
 				e = fig01_launch (h, fb, fc, 3 * ngroups, q. fib0, (unsigned long long *) E -> d_figkeys. p, st);
 				if (e != cudaSuccess) break;
 			}
-			if (ngroups > 0 && q. out -> fic_bits) e = cudaMemcpyAsync (q. out -> fic_bits + (size_t) g0 * 768, fb, (size_t) ngroups * 768, cudaMemcpyDeviceToHost, st);
-			if (e == cudaSuccess && ngroups > 0 && q. out -> fic_crc) e = cudaMemcpyAsync (q. out -> fic_crc + (size_t) g0 * 3, fc, (size_t) ngroups * 3, cudaMemcpyDeviceToHost, st);
+			const int c0 = q. f0 > q. out_skip ? q. f0 : q. out_skip, cg = (q. f0 + q. nv - c0) * p. ficGroups;      // frames [c0, f0 + nv) are delivered
+			const size_t src_g = (size_t) c0 * p. ficGroups, dst_g = (size_t) (c0 - q. out_skip) * p. ficGroups;
+			if (cg > 0 && q. out -> fic_bits) e = cudaMemcpyAsync (q. out -> fic_bits + dst_g * 768, q. ficbits + src_g * 768, (size_t) cg * 768, cudaMemcpyDeviceToHost, st);
+			if (e == cudaSuccess && cg > 0 && q. out -> fic_crc) e = cudaMemcpyAsync (q. out -> fic_crc + dst_g * 3, q. ficcrc + src_g * 3, (size_t) cg * 3, cudaMemcpyDeviceToHost, st);
 			for (size_t i = 0; i < nsub && e == cudaSuccess; i ++) {
-				const size_t fbytes = (size_t) 24 * E -> subch [i]. bitRate;
+				const size_t fbytes = msc_block_bytes (E, E -> subch [i]);
 				if (q. out -> msc_bits && q. out -> msc_bits [i] && n_here [k] [i] > 0)
 					e = cudaMemcpyAsync (q. out -> msc_bits [i] + (size_t) q. nblk [i] * fbytes, q. mscbits [i] + (size_t) q. nblk [i] * fbytes,
 					                     (size_t) n_here [k] [i] * fbytes, cudaMemcpyDeviceToHost, st);
@@ -393,7 +414,9 @@ static int decode_core_inner (dabgpu *h, const void *d_new_v, long long nnew, da
 	const long long total = E -> tail_len + nnew;
 	const long long frame_need = 2ll * p. T_u + (long long) (p. L - 1) * p. T_s + p. T_null;   // worst case from P
 	const long long max_frames_possible = total / p. T_F + 2;
-	long long want = out -> max_frames < max_frames_possible ? out -> max_frames : max_frames_possible;
+	const int skip = E -> out_skip;                          // (multi-GPU shards: leading overlap frames decoded for the de-interleaver only)
+	E -> out_skip = 0;
+	long long want = (long long) out -> max_frames + skip < max_frames_possible ? (long long) out -> max_frames + skip : max_frames_possible;
 	if (want < 0) want = 0;
 	int rc = ensure_frame_capacity (h, want);
 	if (rc) return rc;
@@ -443,6 +466,7 @@ static int decode_core_inner (dabgpu *h, const void *d_new_v, long long nnew, da
 		q. ficbits = (uint8_t *) E -> d_ficbits. p; q. ficcrc = (uint8_t *) E -> d_ficcrc. p;
 		q. mscbits = mscbits. data (); q. nblk = nblk. data (); q. out = out;
 		q. fib0 = (unsigned long long) ((E -> frames_total + f0) * p. ficGroups) * 3ull;
+		q. out_skip = skip;
 		return channel_parts (h, parts);
 	};
 	while (nframes < want) {
@@ -478,7 +502,8 @@ static int decode_core_inner (dabgpu *h, const void *d_new_v, long long nnew, da
 		if (S. nframes > 0) E -> chunk = next_chunk (E -> chunk, S. nframes, E -> ctl, chunk_cap);
 		else if (!acquiring) break;                          // nothing attempted: not enough resident samples for another frame
 	}
-	out -> nframes = nframes;
+	const int ndeliver = nframes > skip ? nframes - skip : 0;
+	out -> nframes = ndeliver;
 	const int ncif = nframes * p. cifsPerFrame;
 	if ((rc = channel (decoded_upto, nframes - decoded_upto))) return rc;
 	for (auto *b : E -> backends) dab_backend_note_cifs (b, ncif);
@@ -486,11 +511,13 @@ static int decode_core_inner (dabgpu *h, const void *d_new_v, long long nnew, da
 	for (size_t i = 0; i < E -> backends. size (); i ++)
 		if (out -> msc_nblocks) out -> msc_nblocks [i] = nblk [i];
 	if (nframes > 0) {
-		if (out -> info) CUDA_TRY (h, cudaMemcpyAsync (out -> info, E -> d_info. p, (size_t) nframes * sizeof (dabgpu_frame_info), cudaMemcpyDeviceToHost, h -> stream));
-		if (out -> soft) {                                   // the int16 form of process_ficBlock / process_mscBlock, on demand
-			const size_t bytes = (size_t) nframes * (p. L - 1) * 2 * p. K * sizeof (int16_t);
+		if (out -> info && ndeliver > 0)
+			CUDA_TRY (h, cudaMemcpyAsync (out -> info, (const dabgpu_frame_info *) E -> d_info. p + skip, (size_t) ndeliver * sizeof (dabgpu_frame_info), cudaMemcpyDeviceToHost, h -> stream));
+		if (out -> soft && ndeliver > 0) {                   // the int16 form of process_ficBlock / process_mscBlock, on demand
+			const size_t bytes = (size_t) ndeliver * (p. L - 1) * 2 * p. K * sizeof (int16_t);
 			CUDA_TRY (h, E -> d_soft16. ensure (bytes));
-			soft16_launch (h, (const uint8_t *) E -> d_fic8. p, (const uint8_t *) E -> d_msc8. p, (int16_t *) E -> d_soft16. p, nframes, h -> stream);
+			soft16_launch (h, (const uint8_t *) E -> d_fic8. p + (size_t) skip * 3 * 2 * p. K, (const uint8_t *) E -> d_msc8. p + (size_t) skip * p. cifsPerFrame * CIF_BITS,
+			               (int16_t *) E -> d_soft16. p, ndeliver, h -> stream);
 			CUDA_TRY (h, cudaMemcpyAsync (out -> soft, E -> d_soft16. p, bytes, cudaMemcpyDeviceToHost, h -> stream));
 		}
 		// time de-interleaver history for the next call: the last 15 CIF rows
@@ -660,7 +687,7 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 	const long long frame_need = 2ll * p. T_u + (long long) (p. L - 1) * p. T_s + p. T_null;
 	const size_t ficw = (size_t) 3 * 2 * p. K, cifw = (size_t) CIF_BITS;
 	std::vector<MultiStream> ms (nstreams);
-	size_t in_bytes = 0, fic_bytes = 0, msc_bytes = 0, info_n = 0, ficbits_bytes = 0, ficcrc_bytes = 0, mscbits_bytes = 0;
+	size_t in_bytes = 0, fic_bytes = 0, msc_bytes = 0, info_n = 0, ngroups_all = 0, mscbits_bytes = 0;
 	auto up = [] (size_t v, size_t a) { return (v + a - 1) / a * a; };
 	for (int i = 0; i < nstreams; i ++) {
 		const dabgpu_stream_job &J = jobs [i];
@@ -675,8 +702,8 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 		m. fic_off = fic_bytes;                     fic_bytes += up (cap * ficw + 16, 256);
 		m. msc_off = msc_bytes;                     msc_bytes += up ((15 + cap * p. cifsPerFrame) * cifw + 16, 256);
 		m. info_off = info_n;                       info_n += cap;
-		m. ficbits_off = ficbits_bytes;             ficbits_bytes += up ((cap * p. ficGroups + 1) * 768, 256);
-		m. ficcrc_off = ficcrc_bytes;               ficcrc_bytes += up ((cap * p. ficGroups + 1) * 3, 256);
+		m. ficbits_off = ngroups_all * 768;         m. ficcrc_off = ngroups_all * 3;      // one group index space for all streams (one CRC launch)
+		ngroups_all += cap * p. ficGroups;
 		m. mscbits_off. resize (nsub);
 		for (size_t s = 0; s < nsub; s ++) { m. mscbits_off [s] = mscbits_bytes; mscbits_bytes += up ((cap * p. cifsPerFrame + 1) * 24 * (size_t) E -> subch [s]. bitRate, 256); }
 		ctl_fresh (&m. ctl);
@@ -690,8 +717,9 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 	CUDA_TRY (h, E -> m_fic8. ensure (fic_bytes + 256));
 	CUDA_TRY (h, E -> m_msc8. ensure (msc_bytes + 256));
 	CUDA_TRY (h, E -> m_info. ensure ((info_n + 1) * sizeof (dabgpu_frame_info)));
-	CUDA_TRY (h, E -> m_ficbits. ensure (ficbits_bytes + 256));
-	CUDA_TRY (h, E -> m_ficcrc. ensure (ficcrc_bytes + 256));
+	CUDA_TRY (h, E -> m_ficbits. ensure ((ngroups_all + 1) * 768));
+	CUDA_TRY (h, E -> m_ficcrc. ensure ((ngroups_all + 1) * 3));
+	if (ngroups_all > 0x7fffffff / 3) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_decode_multi: too many frames in one call");
 	CUDA_TRY (h, E -> m_mscbits. ensure (mscbits_bytes + 256));
 	ChunkBufs cb;
 	int rc = ensure_round_bufs (h, nstreams, MULTI_SLOT_CAP, &cb);
@@ -712,6 +740,7 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 	}
 	StreamDev *hsd = (StreamDev *) E -> h_sd. p;
 	// channel decoding of everything accepted since the last call, all streams in one launch pair
+	dabgpu_result no_copy {};
 	auto channel_all = [&] (bool final) -> int {
 		std::vector<ChanPart> parts;
 		long long pending = 0;
@@ -724,11 +753,14 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 			q. fic8 = (const uint8_t *) E -> m_fic8. p + m. fic_off; q. msc8 = (const uint8_t *) E -> m_msc8. p + m. msc_off;
 			q. f0 = m. decoded_upto; q. nv = m. nframes - m. decoded_upto; q. cifs_before = (int64_t) m. decoded_upto * p. cifsPerFrame;
 			q. ficbits = (uint8_t *) E -> m_ficbits. p + m. ficbits_off; q. ficcrc = (uint8_t *) E -> m_ficcrc. p + m. ficcrc_off;
-			q. mscbits = m. mscbits. data (); q. nblk = m. nblk. data (); q. out = jobs [i]. out; q. fib0 = ~0ull;
+			q. mscbits = m. mscbits. data (); q. nblk = m. nblk. data (); q. out = &no_copy; q. fib0 = ~0ull;      // (results go out in bulk at the end)
 			parts. push_back (q);
 			m. decoded_upto = m. nframes;
 		}
-		return channel_parts (h, parts);
+		// the CRC launch covers every group of every stream: groups not decoded yet give flags nobody reads (they are
+		// recomputed when their bits arrive)
+		const CrcSpan span { (uint8_t *) E -> m_ficbits. p, (uint8_t *) E -> m_ficcrc. p, (int) ngroups_all };
+		return channel_parts (h, parts, &span);
 	};
 	while (true) {
 		int nslots = 0, max_budget = 0;
@@ -778,14 +810,31 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 	}
 	if ((rc = channel_all (true))) return rc;
 	for (int i = 1; i < 4; i ++) CUDA_TRY (h, cudaStreamSynchronize (h -> vctx [i]. st));
+	// results: the streams' outputs lie side by side in four device buffers -- four device-to-host copies into pinned staging,
+	// then plain host copies to the callers' buffers (hundreds of small copies to pageable memory cost more than the decode)
+	const size_t b_fic = ngroups_all * 768, b_crc = ngroups_all * 3, b_info = info_n * sizeof (dabgpu_frame_info);
+	const size_t o_crc = up (b_fic, 256), o_info = o_crc + up (b_crc, 256), o_msc = o_info + up (b_info, 256);
+	CUDA_TRY (h, E -> mh_out. ensure (o_msc + mscbits_bytes + 256));
+	char *ho = (char *) E -> mh_out. p;
+	if (b_fic) CUDA_TRY (h, cudaMemcpyAsync (ho, E -> m_ficbits. p, b_fic, cudaMemcpyDeviceToHost, h -> stream));
+	if (b_crc) CUDA_TRY (h, cudaMemcpyAsync (ho + o_crc, E -> m_ficcrc. p, b_crc, cudaMemcpyDeviceToHost, h -> stream));
+	if (b_info) CUDA_TRY (h, cudaMemcpyAsync (ho + o_info, E -> m_info. p, b_info, cudaMemcpyDeviceToHost, h -> stream));
+	if (mscbits_bytes) CUDA_TRY (h, cudaMemcpyAsync (ho + o_msc, E -> m_mscbits. p, mscbits_bytes, cudaMemcpyDeviceToHost, h -> stream));
+	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
 	for (int i = 0; i < nstreams; i ++) {
 		MultiStream &m = ms [i];
 		dabgpu_result *out = jobs [i]. out;
 		out -> nframes = m. nframes;
 		out -> consumed = m. ctl. pos;
-		for (size_t s = 0; s < nsub; s ++) if (out -> msc_nblocks) out -> msc_nblocks [s] = m. nblk [s];
-		if (m. nframes > 0 && out -> info)
-			CUDA_TRY (h, cudaMemcpyAsync (out -> info, (dabgpu_frame_info *) E -> m_info. p + m. info_off, (size_t) m. nframes * sizeof (dabgpu_frame_info), cudaMemcpyDeviceToHost, h -> stream));
+		const size_t ng = (size_t) m. nframes * p. ficGroups;
+		if (out -> fic_bits && ng) memcpy (out -> fic_bits, ho + m. ficbits_off, ng * 768);
+		if (out -> fic_crc && ng) memcpy (out -> fic_crc, ho + o_crc + m. ficcrc_off, ng * 3);
+		if (out -> info && m. nframes) memcpy (out -> info, ho + o_info + m. info_off * sizeof (dabgpu_frame_info), (size_t) m. nframes * sizeof (dabgpu_frame_info));
+		for (size_t s = 0; s < nsub; s ++) {
+			if (out -> msc_nblocks) out -> msc_nblocks [s] = m. nblk [s];
+			if (out -> msc_bits && out -> msc_bits [s] && m. nblk [s] > 0)
+				memcpy (out -> msc_bits [s], ho + o_msc + m. mscbits_off [s], (size_t) m. nblk [s] * msc_block_bytes (E, E -> subch [s]));
+		}
 		if (m. nframes > 0 && out -> soft) {
 			const size_t bytes = (size_t) m. nframes * (p. L - 1) * 2 * p. K * sizeof (int16_t);
 			CUDA_TRY (h, cudaStreamSynchronize (h -> stream));                  // d_soft16 is reused stream after stream

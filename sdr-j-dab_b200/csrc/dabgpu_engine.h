@@ -88,6 +88,8 @@ struct Engine {
 	std::vector<cudaEvent_t> copy_events;
 	int vit_batch_frames = 128;         // host-input path: frames per channel-decoding launch (cfg.host_batch_frames overrides)
 	unsigned vrr = 0;                   // round robin over the channel-decoding side streams
+	bool msc_packed = false;            // dabgpu_set_msc_output: MSC blocks leave with 8 bits per byte
+	int out_skip = 0;                   // next decode call: FIC / info / soft results of its first out_skip frames are not delivered (multi-GPU shards, dabgpu_group.cu)
 	bool needs_reset = false;           // a call failed half way: the stream state is not trustworthy until dabgpu_state_set / import
 	// multi-stream batch (dabgpu_decode_multi): scratch that lives with the handle
 	DevBuf m_in, m_fic8, m_msc8, m_info, m_ficbits, m_ficcrc, m_mscbits;

@@ -140,7 +140,8 @@ struct VitSimdJob {
 	unsigned one;             // = 1, set by dab_vit_simd_run; opaque to the compiler on purpose (see vs_acs)
 	uint2 *dec;               // [ncw / 32][vs_npad (nsteps) / 2][32] uint4 decision words of a step pair (dabgpu_vit_simd.cu)
 	const uint32_t *prbs;     // packed dispersal sequence or nullptr
-	uint8_t *out;             // [ncw][frameBits]
+	uint8_t *out;             // [ncw][frameBits], or [ncw][frameBits / 8] when packed
+	int packed;               // 1: eight decoded bits per output byte, first bit on top (frameBits must be a multiple of 32)
 };
 cudaError_t vit_simd_launch (dabgpu *h, const VitSimdJob *d_jobs, int njobs, int total_ctas, int total_ctas2, bool convert);
 int vit_simd_cw_per_cta ();

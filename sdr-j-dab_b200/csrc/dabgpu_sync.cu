@@ -21,30 +21,39 @@ __device__ __forceinline__ float2 sy_sample (const SampleWin &w, long long i) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// acquisition: notSynced -> SyncOnNull -> SyncOnEndNull (ofdm-processor.cpp:275-338), one warp per stream.
+// acquisition: notSynced -> SyncOnNull -> SyncOnEndNull (ofdm-processor.cpp:275-338), one CTA of four warps per stream.
 // The reference walks the samples one by one through two recurrences -- the signal level IIR
 // (sLevel = 0.00001 * jan_abs (v) + (1 - 0.00001) * sLevel, in double, rounded to float, :168) and the running sum of a
 // 50-sample envelope window -- and tests a threshold before every sample.  Only the two recurrences are serial.  Per chunk:
-//   1. all lanes convert / mix the samples and prepare everything that does not depend on the recurrences: the
-//      envelope value e_i (|re| + |im|, or the true magnitude in SyncOnEndNull), the double product 0.00001 * jan_abs,
-//      the window difference e_i - e_(i-50);
-//   2. lane 0 runs the two recurrences (one double multiply-add-round chain, one float add chain) and records the
-//      values BEFORE every sample;
-//   3. all lanes evaluate the reference's threshold tests on the recorded values and the first sample that leaves the
-//      state is found by a warp reduction; the state is committed up to there.
-// Same operations in the same order on every value as the reference's loop, hence the same result bit for bit.
+//   1. all threads convert / mix the samples and prepare everything that does not depend on the recurrences: the
+//      envelope value e_i (|re| + |im|, or the true magnitude in SyncOnEndNull), jan_abs, the window difference e_i - e_(i-50);
+//   2. thread 0 runs the two recurrences and records the values BEFORE every sample.  The window sum is a float add chain
+//      (4 cycles a step).  The level IIR as the reference writes it is a chain of four dependent double-precision operations
+//      (widen, multiply, add, round to float: ~85 cycles a step on this part, 12-20 ms per search), so thread 0 runs a float
+//      SURROGATE instead, a' = fma (1e-5f, |v| - a, a) (two dependent float operations), and
+//   2b. all threads VERIFY it: for every step the reference's own double expression is evaluated on the recorded a_i and
+//      compared with the recorded a_(i+1).  The surrogate's error is ~1e-12 a against a float spacing of ~1e-7 a, so the
+//      two differ only when the exact value sits within 1e-12 a of a rounding tie (~3e-5 of the steps); the first such
+//      step is repaired with the exact value and the chain re-run from there.  By induction the recorded sequence is the
+//      reference's, bit for bit, whatever the surrogate did;
+//   3. all threads evaluate the reference's threshold tests on the recorded values and the first sample that leaves the
+//      state is found by a reduction; the state is committed up to there.
 // ---------------------------------------------------------------------------------------------------
-#define ACQ_CHUNK 512
-__global__ void __launch_bounds__ (32) acquire_kernel (StreamDev *sd, OfdmTables T, int T_F, int T_null) {
-	__shared__ float s_e [ACQ_CHUNK], s_d [ACQ_CHUNK], s_sl [ACQ_CHUNK], s_csb [ACQ_CHUNK], s_ring [64];
-	__shared__ double s_ax [ACQ_CHUNK];
+#define ACQ_CHUNK 1024
+#define ACQ_THREADS 128
+__device__ __forceinline__ float acq_level_exact (float a, float ja) {          // ofdm-processor.cpp:168, operation by operation
+	return __double2float_rn (__dadd_rn (__dmul_rn (0.00001, (double) ja), __dmul_rn (1 - 0.00001, (double) a)));
+}
+__global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, OfdmTables T, int T_F, int T_null) {
+	__shared__ float s_e [ACQ_CHUNK], s_d [ACQ_CHUNK + 32], s_sl [ACQ_CHUNK + 32], s_csb [ACQ_CHUNK + 32], s_ja [ACQ_CHUNK], s_t [ACQ_CHUNK + 32], s_ring [64];
+	__shared__ int s_first;
 	StreamDev &S = sd [blockIdx. x];
 	if (!S. do_acquire) return;
 	const SampleWin w = S. w;
 	StreamCtl *ctl = &S. ctl;
-	const int lane = threadIdx. x;
-	const long long total = w. len0 + w. len1;
-	// scalar state, identical in every lane (updated from lane 0's results by shuffles)
+	const int tid = threadIdx. x;
+	const long long total = w. len0 + w. len1 < S. limit ? w. len0 + w. len1 : S. limit;
+	// scalar state, identical in every thread
 	int stage = 0, cnt = 0, counter = 0, idx = 0, done = 0;
 	float sLevel = 0.f, cs = 0.f;
 	long long pos = ctl -> pos, attempt_pos = pos;
@@ -60,58 +69,105 @@ __global__ void __launch_bounds__ (32) acquire_kernel (StreamDev *sd, OfdmTables
 		if (pos + n > total) { done = 2; break; }                    // out of data: rewind to the attempt start
 		const int ph = stage < 2 ? 0 : mod_rate (phi);               // getSample (0) while looking for a signal at all (:279, 285)
 		{	// 1. per-sample values
-			int l = mod_rate ((long long) lp - (long long) (lane + 1) * ph);
-			const int step = mod_rate (32ll * ph);
-			for (int i = lane; i < n; i += 32) {
-				const float2 v = cmul (sy_sample (w, pos + i), nco (T, l));
+			int l = mod_rate ((long long) lp - (long long) (tid + 1) * ph);
+			const int step = mod_rate ((long long) ACQ_THREADS * ph);
+			float2 raw [ACQ_CHUNK / ACQ_THREADS];                    // all of the thread's samples are requested before the first is used
+#pragma unroll
+			for (int k = 0; k < ACQ_CHUNK / ACQ_THREADS; k ++)
+				if (tid + k * ACQ_THREADS < n) raw [k] = sy_sample (w, pos + tid + k * ACQ_THREADS);
+#pragma unroll
+			for (int k = 0; k < ACQ_CHUNK / ACQ_THREADS; k ++) {
+				const int i = tid + k * ACQ_THREADS;
+				if (i >= n) break;
+				const float2 v = cmul (raw [k], nco (T, l));
 				const float ja = fabsf (v. x) + fabsf (v. y);            // jan_abs
-				s_ax [i] = __dmul_rn (0.00001, (double) ja);
+				s_ja [i] = ja; s_t [i] = 0.00001f * ja;
 				s_e [i] = stage == 3 ? hypotf (v. x, v. y) : ja;           // abs () in SyncOnEndNull (:329)
 				l -= step; if (l < 0) l += DAB_INPUT_RATE;
 			}
-			__syncwarp ();
+			__syncthreads ();
 			if (stage >= 1)
-				for (int i = lane; i < n; i += 32)
+				for (int i = tid; i < n; i += ACQ_THREADS)
 					s_d [i] = stage == 1 ? s_e [i] : __fsub_rn (s_e [i], i >= 50 ? s_e [i - 50] : s_ring [(idx + i - 50) & 63]);
-			__syncwarp ();
+			__syncthreads ();
 		}
-		float sl_end = sLevel, cs_end = cs;
-		if (lane == 0) {                                             // 2. the two recurrences
-			float a = sLevel, c = cs;
-			if (stage == 0) {
-#pragma unroll 4
-				for (int i = 0; i < n; i ++)
-					a = __double2float_rn (__dadd_rn (s_ax [i], __dmul_rn (1 - 0.00001, (double) a)));
-			} else {
-#pragma unroll 4
-				for (int i = 0; i < n; i ++) {
-					s_sl [i] = a; s_csb [i] = c;
-					a = __double2float_rn (__dadd_rn (s_ax [i], __dmul_rn (1 - 0.00001, (double) a)));
-					c = __fadd_rn (c, s_d [i]);
+		// 2. the two recurrences: s_sl [i] / s_csb [i] = value before sample i, [n] = value after the chunk.  Thread 0 runs the
+		// level surrogate, thread 32 (another warp, concurrently) the window sum.  Both walk in batches of 16 whose inputs are
+		// fetched into registers one batch ahead, so that only the dependent arithmetic is on the chain (one FFMA / one FADD
+		// a step).  Surrogate: a' = fma (a, c_hi, u), u = fma (a_prev, c_lo, k |v|) with c_hi + c_lo = 1 - 1e-5 to 48 bits; u takes
+		// the level of one step EARLIER (it differs by 1e-5 a, times c_lo ~ 1e-8: invisible), which keeps it off the chain.
+		if (tid == 32) {
+			float c = cs;
+			if (stage >= 1) {
+				float dn [16];
+#pragma unroll
+				for (int k = 0; k < 16; k ++) dn [k] = s_d [k];
+				for (int i = 0; i < n; i += 16) {
+					float dc [16], r [16];
+#pragma unroll
+					for (int k = 0; k < 16; k ++) { dc [k] = dn [k]; dn [k] = s_d [i + 16 + k]; }
+#pragma unroll
+					for (int k = 0; k < 16; k ++) { r [k] = c; c = __fadd_rn (c, dc [k]); }
+#pragma unroll
+					for (int k = 0; k < 16; k ++) s_csb [i + k] = r [k];
+					if (i + 16 == n) s_csb [n] = c;                  // (n inside a batch: r [n - i] above is already the value after the last sample)
 				}
-			}
-			sl_end = a; cs_end = c;
+			} else s_csb [n] = c;
 		}
-		__syncwarp ();
+		int from = 0;                                                // s_sl [from] is known to be exact
+		if (tid == 0) s_sl [0] = sLevel;
+		while (true) {
+			if (tid == 0) {                                          // surrogate chain from `from` on
+				const float c_hi = 0.99999f, c_lo = (float) ((1 - 0.00001) - (double) 0.99999f);
+				float a = s_sl [from], ap = a;
+				float tn [16];
+#pragma unroll
+				for (int k = 0; k < 16; k ++) tn [k] = s_t [from + k];
+				for (int i = from; i < n; i += 16) {
+					float tc [16], r [16];
+#pragma unroll
+					for (int k = 0; k < 16; k ++) { tc [k] = tn [k]; tn [k] = s_t [i + 16 + k]; }
+#pragma unroll
+					for (int k = 0; k < 16; k ++) { const float u = __fmaf_rn (ap, c_lo, tc [k]); ap = a; a = __fmaf_rn (a, c_hi, u); r [k] = a; }
+#pragma unroll
+					for (int k = 0; k < 16; k ++) if (i + k < n) s_sl [i + 1 + k] = r [k];
+				}
+				s_first = n;
+			}
+			__syncthreads ();
+			int bad = n;                                             // 2b. first step whose recorded successor is not the exact one
+			for (int i = from + tid; i < n && bad == n; i += ACQ_THREADS)
+				if (acq_level_exact (s_sl [i], s_ja [i]) != s_sl [i + 1]) bad = i;
+			if (bad < n) atomicMin (&s_first, bad);
+			__syncthreads ();
+			const int first = s_first;
+			if (first == n) break;
+			if (tid == 0) s_sl [first + 1] = acq_level_exact (s_sl [first], s_ja [first]);    // repair, then re-run from there
+			from = first + 1;
+			__syncthreads ();                                        // (everybody has read s_first before thread 0 resets it)
+		}
 		int used = n;
 		if (stage >= 2) {                                            // 3. the threshold tests (:301, :323), in parallel
+			if (tid == 0) s_first = n;
+			__syncthreads ();
 			int first = n;
-			for (int i = lane; i < n && first == n; i += 32) {
+			for (int i = tid; i < n && first == n; i += ACQ_THREADS) {
 				const double lhs = (double) (s_csb [i] / 50.0f), lv = (double) s_sl [i];
 				const bool leave = stage == 2 ? !(lhs > 0.40 * lv) : !(lhs < 0.75 * lv);
 				if (leave) first = i;
 			}
-			for (int o = 16; o > 0; o >>= 1) first = min (first, __shfl_xor_sync (0xffffffffu, first, o));
-			used = first;
+			if (first < n) atomicMin (&s_first, first);
+			__syncthreads ();
+			used = s_first;
 		}
 		// commit the state after `used` samples
-		if (used < n) { sLevel = s_sl [used]; cs = s_csb [used]; }
-		else { sLevel = __shfl_sync (0xffffffffu, sl_end, 0); cs = __shfl_sync (0xffffffffu, cs_end, 0); }
+		sLevel = s_sl [used]; cs = s_csb [used];
+		__syncthreads ();                                            // everybody has read the records before the ring / next chunk overwrite anything
 		if (stage >= 1) {
-			for (int i = lane; i < used; i += 32) if (i >= used - 64) s_ring [(idx + i) & 63] = s_e [i];
+			for (int i = tid; i < used; i += ACQ_THREADS) if (i >= used - 64) s_ring [(idx + i) & 63] = s_e [i];
 			idx += used;
 		}
-		__syncwarp ();
+		__syncthreads ();
 		pos += used;
 		lp = mod_rate ((long long) lp - (long long) used * ph);
 		bool restart = false;
@@ -131,7 +187,7 @@ __global__ void __launch_bounds__ (32) acquire_kernel (StreamDev *sd, OfdmTables
 			attempt_pos = pos; attempt_lp = lp;
 		}
 	}
-	if (lane == 0) {
+	if (tid == 0) {
 		if (done == 1) { ctl -> synced = 1; ctl -> pos = pos; ctl -> lp = lp; ctl -> acq_done = 1; }
 		else           { ctl -> synced = 0; ctl -> pos = attempt_pos; ctl -> lp = attempt_lp; ctl -> acq_done = 0; }
 	}
@@ -337,7 +393,7 @@ int sync_init (dabgpu *h) {
 
 void acquire_launch (dabgpu *h, StreamDev *sd, int nstreams, cudaStream_t st) {
 	ProfScope prof (h, KC_ACQUIRE, st);
-	acquire_kernel<<<nstreams, 32, 0, st>>> (sd, h -> engine -> T, h -> p. T_F, h -> p. T_null);
+	acquire_kernel<<<nstreams, ACQ_THREADS, 0, st>>> (sd, h -> engine -> T, h -> p. T_F, h -> p. T_null);
 	h -> launches ++;
 }
 

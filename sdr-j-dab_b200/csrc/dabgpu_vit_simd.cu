@@ -381,6 +381,21 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 			// (a partial word can only be the first one walked: S is still 0 below the bits it shifts in)
 			w [wd] = nvalid == 32 ? tb_walk_word<true> (S, dq [wi % TB_NBUF], tid, 32) : tb_walk_word<false> (S, dq [wi % TB_NBUF], tid, nvalid);
 		}
+		if (j. packed) {
+			// packed output (dabgpu_set_msc_output): 8 bits per byte, first bit in the byte's top bit -- the thread writes the four
+			// words it has just decoded itself (frameBits is a multiple of 32 here)
+			if (live) {
+				uint32_t *o = reinterpret_cast<uint32_t *> (j. out + (size_t) cw * (size_t) (j. frameBits >> 3)) + 4 * rd;
+#pragma unroll
+				for (int q = 0; q < 4; q ++)
+					if (4 * rd + q < nwords) {
+						uint32_t v = w [q];
+						if (j. prbs) v ^= __ldg (&j. prbs [4 * rd + q]);
+						o [q] = __byte_perm (__brev (v), 0, 0x0123);
+					}
+			}
+			continue;
+		}
 		__syncthreads ();
 #pragma unroll
 		for (int q = 0; q < 4; q ++) bits [tid * 5 + q] = w [q];

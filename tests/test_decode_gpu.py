@@ -202,3 +202,25 @@ def test_device_resident_input_and_pipelined_batches(port):
         for a, b in zip(got.msc, want.msc):
             assert np.array_equal(a, b)
         eng.close()
+
+
+def test_packed_msc_output(port):
+    """dabgpu_set_msc_output: the same decoded blocks with eight bits per byte, first bit on top (what mp4Processor::addtoFrame
+    builds as its first step, audio/mp4processor.cpp:107-117); one stream and the many-stream call"""
+    pkg = engine_pkg()
+    mod = dabmod.Modulator(port, 1, SUBS, 1001)
+    tr = mod.generate(26, cfo_hz=1234.0, snr_db=20.0, lead=7000, tail=5000)
+    subl = [(s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel) for s in mod.sub]
+    a = pkg.DabGpu(mode=1); a.set_subchannels(subl)
+    ra = a.decode(tr["iq"], a.alloc_result(30))
+    b = pkg.DabGpu(mode=1); b.set_subchannels(subl); b.set_msc_output(True)
+    rb = b.decode(tr["iq"], b.alloc_result(30))
+    assert rb.nframes == ra.nframes and np.array_equal(ra.fic_bits, rb.fic_bits)
+    for x, y in zip(ra.msc, rb.msc):
+        assert x.shape[0] == y.shape[0] > 0 and y.shape[1] * 8 == x.shape[1]
+        assert np.array_equal(np.packbits(x, axis=1), y)
+    rc = b.decode_multi([tr["iq"], tr["iq"][:2 * 3000000]], [b.alloc_result(30), b.alloc_result(30)])
+    for x, y in zip(ra.msc, rc[0].msc):
+        assert np.array_equal(np.packbits(x, axis=1), y)
+    assert rc[1].nframes > 8 and np.array_equal(rc[1].msc[0], rc[0].msc[0][:rc[1].msc[0].shape[0]])
+    a.close(); b.close()
