@@ -159,6 +159,126 @@ def cpu_viterbi_only(nthreads, orc_mod, seconds=3.0):
     return sum(done) / (time.perf_counter() - t0) / 1e6
 
 
+def base_config(frames):
+    """the workload description: IDENTICAL in both arms (the driver compares the dicts)"""
+    return {"workload": "Mode I %d-frame batch, FIC + 9 x 96-CU EEP-3A 128 kbit/s sub-channels (864 CU), AWGN 15 dB, CFO +137 Hz" % frames,
+            "frames_per_step": frames, "lead_in_frames": LEAD_FRAMES,
+            "l2": "inputs larger than L2 (%.0f MB of u8 IQ per step)" % (frames * T_F * 2 / 1e6)}
+
+
+def check_against_truth(r, truth, nsub):
+    """decoded batch vs what the modulator sent: every FIB and every block of every sub-channel.  Returns
+    (fraction of FIC groups equal, fraction of MSC blocks equal, frame offset) -- the stream is aligned on its first FIC group"""
+    fibs = truth["fibs"]
+    g0 = next((k for k in range(0, fibs.shape[0] - 8, 4) if np.array_equal(r.fic_bits[0], fibs[k]) and np.array_equal(r.fic_bits[5], fibs[k + 5])), None)
+    if g0 is None:
+        return 0.0, 0.0, None
+    n = r.fic_bits.shape[0]
+    fic_ok = float((r.fic_bits == fibs[g0:g0 + n]).all(axis=1).mean())
+    good = total = 0
+    for i in range(nsub):
+        pay = truth["payloads"][i]
+        c0 = g0 - 15                                             # the time interleaver delays by 15 CIFs (CIF index = FIC group index in Mode I)
+        m = r.msc[i]
+        good += int((m == pay[c0:c0 + m.shape[0]]).all(axis=1).sum())
+        total += m.shape[0]
+    return fic_ok, good / max(total, 1), g0 // 4
+
+
+def same_result(a, b, nsub):
+    return bool(a.nframes == b.nframes and np.array_equal(a.fic_bits, b.fic_bits) and np.array_equal(a.fic_crc, b.fic_crc) and
+                all(np.array_equal(a.msc[i], b.msc[i]) for i in range(nsub)))
+
+
+def timed(fn, steps, barrier):
+    barrier()
+    t = time.perf_counter()
+    for _ in range(steps):
+        r = fn()
+    barrier()
+    return (time.perf_counter() - t) / steps, r
+
+
+def mode_leg(pkg, mode, device, orc_mod, dabmod, steps):
+    """device-resident decode rate of Mode II / IV on the same 864-CU ensemble (configs[2]): a short modulated block whose
+    batch part is tiled to a 48 M-sample step (frames stay T_F apart; the CFO is chosen so that the phase is continuous at the seams)"""
+    import torch
+    port = orc_mod.Oracle("port")
+    p = port.mode_params(mode)
+    nblock, tiles, lead = {2: (64, 16, 192), 4: (32, 16, 96)}[mode]
+    mod = dabmod.Modulator(port, mode, SUBS, 77 + mode)
+    total = lead + nblock + 2
+    truth = mod.frame_bits(total)
+    cfo = round(137.0 * nblock * p.T_F / 2048000.0) / (nblock * p.T_F / 2048000.0)
+    iq = mod.channel(mod.modulate(truth["bits"]), cfo_hz=cfo, snr_db=15.0, rms=30.0, lead=30000, tail=8000)
+    eng = pkg.DabGpu(mode=mode, device=device)
+    eng.set_subchannels([(s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel) for s in mod.sub])
+    r0 = eng.decode(iq[:2 * (30000 + lead * p.T_F - p.T_null // 2)], eng.alloc_result(lead + 2, want_soft=False))
+    st = eng.state_get()
+    block = iq[2 * st.abs_pos:2 * (st.abs_pos + nblock * p.T_F)]
+    batch = np.concatenate([np.tile(block, tiles), iq[2 * (st.abs_pos + nblock * p.T_F):2 * (st.abs_pos + nblock * p.T_F + 6000)]])
+    nframes, nsamp = nblock * tiles, batch.size // 2
+    d_in = torch.from_numpy(batch).to(torch.device("cuda", device))
+    torch.cuda.synchronize()
+    out = eng.alloc_result(nframes, want_soft=False)
+    for i in range(len(SUBS)):
+        out.ptrs[i] = None
+    out.res.info = None
+
+    def run():
+        eng.state_set(pkg.binding.StreamState.from_buffer_copy(bytes(st)))
+        return eng.decode_dev(d_in.data_ptr(), nsamp, out)
+    for _ in range(3):
+        r = run()
+    eng.profile_enable(True); eng.profile_reset()
+    eng.timer_begin()
+    for _ in range(steps):
+        r = run()
+    ms = eng.timer_end() / steps
+    prof = eng.profile()
+    res = {"frames_per_step": int(r.nframes), "frames_per_s": r.nframes / ms * 1e3, "msamples_per_s": r.nframes * p.T_F / ms / 1e3, "ms_per_step": ms,
+           "fic_crc_ok": float(r.fic_crc.mean()), "locked": bool(st.synced == 1 and st.f2Correction == 0),
+           "kernel_ms": {k: round(v[1] / steps, 4) for k, v in prof.items() if v[0]}}
+    eng.close()
+    return res
+
+
+def multi_stream_leg(pkg, eng, iq, device, nstreams, frames_each, steps, barrier):
+    """configs[3] at one GPU's share: `nstreams` independent streams (distinct cuts of the recording, each starting at an
+    arbitrary sample: every one needs its own acquisition and AFC convergence) through ONE dabgpu_decode_multi call"""
+    import torch
+    dev = torch.device("cuda", device)
+    rng = np.random.default_rng(11)
+    span = int((frames_each + 0.3) * T_F)
+    offs = sorted(int(x) for x in rng.integers(0, iq.size // 2 - span - 1, nstreams))
+    pinned = [torch.empty(2 * span, dtype=torch.uint8).pin_memory() for _ in range(nstreams)]
+    for t, o in zip(pinned, offs):
+        t.numpy()[:] = iq[2 * o:2 * (o + span)]
+    d_streams = [t.to(dev) for t in pinned]
+    torch.cuda.synchronize()
+    outs = [eng.alloc_result(frames_each + 2, want_soft=False) for _ in range(nstreams)]
+    host = lambda: eng.decode_multi([(t.data_ptr(), span) for t in pinned], outs, host_ptrs=True)
+    devc = lambda: eng.decode_multi(None, outs, dev_ptrs=[(t.data_ptr(), span) for t in d_streams])
+    res_h = host()
+    snap = [(r.nframes, r.fic_bits.copy(), [m.copy() for m in r.msc]) for r in res_h]
+    res_d = devc()
+    same_dev = all(a[0] == b.nframes and np.array_equal(a[1], b.fic_bits) and all(np.array_equal(x, y) for x, y in zip(a[2], b.msc)) for a, b in zip(snap, res_d))
+    # every fourth stream once more through a fresh single-stream handle
+    same_single = True
+    for i in range(0, nstreams, 4):
+        e1 = pkg.DabGpu(mode=MODE, device=device)
+        e1.set_subchannels(SUB5)
+        one = e1.decode((pinned[i].data_ptr(), span), e1.alloc_result(frames_each + 2, want_soft=False))
+        same_single = same_single and one.nframes == snap[i][0] and np.array_equal(one.fic_bits, snap[i][1]) and all(np.array_equal(x, y) for x, y in zip(one.msc, snap[i][2]))
+        e1.close()
+    frames = sum(a[0] for a in snap)
+    t_dev, _ = timed(devc, steps, barrier)
+    t_host, _ = timed(host, steps, barrier)
+    return {"streams": nstreams, "frames_per_stream_offered": frames_each, "frames_decoded": int(frames), "frames_per_s": frames / t_dev, "e2e_frames_per_s": frames / t_host,
+            "ms_per_call_dev": t_dev * 1e3, "ms_per_call_host": t_host * 1e3, "equal_to_single_handle": bool(same_single), "dev_equals_host_input": bool(same_dev),
+            "note": "one dabgpu_decode_multi call; every stream starts unsynchronised at an arbitrary sample (acquisition + coarse / fine AFC convergence inside the timed call)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,8 +288,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline legs only (no modes / multi_stream / split_recording / unlocked legs)")
     ap.add_argument("--dev-batch", type=int, default=0, help="frames per channel-decoding launch on the device-resident path; 0 = one launch per step")
     ap.add_argument("--host-batch", type=int, default=0, help="frames per channel-decoding launch on the host-input (e2e) path; 0 = engine default")
+    ap.add_argument("--split-frames", type=int, default=4096, help="frames of the split recording (N > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -178,9 +300,7 @@ def main():
 
     import dabmod
     import orc as orc_mod
-    config = {"workload": "Mode I %d-frame batch, FIC + 9 x 96-CU EEP-3A 128 kbit/s sub-channels (864 CU), AWGN 15 dB, CFO +137 Hz"
-                          % args.frames, "frames_per_step": args.frames, "lead_in_frames": LEAD_FRAMES,
-              "l2": "inputs larger than L2 (%.0f MB of u8 IQ per step)" % (args.frames * T_F * 2 / 1e6)}
+    config = base_config(args.frames)
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -196,7 +316,9 @@ def main():
                 "config": config,
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": nthreads, "kind": kind,
                                  "sample": "%d threads x (%d lead-in + %d frames) of the same stream, full chain incl. all 9 sub-channels; "
-                                           "%d frames decoded per step; FFT = labelled FFTW stand-in" % (nthreads, LEAD_FRAMES, fpp, frames)},
+                                           "%d frames decoded per step, the lead-in frames counted as work although the first 16 CIFs of every "
+                                           "thread skip the Viterbi (de-interleaver warm-up: flatters the CPU by ~4 %%); FFT = labelled FFTW stand-in"
+                                           % (nthreads, LEAD_FRAMES, fpp, frames)},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -215,6 +337,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     iq, mod, truth = make_workload(args.frames, 1002 + rank, orc_mod, dabmod)
     subs = [(s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel) for s in mod.sub]
+    nsub = len(subs)
     eng = pkg.DabGpu(mode=MODE, device=local_rank, host_batch_frames=args.host_batch, dev_batch_frames=args.dev_batch)
     eng.set_subchannels(subs)
 
@@ -223,7 +346,7 @@ def main():
     out_lead = eng.alloc_result(LEAD_FRAMES + 2, want_soft=False)
     r0 = eng.decode(iq[:2 * lead_samples], out_lead)
     st = eng.state_get()
-    hist_frames = r0.nframes
+    blob = eng.export_state()                                 # incl. the de-interleaver history the batch starts from
     # the batch = everything after what the lead-in consumed
     batch_first = st.abs_pos
     assert st.synced == 1 and st.f2Correction == 0, "lead-in did not lock (synced %d, coarse search %d)" % (st.synced, st.f2Correction)
@@ -233,23 +356,24 @@ def main():
     h_in = torch.empty(batch.size, dtype=torch.uint8).pin_memory()
     h_in.numpy()[:] = batch
     d_in = h_in.to(dev)
-    # pinned result buffers for the e2e leg
+
     def pinned(shape, dtype):
         assert dtype == np.uint8
         return torch.empty(shape, dtype=torch.uint8).pin_memory().numpy()
-    out_e2e = eng.alloc_result(args.frames, want_soft=False, alloc=pinned)
-    # device-resident leg: no result download
-    out_dev = eng.alloc_result(args.frames, want_soft=False)
+    out_e2e = eng.alloc_result(args.frames, want_soft=False, alloc=pinned)      # pinned result buffers for the e2e leg
+    out_chk = eng.alloc_result(args.frames, want_soft=False)
+    out_dev = eng.alloc_result(args.frames, want_soft=False)                    # device-resident leg: no result download
     out_dev.res.fic_bits = None; out_dev.res.fic_crc = None; out_dev.res.info = None
-    for i in range(len(subs)):
+    for i in range(nsub):
         out_dev.ptrs[i] = None
-    hist0 = None
 
-    def restore():
-        # back to the locked state right after the lead-in (the history rows are restored by the engine's
-        # own lead-in decode only once; the de-interleaver history content does not change the work done)
-        s = pkg.binding.StreamState.from_buffer_copy(bytes(st))
-        eng.state_set(s)
+    def restore(full=False):
+        # back to the locked state right after the lead-in (the sample tail is dropped: the batch starts at abs_pos).
+        # full: the de-interleaver history too (checked runs); the timed steps leave the history rows as the previous step
+        # left them -- their content does not change the work done
+        if full:
+            eng.import_state(blob)
+        eng.state_set(pkg.binding.StreamState.from_buffer_copy(bytes(st)))
 
     def barrier():
         torch.cuda.synchronize()
@@ -257,23 +381,33 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_dev():
-        restore()
-        return eng.decode_dev(d_in.data_ptr(), nsamp, out_dev)
+    def run_dev(out=out_dev, full=False):
+        restore(full)
+        return eng.decode_dev(d_in.data_ptr(), nsamp, out)
 
-    def run_e2e():
-        restore()
+    def run_e2e(full=False):
+        restore(full)
         return eng.decode((h_in.data_ptr(), nsamp), out_e2e)
 
-    # correctness gate before timing: FIC CRCs of the batch are ok and the payload comes out
-    r = run_e2e()
+    def e2e_pipelined(steps, out=out_e2e):
+        """K steps as a streaming caller makes them: the upload of step k + 1 is announced (dabgpu_prefetch) before step k is
+        decoded, so the PCIe link does not idle while a step finishes.  Every step's input still goes host -> device once."""
+        eng.prefetch((h_in.data_ptr(), nsamp))
+        for k in range(steps):
+            if k + 1 < steps:
+                eng.prefetch((h_in.data_ptr(), nsamp))
+            restore(False)
+            r_ = eng.decode((h_in.data_ptr(), nsamp), out)
+        return r_
+
+    # correctness gate before timing: EVERY FIB and EVERY block of EVERY sub-channel against what the modulator sent
+    r = run_e2e(True)
     assert r.nframes == args.frames, r.nframes
     crc_ok = float(r.fic_crc.mean())
-    blocks = r.msc[0].shape[0]
-    pay = truth["payloads"][0]
-    k0 = next((k for k in range(pay.shape[0] - 4) if np.array_equal(r.msc[0][blocks - 4:blocks], pay[k:k + 4])), None)
-    assert crc_ok > 0.99 and k0 is not None, (crc_ok, k0)
+    fic_eq, msc_eq, f0 = check_against_truth(r, truth, nsub)
+    assert crc_ok > 0.99 and fic_eq > 0.99 and msc_eq > 0.999, (crc_ok, fic_eq, msc_eq, f0)
     frames_per_step = r.nframes
+    e2e_snap = (r.nframes, r.fic_bits.copy(), r.fic_crc.copy(), [m.copy() for m in r.msc])
 
     for _ in range(warmup):
         run_dev()
@@ -294,29 +428,102 @@ def main():
     prof = eng.profile()
     eng.profile_enable(False)
     clocks = sampler.result()
+    # what was timed is what is checked: the very same call once more with its outputs enabled equals the e2e result
+    rd = run_dev(out_chk, True)
+    timed_leg_equal = bool(rd.nframes == e2e_snap[0] and np.array_equal(rd.fic_bits, e2e_snap[1]) and np.array_equal(rd.fic_crc, e2e_snap[2]) and
+                           all(np.array_equal(rd.msc[i], e2e_snap[3][i]) for i in range(nsub)))
+    assert timed_leg_equal, "the device-resident (timed) leg and the host-input leg disagree"
 
     # e2e: host (pinned) input in, decoded bits out, per step, wall clock with sync on both sides
     for _ in range(2):
         run_e2e()
+    e2e_plain_step, _ = timed(run_e2e, args.steps, barrier)      # call after call, nothing announced ahead
+    e2e_pipelined(2)
     barrier()
     t1 = time.perf_counter()
-    for _ in range(args.steps):
-        run_e2e()
+    rq = e2e_pipelined(args.steps)
     barrier()
     e2e_wall = time.perf_counter() - t1
+    restore(True)
+    eng.prefetch((h_in.data_ptr(), nsamp))
+    rq = eng.decode((h_in.data_ptr(), nsamp), out_e2e)
+    pipelined_equal = bool(rq.nframes == e2e_snap[0] and np.array_equal(rq.fic_bits, e2e_snap[1]) and all(np.array_equal(rq.msc[i], e2e_snap[3][i]) for i in range(nsub)))
+    # the PCIe floor of that call on this box: the same bytes up (pinned) with nothing else going on
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_tmp = torch.empty_like(d_in)
+    d_tmp.copy_(h_in, non_blocking=True)
+    barrier()
+    ev0.record()
+    for _ in range(3):
+        d_tmp.copy_(h_in, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_floor_ms = ev0.elapsed_time(ev1) / 3
+    del d_tmp
+    # the same with packed MSC output (8 bits per byte: an eighth of the device-to-host traffic)
+    eng.set_msc_output(True)
+    out_pk = eng.alloc_result(args.frames, want_soft=False, alloc=pinned)
+
+    restore(True)
+    rp = eng.decode((h_in.data_ptr(), nsamp), out_pk)
+    packed_equal = bool(all(np.array_equal(np.packbits(e2e_snap[3][i], axis=1), rp.msc[i]) for i in range(nsub)))
+    e2e_pipelined(2, out_pk)
+    barrier()
+    t1 = time.perf_counter()
+    e2e_pipelined(args.steps, out_pk)
+    barrier()
+    e2e_pk_step = (time.perf_counter() - t1) / args.steps
+    eng.set_msc_output(False)
+
+    extras = {}
+    if not args.no_extras:
+        # ---- unlocked regime: the lead-in itself (acquisition, coarse search, fine corrector converging), device resident
+        d_lead = torch.from_numpy(iq[:2 * lead_samples].copy()).to(dev)
+        fresh = pkg.binding.StreamState(synced=0, coarse=0, fine=0, f2Correction=1, previous_1=1000, previous_2=999, localPhase=0, abs_pos=0, frames=0, cifs=0)
+        out_un = eng.alloc_result(LEAD_FRAMES + 2, want_soft=False)
+
+        def run_unlocked():
+            eng.state_set(pkg.binding.StreamState.from_buffer_copy(bytes(fresh)))
+            return eng.decode_dev(d_lead.data_ptr(), lead_samples, out_un)
+        run_unlocked()
+        t_un, ru = timed(run_unlocked, 3, barrier)
+        extras["unlocked"] = {"frames_per_s": ru.nframes / t_un, "frames": int(ru.nframes), "ms_per_call": t_un * 1e3,
+                              "note": "one stream from its first sample: null-symbol search, coarse offset search and the fine corrector converging "
+                                      "(%d-frame lead-in, device resident); the headline value is the locked steady state" % LEAD_FRAMES}
+        del d_lead
+        # ---- other transmission modes (configs[2]) and many short streams (configs[3])
+        if rank == 0:
+            extras["modes"] = {"mode_%d" % m: mode_leg(pkg, m, local_rank, orc_mod, dabmod, max(args.steps, 3)) for m in (2, 4)}
+        global SUB5
+        SUB5 = subs
+        extras["multi_stream"] = multi_stream_leg(pkg, eng, iq, local_rank, 32, 48, 3, barrier)
 
     elapsed = max(dev_ms / 1e3, 0.0)
     if dist is not None:
-        tt = torch.tensor([elapsed, wall, e2e_wall], device=dev, dtype=torch.float64)
+        tt = torch.tensor([elapsed, wall, e2e_wall, e2e_pk_step, e2e_plain_step, h2d_floor_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed, wall, e2e_wall = tt.tolist()
+        elapsed, wall, e2e_wall, e2e_pk_step, e2e_plain_step, h2d_floor_ms = tt.tolist()
         ff = torch.tensor([frames_per_step], device=dev, dtype=torch.float64)
         dist.all_reduce(ff, op=dist.ReduceOp.SUM)
         total_frames = ff.item()
+        if "multi_stream" in extras:                             # whole-job aggregate: frames of all ranks / slowest rank
+            ms_ = extras["multi_stream"]
+            t = torch.tensor([ms_["ms_per_call_dev"], ms_["ms_per_call_host"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            f = torch.tensor([ms_["frames_decoded"], ms_["streams"], int(ms_["equal_to_single_handle"] and ms_["dev_equals_host_input"])], device=dev, dtype=torch.float64)
+            fsum = f.clone(); dist.all_reduce(fsum, op=dist.ReduceOp.SUM)
+            fmin = f.clone(); dist.all_reduce(fmin, op=dist.ReduceOp.MIN)
+            ms_.update(streams=int(fsum[1].item()), frames_decoded=int(fsum[0].item()), frames_per_s=fsum[0].item() / (t[0].item() * 1e-3),
+                       e2e_frames_per_s=fsum[0].item() / (t[1].item() * 1e-3), ms_per_call_dev=t[0].item(), ms_per_call_host=t[1].item(),
+                       all_ranks_equal=bool(fmin[2].item() > 0))
     else:
         total_frames = frames_per_step
     value = total_frames * args.steps / elapsed
     e2e_value = total_frames * args.steps / e2e_wall
+
+    # ---- one long recording split over the ranks (configs[4]; N > 1): strong scaling, every rank uploads only its own range
+    if dist is not None and not args.no_extras:
+        extras["split_recording"] = split_recording_leg(pkg, iq, st, batch_first, subs, rank, world, local_rank, dist, dev, args.split_frames, barrier)
 
     line = None
     if rank == 0:
@@ -327,11 +534,12 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        traffic = {}
-        try:                                                     # per-launch DRAM bytes of the committed ncu capture (same launch shape only)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic, insts = {}, {}
+        try:                                                     # per-launch DRAM bytes / warp instructions of the committed ncu capture (same launch shape only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             if tj.get("frames_per_launch") == frames_per_step and not args.dev_batch:
                 traffic = {k: v["read"] + v["write"] for k, v in tj.items() if isinstance(v, dict)}
+                insts = {k: v.get("warp_instructions") for k, v in tj.items() if isinstance(v, dict)}
         except Exception:
             pass
         ip = eng.int_peak()
@@ -349,34 +557,50 @@ def main():
         sym_avg_ms = ms_sym / n_sym_work
         sym_gbs = ALG_BYTES_PER_FRAME * sym_frames / (sym_avg_ms * 1e-3) / 1e9 if n_sym else 0.0
         shares = {k: round(v[1] / (dev_ms if dev_ms > 0 else 1.0), 4) for k, v in prof.items() if v[0]}
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        issue_slots = lambda ms: 148 * 4 * ms * 1e-3 * sm_hz     # warp-instruction issue slots of the chip during a launch
         line = {
             "metric": "Mode I frames/s (sync+FFT+demod+Viterbi)", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": elapsed * 1e3 / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (FFT/demod) + u16/u32 (Viterbi metrics)", "data": "synthetic",
-            "config": dict(config, frames_decoded_per_step=frames_per_step, parallelism="1 stream per GPU, frame-parallel inside",
-                           fic_crc_ok=crc_ok),
+            "config": config,
+            "check": {"frames_decoded_per_step": frames_per_step, "fic_crc_ok": crc_ok, "fic_groups_equal_to_sent": fic_eq, "msc_blocks_equal_to_sent": msc_eq,
+                      "timed_leg_equals_e2e_leg": timed_leg_equal, "packed_equals_unpacked": packed_equal, "pipelined_equals_plain": pipelined_equal,
+                      "parallelism": "1 stream per GPU, frame-parallel inside"},
             "msamples_per_s": value * T_F / 1e6,
             "viterbi_gbit_per_s": (frames_per_step * args.steps * (4 * 9 * 3072 + 4 * 768)) / ((ms_vit + ms_tb) * 1e-3) / 1e9 if n_vit else None,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(nsamp * 2),
-                    "d2h_bytes_per_step": int(frames_per_step * (4 * 768 + 12) + sum(m.shape[0] * m.shape[1] for m in r.msc)),
-                    "ms_per_step": e2e_wall * 1e3 / args.steps, "timing": "wall clock, synchronised on both sides, pinned host buffers"},
+                    "d2h_bytes_per_step": int(frames_per_step * (4 * 768 + 12) + sum(m.shape[0] * m.shape[1] for m in e2e_snap[3])),
+                    "ms_per_step": e2e_wall * 1e3 / args.steps,
+                    "timing": "wall clock over K steps, synchronised on both sides, pinned host buffers; steps are issued as a streaming caller does: "
+                              "dabgpu_prefetch announces step k + 1 before dabgpu_decode of step k, every step's input crosses PCIe once inside the timed region",
+                    "plain_calls": {"value": total_frames / e2e_plain_step, "ms_per_step": e2e_plain_step * 1e3, "note": "dabgpu_decode call after call, nothing announced ahead"},
+                    "h2d_floor_ms": h2d_floor_ms, "h2d_floor_note": "the step's input bytes alone over PCIe from pinned memory (CUDA events, max over ranks, all ranks copying at the same time)",
+                    "packed_output": {"value": total_frames / e2e_pk_step, "ms_per_step": e2e_pk_step * 1e3,
+                                      "d2h_bytes_per_step": int(frames_per_step * (4 * 768 + 12) + sum(m.shape[0] * m.shape[1] for m in e2e_snap[3]) // 8)}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             # dominant kernel by time: the Viterbi forward pass; integer-ALU bound
             "roofline": {"kernel": "vit_simd_forward (add-compare-select of FIC + 9 sub-channels, one launch per step)", "bound": "alu", "achieved": vit_ops / 1e12, "peak": int_peak / 1e12,
                          "unit": "Tint-op/s", "frac": vit_ops / int_peak if int_peak else None, "traffic": traffic.get("vit_simd_forward"),
                          "avg_launch_ms": vit_avg_ms, "launches": n_vit, "share_of_step": shares.get("viterbi_msc"),
+                         "issue_frac": insts["vit_simd_forward"] / issue_slots(vit_avg_ms) if insts.get("vit_simd_forward") else None,
                          "peak_source": "measured live by dabgpu_int_peak (add / min / add+mad.lo micro-benchmark): %s" %
                                         {k: round(v / 1e12, 2) for k, v in ip.items()},
                          "algorithmic": "272 int-ops per trellis step (SURVEY.md 8d) x %d steps per launch" % steps_per_launch},
-            "roofline_hbm": {"kernel": "symbol_kernel (FFT+demod group)", "bound": "hbm", "achieved": sym_gbs, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": sym_gbs / hbm_peak, "traffic": traffic.get("symbol_kernel_r8"), "avg_launch_ms": sym_avg_ms, "launches": n_sym_work,
+            "roofline_hbm": {"kernel": "symbol_kernel_p<1,0> (FFT+demod group)", "bound": "hbm", "achieved": sym_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": sym_gbs / hbm_peak, "traffic": traffic.get("symbol_kernel_p"), "avg_launch_ms": sym_avg_ms, "launches": n_sym_work,
                              "share_of_step": shares.get("symbol"), "peak_source": peak_src,
-                             "algorithmic": "854016 B per Mode I frame (SURVEY.md 8d) x %.1f frames per working launch (+ %d no-op verification launches)" % (sym_frames, n_sym - n_sym_work),
+                             "issue_frac": insts["symbol_kernel_p"] / issue_slots(sym_avg_ms) if insts.get("symbol_kernel_p") else None,
+                             "issue_frac_note": "warp instructions of the launch (ncu, profiles/) / (148 SMs x 4 schedulers x cycles): the kernel is bound by shared-memory "
+                                                "exchange latency and instruction issue, not by HBM",
+                             "algorithmic": "854016 B per Mode I frame (SURVEY.md 8d: 2 T_F of u8 IQ in + int16 soft bits out) x %.1f frames per working launch (+ %d no-op verification launches); "
+                                            "the kernel itself writes the soft bits as bytes only (623616 B per frame)" % (sym_frames, n_sym - n_sym_work),
                              "fp32_tflops": 11.9e6 * sym_frames / (sym_avg_ms * 1e-3) / 1e12 if n_sym else None},
             "kernel_shares": shares,
             "wall_ms_per_step": wall * 1e3 / args.steps,
         }
+        line.update(extras)
     # CPU baseline on rank 0 at N = 1 only
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         nthreads = args.cpu_threads or (os.cpu_count() or 1)
@@ -393,7 +617,98 @@ def main():
         print(json.dumps(line))
     eng.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+SUB5 = None
+
+
+def split_recording_leg(pkg, iq, st, batch_first, subs, rank, world, local_rank, dist, dev, nframes, barrier):
+    """BASELINE configs[4]: ONE long Mode I recording (lead-in + nframes frames: the 1024-frame batch of rank 0's stream tiled,
+    frames stay T_F apart) decoded by all ranks together with sdr-j-dab_b200/parallel.py: rank 0 decodes the lead-in and
+    broadcasts the locked state, every rank decodes its contiguous frame range from the predicted state 16 CIFs early (no
+    soft-bit halo travels), every boundary is verified against the left neighbour's true final state over NCCL.  Strong
+    scaling: the recording is fixed, every rank uploads only its own range.  Rank 0 then decodes the whole recording alone
+    and the concatenation of the ranks' outputs is compared with it bit for bit."""
+    import torch
+    par = importlib.import_module("sdr-j-dab_b200.parallel")
+    # every rank needs the same recording: rank 0's stream
+    n_lead = batch_first + 0
+    block_frames = 1024 if iq.size // 2 >= batch_first + 1024 * T_F + 6000 else (iq.size // 2 - batch_first - 6000) // T_F
+    hdr = torch.tensor([n_lead, block_frames], device=dev, dtype=torch.int64)
+    dist.broadcast(hdr, 0)
+    n_lead, block_frames = int(hdr[0].item()), int(hdr[1].item())
+    nbytes = 2 * (n_lead + block_frames * T_F + 6000)
+    src = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        src.copy_(torch.from_numpy(iq[:nbytes].copy()))
+    dist.broadcast(src, 0)
+    base = src.cpu().numpy()
+    del src
+    tiles = max(1, nframes // block_frames)
+    block = base[2 * n_lead:2 * (n_lead + block_frames * T_F)]
+    rec = np.concatenate([base[:2 * n_lead]] + [block] * tiles + [base[2 * (n_lead + block_frames * T_F):]])
+    total_frames = tiles * block_frames
+    nsamp = rec.size // 2
+    cap = total_frames + LEAD_FRAMES + 8
+
+    def run():
+        e = pkg.DabGpu(mode=MODE, device=local_rank)
+        e.set_subchannels(subs)
+        res, first, mode_used = par.decode_sharded(e, rec, lambda n: e.alloc_result(n, want_soft=False), rank, world, dist, dev, lead_frames=LEAD_FRAMES)
+        e.close()
+        return res, first, mode_used
+    res, first, mode_used = run()                                # warm-up (allocations, NCCL connections)
+    barrier()
+    t0 = time.perf_counter()
+    res, first, mode_used = run()
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = tt.item()
+    # gather the ranks' outputs on rank 0 (sizes first), then compare with the one-GPU decode
+    counts = torch.tensor([res.nframes] + [m.shape[0] for m in res.msc], device=dev, dtype=torch.int64)
+    allc = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(allc, counts)
+    nfr = [int(c[0].item()) for c in allc]
+
+    def gather(arr, sizes, width):
+        mine = torch.from_numpy(np.ascontiguousarray(arr)).to(dev).reshape(-1)
+        out = None
+        if rank == 0:
+            parts = [mine]
+            for r in range(1, world):
+                buf = torch.empty(sizes[r] * width, dtype=torch.uint8, device=dev)
+                if sizes[r]:
+                    dist.recv(buf, r)
+                parts.append(buf)
+            out = torch.cat(parts).cpu().numpy().reshape(-1, width)
+        elif mine.numel():
+            dist.send(mine, 0)
+        return out
+    fic = gather(res.fic_bits, [4 * n for n in nfr], 768)
+    msc = [gather(res.msc[i], [int(c[1 + i].item()) for c in allc], res.msc[i].shape[1]) for i in range(len(subs))]
+    equal = None
+    one_ms = None
+    if rank == 0:
+        e = pkg.DabGpu(mode=MODE, device=local_rank)
+        e.set_subchannels(subs)
+        t1 = time.perf_counter()
+        one = e.decode(rec, e.alloc_result(cap, want_soft=False))
+        one_ms = (time.perf_counter() - t1) * 1e3
+        equal = bool(one.nframes == sum(nfr) and np.array_equal(one.fic_bits, fic) and all(np.array_equal(one.msc[i], msc[i]) for i in range(len(subs))))
+        e.close()
+    flag = torch.tensor([1 if (equal or rank != 0) else 0], device=dev, dtype=torch.int64)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return {"frames": int(sum(nfr)), "frames_per_rank": nfr, "e2e_frames_per_s": sum(nfr) / dt, "ms": dt * 1e3, "mode": mode_used,
+            "one_gpu_ms": one_ms, "speedup_vs_one_gpu": (one_ms / (dt * 1e3)) if one_ms else None,
+            "halo_or_overlap_bytes": 0 if mode_used == "parallel" else 15 * 55296 + 8 * T_F,
+            "overlap_frames_per_boundary": 4 if mode_used == "parallel" else 0,
+            "equal_to_one_shot": bool(flag.item() > 0), "scaling": "strong",
+            "note": "host (pageable) input in, decoded bits out, wall clock max over ranks incl. engine creation; scheme 'parallel' = predicted state + 16-CIF overlap, "
+                    "boundaries verified over NCCL (no soft-bit halo); 'chain' = serial hand-over of the state blob (fallback)"}
 
 
 if __name__ == "__main__":

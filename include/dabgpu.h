@@ -202,6 +202,15 @@ int dabgpu_set_subchannels (dabgpu_t *h, const dabgpu_subch *sc, int32_t nsub); 
  * traffic of the decoded bits by 8.  FIC bits stay one per byte (fib_processor::process_FIB reads them that way). */
 int dabgpu_set_msc_output (dabgpu_t *h, int32_t packed);
 int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out);
+/* Streaming from host memory: announces the block the NEXT dabgpu_decode / _cf32 / _i16 call of this handle will be given (same
+ * pointer, same size, same format: 0 = u8, 1 = complex float, 2 = int16) and starts its host-to-device copy at once, so that it
+ * runs while the call in between is still busy with its last frames -- the reference's reader thread does the same for its
+ * consumer (rawfiles.cpp:136-161 fills the ring buffer ahead of ofdmProcessor).  Up to two blocks may be announced; call
+ * order for blocks B0, B1, ...:  prefetch (B0); prefetch (B1); decode (B0); prefetch (B2); decode (B1); ...  An announced
+ * buffer must stay unchanged until its decode call returns.  A decode call whose block was not announced uploads it itself (behind
+ * whatever is already on its way).  Pinned host memory makes the copy asynchronous; pageable memory is staged (the staging memcpy
+ * happens inside dabgpu_prefetch).  Returns DABGPU_ERR_STATE when two blocks are announced already. */
+int dabgpu_prefetch (dabgpu_t *h, const void *iq, size_t nsamples, int32_t sample_format);
 /* same with the input already resident on the handle's device (result pointers stay host pointers) */
 int dabgpu_decode_dev (dabgpu_t *h, const uint8_t *d_iq_u8, size_t nsamples, dabgpu_result *out);
 /* The same stream engine fed with complex float samples (interleaved re, im at 2.048 MS/s): the form in which

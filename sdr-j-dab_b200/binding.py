@@ -400,6 +400,18 @@ class DabGpu:
         self._check(self.lib.dabgpu_decode(self.h, ptr, nsamples, C.byref(out.res)))
         return self._trim(out)
 
+    def prefetch(self, iq):
+        """dabgpu_prefetch: announce the block a later decode() call will be given (numpy array kept alive by the caller, or a
+        (host address, nsamples) tuple of u8 samples); its upload starts at once"""
+        self.lib.dabgpu_prefetch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32]
+        if isinstance(iq, tuple):
+            ptr, ns, fmt = iq[0], iq[1], 0
+        else:
+            assert iq.flags["C_CONTIGUOUS"]
+            fmt = 1 if iq.dtype == np.float32 else 2 if iq.dtype == np.int16 else 0
+            ptr, ns = iq.ctypes.data, iq.size // 2
+        self._check(self.lib.dabgpu_prefetch(self.h, ptr, ns, fmt))
+
     def decode_dev(self, d_ptr, nsamples, out):
         self._check(self.lib.dabgpu_decode_dev(self.h, d_ptr, nsamples, C.byref(out.res)))
         return self._trim(out)
@@ -410,7 +422,7 @@ class DabGpu:
         self._check(self.lib.dabgpu_set_msc_output(self.h, 1 if packed else 0))
         self._packed = bool(packed)
 
-    def decode_multi(self, streams, outs, dev_ptrs=None):
+    def decode_multi(self, streams, outs, dev_ptrs=None, host_ptrs=False):
         """dabgpu_decode_multi: `streams` = list of numpy arrays (all uint8, float32 or int16, interleaved I,Q), one per
         independent stream; outs = one alloc_result buffer per stream.  dev_ptrs: [(device pointer, nsamples)] instead of
         host arrays (dabgpu_decode_multi_dev, sample format u8).  -> list of trimmed results"""
@@ -419,9 +431,12 @@ class DabGpu:
         keep = []
         fmt = 0
         if dev_ptrs is None:
-            dt = np.asarray(streams[0]).dtype if n else np.dtype(np.uint8)
+            dt = np.asarray(streams[0]).dtype if n and not host_ptrs else np.dtype(np.uint8)
             fmt = 1 if dt == np.float32 else 2 if dt == np.int16 else 0
             for i, x in enumerate(streams):
+                if host_ptrs:                                # (host address of u8 samples, nsamples): e.g. pinned memory
+                    jobs[i].iq, jobs[i].nsamples = x
+                    continue
                 a = np.ascontiguousarray(x, dt)
                 keep.append(a)
                 jobs[i].iq, jobs[i].nsamples = a.ctypes.data, a.size // 2

@@ -51,7 +51,7 @@ void dab_engine_free (dabgpu *h) {
 	for (auto *b : E -> backends) dabgpu_backend_destroy (b);
 	if (E -> d_phaseRef) cudaFree (E -> d_phaseRef);
 	if (E -> copy_st) { cudaStreamSynchronize (E -> copy_st); cudaStreamDestroy (E -> copy_st); }
-	for (auto e : E -> copy_events) cudaEventDestroy (e);
+	for (auto &v : E -> copy_events) for (auto e : v) cudaEventDestroy (e);
 	E -> tail. release (); E -> tail_spare. release (); E -> d_sd. release (); E -> h_sd. release ();
 	E -> d_frameout. release (); E -> d_framein. release (); E -> d_fcpart. release (); E -> d_spec0. release (); E -> d_info. release ();
 	E -> d_soft16. release (); E -> d_hist8. release (); E -> d_fic8. release (); E -> d_msc8. release ();
@@ -60,6 +60,7 @@ void dab_engine_free (dabgpu *h) {
 	E -> m_in. release (); E -> m_fic8. release (); E -> m_msc8. release (); E -> m_info. release ();
 	E -> m_ficbits. release (); E -> m_ficcrc. release (); E -> m_mscbits. release ();
 	E -> mh_in. release (); E -> mh_out. release ();
+	for (int i = 0; i < 2; i ++) { E -> d_inbuf [i]. release (); E -> h_stage [i]. release (); }
 	delete E;
 	h -> engine = nullptr;
 }
@@ -610,42 +611,79 @@ extern "C" int dabgpu_decode (dabgpu_t *h, const uint8_t *iq_u8, size_t nsamples
 extern "C" int dabgpu_decode_i16 (dabgpu_t *h, const int16_t *iq, size_t nsamples, dabgpu_result *out) { return decode_host (h, iq, nsamples, 2, out); }
 extern "C" int dabgpu_decode_cf32 (dabgpu_t *h, const float *iq, size_t nsamples, dabgpu_result *out) { return decode_host (h, iq, nsamples, 1, out); }
 
-static int decode_host_inner (dabgpu *h, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out) {
+// The input of a host call goes up in pieces on its own stream, into one of two device buffers; every chunk of frames waits only
+// for the pieces it reads, so the host-to-device copy overlaps the decode of the frames already there.  dabgpu_prefetch starts
+// the upload of the NEXT block while the current call is still busy with its last frames (the link never idles between calls).
+static const long long UPLOAD_PIECE = 8ll << 20;             // samples per piece (16 MB of u8 IQ)
+
+static int issue_upload (dabgpu *h, const uint8_t *iq_u8, size_t nsamples, int fmt, int b, std::vector<cudaEvent_t> *ready) {
 	Engine *E = h -> engine;
-	const size_t sb = E -> sample_bytes ();
-	const size_t bytes = nsamples * sb;
-	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
-	CUDA_TRY (h, h -> d_in. ensure (bytes + 16));
-	// the input goes up in pieces on its own stream; every chunk of frames waits only for the pieces it reads, so
-	// the host-to-device copy overlaps the decode of the frames already there
-	const long long piece = 8ll << 20;                       // samples per piece (16 MB of u8 IQ)
-	std::vector<cudaEvent_t> ready;
-	if (bytes) {
-		cudaPointerAttributes attr;
-		const bool pinned = cudaPointerGetAttributes (&attr, iq_u8) == cudaSuccess && attr. type == cudaMemoryTypeHost;
-		cudaGetLastError ();
-		const uint8_t *src = iq_u8;
-		if (!pinned) {
-			CUDA_TRY (h, h -> h_in. ensure (bytes));
-			memcpy (h -> h_in. p, iq_u8, bytes);
-			src = (const uint8_t *) h -> h_in. p;
-		}
-		const size_t npieces = (nsamples + piece - 1) / piece;
-		while (E -> copy_events. size () < npieces) {
-			cudaEvent_t e;
-			CUDA_TRY (h, cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
-			E -> copy_events. push_back (e);
-		}
-		for (size_t k = 0; k < npieces; k ++) {
-			const size_t off = k * (size_t) piece * sb, len = (k + 1 == npieces ? bytes - off : (size_t) piece * sb);
-			CUDA_TRY (h, cudaMemcpyAsync ((char *) h -> d_in. p + off, src + off, len, cudaMemcpyHostToDevice, E -> copy_st));
-			CUDA_TRY (h, cudaEventRecord (E -> copy_events [k], E -> copy_st));
-			ready. push_back (E -> copy_events [k]);
-		}
+	const size_t sb = dab_sample_bytes (fmt), bytes = nsamples * sb;
+	ready -> clear ();
+	CUDA_TRY (h, E -> d_inbuf [b]. ensure (bytes + 16));
+	if (!bytes) return DABGPU_OK;
+	cudaPointerAttributes attr;
+	const bool pinned = cudaPointerGetAttributes (&attr, iq_u8) == cudaSuccess && attr. type == cudaMemoryTypeHost;
+	cudaGetLastError ();
+	const uint8_t *src = iq_u8;
+	if (!pinned) {                                           // pageable memory: through the handle's pinned staging buffer of this slot
+		CUDA_TRY (h, E -> h_stage [b]. ensure (bytes));
+		memcpy (E -> h_stage [b]. p, iq_u8, bytes);
+		src = (const uint8_t *) E -> h_stage [b]. p;
 	}
+	const size_t npieces = (nsamples + UPLOAD_PIECE - 1) / UPLOAD_PIECE;
+	std::vector<cudaEvent_t> &ev = E -> copy_events [b];
+	while (ev. size () < npieces) {
+		cudaEvent_t e;
+		CUDA_TRY (h, cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
+		ev. push_back (e);
+	}
+	for (size_t k = 0; k < npieces; k ++) {
+		const size_t off = k * (size_t) UPLOAD_PIECE * sb, len = (k + 1 == npieces ? bytes - off : (size_t) UPLOAD_PIECE * sb);
+		CUDA_TRY (h, cudaMemcpyAsync ((char *) E -> d_inbuf [b]. p + off, src + off, len, cudaMemcpyHostToDevice, E -> copy_st));
+		CUDA_TRY (h, cudaEventRecord (ev [k], E -> copy_st));
+		ready -> push_back (ev [k]);
+	}
+	return DABGPU_OK;
+}
+
+extern "C" int dabgpu_prefetch (dabgpu_t *h, const void *iq, size_t nsamples, int32_t sample_format) {
+	if (!h || (nsamples > 0 && !iq) || sample_format < 0 || sample_format > 2) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_prefetch: bad argument");
+	CUDA_TRY (h, cudaSetDevice (h -> device));
+	Engine *E = h -> engine;
+	int b = !E -> pending [0]. valid ? 0 : !E -> pending [1]. valid ? 1 : -1;      // no call is running now: a buffer without an announcement is free
+	if (b < 0) return dab_fail (h, DABGPU_ERR_STATE, "dabgpu_prefetch: two blocks are announced already (decode one first)");
+	int rc = issue_upload (h, (const uint8_t *) iq, nsamples, sample_format, b, &E -> pending [b]. ready);
+	if (rc) { cudaStreamSynchronize (E -> copy_st); return rc; }
+	Engine::Pending &P = E -> pending [b];
+	P. host = iq; P. nsamples = nsamples; P. fmt = sample_format; P. seq = ++ E -> pending_seq; P. valid = true;
+	return DABGPU_OK;
+}
+
+static int decode_host_inner (dabgpu *h, const uint8_t *iq_u8, size_t nsamples, dabgpu_result *out, cudaEvent_t *last) {
+	Engine *E = h -> engine;
+	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+	std::vector<cudaEvent_t> ready;
+	int b = -1;
+	for (int i = 0; i < 2; i ++) {                            // announced by dabgpu_prefetch (the older one if both match): already on its way
+		const Engine::Pending &P = E -> pending [i];
+		if (P. valid && P. host == (const void *) iq_u8 && P. nsamples == nsamples && P. fmt == E -> cf32 && (b < 0 || P. seq < E -> pending [b]. seq)) b = i;
+	}
+	if (b >= 0) { ready = E -> pending [b]. ready; E -> pending [b]. valid = false; }
+	else {
+		b = !E -> pending [0]. valid ? 0 : !E -> pending [1]. valid ? 1 : -1;
+		if (b < 0) {                                         // both buffers hold announcements for other blocks: drop them
+			cudaStreamSynchronize (E -> copy_st);
+			E -> pending [0]. valid = E -> pending [1]. valid = false;
+			b = 0;
+		}
+		int rc = issue_upload (h, iq_u8, nsamples, E -> cf32, b, &ready);
+		if (rc) return rc;
+	}
+	if (!ready. empty ()) *last = ready. back ();
 	// host input: the PCIe copy paces the call and the GPU idles most of the time, so channel decoding follows the
 	// OFDM part in small batches: what is left to do once the last sample has arrived is then short
-	return decode_core (h, h -> d_in. p, (long long) nsamples, out, &ready, piece,
+	return decode_core (h, E -> d_inbuf [b]. p, (long long) nsamples, out, &ready, UPLOAD_PIECE,
 	                    h -> cfg. host_batch_frames > 0 ? h -> cfg. host_batch_frames : E -> vit_batch_frames);
 }
 
@@ -654,8 +692,12 @@ static int decode_host (dabgpu *h, const void *iq_v, size_t nsamples, int cf32, 
 	CUDA_TRY (h, cudaSetDevice (h -> device));
 	int rc = set_format (h, cf32);
 	if (rc) return rc;
-	rc = decode_host_inner (h, (const uint8_t *) iq_v, nsamples, out);
-	cudaStreamSynchronize (h -> engine -> copy_st);          // on every path: the caller's buffer and h_in / d_in are free again when the call returns
+	cudaEvent_t last = nullptr;
+	rc = decode_host_inner (h, (const uint8_t *) iq_v, nsamples, out, &last);
+	// on every path the caller's buffer is free again when the call returns: this call's own last piece has landed (a block
+	// announced by dabgpu_prefetch may still be on its way -- that is the point of it)
+	if (rc) { cudaStreamSynchronize (h -> engine -> copy_st); h -> engine -> pending [0]. valid = h -> engine -> pending [1]. valid = false; }
+	else if (last) cudaEventSynchronize (last);
 	return rc;
 }
 

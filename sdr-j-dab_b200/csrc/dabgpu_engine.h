@@ -85,7 +85,11 @@ struct Engine {
 	int groups = 5;                     // symbol groups (CTAs) per frame for small chunks; big chunks use 3
 	bool groups_fixed = false;          // DABGPU_GROUPS given: use it for every chunk
 	cudaStream_t copy_st = nullptr;     // piecewise host-to-device input copies
-	std::vector<cudaEvent_t> copy_events;
+	std::vector<cudaEvent_t> copy_events [2];
+	DevBuf d_inbuf [2]; PinBuf h_stage [2];                  // host input: two device buffers (+ pinned staging for pageable callers), ping-pong
+	struct Pending { const void *host = nullptr; size_t nsamples = 0; int fmt = 0; unsigned long long seq = 0; bool valid = false; std::vector<cudaEvent_t> ready; };
+	Pending pending [2];                // dabgpu_prefetch: the block announced for (and on its way into) input buffer 0 / 1
+	unsigned long long pending_seq = 0;
 	int vit_batch_frames = 128;         // host-input path: frames per channel-decoding launch (cfg.host_batch_frames overrides)
 	unsigned vrr = 0;                   // round robin over the channel-decoding side streams
 	bool msc_packed = false;            // dabgpu_set_msc_output: MSC blocks leave with 8 bits per byte

@@ -59,6 +59,8 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 	long long pos = ctl -> pos, attempt_pos = pos;
 	int lp = ctl -> lp, attempt_lp = lp;
 	const int phi = ctl -> coarse + ctl -> fine;
+	float2 rawn [ACQ_CHUNK / ACQ_THREADS];
+	long long next_pos = -1;
 	while (true) {
 		int n;                                                       // samples until the stage can change by COUNT
 		if (stage == 0) n = 20 * T. T_s - cnt;                       // :278-280
@@ -71,10 +73,15 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 		{	// 1. per-sample values
 			int l = mod_rate ((long long) lp - (long long) (tid + 1) * ph);
 			const int step = mod_rate ((long long) ACQ_THREADS * ph);
-			float2 raw [ACQ_CHUNK / ACQ_THREADS];                    // all of the thread's samples are requested before the first is used
+			float2 raw [ACQ_CHUNK / ACQ_THREADS];                    // all of the thread's samples are requested before the first is used;
+			if (next_pos == pos) {                                   // normally they were requested while the previous chunk's chains ran
 #pragma unroll
-			for (int k = 0; k < ACQ_CHUNK / ACQ_THREADS; k ++)
-				if (tid + k * ACQ_THREADS < n) raw [k] = sy_sample (w, pos + tid + k * ACQ_THREADS);
+				for (int k = 0; k < ACQ_CHUNK / ACQ_THREADS; k ++) raw [k] = rawn [k];
+			} else {
+#pragma unroll
+				for (int k = 0; k < ACQ_CHUNK / ACQ_THREADS; k ++)
+					if (tid + k * ACQ_THREADS < n) raw [k] = sy_sample (w, pos + tid + k * ACQ_THREADS);
+			}
 #pragma unroll
 			for (int k = 0; k < ACQ_CHUNK / ACQ_THREADS; k ++) {
 				const int i = tid + k * ACQ_THREADS;
@@ -91,6 +98,11 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 					s_d [i] = stage == 1 ? s_e [i] : __fsub_rn (s_e [i], i >= 50 ? s_e [i - 50] : s_ring [(idx + i - 50) & 63]);
 			__syncthreads ();
 		}
+		// the samples of the NEXT chunk (if this one runs to its end) are requested now: their HBM latency passes behind the chains
+		next_pos = pos + n;
+#pragma unroll
+		for (int k = 0; k < ACQ_CHUNK / ACQ_THREADS; k ++)
+			if (next_pos + tid + k * ACQ_THREADS < total) rawn [k] = sy_sample (w, next_pos + tid + k * ACQ_THREADS);
 		// 2. the two recurrences: s_sl [i] / s_csb [i] = value before sample i, [n] = value after the chunk.  Thread 0 runs the
 		// level surrogate, thread 32 (another warp, concurrently) the window sum.  Both walk in batches of 16 whose inputs are
 		// fetched into registers one batch ahead, so that only the dependent arithmetic is on the chain (one FFMA / one FADD

@@ -224,3 +224,44 @@ def test_packed_msc_output(port):
         assert np.array_equal(np.packbits(x, axis=1), y)
     assert rc[1].nframes > 8 and np.array_equal(rc[1].msc[0], rc[0].msc[0][:rc[1].msc[0].shape[0]])
     a.close(); b.close()
+
+
+def test_prefetch_pipelining_equals_plain_calls(port):
+    """dabgpu_prefetch: blocks announced one or two ahead (pinned and pageable memory), an announcement that is never
+    used, an unannounced block in between -- the decoded stream is the same as with plain calls"""
+    import torch
+    pkg = engine_pkg()
+    mod = dabmod.Modulator(port, 1, SUBS[:2], 321)
+    tr = mod.generate(40, cfo_hz=-1500.0, snr_db=20.0, lead=9000, tail=7000)
+    iq = tr["iq"]
+    subl = [(s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel) for s in mod.sub]
+    n = iq.size // 2
+    cuts = [0, n // 5, n // 5 + 777777, n // 2, n // 2 + 3, 4 * n // 5, n]
+    blocks = [np.ascontiguousarray(iq[2 * a:2 * b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    a = pkg.DabGpu(mode=1); a.set_subchannels(subl)
+    plain = [a.decode(b, a.alloc_result(44)) for b in blocks]
+    pins = []
+    for b in blocks:
+        t = torch.empty(b.size, dtype=torch.uint8).pin_memory(); t.numpy()[:] = b; pins.append(t)
+    for use_pinned in (True, False):
+        e = pkg.DabGpu(mode=1); e.set_subchannels(subl)
+        src = [(t.data_ptr(), t.numel() // 2) for t in pins] if use_pinned else blocks
+        got = []
+        e.prefetch(src[0]); e.prefetch(src[1])
+        with pytest.raises(pkg.DabGpuError, match="announced already"):
+            e.prefetch(src[2])
+        for k in range(len(blocks)):
+            if k == 3:                                          # an unannounced block while another announcement is pending
+                got.append(e.decode(src[k], e.alloc_result(44)))
+                continue
+            got.append(e.decode(src[k], e.alloc_result(44)))
+            if k + 2 < len(blocks) and k + 2 != 3:
+                e.prefetch(src[k + 2])
+        assert [g.nframes for g in got] == [p_.nframes for p_ in plain]
+        for g, p_ in zip(got, plain):
+            assert np.array_equal(g.fic_bits, p_.fic_bits) and np.array_equal(g.soft, p_.soft)
+            for x, y in zip(g.msc, p_.msc):
+                assert np.array_equal(x, y)
+        e.close()
+    assert sum(p_.nframes for p_ in plain) >= 36
+    a.close()

@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 cp sdr-j-dab_b200/libdabgpu.so /tmp/libdabgpu.orig.so
 for v in "$@"; do
   cp sdr-j-dab_b200/variants/lib_$v.so sdr-j-dab_b200/libdabgpu.so
-  python bench.py --steps 5 --no-cpu-baseline > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
+  python bench.py --steps 5 --no-cpu-baseline --no-extras > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python - "$v" <<'PY'
 import json, sys
 v = sys.argv[1]

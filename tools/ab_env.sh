@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 name=$1; shift
 for v in "$@"; do
-  env $name=$v python bench.py --steps 5 --no-cpu-baseline > gpurun_out/abe_$v.json 2> gpurun_out/abe_$v.err
+  env $name=$v python bench.py --steps 5 --no-cpu-baseline --no-extras > gpurun_out/abe_$v.json 2> gpurun_out/abe_$v.err
   python - "$name=$v" gpurun_out/abe_$v.json <<'PY'
 import json, sys
 try:
