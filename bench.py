@@ -648,7 +648,13 @@ def split_recording_leg(pkg, iq, st, batch_first, subs, rank, world, local_rank,
     del src
     tiles = max(1, nframes // block_frames)
     block = base[2 * n_lead:2 * (n_lead + block_frames * T_F)]
-    rec = np.concatenate([base[:2 * n_lead]] + [block] * tiles + [base[2 * (n_lead + block_frames * T_F):]])
+    rest = base[2 * (n_lead + block_frames * T_F):]
+    rec_t = torch.empty(2 * n_lead + tiles * block.size + rest.size, dtype=torch.uint8).pin_memory()     # the recording in pinned host memory
+    rec = rec_t.numpy()
+    rec[:2 * n_lead] = base[:2 * n_lead]
+    for k in range(tiles):
+        rec[2 * n_lead + k * block.size:2 * n_lead + (k + 1) * block.size] = block
+    rec[2 * n_lead + tiles * block.size:] = rest
     total_frames = tiles * block_frames
     nsamp = rec.size // 2
     cap = total_frames + LEAD_FRAMES + 8
@@ -695,9 +701,16 @@ def split_recording_leg(pkg, iq, st, batch_first, subs, rank, world, local_rank,
     if rank == 0:
         e = pkg.DabGpu(mode=MODE, device=local_rank)
         e.set_subchannels(subs)
-        t1 = time.perf_counter()
-        one = e.decode(rec, e.alloc_result(cap, want_soft=False))
-        one_ms = (time.perf_counter() - t1) * 1e3
+        out1 = e.alloc_result(cap, want_soft=False)
+        for _ in range(2):                                       # second pass timed: buffers allocated, same conditions as the ranks' second run
+            e.state_set(pkg.binding.StreamState(synced=0, coarse=0, fine=0, f2Correction=1, previous_1=1000, previous_2=999, localPhase=0, abs_pos=0, frames=0, cifs=0))
+            e2 = pkg.DabGpu(mode=MODE, device=local_rank)
+            e2.set_subchannels(subs)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            one = e2.decode(rec, out1)
+            one_ms = (time.perf_counter() - t1) * 1e3
+            e2.close()
         equal = bool(one.nframes == sum(nfr) and np.array_equal(one.fic_bits, fic) and all(np.array_equal(one.msc[i], msc[i]) for i in range(len(subs))))
         e.close()
     flag = torch.tensor([1 if (equal or rank != 0) else 0], device=dev, dtype=torch.int64)
@@ -707,7 +720,7 @@ def split_recording_leg(pkg, iq, st, batch_first, subs, rank, world, local_rank,
             "halo_or_overlap_bytes": 0 if mode_used == "parallel" else 15 * 55296 + 8 * T_F,
             "overlap_frames_per_boundary": 4 if mode_used == "parallel" else 0,
             "equal_to_one_shot": bool(flag.item() > 0), "scaling": "strong",
-            "note": "host (pageable) input in, decoded bits out, wall clock max over ranks incl. engine creation; scheme 'parallel' = predicted state + 16-CIF overlap, "
+            "note": "pinned host input in, decoded bits out (pageable), wall clock max over ranks incl. engine creation; scheme 'parallel' = predicted state + 16-CIF overlap, "
                     "boundaries verified over NCCL (no soft-bit halo); 'chain' = serial hand-over of the state blob (fallback)"}
 
 

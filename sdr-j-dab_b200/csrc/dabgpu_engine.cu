@@ -331,7 +331,9 @@ static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts, const CrcSpan
 	// even for a single frame (measured: 9 sub-channels, 1-32 frames per call: 2.9 ms against 0.6 ms)
 	const bool simd = dab_use_simd (h, ncw) || (h -> cfg. viterbi_path == 0 && (nsub >= 2 || parts. size () >= 2) && ncif_all > 0) ||
 	                  (E -> msc_packed && ncif_all > 0 && nsub > 0);      // (packing is done by the throughput kernels' chain-back)
-	std::vector<VitSimdJob> jobs;
+	// job order = CTA order: the long MSC code words first, the FIC's short ones (774 steps against up to 9000) last, so that
+	// the hardware hands the cheap CTAs out as the LAST ones of every SM's share instead of letting them occupy slots from the start
+	std::vector<VitSimdJob> jobs, fic_jobs;
 	std::vector<std::vector<int>> n_here (parts. size (), std::vector<int> (nsub, 0));
 	do {
 		for (size_t k = 0; k < parts. size () && !rc; k ++) {
@@ -340,10 +342,10 @@ static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts, const CrcSpan
 			if (ngroups > 0) {
 				const uint8_t *soft8 = q. fic8 + (size_t) q. f0 * 3 * 2 * p. K;
 				if (simd) {
-					jobs. emplace_back ();
-					if ((rc = dab_fic_simd_job (h, nullptr, 2304, ngroups, q. ficbits + (size_t) g0 * 768, &jobs. back ()))) break;
-					jobs. back (). sym8 = const_cast<uint8_t *> (soft8);      // written by the symbol kernel
-					jobs. back (). stride8 = 2304;
+					fic_jobs. emplace_back ();
+					if ((rc = dab_fic_simd_job (h, nullptr, 2304, ngroups, q. ficbits + (size_t) g0 * 768, &fic_jobs. back ()))) break;
+					fic_jobs. back (). sym8 = const_cast<uint8_t *> (soft8);      // written by the symbol kernel
+					fic_jobs. back (). stride8 = 2304;
 				} else if ((rc = dab_fic_decode_dev (h, nullptr, soft8, 2304, ngroups, q. ficbits + (size_t) g0 * 768, q. ficcrc + (size_t) g0 * 3))) break;
 			}
 			for (size_t i = 0; i < nsub && ncif > 0; i ++) {
@@ -362,6 +364,7 @@ static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts, const CrcSpan
 		}
 		if (rc) break;
 		if (simd) {
+			jobs. insert (jobs. end (), fic_jobs. begin (), fic_jobs. end ());
 			if ((rc = dab_vit_simd_run (h, jobs))) break;
 			if (span) {
 				cudaError_t e = fib_crc_launch (h, span -> bits, 3 * span -> ngroups, span -> crc);

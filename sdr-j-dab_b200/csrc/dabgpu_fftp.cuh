@@ -36,6 +36,9 @@ __device__ __forceinline__ c32 p_cmulc (c32 a, c32 w) {
 	return __ffma2_rn (p_j (a), make_float2 (- w. y, - w. y), __fmul2_rn (a, make_float2 (w. x, w. x)));
 }
 
+// a * w with w given as its real part and the prepared pair (-w.y, w.y): two instructions (for factors that are reused)
+__device__ __forceinline__ c32 p_cmul_pre (c32 a, float wx, c32 wyy) { return __ffma2_rn (p_swap (a), wyy, __fmul2_rn (a, make_float2 (wx, wx))); }
+
 // 4-point DFT (forward): y_q = sum_m c_m exp (-2 pi i m q / 4); 8 packed instructions
 __device__ __forceinline__ void p_dft4 (c32 c0, c32 c1, c32 c2, c32 c3, c32 &y0, c32 &y1, c32 &y2, c32 &y3) {
 	const c32 d0 = p_add (c0, c2), d2 = p_sub (c0, c2), d1 = p_add (c1, c3), e = p_sub (c1, c3);

@@ -41,11 +41,12 @@ __device__ __forceinline__ void load_win_nco (float2 *dst, const SampleWin &w, l
 
 // where the soft bits of symbol l (1 .. L-1) of output frame slot `slot` go: FIC symbols 1..3, MSC symbols 4.. as CIF rows
 // (fic-handler.cpp:143-153; msc-handler.cpp:125-193: row = CIF, 15 history rows in front)
+// A CIF is blocksPerCIF symbols of 2K soft bits = exactly CIF_BITS in every mode (18 x 3072, 72 x 768, 36 x 1536), so the MSC
+// symbols of a frame are contiguous: symbol l >= 4 sits (l - 4) * 2K behind the frame's first CIF row.
 struct SymGeom { int K2, blocksPerCIF, cifsPerFrame; };
 __device__ __forceinline__ uint8_t *sym_out (const StreamDev &S, const SymGeom &g, int slot, int l) {
 	if (l < 4) return S. fic8 + ((size_t) slot * 3 + (l - 1)) * g. K2;
-	const int m = l - 4;
-	return S. msc8 + ((size_t) 15 + (size_t) slot * g. cifsPerFrame + m / g. blocksPerCIF) * CIF_BITS + (size_t) (m % g. blocksPerCIF) * g. K2;
+	return S. msc8 + ((size_t) 15 + (size_t) slot * g. cifsPerFrame) * CIF_BITS + (size_t) (l - 4) * g. K2;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__ (256, FMT == 1 ? 2 : P_MINB) symbol_kernel_p (
 	unsigned char *raw = reinterpret_cast<unsigned char *> (tw3 + P_TW3);
 	__shared__ float2 s_fc [8];
 	__shared__ int s_fail;
+	__shared__ int s_off [2];
 	__shared__ __align__ (8) unsigned long long s_mbar [2];
 	constexpr int G = 256 / NSYM, N = 2048 / NSYM, Ts = 2552 / NSYM, Tg = 504 / NSYM, K = 1536 / NSYM, B = RawFmt<FMT>::B;
 	constexpr int RAW = P_RAW (FMT), GSH = 8 / NSYM;                    // N - Tg = 6 G + GSH
@@ -235,6 +237,7 @@ __global__ void __launch_bounds__ (256, FMT == 1 ? 2 : P_MINB) symbol_kernel_p (
 	const int iu = j * Ts + Tg + u, ig = j * Ts + u - GSH;                 // (ig < j Ts: useful sample 6 G + u has no guard partner)
 	const int offU = mod_rate ((long long) (iu + 1) * phB), offG = mod_rate ((long long) (ig + 1) * phB);
 	const int dPass = mod_rate ((long long) NSYM * Ts * phB);
+	const c32 rotGn = make_float2 (- rotG. y, rotG. y);                    // (the rotation is applied nine times per pass: its sign-prepared pair is kept)
 	c32 x [8];
 	float2 tw1 [6];
 	const uint32_t mbar0 = (uint32_t) __cvta_generic_to_shared (&s_mbar [0]);
@@ -249,45 +252,48 @@ __global__ void __launch_bounds__ (256, FMT == 1 ? 2 : P_MINB) symbol_kernel_p (
 	__syncthreads ();
 	if (s_fail) { if (t == 0) atomicOr (const_cast<int *> (&S. ctl. fault), 1); return; }
 
-	// raw samples of the pass starting with symbol l (nv symbols of it are wanted) -> raw buffer b; returns the byte offset of
-	// the pass's first sample inside the buffer.  Fast path: ONE bulk copy by the TMA engine from the 16-byte-aligned address
-	// below the first sample; a pass that straddles the seam between the kept tail and the new input, or touches a buffer
-	// end, is copied by the threads.
-	auto stage = [&] (int l, int b) -> int {
-		const int nv = min (NSYM, l1 - l);
+	// raw samples of the pass starting with symbol l (nv symbols of it are wanted) -> raw buffer b.  Thread 0 alone works out
+	// where they are and issues ONE bulk copy by the TMA engine from the 16-byte-aligned address below the first sample; it
+	// leaves the byte offset of the pass's first sample inside the buffer in s_off [b].  A pass that straddles the seam between
+	// the kept tail and the new input, or touches a buffer end, cannot be copied that way: s_off [b] = -1, and all threads copy
+	// it by hand when the pass is consumed (rare: at most one pass per seam).
+	auto stage = [&] (int l, int b) {
+		if (t != 0) return;
+		const int ns = min (NSYM, l1 - l) * Ts;
 		const long long first = F + N + (long long) (l - 1) * Ts;
-		const int ns = nv * Ts;
-		unsigned char *dst = raw + b * RAW;
 		const unsigned char *seg = nullptr; long long rel = 0, seglen = 0;
 		if (first + ns <= w. len0) { seg = reinterpret_cast<const unsigned char *> (w. seg0); rel = first; seglen = w. len0; }
 		else if (first >= w. len0) { seg = reinterpret_cast<const unsigned char *> (w. seg1); rel = first - w. len0; seglen = w. len1; }
-		int off = 0;
-		bool fast = seg != nullptr;
-		if (fast) {
+		int off = -1;
+		const uint32_t mb = mbar0 + 8u * (uint32_t) b;
+		if (seg != nullptr) {
 			const unsigned long long p = (unsigned long long) (seg + rel * B), pa = p & ~15ull;
-			off = (int) (p - pa);
-			const int n16 = (off + B * ns + 15) >> 4;
-			fast = pa >= (unsigned long long) seg && pa + 16ull * n16 <= (unsigned long long) (seg + seglen * B);
-			if (fast && t == 0) {
-				const uint32_t bytes = 16u * (uint32_t) n16, mb = mbar0 + 8u * (uint32_t) b;
+			const int n16 = ((int) (p - pa) + B * ns + 15) >> 4;
+			if (pa >= (unsigned long long) seg && pa + 16ull * n16 <= (unsigned long long) (seg + seglen * B)) {
+				off = (int) (p - pa);
+				const uint32_t bytes = 16u * (uint32_t) n16;
 				asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer's last readers (generic proxy) are past a CTA barrier
 				asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r" (mb), "r" (bytes) : "memory");
 				asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-				              :: "r" ((uint32_t) __cvta_generic_to_shared (dst)), "l" (pa), "r" (bytes), "r" (mb) : "memory");
+				              :: "r" ((uint32_t) __cvta_generic_to_shared (raw + b * RAW)), "l" (pa), "r" (bytes), "r" (mb) : "memory");
 			}
 		}
-		if (!fast) {
-			off = 0;
-			if (FMT == 0) for (int i = t; i < ns; i += 256) reinterpret_cast<uchar2 *> (dst) [i] = win_fetch (w, first + i);
-			else if (FMT == 2) {
-				for (int i = t; i < ns; i += 256) {
-					const long long q = first + i;
-					reinterpret_cast<short2 *> (dst) [i] = q < w. len0 ? __ldg (reinterpret_cast<const short2 *> (w. seg0) + q) : __ldg (reinterpret_cast<const short2 *> (w. seg1) + (q - w. len0));
-				}
-			} else for (int i = t; i < ns; i += 256) reinterpret_cast<float2 *> (dst) [i] = win_sample (w, first + i);
-			if (t == 0) asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r" (mbar0 + 8u * (uint32_t) b) : "memory");   // nothing in flight: the CTA barrier below orders the stores
-		}
-		return off;
+		if (off < 0) asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r" (mb) : "memory");   // nothing in flight: the phase completes at once
+		s_off [b] = off;
+	};
+	// the by-hand copy of a pass (all threads), then a CTA barrier
+	auto stage_by_hand = [&] (int l, int b) {
+		const int ns = min (NSYM, l1 - l) * Ts;
+		const long long first = F + N + (long long) (l - 1) * Ts;
+		unsigned char *dst = raw + b * RAW;
+		if (FMT == 0) for (int i = t; i < ns; i += 256) reinterpret_cast<uchar2 *> (dst) [i] = win_fetch (w, first + i);
+		else if (FMT == 2) {
+			for (int i = t; i < ns; i += 256) {
+				const long long q = first + i;
+				reinterpret_cast<short2 *> (dst) [i] = q < w. len0 ? __ldg (reinterpret_cast<const short2 *> (w. seg0) + q) : __ldg (reinterpret_cast<const short2 *> (w. seg1) + (q - w. len0));
+			}
+		} else for (int i = t; i < ns; i += 256) reinterpret_cast<float2 *> (dst) [i] = win_sample (w, first + i);
+		__syncthreads ();
 	};
 	// wait for raw buffer b (use = how often it has been waited for before).  A copy that never arrives must not hang the
 	// GPU: after 2 s (global timer) the CTA gives up together and reports through StreamCtl::fault.
@@ -306,7 +312,7 @@ __global__ void __launch_bounds__ (256, FMT == 1 ? 2 : P_MINB) symbol_kernel_p (
 		}
 	};
 
-	int off_cur = stage (l0, 0);
+	stage (l0, 0);
 	// ---- phase reference of the first symbol: spectrum of symbol l0 - 1 -> block NSYM - 1 of buf1 ----
 	if (l0 == 1) {
 		const float2 *p0 = a. spec0 + (size_t) c * N;
@@ -347,24 +353,25 @@ __global__ void __launch_bounds__ (256, FMT == 1 ? 2 : P_MINB) symbol_kernel_p (
 	int pass = 0;
 	for (int l = l0; l < l1; l += NSYM, pass ++) {
 		const int b = pass & 1;
-		int off_next = 0;
-		if (l + NSYM < l1) off_next = stage (l + NSYM, b ^ 1);
+		if (l + NSYM < l1) stage (l + NSYM, b ^ 1);
 		c32 phg = phg_n, ph = ph_n;
 		lpb -= dPass; if (lpb < 0) lpb += DAB_INPUT_RATE;
 		phasors (lpb, phg_n, ph_n);                                        // looked up one pass ahead
 		wait_raw (b, pass >> 1);
 		__syncthreads ();                                                  // raw buffer b complete; last pass's demod reads done
 		if (*(volatile int *) &s_fail) { if (t == 0) atomicOr (const_cast<int *> (&S. ctl. fault), 2); return; }
+		int off_cur = s_off [b];
+		if (off_cur < 0) { stage_by_hand (l, b); off_cur = 0; }
 		const unsigned char *rs = raw + b * RAW + off_cur;
 		const bool live = l + j < l1;                                      // a partial last pass: the trailing thread groups idle
 		// guard samples ig and ig + G (the ones x[6] and x[7] are correlated with), mixed like every other sample
 		c32 g6 = make_float2 (0.f, 0.f), g7;
-		g7 = p_cmul (raw_sample<FMT> (rs, ig + G), p_cmul (phg, rotG));
+		g7 = p_cmul (raw_sample<FMT> (rs, ig + G), p_cmul_pre (phg, rotG. x, rotGn));
 		if (u >= GSH) g6 = p_cmul (raw_sample<FMT> (rs, ig), phg);
 #pragma unroll
 		for (int k = 0; k < 8; k ++) {
 			x [k] = p_cmul (raw_sample<FMT> (rs, iu + G * k), ph);
-			ph = p_cmul (ph, rotG);
+			ph = p_cmul_pre (ph, rotG. x, rotGn);
 		}
 		// FreqCorr += x[i] * conj (x[i - T_u]), i in [T_u, T_s): useful sample e pairs with guard sample e - (T_u - T_g)
 		if (live) { acc = p_add (acc, p_cmulc (x [7], g7)); if (u >= GSH) acc = p_add (acc, p_cmulc (x [6], g6)); }
@@ -390,7 +397,6 @@ __global__ void __launch_bounds__ (256, FMT == 1 ? 2 : P_MINB) symbol_kernel_p (
 				*reinterpret_cast<unsigned short *> (out8 + K + i) = (unsigned short) (im [0] + 256 * im [1] + 0x7f7f);
 			}
 		}
-		off_cur = off_next;
 	}
 	for (int o = 16; o > 0; o >>= 1) {
 		acc. x += __shfl_xor_sync (0xffffffffu, acc. x, o);

@@ -210,8 +210,8 @@ __device__ __forceinline__ void vs_cp_async16 (void *smem, const void *gmem) {
 
 __global__ void __launch_bounds__ (VS_THREADS, VS_MINB) vit_simd_forward (const VitSimdJob *jobs, int njobs) {
 	__shared__ __align__ (16) uint8_t tile [2 * VS_TILE];
-	int jb = 0;
-	while (jb + 1 < njobs && (int) blockIdx. x >= jobs [jb + 1]. cta_first2) jb ++;
+	int jb = 0;                                                // the job this CTA belongs to: last one with cta_first2 <= blockIdx (hundreds of jobs with many streams: bisection)
+	for (int hi = njobs; hi - jb > 1; ) { const int mid = (jb + hi) >> 1; if ((int) blockIdx. x >= __ldg (&jobs [mid]. cta_first2)) jb = mid; else hi = mid; }
 	const VitSimdJob j = jobs [jb];
 	const int c0 = ((int) blockIdx. x - j. cta_first2) * VS_CW;   // first code word of this CTA
 	const int tid = threadIdx. x;
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__ (TB_THREADS) vit_simd_traceback (const VitSimd
 	__shared__ uint32_t bits [TB_THREADS * 5];               // 128 decoded bits per code word per round, row stride 5 words
 	__shared__ __align__ (16) uint4 dq [TB_NBUF][16][TB_THREADS];  // the decision words of TB_NBUF output words (16 step pairs each) per thread
 	int jb = 0;
-	while (jb + 1 < njobs && (int) blockIdx. x >= jobs [jb + 1]. cta_first) jb ++;
+	for (int hi = njobs; hi - jb > 1; ) { const int mid = (jb + hi) >> 1; if ((int) blockIdx. x >= __ldg (&jobs [mid]. cta_first)) jb = mid; else hi = mid; }
 	const VitSimdJob j = jobs [jb];
 	const int c0 = ((int) blockIdx. x - j. cta_first) * TB_THREADS;
 	const int tid = threadIdx. x, lane = tid & 31, warp = tid >> 5;
