@@ -249,6 +249,7 @@ int dabgpu_decode_multi_dev (dabgpu_t *h, const dabgpu_stream_job *jobs, int32_t
  * CIFs the time de-interleaver remembers (dab-concurrent.cpp:41-43, 162-175).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct dabgpu_group dabgpu_group_t;
+int32_t dabgpu_device_count (void);                                        /* usable CUDA devices (0 without a driver / device) */
 /* one handle per entry of devices[] (NULL: devices 0 .. ndev-1; the same device may appear more than once), all with cfg */
 int  dabgpu_group_create (const dabgpu_config *cfg, const int32_t *devices, int32_t ndev, dabgpu_group_t **out);
 void dabgpu_group_destroy (dabgpu_group_t *g);

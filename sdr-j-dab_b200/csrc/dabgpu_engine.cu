@@ -617,7 +617,11 @@ extern "C" int dabgpu_decode_cf32 (dabgpu_t *h, const float *iq, size_t nsamples
 // The input of a host call goes up in pieces on its own stream, into one of two device buffers; every chunk of frames waits only
 // for the pieces it reads, so the host-to-device copy overlaps the decode of the frames already there.  dabgpu_prefetch starts
 // the upload of the NEXT block while the current call is still busy with its last frames (the link never idles between calls).
-static const long long UPLOAD_PIECE = 8ll << 20;             // samples per piece (16 MB of u8 IQ)
+static long long upload_piece_init () {                      // samples per piece: 8 M (16 MB of u8 IQ); DABGPU_PIECE_MSAMPLES overrides (A/B runs)
+	if (const char *e = getenv ("DABGPU_PIECE_MSAMPLES")) { const long long v = atoll (e); if (v >= 1 && v <= 1024) return v << 20; }
+	return 8ll << 20;
+}
+static const long long UPLOAD_PIECE = upload_piece_init ();
 
 static int issue_upload (dabgpu *h, const uint8_t *iq_u8, size_t nsamples, int fmt, int b, std::vector<cudaEvent_t> *ready) {
 	Engine *E = h -> engine;

@@ -75,10 +75,15 @@ __device__ __forceinline__ void p_fft512_tail (c32 (&a) [8], const uint32_t Ab, 
 #pragma unroll
 			for (int m = 0; m < 8; m ++) a [m] = r8_lds (((m & 1) ? bo : be) + 8 * 64 * m);
 		}
+		// (the stores below are compiler barriers: the seven twiddles are fetched up front, next to the data, instead of one
+		// by one between the stores -- a chain of seven shared-memory latencies otherwise)
+		float2 w [7];
+#pragma unroll
+		for (int q = 1; q < 8; q ++) w [q - 1] = tw2 [64 * (q - 1) + n];
 		p_dft8 (a);
 		r8_sts (be, a [0]);
 #pragma unroll
-		for (int q = 1; q < 8; q ++) r8_sts (((q & 1) ? bo : be) + 8 * 64 * q, p_cmul (a [q], tw2 [64 * (q - 1) + n]));
+		for (int q = 1; q < 8; q ++) r8_sts (((q & 1) ? bo : be) + 8 * 64 * q, p_cmul (a [q], w [q - 1]));
 	}
 	switch (t >> 6) {                                        // the block's two warps only (literal ids, see fft2048_r8)
 	case 0:  asm volatile ("bar.sync 1, 64;" ::: "memory"); break;
@@ -91,10 +96,13 @@ __device__ __forceinline__ void p_fft512_tail (c32 (&a) [8], const uint32_t Ab, 
 		const uint32_t base = Ab + ((512 * bb + 8 * (n ^ (4 * (bb & 1)))) ^ (64 * (bb & 1)));
 #pragma unroll
 		for (int m = 0; m < 8; m ++) a [m] = r8_lds (base ^ (8 * ((m >> 1) & 3) + 64 * (m & 1) + 128 * (m >> 1)));
+		float2 w [7];
+#pragma unroll
+		for (int q = 1; q < 8; q ++) w [q - 1] = tw3 [8 * (q - 1) + n];
 		p_dft8 (a);
 		r8_sts (base, a [0]);
 #pragma unroll
-		for (int q = 1; q < 8; q ++) r8_sts (base ^ (8 * ((q >> 1) & 3) + 64 * (q & 1) + 128 * (q >> 1)), p_cmul (a [q], tw3 [8 * (q - 1) + n]));
+		for (int q = 1; q < 8; q ++) r8_sts (base ^ (8 * ((q >> 1) & 3) + 64 * (q & 1) + 128 * (q >> 1)), p_cmul (a [q], w [q - 1]));
 	}
 	__syncwarp ();
 	{	// stage 4: radix 8 on 8 consecutive points, no twiddles

@@ -29,6 +29,12 @@ struct dabgpu_group {
 
 static int group_fail (dabgpu_group *g, int code, const std::string &msg) { if (g) g -> err = msg; return code; }
 
+extern "C" int32_t dabgpu_device_count (void) {
+	int n = 0;
+	if (cudaGetDeviceCount (&n) != cudaSuccess) { cudaGetLastError (); return 0; }
+	return n;
+}
+
 extern "C" const char *dabgpu_group_last_error (const dabgpu_group_t *g) { return g ? g -> err. c_str () : "null group"; }
 extern "C" int32_t dabgpu_group_size (const dabgpu_group_t *g) { return g ? (int32_t) g -> h. size () : 0; }
 extern "C" dabgpu_t *dabgpu_group_handle (dabgpu_group_t *g, int32_t i) { return g && i >= 0 && i < (int32_t) g -> h. size () ? g -> h [i] : nullptr; }

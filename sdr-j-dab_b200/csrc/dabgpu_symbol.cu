@@ -381,18 +381,23 @@ __global__ void __launch_bounds__ (256, FMT == 1 ? 2 : P_MINB) symbol_kernel_p (
 		if (live) {
 			uint8_t *out8 = sym_out (S, a. geo, in. slot, l + j);
 			const float2 *cb = cur + j * N, *pb = j > 0 ? cur + (j - 1) * N : oth + (NSYM - 1) * N;
+			// all six carriers (and their references) are fetched before the first result is stored: the stores go through a
+			// generic pointer the compiler cannot tell apart from the spectrum buffers, so it would not move a later load above one
+			c32 cc [6], pr [6];
+#pragma unroll
+			for (int m = 0; m < 3; m ++)
+#pragma unroll
+				for (int q = 0; q < 2; q ++) {
+					const int idx = (int) (q ? pidx [m] >> 16 : pidx [m] & 0xffffu);
+					cc [2 * m + q] = cb [idx];
+					if (NSYM == 1) { pr [2 * m + q] = pv [2 * m + q]; pv [2 * m + q] = cc [2 * m + q]; } else pr [2 * m + q] = pb [idx];
+				}
 #pragma unroll
 			for (int m = 0; m < 3; m ++) {
 				const int i = 2 * u + 2 * G * m;
 				int re [2], im [2];
 #pragma unroll
-				for (int q = 0; q < 2; q ++) {
-					const int idx = (int) (q ? pidx [m] >> 16 : pidx [m] & 0xffffu);
-					const c32 cc = cb [idx];
-					c32 pr;
-					if (NSYM == 1) { pr = pv [2 * m + q]; pv [2 * m + q] = cc; } else pr = pb [idx];
-					quant_pair (p_cmulc (cc, pr), re [q], im [q]);
-				}
+				for (int q = 0; q < 2; q ++) quant_pair (p_cmulc (cc [2 * m + q], pr [2 * m + q]), re [q], im [q]);
 				*reinterpret_cast<unsigned short *> (out8 + i)     = (unsigned short) (re [0] + 256 * re [1] + 0x7f7f);
 				*reinterpret_cast<unsigned short *> (out8 + K + i) = (unsigned short) (im [0] + 256 * im [1] + 0x7f7f);
 			}

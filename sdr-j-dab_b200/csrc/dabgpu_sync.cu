@@ -20,6 +20,45 @@ __device__ __forceinline__ float2 sy_sample (const SampleWin &w, long long i) {
 	return make_float2 ((float) ((int) s. x - 128) * (1.0f / 128.0f), (float) ((int) s. y - 128) * (1.0f / 128.0f));
 }
 
+// the same in two steps -- the bare load (nothing waits for it) and the conversion -- for loads issued long before their use
+__device__ __forceinline__ uint2 sy_raw (const SampleWin &w, long long i) {
+	const bool first = i < w. len0;
+	const long long k = first ? i : i - w. len0;
+	const uchar2 *seg = first ? w. seg0 : w. seg1;
+	if (w. cf32 == 1) { const float2 v = __ldg (reinterpret_cast<const float2 *> (seg) + k); return make_uint2 (__float_as_uint (v. x), __float_as_uint (v. y)); }
+	if (w. cf32 == 2) return make_uint2 (__ldg (reinterpret_cast<const unsigned int *> (seg) + k), 0u);
+	return make_uint2 ((unsigned int) __ldg (reinterpret_cast<const unsigned short *> (seg) + k), 0u);
+}
+// the thread's ACQ_CHUNK / ACQ_THREADS samples of the chunk starting at window position p (those below `end`): the chunk
+// normally lies inside one segment, so the segment and the format are picked once, not per sample
+template <int NPER, int STRIDE>
+__device__ __forceinline__ void sy_raw_chunk (const SampleWin &w, long long p, long long end, int tid, uint2 (&r) [NPER]) {
+	const bool in0 = p + (long long) NPER * STRIDE <= w. len0, in1 = p >= w. len0;
+	if (in0 || in1) {
+		const uchar2 *seg = in0 ? w. seg0 : w. seg1;
+		const long long k0 = (in0 ? p : p - w. len0) + tid;
+		const int lim = (int) (end - p < (long long) NPER * STRIDE ? end - p : (long long) NPER * STRIDE) - tid;     // samples k STRIDE < lim exist
+		if (w. cf32 == 1) {
+#pragma unroll
+			for (int k = 0; k < NPER; k ++) if (k * STRIDE < lim) { const float2 v = __ldg (reinterpret_cast<const float2 *> (seg) + k0 + k * STRIDE); r [k] = make_uint2 (__float_as_uint (v. x), __float_as_uint (v. y)); }
+		} else if (w. cf32 == 2) {
+#pragma unroll
+			for (int k = 0; k < NPER; k ++) if (k * STRIDE < lim) r [k] = make_uint2 (__ldg (reinterpret_cast<const unsigned int *> (seg) + k0 + k * STRIDE), 0u);
+		} else {
+#pragma unroll
+			for (int k = 0; k < NPER; k ++) if (k * STRIDE < lim) r [k] = make_uint2 ((unsigned int) __ldg (reinterpret_cast<const unsigned short *> (seg) + k0 + k * STRIDE), 0u);
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < NPER; k ++) if (p + tid + k * STRIDE < end) r [k] = sy_raw (w, p + tid + k * STRIDE);
+	}
+}
+__device__ __forceinline__ float2 sy_conv (const SampleWin &w, uint2 r) {
+	if (w. cf32 == 1) return make_float2 (__uint_as_float (r. x), __uint_as_float (r. y));
+	if (w. cf32 == 2) return make_float2 ((float) (short) (r. x & 0xffffu) * (1.0f / 32768.0f), (float) (short) (r. x >> 16) * (1.0f / 32768.0f));
+	return make_float2 ((float) ((int) (r. x & 0xffu) - 128) * (1.0f / 128.0f), (float) ((int) ((r. x >> 8) & 0xffu) - 128) * (1.0f / 128.0f));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // acquisition: notSynced -> SyncOnNull -> SyncOnEndNull (ofdm-processor.cpp:275-338), one CTA of four warps per stream.
 // The reference walks the samples one by one through two recurrences -- the signal level IIR
@@ -40,12 +79,17 @@ __device__ __forceinline__ float2 sy_sample (const SampleWin &w, long long i) {
 //      state is found by a reduction; the state is committed up to there.
 // ---------------------------------------------------------------------------------------------------
 #define ACQ_CHUNK 1024
+#ifdef ACQ_PROF
+#define ACQ_T(k) { const long long now_ = clock64 (); prof_t [k] += now_ - prof_last; prof_last = now_; }
+#else
+#define ACQ_T(k)
+#endif
 #define ACQ_THREADS 128
 __device__ __forceinline__ float acq_level_exact (float a, float ja) {          // ofdm-processor.cpp:168, operation by operation
 	return __double2float_rn (__dadd_rn (__dmul_rn (0.00001, (double) ja), __dmul_rn (1 - 0.00001, (double) a)));
 }
 __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, OfdmTables T, int T_F, int T_null) {
-	__shared__ float s_e [ACQ_CHUNK], s_d [ACQ_CHUNK + 32], s_sl [ACQ_CHUNK + 32], s_csb [ACQ_CHUNK + 32], s_ja [ACQ_CHUNK], s_t [ACQ_CHUNK + 32], s_ring [64];
+	__shared__ __align__ (16) float s_e [ACQ_CHUNK], s_d [ACQ_CHUNK + 64], s_sl [ACQ_CHUNK + 64], s_csb [ACQ_CHUNK + 64], s_ja [ACQ_CHUNK], s_t [ACQ_CHUNK + 64], s_ring [64];
 	__shared__ int s_first;
 	StreamDev &S = sd [blockIdx. x];
 	if (!S. do_acquire) return;
@@ -59,7 +103,10 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 	long long pos = ctl -> pos, attempt_pos = pos;
 	int lp = ctl -> lp, attempt_lp = lp;
 	const int phi = ctl -> coarse + ctl -> fine;
-	float2 rawn [ACQ_CHUNK / ACQ_THREADS];
+	uint2 rawn [ACQ_CHUNK / ACQ_THREADS];                       // the next chunk's samples as loaded (converted when used)
+#ifdef ACQ_PROF
+	long long prof_t [8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_last = clock64 (), prof_chunks = 0;
+#endif
 	long long next_pos = -1;
 	while (true) {
 		int n;                                                       // samples until the stage can change by COUNT
@@ -70,82 +117,91 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 		if (n > ACQ_CHUNK) n = ACQ_CHUNK;
 		if (pos + n > total) { done = 2; break; }                    // out of data: rewind to the attempt start
 		const int ph = stage < 2 ? 0 : mod_rate (phi);               // getSample (0) while looking for a signal at all (:279, 285)
+		ACQ_T (0)
 		{	// 1. per-sample values
 			int l = mod_rate ((long long) lp - (long long) (tid + 1) * ph);
 			const int step = mod_rate ((long long) ACQ_THREADS * ph);
-			float2 raw [ACQ_CHUNK / ACQ_THREADS];                    // all of the thread's samples are requested before the first is used;
-			if (next_pos == pos) {                                   // normally they were requested while the previous chunk's chains ran
-#pragma unroll
-				for (int k = 0; k < ACQ_CHUNK / ACQ_THREADS; k ++) raw [k] = rawn [k];
-			} else {
-#pragma unroll
-				for (int k = 0; k < ACQ_CHUNK / ACQ_THREADS; k ++)
-					if (tid + k * ACQ_THREADS < n) raw [k] = sy_sample (w, pos + tid + k * ACQ_THREADS);
-			}
+			if (next_pos != pos)                                     // (normally the samples were requested while the previous chunk's chains ran)
+				sy_raw_chunk<ACQ_CHUNK / ACQ_THREADS, ACQ_THREADS> (w, pos, pos + n, tid, rawn);
 #pragma unroll
 			for (int k = 0; k < ACQ_CHUNK / ACQ_THREADS; k ++) {
 				const int i = tid + k * ACQ_THREADS;
 				if (i >= n) break;
-				const float2 v = cmul (raw [k], nco (T, l));
+				const float2 v = cmul (sy_conv (w, rawn [k]), nco (T, l));
 				const float ja = fabsf (v. x) + fabsf (v. y);            // jan_abs
 				s_ja [i] = ja; s_t [i] = 0.00001f * ja;
 				s_e [i] = stage == 3 ? hypotf (v. x, v. y) : ja;           // abs () in SyncOnEndNull (:329)
 				l -= step; if (l < 0) l += DAB_INPUT_RATE;
 			}
+			ACQ_T (1)
 			__syncthreads ();
+			ACQ_T (2)
 			if (stage >= 1)
 				for (int i = tid; i < n; i += ACQ_THREADS)
 					s_d [i] = stage == 1 ? s_e [i] : __fsub_rn (s_e [i], i >= 50 ? s_e [i - 50] : s_ring [(idx + i - 50) & 63]);
 			__syncthreads ();
 		}
+		ACQ_T (3)
 		// the samples of the NEXT chunk (if this one runs to its end) are requested now: their HBM latency passes behind the chains
 		next_pos = pos + n;
-#pragma unroll
-		for (int k = 0; k < ACQ_CHUNK / ACQ_THREADS; k ++)
-			if (next_pos + tid + k * ACQ_THREADS < total) rawn [k] = sy_sample (w, next_pos + tid + k * ACQ_THREADS);
-		// 2. the two recurrences: s_sl [i] / s_csb [i] = value before sample i, [n] = value after the chunk.  Thread 0 runs the
-		// level surrogate, thread 32 (another warp, concurrently) the window sum.  Both walk in batches of 16 whose inputs are
-		// fetched into registers one batch ahead, so that only the dependent arithmetic is on the chain (one FFMA / one FADD
-		// a step).  Surrogate: a' = fma (a, c_hi, u), u = fma (a_prev, c_lo, k |v|) with c_hi + c_lo = 1 - 1e-5 to 48 bits; u takes
-		// the level of one step EARLIER (it differs by 1e-5 a, times c_lo ~ 1e-8: invisible), which keeps it off the chain.
-		if (tid == 32) {
+		sy_raw_chunk<ACQ_CHUNK / ACQ_THREADS, ACQ_THREADS> (w, next_pos, total, tid, rawn);
+		// 2. the two recurrences: s_sl [i] / s_csb [i] = value before sample i, [n] = value after the chunk.  Warp 0 runs the level
+		// surrogate, warp 1 (concurrently) the window sum.  The inputs of 32 steps come in with eight 128-bit broadcast loads,
+		// requested a block ahead, so only the dependent arithmetic is on the chain -- ONE FFMA / FADD a step; all lanes of the
+		// warp compute the same chain and lane 0 records it (a predicated store per step, nothing waits for it).
+		// Surrogate: a' = fma (a, c_hi, u), u = fma (a_prev, c_lo, k |v|) with c_hi + c_lo = 1 - 1e-5 to 48 bits; u takes the level
+		// of one step EARLIER (it differs by 1e-5 a, times c_lo ~ 1e-8: invisible), which keeps it off the chain.
+		const int lane = tid & 31;
+		if (tid >= 32 && tid < 64) {
 			float c = cs;
 			if (stage >= 1) {
-				float dn [16];
+				float4 dn [8];
 #pragma unroll
-				for (int k = 0; k < 16; k ++) dn [k] = s_d [k];
-				for (int i = 0; i < n; i += 16) {
-					float dc [16], r [16];
+				for (int k = 0; k < 8; k ++) dn [k] = reinterpret_cast<const float4 *> (s_d) [k];
+				for (int i0 = 0; i0 < n; i0 += 32) {
+					float dc [32];
 #pragma unroll
-					for (int k = 0; k < 16; k ++) { dc [k] = dn [k]; dn [k] = s_d [i + 16 + k]; }
+					for (int k = 0; k < 8; k ++) { dc [4 * k] = dn [k]. x; dc [4 * k + 1] = dn [k]. y; dc [4 * k + 2] = dn [k]. z; dc [4 * k + 3] = dn [k]. w; dn [k] = reinterpret_cast<const float4 *> (s_d + i0 + 32) [k]; }
 #pragma unroll
-					for (int k = 0; k < 16; k ++) { r [k] = c; c = __fadd_rn (c, dc [k]); }
-#pragma unroll
-					for (int k = 0; k < 16; k ++) s_csb [i + k] = r [k];
-					if (i + 16 == n) s_csb [n] = c;                  // (n inside a batch: r [n - i] above is already the value after the last sample)
+					for (int k = 0; k < 32; k ++) {
+						if (lane == 0) s_csb [i0 + k] = c;
+						c = __fadd_rn (c, dc [k]);
+					}
 				}
-			} else s_csb [n] = c;
+				if ((n & 31) == 0 && lane == 0) s_csb [n] = c;       // (n inside a block: the record of sample n there is the value after n - 1 already)
+			} else if (lane == 0) s_csb [n] = c;
 		}
+		ACQ_T (7)
 		int from = 0;                                                // s_sl [from] is known to be exact
 		if (tid == 0) s_sl [0] = sLevel;
+		__syncwarp ();
 		while (true) {
-			if (tid == 0) {                                          // surrogate chain from `from` on
+			if (tid < 32) {                                          // surrogate chain from `from` on
 				const float c_hi = 0.99999f, c_lo = (float) ((1 - 0.00001) - (double) 0.99999f);
+				int i0 = from;
 				float a = s_sl [from], ap = a;
-				float tn [16];
-#pragma unroll
-				for (int k = 0; k < 16; k ++) tn [k] = s_t [from + k];
-				for (int i = from; i < n; i += 16) {
-					float tc [16], r [16];
-#pragma unroll
-					for (int k = 0; k < 16; k ++) { tc [k] = tn [k]; tn [k] = s_t [i + 16 + k]; }
-#pragma unroll
-					for (int k = 0; k < 16; k ++) { const float u = __fmaf_rn (ap, c_lo, tc [k]); ap = a; a = __fmaf_rn (a, c_hi, u); r [k] = a; }
-#pragma unroll
-					for (int k = 0; k < 16; k ++) if (i + k < n) s_sl [i + 1 + k] = r [k];
+				for (; (i0 & 31) != 0 && i0 < n; i0 ++) {                // (after a repair: up to the next block boundary one by one)
+					const float u = __fmaf_rn (ap, c_lo, s_t [i0]); ap = a; a = __fmaf_rn (a, c_hi, u);
+					if (lane == 0) s_sl [i0 + 1] = a;
 				}
-				s_first = n;
+				float4 tn [8];
+				if (i0 < n) {                                        // (i0 is a multiple of 32 here)
+#pragma unroll
+					for (int k = 0; k < 8; k ++) tn [k] = reinterpret_cast<const float4 *> (s_t + i0) [k];
+				}
+				for (; i0 < n; i0 += 32) {
+					float tc [32];
+#pragma unroll
+					for (int k = 0; k < 8; k ++) { tc [4 * k] = tn [k]. x; tc [4 * k + 1] = tn [k]. y; tc [4 * k + 2] = tn [k]. z; tc [4 * k + 3] = tn [k]. w; tn [k] = reinterpret_cast<const float4 *> (s_t + i0 + 32) [k]; }
+#pragma unroll
+					for (int k = 0; k < 32; k ++) {
+						const float u = __fmaf_rn (ap, c_lo, tc [k]); ap = a; a = __fmaf_rn (a, c_hi, u);
+						if (lane == 0) s_sl [i0 + 1 + k] = a;
+					}
+				}
+				if (lane == 0) s_first = n;
 			}
+			ACQ_T (4)
 			__syncthreads ();
 			int bad = n;                                             // 2b. first step whose recorded successor is not the exact one
 			for (int i = from + tid; i < n && bad == n; i += ACQ_THREADS)
@@ -158,6 +214,7 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 			from = first + 1;
 			__syncthreads ();                                        // (everybody has read s_first before thread 0 resets it)
 		}
+		ACQ_T (5)
 		int used = n;
 		if (stage >= 2) {                                            // 3. the threshold tests (:301, :323), in parallel
 			if (tid == 0) s_first = n;
@@ -180,6 +237,10 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 			idx += used;
 		}
 		__syncthreads ();
+		ACQ_T (6)
+#ifdef ACQ_PROF
+		prof_chunks ++;
+#endif
 		pos += used;
 		lp = mod_rate ((long long) lp - (long long) used * ph);
 		bool restart = false;
@@ -199,6 +260,10 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 			attempt_pos = pos; attempt_lp = lp;
 		}
 	}
+#ifdef ACQ_PROF
+	if (tid == 0) printf ("acquire: %lld chunks; cycles per chunk: head %lld prep %lld sync %lld diff %lld prefetch+cs %lld chain %lld verify %lld tests+commit %lld\n", prof_chunks, prof_t [0] / prof_chunks, prof_t [1] / prof_chunks,
+	                      prof_t [2] / prof_chunks, prof_t [3] / prof_chunks, prof_t [7] / prof_chunks, prof_t [4] / prof_chunks, prof_t [5] / prof_chunks, prof_t [6] / prof_chunks);
+#endif
 	if (tid == 0) {
 		if (done == 1) { ctl -> synced = 1; ctl -> pos = pos; ctl -> lp = lp; ctl -> acq_done = 1; }
 		else           { ctl -> synced = 0; ctl -> pos = attempt_pos; ctl -> lp = attempt_lp; ctl -> acq_done = 0; }

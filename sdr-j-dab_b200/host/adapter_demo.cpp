@@ -99,6 +99,47 @@ int main (int argc, char **argv) {
 				printf ("%s %d %016llx %d %016llx %016llx %d\n", conc ? "handlers_concurrent" : "handlers_serial", fibs, facc, frames, macc, macc_skip1, (int) fic. get_ficRatio ());
 			}
 		}
+		if (argc > 4) {	// dabgpu_group_*: ONE recording (u8 IQ file) decoded by a group of handles -- two GPUs when the box has them, two
+			// handles on one GPU otherwise -- against a single handle: parallel scheme, forced chain
+			FILE *fp = fopen (argv [4], "rb");
+			if (!fp) throw std::runtime_error ("cannot open the u8 IQ file");
+			std::vector<uint8_t> iq;
+			{ uint8_t buf [65536]; size_t n; while ((n = fread (buf, 1, sizeof (buf), fp)) > 0) iq. insert (iq. end (), buf, buf + n); }
+			fclose (fp);
+			const size_t nsamp = iq. size () / 2;
+			const int cap = (int) (nsamp / 196608) + 4;
+			dabgpu_subch sc [2] = { { 0, 96, 128, 1, 0103 }, { 96, 96, 128, 0, 3 } };
+			struct Out { std::vector<uint8_t> fic, crc, m0, m1; std::vector<dabgpu_frame_info> info; uint8_t *mp [2]; int32_t nblk [2]; dabgpu_result r; };
+			auto mk = [&] (Out &o) {
+				o. fic. assign ((size_t) cap * 4 * 768, 0); o. crc. assign ((size_t) cap * 12, 0); o. m0. assign ((size_t) cap * 4 * 3072, 0); o. m1. assign ((size_t) cap * 4 * 3072, 0);
+				o. info. resize (cap); o. mp [0] = o. m0. data (); o. mp [1] = o. m1. data ();
+				o. r = dabgpu_result {}; o. r. max_frames = cap; o. r. info = o. info. data (); o. r. fic_bits = o. fic. data (); o. r. fic_crc = o. crc. data ();
+				o. r. msc_bits = o. mp; o. r. msc_nblocks = o. nblk;
+			};
+			auto digest = [&] (Out &o) {
+				unsigned long long h = fnv (o. fic. data (), (size_t) o. r. nframes * 4 * 768);
+				h = h * 31 + fnv (o. m0. data (), (size_t) o. nblk [0] * 3072); h = h * 31 + fnv (o. m1. data (), (size_t) o. nblk [1] * 3072);
+				for (int i = 0; i < o. r. nframes; i ++) h = h * 31 + (unsigned long long) o. info [i]. pos * 7 + (unsigned) o. info [i]. fine;
+				return h;
+			};
+			dabgpu_config cfg = {}; cfg. device = 0; cfg. dabMode = 1; cfg. threshold = 3; cfg. freqSyncMethod = 1;
+			dabgpu_t *one; if (dabgpu_create (&cfg, &one)) throw std::runtime_error (dabgpu_last_error (nullptr));
+			dabgpu_host::check (one, dabgpu_set_subchannels (one, sc, 2));
+			Out a; mk (a);
+			dabgpu_host::check (one, dabgpu_decode (one, iq. data (), nsamp, &a. r));
+			const int ndev = dabgpu_device_count ();
+			int32_t devs [2] = { 0, ndev > 1 ? 1 : 0 };
+			dabgpu_group_t *grp;
+			if (dabgpu_group_create (&cfg, devs, 2, &grp)) throw std::runtime_error (dabgpu_last_error (nullptr));
+			if (dabgpu_group_set_subchannels (grp, sc, 2)) throw std::runtime_error (dabgpu_group_last_error (grp));
+			for (int scheme = 1; scheme >= 0; scheme --) {
+				Out b; mk (b);
+				int32_t used = -1;
+				if (dabgpu_group_decode (grp, iq. data (), nsamp, &b. r, 40, scheme, &used)) throw std::runtime_error (dabgpu_group_last_error (grp));
+				printf ("group_scheme%d %d %d %d %016llx %016llx %d\n", scheme, used, a. r. nframes, b. r. nframes, digest (a), digest (b), devs [1]);
+			}
+			dabgpu_group_destroy (grp); dabgpu_destroy (one);
+		}
 	} catch (const std::exception &e) { fprintf (stderr, "adapter_demo: %s\n", e. what ()); return 1; }
 	return 0;
 }

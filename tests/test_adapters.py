@@ -64,8 +64,12 @@ def test_adapter_demo_matches_oracle(port):
     sym, finfo = port.ofdm_run(1, f32, 30)
     softpath = os.path.join(HOST, "adapter_demo_soft.bin")
     np.ascontiguousarray(sym, np.int16).tofile(softpath)
-    r = subprocess.run([EXE, path, iqpath, softpath], capture_output=True, text=True, timeout=180)
-    os.remove(path); os.remove(iqpath); os.remove(softpath)
+    # a longer u8 recording for the C++ multi-GPU group (dabgpu_group_*): two sub-channels, 64 frames
+    mod2 = dabmod.Modulator(port, 1, [(0, 128, 1, 0o103), (96, 128, 0, 3)], 5151)
+    u8path = os.path.join(HOST, "adapter_demo_u8.bin")
+    mod2.generate(64, cfo_hz=137.0, snr_db=18.0, lead=9000, tail=6000)["iq"].tofile(u8path)
+    r = subprocess.run([EXE, path, iqpath, softpath, u8path], capture_output=True, text=True, timeout=300)
+    os.remove(path); os.remove(iqpath); os.remove(softpath); os.remove(u8path)
     assert r.returncode == 0, r.stderr
     got = dict(line.split(" ", 1) for line in r.stdout.strip().splitlines())
     g = _lcg_stream(12345)
@@ -110,6 +114,11 @@ def test_adapter_demo_matches_oracle(port):
         macc = (macc * 31 + _fnv(blk)) & M
     assert int(nmsc) == len(frames) > 30 and int(mh, 16) == macc
     assert int(ratio) == 100 * cnt // (12 * n)
+    # dabgpu_group_decode from C++ (two GPUs when the box has them, else two handles on one): equal to one handle, both schemes
+    for scheme in (1, 0):
+        used, n1, n2, h1, h2, dev1 = got["group_scheme%d" % scheme].split()
+        assert int(n1) == int(n2) >= 56 and h1 == h2, (scheme, got["group_scheme%d" % scheme])
+        assert int(used) == scheme
     # ficHandler::process_ficBlock / mscHandler::process_mscBlock fed symbol by symbol with the oracle's soft bits of ALL
     # its frames: the same FIBs (with ficno) and frames as the oracle's FIC / MSC chain; behind mscHandler once
     # dabConcurrent (16-CIF warm-up) and once dabSerial (15: one frame more at the start, the rest identical)
