@@ -19,6 +19,10 @@
 #include <stdlib.h>
 #include <algorithm>
 #include "dabgpu_engine.h"
+#include <atomic>
+#include <chrono>
+#include <thread>
+static double now_ms () { return std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now (). time_since_epoch ()). count (); }
 
 // ---------------------------------------------------------------------------------------------------
 // handle life cycle, control members
@@ -51,6 +55,7 @@ void dab_engine_free (dabgpu *h) {
 	for (auto *b : E -> backends) dabgpu_backend_destroy (b);
 	if (E -> d_phaseRef) cudaFree (E -> d_phaseRef);
 	if (E -> copy_st) { cudaStreamSynchronize (E -> copy_st); cudaStreamDestroy (E -> copy_st); }
+	for (int k = 0; k < 4; k ++) if (E -> acq_st [k]) { cudaStreamSynchronize (E -> acq_st [k]); cudaStreamDestroy (E -> acq_st [k]); }
 	for (auto &v : E -> copy_events) for (auto e : v) cudaEventDestroy (e);
 	E -> tail. release (); E -> tail_spare. release (); E -> d_sd. release (); E -> h_sd. release ();
 	E -> d_frameout. release (); E -> d_framein. release (); E -> d_fcpart. release (); E -> d_spec0. release (); E -> d_info. release ();
@@ -59,7 +64,7 @@ void dab_engine_free (dabgpu *h) {
 	for (auto &b : E -> d_mscbits) b. release ();
 	E -> m_in. release (); E -> m_fic8. release (); E -> m_msc8. release (); E -> m_info. release ();
 	E -> m_ficbits. release (); E -> m_ficcrc. release (); E -> m_mscbits. release ();
-	E -> mh_in. release (); E -> mh_out. release ();
+	E -> mh_in. release (); E -> mh_out. release (); E -> mh_acq. release (); E -> m_offs. release ();
 	for (int i = 0; i < 2; i ++) { E -> d_inbuf [i]. release (); E -> h_stage [i]. release (); }
 	delete E;
 	h -> engine = nullptr;
@@ -253,8 +258,12 @@ static int run_round (dabgpu *h, int nstreams, int nslots, int max_budget, bool 
 	Engine *E = h -> engine;
 	cudaStream_t st = h -> stream;
 	StreamDev *hsd = (StreamDev *) E -> h_sd. p, *dsd = (StreamDev *) E -> d_sd. p;
+	static const bool trace = getenv ("DABGPU_TRACE") != nullptr && atoi (getenv ("DABGPU_TRACE")) >= 2;     // (level 2: with a synchronisation after every step)
+	const double t0 = trace ? now_ms () : 0;
+	if (trace) { cudaStreamSynchronize (st); fprintf (stderr, "[round] stream idle after %.3f ms\n", now_ms () - t0); }
 	CUDA_TRY (h, cudaMemcpyAsync (dsd, hsd, (size_t) nstreams * sizeof (StreamDev), cudaMemcpyHostToDevice, st));
 	if (any_acquire) acquire_launch (h, dsd, nstreams, st);
+	if (trace) { cudaStreamSynchronize (st); fprintf (stderr, "[round] table up + acquire: at %.3f ms\n", now_ms () - t0); }
 	predict_launch (h, dsd, nstreams, cb, st);
 	// symbol groups (CTAs) per frame: every group first recomputes the spectrum of the symbol before its own as phase
 	// reference, so few groups mean less redundant work and many groups more CTAs.  A big round fills the GPU anyway
@@ -266,6 +275,7 @@ static int run_round (dabgpu *h, int nstreams, int nslots, int max_budget, bool 
 		front_launch (h, dsd, nslots, cb, which, st);
 		symbol_launch (h, dsd, nslots, groups, cb, which, fmt, st);
 		scan_launch (h, dsd, nstreams, max_budget, groups, cb, pass == 0 ? 1 : 0, st);
+		if (trace) { cudaStreamSynchronize (st); fprintf (stderr, "[round] pass %d done at %.3f ms\n", pass, now_ms () - t0); }
 	}
 	CUDA_TRY (h, cudaGetLastError ());
 	CUDA_TRY (h, cudaMemcpyAsync (hsd, dsd, (size_t) nstreams * sizeof (StreamDev), cudaMemcpyDeviceToHost, st));
@@ -279,8 +289,11 @@ static int run_round (dabgpu *h, int nstreams, int nslots, int max_budget, bool 
 
 // chunk policy: grow while the speculation holds outright; a chunk that needed recomputation (correctors still
 // moving) or was cut short shrinks, so a converging loop costs little and a locked one runs in one pass
-static int next_chunk (int chunk, int attempted, const StreamCtl &c, int cap) {
-	if (c. n_valid == attempted && c. n_redo == 0) chunk *= 2;
+// eager (many streams in lockstep): a round costs its latency whatever it carries, so the chunk also grows when the derive pass
+// predicted the whole chunk right and only the recomputation was needed
+static int next_chunk (int chunk, int attempted, const StreamCtl &c, int cap, bool eager = false) {
+	if (c. n_valid == attempted && eager) chunk *= 4;
+	else if (c. n_valid == attempted && c. n_redo == 0) chunk *= 2;
 	else if (c. n_valid == attempted) chunk = chunk > 16 ? chunk / 2 : (chunk < 8 ? chunk * 2 : chunk);
 	else chunk = chunk > 2 ? chunk / 2 : 1;
 	return chunk > cap ? cap : (chunk < 1 ? 1 : chunk);
@@ -312,18 +325,16 @@ struct ChanPart {                                           // frames [f0, f0 + 
 
 // queued on a side stream so that it overlaps the OFDM work of the next chunk; results are copied to the callers'
 // buffers on the same stream.  All parts go through ONE launch pair of the throughput kernels when that path is taken.
-// span: one FIB-CRC launch over a whole buffer of FIC groups instead of one per part.  It also covers groups decoded by
-// EARLIER calls, so all calls that share the buffer must then use the same side stream (stream order keeps a group's bits
-// complete before any later launch re-reads them): such callers always get context 1.
-struct CrcSpan { uint8_t *bits, *crc; int ngroups; };
-static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts, const CrcSpan *span = nullptr) {
+// defer_crc: no CRC launch and no delivery of CRC flags here (dabgpu_decode_multi checks every group of the call in one launch at
+// its end, so that its channel-decoding batches are independent of each other and may run on different side streams)
+static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts, bool defer_crc = false) {
 	Engine *E = h -> engine;
 	const DabParams &p = h -> p;
 	const size_t nsub = E -> backends. size ();
 	long long ncw = 0, ncif_all = 0;
 	for (auto &q : parts) { ncw += (long long) q. nv * p. ficGroups + (long long) q. nv * p. cifsPerFrame * (long long) nsub; ncif_all += (long long) q. nv * p. cifsPerFrame; }
 	if (ncw == 0) return DABGPU_OK;
-	h -> cur = span ? 1 : 1 + (E -> vrr ++ % 3);
+	h -> cur = 1 + (E -> vrr ++ % 3);
 	cudaStream_t st = h -> vst ();
 	int rc = DABGPU_OK;
 	// the throughput kernels take every job of the chunk in ONE launch pair; the warp-cooperative kernel is launched once per
@@ -366,10 +377,7 @@ static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts, const CrcSpan
 		if (simd) {
 			jobs. insert (jobs. end (), fic_jobs. begin (), fic_jobs. end ());
 			if ((rc = dab_vit_simd_run (h, jobs))) break;
-			if (span) {
-				cudaError_t e = fib_crc_launch (h, span -> bits, 3 * span -> ngroups, span -> crc);
-				if (e != cudaSuccess) rc = dab_fail (h, DABGPU_ERR_CUDA, "crc launch: %s", cudaGetErrorString (e));
-			} else for (auto &q : parts) {
+			if (!defer_crc) for (auto &q : parts) {
 				const int ngroups = q. nv * p. ficGroups, g0 = q. f0 * p. ficGroups;
 				if (ngroups <= 0) continue;
 				cudaError_t e = fib_crc_launch (h, q. ficbits + (size_t) g0 * 768, 3 * ngroups, q. ficcrc + (size_t) g0 * 3);
@@ -389,7 +397,7 @@ static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts, const CrcSpan
 			const int c0 = q. f0 > q. out_skip ? q. f0 : q. out_skip, cg = (q. f0 + q. nv - c0) * p. ficGroups;      // frames [c0, f0 + nv) are delivered
 			const size_t src_g = (size_t) c0 * p. ficGroups, dst_g = (size_t) (c0 - q. out_skip) * p. ficGroups;
 			if (cg > 0 && q. out -> fic_bits) e = cudaMemcpyAsync (q. out -> fic_bits + dst_g * 768, q. ficbits + src_g * 768, (size_t) cg * 768, cudaMemcpyDeviceToHost, st);
-			if (e == cudaSuccess && cg > 0 && q. out -> fic_crc) e = cudaMemcpyAsync (q. out -> fic_crc + dst_g * 3, q. ficcrc + src_g * 3, (size_t) cg * 3, cudaMemcpyDeviceToHost, st);
+			if (e == cudaSuccess && cg > 0 && q. out -> fic_crc && !defer_crc) e = cudaMemcpyAsync (q. out -> fic_crc + dst_g * 3, q. ficcrc + src_g * 3, (size_t) cg * 3, cudaMemcpyDeviceToHost, st);
 			for (size_t i = 0; i < nsub && e == cudaSuccess; i ++) {
 				const size_t fbytes = msc_block_bytes (E, E -> subch [i]);
 				if (q. out -> msc_bits && q. out -> msc_bits [i] && n_here [k] [i] > 0)
@@ -715,6 +723,13 @@ static int decode_host (dabgpu *h, const void *iq_v, size_t nsamples, int cf32, 
 // ---------------------------------------------------------------------------------------------------
 #define MULTI_SLOT_CAP 4096                                  // chunk slots of one round, all streams together
 
+// rows 0..14 of every stream's MSC plane = byte symbol 127 (dab-concurrent.cpp:70-74: zero soft bits = erasures); planes are 256-byte aligned
+__global__ void __launch_bounds__ (256) hist_fill_kernel (uint8_t *base, const unsigned long long *offs) {
+	uint4 *row = reinterpret_cast<uint4 *> (base + offs [blockIdx. y] + (size_t) blockIdx. x * CIF_BITS);
+	const uint4 v = make_uint4 (0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
+	for (int i = threadIdx. x; i < CIF_BITS / 16; i += 256) row [i] = v;
+}
+
 struct MultiStream {
 	long long nsamples, in_off;                              // samples, byte offset of the stream's input in m_in
 	long long want;                                          // frames wanted at most
@@ -723,11 +738,17 @@ struct MultiStream {
 	StreamCtl ctl;
 	int chunk, nframes, decoded_upto;
 	bool done;
+	bool direct;                                             // every result buffer of the stream is pinned host memory: results are copied straight into them
+	long long limit;                                         // samples known to be resident (host input goes up in pieces)
+	long long acq_tried = -1;                                // an acquisition ran out of samples at this limit
+	long long acq_limit = 0;                                 // limit the search in flight was started with
+	int acq_wave = 0;                                        // launch number of the stream's search in flight (0 = none)
 	std::vector<int> nblk;
 	std::vector<uint8_t *> mscbits;
 };
 
 static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstreams, int fmt, bool dev_input) {
+	const double t_entry = now_ms ();
 	Engine *E = h -> engine;
 	const DabParams &p = h -> p;
 	if (p. dabMode == 3)
@@ -759,6 +780,11 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 		m. chunk = 1; m. nframes = 0; m. decoded_upto = 0; m. done = m. want == 0;
 		m. nblk. assign (nsub, 0);
 		J. out -> nframes = 0; J. out -> consumed = 0;
+		// results go straight from the side stream into the caller's buffers when all of them are pinned (asynchronous copies that
+		// overlap the following rounds); otherwise through the bulk staging copies at the end of the call
+		auto is_pinned = [] (const void *q) { cudaPointerAttributes a; const bool ok = cudaPointerGetAttributes (&a, q) == cudaSuccess && a. type == cudaMemoryTypeHost; cudaGetLastError (); return ok; };
+		m. direct = !J. out -> soft && (!J. out -> fic_bits || is_pinned (J. out -> fic_bits)) && (!J. out -> fic_crc || is_pinned (J. out -> fic_crc));
+		for (size_t s = 0; s < nsub && m. direct && J. out -> msc_bits; s ++) m. direct = !J. out -> msc_bits [s] || is_pinned (J. out -> msc_bits [s]);
 	}
 	for (int i = 1; i < 4; i ++) CUDA_TRY (h, cudaStreamSynchronize (h -> vctx [i]. st));
 	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
@@ -774,18 +800,53 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 	int rc = ensure_round_bufs (h, nstreams, MULTI_SLOT_CAP, &cb);
 	if (rc) return rc;
 	// inputs: one copy per stream on the copy stream (pinned or pageable, as the caller has them); history rows = erasures
+	// Host input goes up on the copy stream in NPIECE pieces per stream, piece k of every stream before piece k + 1 of any: the first
+	// piece covers what an acquisition normally reads (6.6 frames), so the null search starts after a fraction of the upload and the
+	// rounds follow the arriving samples (StreamDev::limit; the scan cuts a chunk at the first frame whose window is not resident)
+	const int NPIECE = 4;
+	const long long first_piece = (long long) (6.6 * p. T_F);
+	auto piece_end = [&] (const MultiStream &m, int k) -> long long {      // samples of the stream resident once piece k has arrived
+		if (m. nsamples <= first_piece || k >= NPIECE - 1) return m. nsamples;
+		return first_piece + (m. nsamples - first_piece) * k / (NPIECE - 1);
+	};
+	std::vector<cudaEvent_t> &pev = E -> copy_events [0];
+	int pieces_waited = dev_input ? NPIECE : 0;
 	std::vector<const void *> d_in (nstreams);
+	if (!dev_input) {
+		while ((int) pev. size () < NPIECE) { cudaEvent_t e; CUDA_TRY (h, cudaEventCreateWithFlags (&e, cudaEventDisableTiming)); pev. push_back (e); }
+		for (int k = 0; k < NPIECE; k ++) {
+			for (int i = 0; i < nstreams; i ++) {
+				const MultiStream &m = ms [i];
+				const long long a = k ? piece_end (m, k - 1) : 0, b = piece_end (m, k);
+				if (b > a)
+					CUDA_TRY (h, cudaMemcpyAsync ((char *) E -> m_in. p + m. in_off + (size_t) a * sb, (const char *) jobs [i]. iq + (size_t) a * sb, (size_t) (b - a) * sb, cudaMemcpyHostToDevice, E -> copy_st));
+			}
+			CUDA_TRY (h, cudaEventRecord (pev [k], E -> copy_st));
+		}
+	}
+	// pieces [0, upto) must have arrived before the main stream goes on (the host does not wait)
+	auto wait_pieces = [&] (int upto) -> cudaError_t {
+		cudaError_t e = cudaSuccess;
+		if (upto > NPIECE) upto = NPIECE;
+		if (upto > pieces_waited) { e = cudaStreamWaitEvent (h -> stream, pev [upto - 1], 0); pieces_waited = upto; }
+		for (auto &m : ms) m. limit = piece_end (m, pieces_waited - 1);
+		return e;
+	};
 	for (int i = 0; i < nstreams; i ++) {
 		MultiStream &m = ms [i];
-		if (dev_input) d_in [i] = jobs [i]. iq;
-		else {
-			d_in [i] = (const char *) E -> m_in. p + m. in_off;
-			if (m. nsamples > 0)
-				CUDA_TRY (h, cudaMemcpyAsync ((void *) d_in [i], jobs [i]. iq, (size_t) m. nsamples * sb, cudaMemcpyHostToDevice, h -> stream));
-		}
-		CUDA_TRY (h, cudaMemsetAsync ((char *) E -> m_msc8. p + m. msc_off, 127, 15 * cifw, h -> stream));
+		m. limit = dev_input ? m. nsamples : 0;
+		d_in [i] = dev_input ? jobs [i]. iq : (const void *) ((const char *) E -> m_in. p + m. in_off);
 		m. mscbits. resize (nsub);
 		for (size_t s = 0; s < nsub; s ++) m. mscbits [s] = (uint8_t *) E -> m_mscbits. p + m. mscbits_off [s];
+	}
+	{	// the 15 history rows of every stream = erasures: ONE launch (a cudaMemsetAsync per stream cost 0.35 ms each on B200)
+		CUDA_TRY (h, E -> mh_in. ensure ((size_t) nstreams * sizeof (unsigned long long)));
+		CUDA_TRY (h, E -> m_offs. ensure ((size_t) nstreams * sizeof (unsigned long long)));
+		unsigned long long *ho = (unsigned long long *) E -> mh_in. p;
+		for (int i = 0; i < nstreams; i ++) ho [i] = (unsigned long long) ms [i]. msc_off;
+		CUDA_TRY (h, cudaMemcpyAsync (E -> m_offs. p, ho, (size_t) nstreams * sizeof (unsigned long long), cudaMemcpyHostToDevice, h -> stream));
+		hist_fill_kernel<<<dim3 (15, nstreams), 256, 0, h -> stream>>> ((uint8_t *) E -> m_msc8. p, (const unsigned long long *) E -> m_offs. p);
+		h -> launches ++;
 	}
 	StreamDev *hsd = (StreamDev *) E -> h_sd. p;
 	// channel decoding of everything accepted since the last call, all streams in one launch pair
@@ -794,7 +855,9 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 		std::vector<ChanPart> parts;
 		long long pending = 0;
 		for (auto &m : ms) pending += m. nframes - m. decoded_upto;
-		if (pending == 0 || (!final && pending < 256)) return DABGPU_OK;
+		// a batch of the throughput Viterbi kernels takes the time of ONE code word's walk (1.4 ms for 3078 steps) however small it
+		// is, as long as it stays below a wave: batches start early and overlap each other on the three side streams
+		if (pending == 0 || (!final && pending < 128)) return DABGPU_OK;
 		for (int i = 0; i < nstreams; i ++) {
 			MultiStream &m = ms [i];
 			if (m. nframes == m. decoded_upto) continue;
@@ -802,18 +865,74 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 			q. fic8 = (const uint8_t *) E -> m_fic8. p + m. fic_off; q. msc8 = (const uint8_t *) E -> m_msc8. p + m. msc_off;
 			q. f0 = m. decoded_upto; q. nv = m. nframes - m. decoded_upto; q. cifs_before = (int64_t) m. decoded_upto * p. cifsPerFrame;
 			q. ficbits = (uint8_t *) E -> m_ficbits. p + m. ficbits_off; q. ficcrc = (uint8_t *) E -> m_ficcrc. p + m. ficcrc_off;
-			q. mscbits = m. mscbits. data (); q. nblk = m. nblk. data (); q. out = &no_copy; q. fib0 = ~0ull;      // (results go out in bulk at the end)
+			q. mscbits = m. mscbits. data (); q. nblk = m. nblk. data (); q. fib0 = ~0ull;
+			q. out = m. direct ? jobs [i]. out : &no_copy;      // (pageable result buffers: in bulk at the end)
 			parts. push_back (q);
 			m. decoded_upto = m. nframes;
 		}
-		// the CRC launch covers every group of every stream: groups not decoded yet give flags nobody reads (they are
-		// recomputed when their bits arrive)
-		const CrcSpan span { (uint8_t *) E -> m_ficbits. p, (uint8_t *) E -> m_ficcrc. p, (int) ngroups_all };
-		return channel_parts (h, parts, &span);
+		return channel_parts (h, parts, true);      // (CRC flags: one launch over every group of the call at its end)
+	};
+	const bool trace = getenv ("DABGPU_TRACE") != nullptr;
+	const double t_call0 = now_ms ();
+	if (trace) fprintf (stderr, "[multi] set-up took %.3f ms of host time\n", t_call0 - t_entry);
+	int round_no = 0;
+	// Acquisitions run ASYNCHRONOUSLY beside the rounds: the streams that need one are enrolled into a launch of the acquisition
+	// kernel on a side stream; the kernel reads a stream's entry from pinned host memory and publishes the outcome there, stream
+	// by stream, the moment that stream's search ends.  The rounds go on with whatever streams are in sync, so neither the slowest
+	// null search nor a stream that lost sync holds the others up.
+	CUDA_TRY (h, E -> mh_acq. ensure (up ((size_t) nstreams * sizeof (StreamDev), 64) + (size_t) nstreams * sizeof (int)));
+	StreamDev *acq_sd = (StreamDev *) E -> mh_acq. p;
+	volatile int *acq_flag = (volatile int *) ((char *) E -> mh_acq. p + up ((size_t) nstreams * sizeof (StreamDev), 64));
+	for (int i = 0; i < nstreams; i ++) acq_flag [i] = 0;
+	for (int k = 0; k < 4; k ++) if (!E -> acq_st [k]) CUDA_TRY (h, cudaStreamCreateWithFlags (&E -> acq_st [k], cudaStreamNonBlocking));
+	int wave = 0, inflight = 0;
+	auto collect = [&] () -> int {                           // outcomes published since the last look
+		int got = 0;
+		for (int i = 0; i < nstreams && inflight > 0; i ++) {
+			MultiStream &m = ms [i];
+			if (!m. acq_wave || acq_flag [i] != m. acq_wave) continue;
+			std::atomic_thread_fence (std::memory_order_acquire);
+			const StreamCtl &c = acq_sd [i]. ctl;
+			m. ctl. synced = c. synced; m. ctl. pos = c. pos; m. ctl. lp = c. lp; m. ctl. acq_done = c. acq_done;
+			m. acq_wave = 0; inflight --; got ++;
+			if (m. ctl. synced) m. chunk = 4;
+			else if (m. acq_limit < m. nsamples) m. acq_tried = m. acq_limit;      // out of the samples that had arrived: once more when there are more
+			else m. done = true;                                                   // out of samples inside the attempt
+		}
+		return got;
 	};
 	while (true) {
+		if (!dev_input) {                                        // pieces that have landed by now (at least the first): no waiting for more than that
+			int k = pieces_waited;
+			while (k < NPIECE && cudaEventQuery (pev [k]) == cudaSuccess) k ++;
+			cudaGetLastError ();
+			CUDA_TRY (h, wait_pieces (k < 1 ? 1 : k));
+		}
+		const bool all_in = pieces_waited >= NPIECE;
+		collect ();
+		int enrolled = 0;
+		bool starved = false;                                    // some stream can do nothing until more of its samples have arrived
+		for (int i = 0; i < nstreams; i ++) {
+			MultiStream &m = ms [i];
+			if (m. done || m. ctl. synced || m. acq_wave) continue;
+			if (!all_in && m. limit <= m. acq_tried) { starved = true; continue; }     // (the search ran out of resident samples at this limit already)
+			StreamDev &A = acq_sd [i];
+			memset (&A, 0, sizeof (A));
+			A. w = SampleWin { nullptr, 0, (const uchar2 *) d_in [i], m. nsamples, fmt };
+			A. ctl = m. ctl; A. limit = m. limit; A. do_acquire = wave + 1;
+			m. acq_wave = wave + 1; m. acq_limit = m. limit;
+			enrolled ++;
+		}
+		if (enrolled) {
+			wave ++;
+			cudaStream_t ast = E -> acq_st [wave & 3];
+			if (!dev_input) CUDA_TRY (h, cudaStreamWaitEvent (ast, pev [pieces_waited - 1], 0));
+			acquire_launch (h, acq_sd, nstreams, ast, wave, (int *) acq_flag);
+			CUDA_TRY (h, cudaGetLastError ());
+			inflight += enrolled;
+		}
 		int nslots = 0, max_budget = 0;
-		bool any = false, any_acquire = false;
+		bool any = false;
 		for (int i = 0; i < nstreams; i ++) {
 			MultiStream &m = ms [i];
 			StreamDev &S = hsd [i];
@@ -822,53 +941,73 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 			S. ctl = m. ctl; S. ctl. fault = 0;
 			S. fic8 = (uint8_t *) E -> m_fic8. p + m. fic_off; S. msc8 = (uint8_t *) E -> m_msc8. p + m. msc_off;
 			S. info = (dabgpu_frame_info *) E -> m_info. p + m. info_off;
-			S. abs_base = 0; S. limit = m. nsamples; S. first = nslots; S. slot0 = m. nframes;
+			S. abs_base = 0; S. limit = m. limit; S. first = nslots; S. slot0 = m. nframes;
 			int C = 0;
-			if (!m. done) {
-				if (!m. ctl. synced) { S. do_acquire = 1; m. chunk = 1; C = 1; any_acquire = true; }
-				else if (m. nsamples - m. ctl. pos >= frame_need) {
-					const long long avail = (m. nsamples - m. ctl. pos - frame_need) / p. T_F + 1;
+			if (!m. done && m. ctl. synced && !m. acq_wave) {
+				bool wait_data = false;
+				if (m. limit - m. ctl. pos >= frame_need) {
+					const long long avail = (m. limit - m. ctl. pos - frame_need) / p. T_F + 1;
 					C = m. chunk < E -> max_chunk ? m. chunk : E -> max_chunk;
 					if (C > avail) C = (int) avail;
 					if (C > m. want - m. nframes) C = (int) (m. want - m. nframes);
-				}
+				} else wait_data = m. limit < m. nsamples;
 				if (C > MULTI_SLOT_CAP - nslots) C = MULTI_SLOT_CAP - nslots;    // (a stream left without slots waits a round)
-				if (C <= 0 && !(m. ctl. synced && m. nsamples - m. ctl. pos >= frame_need && m. nframes < m. want)) m. done = true;
+				if (C <= 0 && !wait_data && !(m. nsamples - m. ctl. pos >= frame_need && m. nframes < m. want)) m. done = true;
+				starved = starved || (C <= 0 && wait_data);
 			}
 			S. budget = C > 0 ? C : 0;
-			if (S. budget == 0) S. do_acquire = 0;
 			nslots += S. budget;
 			if (S. budget > max_budget) max_budget = S. budget;
 			any = any || S. budget > 0;
 		}
-		if (!any) break;
-		if ((rc = run_round (h, nstreams, nslots, max_budget, any_acquire, fmt, cb))) return rc;
+		if (!any) {
+			if (inflight > 0) {                                  // nothing but searches going on: decode what is pending, then wait for the next outcome
+				if ((rc = channel_all (true))) return rc;
+				while (collect () == 0) std::this_thread::yield ();
+				continue;
+			}
+			if (starved && !all_in) { CUDA_TRY (h, wait_pieces (pieces_waited + 1)); continue; }   // let the main stream wait for the next piece
+			break;
+		}
+		const double t_r0 = trace ? now_ms () : 0;
+		if ((rc = run_round (h, nstreams, nslots, max_budget, false, fmt, cb))) return rc;
+		if (trace) {
+			int acc = 0, redo = 0, att = 0;
+			for (int i = 0; i < nstreams; i ++) { acc += hsd [i]. ctl. n_valid * (hsd [i]. budget > 0); redo += hsd [i]. ctl. n_redo * (hsd [i]. budget > 0); att += hsd [i]. nframes; }
+			fprintf (stderr, "[multi] round %d: pieces %d slots %d max %d searches in flight %d attempted %d accepted %d redo %d  %.3f ms (at %.3f)\n", ++ round_no, pieces_waited, nslots, max_budget, inflight, att, acc, redo, now_ms () - t_r0, now_ms () - t_call0);
+		}
 		for (int i = 0; i < nstreams; i ++) {
 			MultiStream &m = ms [i];
 			const StreamDev &S = hsd [i];
 			if (S. budget == 0) continue;
-			const bool was_acquiring = S. do_acquire != 0;
-			m. ctl = S. ctl;
-			if (was_acquiring && !m. ctl. synced && m. ctl. n_valid == 0 && !m. ctl. lost) { m. done = true; continue; }    // out of samples inside the attempt
+			m. ctl = S. ctl;                                     // (a failed findIndex leaves synced = 0: the stream is enrolled for a new search)
 			m. nframes += m. ctl. n_valid;
-			if (S. nframes > 0) m. chunk = next_chunk (m. chunk, S. nframes, m. ctl, E -> max_chunk);
-			else if (!was_acquiring) m. done = true;
+			if (S. nframes > 0) m. chunk = next_chunk (m. chunk, S. nframes, m. ctl, E -> max_chunk, true);
+			else if (S. limit >= m. nsamples) m. done = true;
 			if (m. nframes >= m. want) m. done = true;
 		}
 		if ((rc = channel_all (false))) return rc;
 	}
+	if (trace) fprintf (stderr, "[multi] rounds done at %.3f ms\n", now_ms () - t_call0);
 	if ((rc = channel_all (true))) return rc;
 	for (int i = 1; i < 4; i ++) CUDA_TRY (h, cudaStreamSynchronize (h -> vctx [i]. st));
+	if (trace) fprintf (stderr, "[multi] channel decoding done at %.3f ms\n", now_ms () - t_call0);
+	if (ngroups_all > 0) {                                   // FIB CRCs of every group of every stream (groups never decoded give flags nobody reads)
+		cudaError_t e = fib_crc_launch (h, (const uint8_t *) E -> m_ficbits. p, 3 * (int) ngroups_all, (uint8_t *) E -> m_ficcrc. p);
+		if (e != cudaSuccess) return dab_fail (h, DABGPU_ERR_CUDA, "crc launch: %s", cudaGetErrorString (e));
+	}
 	// results: the streams' outputs lie side by side in four device buffers -- four device-to-host copies into pinned staging,
 	// then plain host copies to the callers' buffers (hundreds of small copies to pageable memory cost more than the decode)
 	const size_t b_fic = ngroups_all * 768, b_crc = ngroups_all * 3, b_info = info_n * sizeof (dabgpu_frame_info);
 	const size_t o_crc = up (b_fic, 256), o_info = o_crc + up (b_crc, 256), o_msc = o_info + up (b_info, 256);
 	CUDA_TRY (h, E -> mh_out. ensure (o_msc + mscbits_bytes + 256));
 	char *ho = (char *) E -> mh_out. p;
-	if (b_fic) CUDA_TRY (h, cudaMemcpyAsync (ho, E -> m_ficbits. p, b_fic, cudaMemcpyDeviceToHost, h -> stream));
+	bool all_direct = true;
+	for (auto &m : ms) all_direct = all_direct && m. direct;
+	if (b_fic && !all_direct) CUDA_TRY (h, cudaMemcpyAsync (ho, E -> m_ficbits. p, b_fic, cudaMemcpyDeviceToHost, h -> stream));
 	if (b_crc) CUDA_TRY (h, cudaMemcpyAsync (ho + o_crc, E -> m_ficcrc. p, b_crc, cudaMemcpyDeviceToHost, h -> stream));
 	if (b_info) CUDA_TRY (h, cudaMemcpyAsync (ho + o_info, E -> m_info. p, b_info, cudaMemcpyDeviceToHost, h -> stream));
-	if (mscbits_bytes) CUDA_TRY (h, cudaMemcpyAsync (ho + o_msc, E -> m_mscbits. p, mscbits_bytes, cudaMemcpyDeviceToHost, h -> stream));
+	if (mscbits_bytes && !all_direct) CUDA_TRY (h, cudaMemcpyAsync (ho + o_msc, E -> m_mscbits. p, mscbits_bytes, cudaMemcpyDeviceToHost, h -> stream));
 	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
 	for (int i = 0; i < nstreams; i ++) {
 		MultiStream &m = ms [i];
@@ -876,12 +1015,12 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 		out -> nframes = m. nframes;
 		out -> consumed = m. ctl. pos;
 		const size_t ng = (size_t) m. nframes * p. ficGroups;
-		if (out -> fic_bits && ng) memcpy (out -> fic_bits, ho + m. ficbits_off, ng * 768);
+		if (out -> fic_bits && ng && !m. direct) memcpy (out -> fic_bits, ho + m. ficbits_off, ng * 768);
 		if (out -> fic_crc && ng) memcpy (out -> fic_crc, ho + o_crc + m. ficcrc_off, ng * 3);
 		if (out -> info && m. nframes) memcpy (out -> info, ho + o_info + m. info_off * sizeof (dabgpu_frame_info), (size_t) m. nframes * sizeof (dabgpu_frame_info));
 		for (size_t s = 0; s < nsub; s ++) {
 			if (out -> msc_nblocks) out -> msc_nblocks [s] = m. nblk [s];
-			if (out -> msc_bits && out -> msc_bits [s] && m. nblk [s] > 0)
+			if (out -> msc_bits && out -> msc_bits [s] && m. nblk [s] > 0 && !m. direct)
 				memcpy (out -> msc_bits [s], ho + o_msc + m. mscbits_off [s], (size_t) m. nblk [s] * msc_block_bytes (E, E -> subch [s]));
 		}
 		if (m. nframes > 0 && out -> soft) {
@@ -893,6 +1032,7 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 		}
 	}
 	CUDA_TRY (h, cudaStreamSynchronize (h -> stream));
+	if (trace) fprintf (stderr, "[multi] results delivered at %.3f ms\n", now_ms () - t_call0);
 	return DABGPU_OK;
 }
 
@@ -900,10 +1040,16 @@ static int decode_multi (dabgpu *h, const dabgpu_stream_job *jobs, int32_t nstre
 	if (!h || nstreams < 0 || (nstreams > 0 && !jobs) || fmt < 0 || fmt > 2) return dab_fail (h, DABGPU_ERR_ARG, "dabgpu_decode_multi: bad argument");
 	if (nstreams == 0) return DABGPU_OK;
 	CUDA_TRY (h, cudaSetDevice (h -> device));
+	const bool trace = getenv ("DABGPU_TRACE") != nullptr;
+	const double t0 = now_ms ();
 	const int rc = decode_multi_core (h, jobs, nstreams, fmt, dev_input);
+	const double t1 = now_ms ();
+	if (!dev_input) cudaStreamSynchronize (h -> engine -> copy_st);      // the callers' input buffers are free again on every path
+	if (trace) fprintf (stderr, "[multi] call: core %.3f ms, copy stream drained after %.3f ms more\n", t1 - t0, now_ms () - t1);
 	if (rc) {                                                // nothing of a failed call may still be running when it returns
 		const std::string msg = h -> err;
 		cudaStreamSynchronize (h -> stream);
+		for (int k = 0; k < 4; k ++) if (h -> engine -> acq_st [k]) cudaStreamSynchronize (h -> engine -> acq_st [k]);
 		for (int i = 1; i < 4; i ++) cudaStreamSynchronize (h -> vctx [i]. st);
 		cudaGetLastError ();
 		h -> cur = 0;

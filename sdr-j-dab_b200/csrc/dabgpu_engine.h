@@ -96,8 +96,9 @@ struct Engine {
 	int out_skip = 0;                   // next decode call: FIC / info / soft results of its first out_skip frames are not delivered (multi-GPU shards, dabgpu_group.cu)
 	bool needs_reset = false;           // a call failed half way: the stream state is not trustworthy until dabgpu_state_set / import
 	// multi-stream batch (dabgpu_decode_multi): scratch that lives with the handle
-	DevBuf m_in, m_fic8, m_msc8, m_info, m_ficbits, m_ficcrc, m_mscbits;
-	PinBuf mh_in, mh_out;
+	DevBuf m_in, m_fic8, m_msc8, m_info, m_ficbits, m_ficcrc, m_mscbits, m_offs;
+	PinBuf mh_in, mh_out, mh_acq;       // mh_acq: StreamDev [n] + completion flags of the asynchronous acquisitions (read / written by the kernel in place)
+	cudaStream_t acq_st [4] = { nullptr, nullptr, nullptr, nullptr };
 };
 
 int ofdm_tables_init (dabgpu *h, OfdmTables *T);
@@ -107,7 +108,7 @@ struct ChunkBufs {                      // per-round scratch, indexed by chunk s
 	FrameIn *fin; FrameOut *fo; float2 *spec0; float2 *fcpart;
 };
 int  sync_init (dabgpu *h);
-void acquire_launch (dabgpu *h, StreamDev *sd, int nstreams, cudaStream_t st);
+void acquire_launch (dabgpu *h, StreamDev *sd, int nstreams, cudaStream_t st, int wave = 0, int *flags = nullptr);
 void predict_launch (dabgpu *h, StreamDev *sd, int nstreams, const ChunkBufs &cb, cudaStream_t st);
 void scan_launch (dabgpu *h, StreamDev *sd, int nstreams, int max_frames, int groups, const ChunkBufs &cb, int derive, cudaStream_t st);
 int  symbol_init (dabgpu *h);

@@ -88,11 +88,16 @@ __device__ __forceinline__ float2 sy_conv (const SampleWin &w, uint2 r) {
 __device__ __forceinline__ float acq_level_exact (float a, float ja) {          // ofdm-processor.cpp:168, operation by operation
 	return __double2float_rn (__dadd_rn (__dmul_rn (0.00001, (double) ja), __dmul_rn (1 - 0.00001, (double) a)));
 }
-__global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, OfdmTables T, int T_F, int T_null) {
-	__shared__ __align__ (16) float s_e [ACQ_CHUNK], s_d [ACQ_CHUNK + 64], s_sl [ACQ_CHUNK + 64], s_csb [ACQ_CHUNK + 64], s_ja [ACQ_CHUNK], s_t [ACQ_CHUNK + 64], s_ring [64];
+// wave / flags: the asynchronous form used by dabgpu_decode_multi.  sd and flags then lie in pinned host memory (read once at the
+// start, written once at the end), only the streams with do_acquire == wave take part, and a stream's CTA publishes its result by
+// writing flags [stream] = wave after a system-wide fence: the host picks up every stream the moment ITS search ends, not when the
+// slowest search of the launch does.
+__global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, OfdmTables T, int T_F, int T_null, int wave, volatile int *flags) {
+	__shared__ __align__ (16) float s_e [ACQ_CHUNK], s_d [ACQ_CHUNK + 64], s_sl_raw [ACQ_CHUNK + 64 + 4], s_csb [ACQ_CHUNK + 64], s_ja [ACQ_CHUNK], s_t [ACQ_CHUNK + 64], s_ring [64];
+	float *const s_sl = s_sl_raw + 3;                            // &s_sl [1 + 4 j] is 16-byte aligned: the chain records four steps per store
 	__shared__ int s_first;
 	StreamDev &S = sd [blockIdx. x];
-	if (!S. do_acquire) return;
+	if (flags ? S. do_acquire != wave : !S. do_acquire) return;
 	const SampleWin w = S. w;
 	StreamCtl *ctl = &S. ctl;
 	const int tid = threadIdx. x;
@@ -123,15 +128,21 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 			const int step = mod_rate ((long long) ACQ_THREADS * ph);
 			if (next_pos != pos)                                     // (normally the samples were requested while the previous chunk's chains ran)
 				sy_raw_chunk<ACQ_CHUNK / ACQ_THREADS, ACQ_THREADS> (w, pos, pos + n, tid, rawn);
+			float2 oh [ACQ_CHUNK / ACQ_THREADS], ol [ACQ_CHUNK / ACQ_THREADS];     // all table lookups first (independent loads), then the arithmetic
+#pragma unroll
+			for (int k = 0; k < ACQ_CHUNK / ACQ_THREADS; k ++) {
+				oh [k] = __ldg (&T. osc_hi [l >> 11]); ol [k] = __ldg (&T. osc_lo [l & 2047]);
+				l -= step; if (l < 0) l += DAB_INPUT_RATE;
+			}
 #pragma unroll
 			for (int k = 0; k < ACQ_CHUNK / ACQ_THREADS; k ++) {
 				const int i = tid + k * ACQ_THREADS;
-				if (i >= n) break;
-				const float2 v = cmul (sy_conv (w, rawn [k]), nco (T, l));
-				const float ja = fabsf (v. x) + fabsf (v. y);            // jan_abs
-				s_ja [i] = ja; s_t [i] = 0.00001f * ja;
-				s_e [i] = stage == 3 ? hypotf (v. x, v. y) : ja;           // abs () in SyncOnEndNull (:329)
-				l -= step; if (l < 0) l += DAB_INPUT_RATE;
+				if (i < n) {
+					const float2 v = cmul (sy_conv (w, rawn [k]), cmul (oh [k], ol [k]));
+					const float ja = fabsf (v. x) + fabsf (v. y);        // jan_abs
+					s_ja [i] = ja; s_t [i] = 0.00001f * ja;
+					s_e [i] = stage == 3 ? hypotf (v. x, v. y) : ja;       // abs () in SyncOnEndNull (:329)
+				}
 			}
 			ACQ_T (1)
 			__syncthreads ();
@@ -163,9 +174,10 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 #pragma unroll
 					for (int k = 0; k < 8; k ++) { dc [4 * k] = dn [k]. x; dc [4 * k + 1] = dn [k]. y; dc [4 * k + 2] = dn [k]. z; dc [4 * k + 3] = dn [k]. w; dn [k] = reinterpret_cast<const float4 *> (s_d + i0 + 32) [k]; }
 #pragma unroll
-					for (int k = 0; k < 32; k ++) {
-						if (lane == 0) s_csb [i0 + k] = c;
-						c = __fadd_rn (c, dc [k]);
+					for (int k = 0; k < 32; k += 4) {                   // (one 128-bit record per four steps: a store per step cost more than the chain)
+						const float c1 = __fadd_rn (c, dc [k]), c2 = __fadd_rn (c1, dc [k + 1]), c3 = __fadd_rn (c2, dc [k + 2]);
+						if (lane == 0) *reinterpret_cast<float4 *> (&s_csb [i0 + k]) = make_float4 (c, c1, c2, c3);
+						c = __fadd_rn (c3, dc [k + 3]);
 					}
 				}
 				if ((n & 31) == 0 && lane == 0) s_csb [n] = c;       // (n inside a block: the record of sample n there is the value after n - 1 already)
@@ -194,9 +206,11 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 #pragma unroll
 					for (int k = 0; k < 8; k ++) { tc [4 * k] = tn [k]. x; tc [4 * k + 1] = tn [k]. y; tc [4 * k + 2] = tn [k]. z; tc [4 * k + 3] = tn [k]. w; tn [k] = reinterpret_cast<const float4 *> (s_t + i0 + 32) [k]; }
 #pragma unroll
-					for (int k = 0; k < 32; k ++) {
-						const float u = __fmaf_rn (ap, c_lo, tc [k]); ap = a; a = __fmaf_rn (a, c_hi, u);
-						if (lane == 0) s_sl [i0 + 1 + k] = a;
+					for (int k = 0; k < 32; k += 4) {
+						float r [4];
+#pragma unroll
+						for (int j = 0; j < 4; j ++) { const float u = __fmaf_rn (ap, c_lo, tc [k + j]); ap = a; a = __fmaf_rn (a, c_hi, u); r [j] = a; }
+						if (lane == 0) *reinterpret_cast<float4 *> (&s_sl [i0 + 1 + k]) = make_float4 (r [0], r [1], r [2], r [3]);
 					}
 				}
 				if (lane == 0) s_first = n;
@@ -204,8 +218,11 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 			ACQ_T (4)
 			__syncthreads ();
 			int bad = n;                                             // 2b. first step whose recorded successor is not the exact one
-			for (int i = from + tid; i < n && bad == n; i += ACQ_THREADS)
-				if (acq_level_exact (s_sl [i], s_ja [i]) != s_sl [i + 1]) bad = i;
+#pragma unroll
+			for (int k = ACQ_CHUNK / ACQ_THREADS - 1; k >= 0; k --) {    // (independent iterations, highest first: the lowest bad index wins)
+				const int i = from + tid + k * ACQ_THREADS;
+				if (i < n && acq_level_exact (s_sl [i], s_ja [i]) != s_sl [i + 1]) bad = i;
+			}
 			if (bad < n) atomicMin (&s_first, bad);
 			__syncthreads ();
 			const int first = s_first;
@@ -220,10 +237,12 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 			if (tid == 0) s_first = n;
 			__syncthreads ();
 			int first = n;
-			for (int i = tid; i < n && first == n; i += ACQ_THREADS) {
+#pragma unroll
+			for (int k = ACQ_CHUNK / ACQ_THREADS - 1; k >= 0; k --) {
+				const int i = tid + k * ACQ_THREADS;
 				const double lhs = (double) (s_csb [i] / 50.0f), lv = (double) s_sl [i];
 				const bool leave = stage == 2 ? !(lhs > 0.40 * lv) : !(lhs < 0.75 * lv);
-				if (leave) first = i;
+				if (i < n && leave) first = i;
 			}
 			if (first < n) atomicMin (&s_first, first);
 			__syncthreads ();
@@ -261,12 +280,13 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 		}
 	}
 #ifdef ACQ_PROF
-	if (tid == 0) printf ("acquire: %lld chunks; cycles per chunk: head %lld prep %lld sync %lld diff %lld prefetch+cs %lld chain %lld verify %lld tests+commit %lld\n", prof_chunks, prof_t [0] / prof_chunks, prof_t [1] / prof_chunks,
+	if (tid == 0) printf ("acquire: stream %d, %lld samples from %lld, done %d; %lld chunks; cycles per chunk: head %lld prep %lld sync %lld diff %lld prefetch+cs %lld chain %lld verify %lld tests+commit %lld\n", (int) blockIdx. x, pos - ctl -> pos, ctl -> pos, done, prof_chunks, prof_t [0] / prof_chunks, prof_t [1] / prof_chunks,
 	                      prof_t [2] / prof_chunks, prof_t [3] / prof_chunks, prof_t [7] / prof_chunks, prof_t [4] / prof_chunks, prof_t [5] / prof_chunks, prof_t [6] / prof_chunks);
 #endif
 	if (tid == 0) {
 		if (done == 1) { ctl -> synced = 1; ctl -> pos = pos; ctl -> lp = lp; ctl -> acq_done = 1; }
 		else           { ctl -> synced = 0; ctl -> pos = attempt_pos; ctl -> lp = attempt_lp; ctl -> acq_done = 0; }
+		if (flags) { __threadfence_system (); flags [blockIdx. x] = wave; }
 	}
 }
 
@@ -468,9 +488,9 @@ int sync_init (dabgpu *h) {
 	return DABGPU_OK;
 }
 
-void acquire_launch (dabgpu *h, StreamDev *sd, int nstreams, cudaStream_t st) {
+void acquire_launch (dabgpu *h, StreamDev *sd, int nstreams, cudaStream_t st, int wave, int *flags) {
 	ProfScope prof (h, KC_ACQUIRE, st);
-	acquire_kernel<<<nstreams, ACQ_THREADS, 0, st>>> (sd, h -> engine -> T, h -> p. T_F, h -> p. T_null);
+	acquire_kernel<<<nstreams, ACQ_THREADS, 0, st>>> (sd, h -> engine -> T, h -> p. T_F, h -> p. T_null, wave, flags);
 	h -> launches ++;
 }
 

@@ -112,3 +112,37 @@ def test_multi_float_and_device_input(port):
         assert np.array_equal(x.msc[0], y.msc[0]) and np.array_equal(x.msc[0], z.msc[0])
         assert np.array_equal(x.fic_bits, z.fic_bits)
     eng.close()
+
+
+def test_multi_pinned_results_and_late_start(port):
+    """pinned result buffers (results are copied straight into them while later rounds run) give what pageable ones give;
+    a stream whose signal starts after the first upload piece (the null search runs out of resident samples and is
+    repeated when more have arrived) equals its single-handle decode"""
+    import torch
+    pkg = engine_pkg()
+    iqs, mods = _streams(port, 1, 4, SUBS)
+    mod = dabmod.Modulator(port, 1, SUBS, 3001)
+    iqs.append(mod.generate(12, cfo_hz=410.0, snr_db=15.0, lead=1500000, tail=6000)["iq"])      # 7.6 frames of noise first
+    subl = [(s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel) for s in mods[0].sub]
+    eng = pkg.DabGpu(mode=1)
+    eng.set_subchannels(subl)
+
+    def pinned(shape, dtype):
+        assert dtype == np.uint8
+        return torch.empty(shape, dtype=torch.uint8).pin_memory().numpy()
+    a = eng.decode_multi(iqs, [eng.alloc_result(40, want_soft=False) for _ in iqs])
+    b = eng.decode_multi(iqs, [eng.alloc_result(40, want_soft=False, alloc=pinned) for _ in iqs])
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert x.nframes == y.nframes > 5, (i, x.nframes, y.nframes)
+        assert np.array_equal(x.fic_bits, y.fic_bits) and np.array_equal(x.fic_crc, y.fic_crc), i
+        assert [(f.pos, f.fine) for f in x.info] == [(f.pos, f.fine) for f in y.info], i
+        for s, t in zip(x.msc, y.msc):
+            assert s.shape == t.shape and np.array_equal(s, t), i
+    e1 = pkg.DabGpu(mode=1)
+    e1.set_subchannels(subl)
+    one = e1.decode(iqs[-1], e1.alloc_result(40, want_soft=False))
+    assert one.nframes == b[-1].nframes and np.array_equal(one.fic_bits, b[-1].fic_bits) and one.consumed == b[-1].consumed
+    for s, t in zip(one.msc, b[-1].msc):
+        assert np.array_equal(s, t)
+    e1.close()
+    eng.close()
