@@ -109,6 +109,16 @@ class Modulator:
         fibs = np.zeros((g, 768), np.uint8)
         for i in range(g):
             for j in range(3):
+                if getattr(self, "wellformed_fibs", False):
+                    # FIG 0/1 with a few random (valid) sub-channel entries, then the end marker: what a parser of real FIBs can
+                    # digest (the reference's fib_processor loops forever / reads wild on random bits with a good CRC)
+                    import figutil
+                    ent = [("short", int(self.rng.integers(0, 64)), int(self.rng.integers(0, 864)), int(self.rng.integers(0, 64)))
+                           if self.rng.integers(0, 2) else
+                           ("long", int(self.rng.integers(0, 64)), int(self.rng.integers(0, 864)), int(self.rng.integers(0, 2)), int(self.rng.integers(1, 5)), int(self.rng.integers(6, 400)))
+                           for _ in range(int(self.rng.integers(0, 5)))]
+                    fibs[i, 256 * j:256 * j + 256] = figutil.fib([figutil.fig01(ent)] if ent else [])
+                    continue
                 body = self.rng.integers(0, 2, 240, dtype=np.uint8)
                 fibs[i, 256 * j:256 * j + 240] = body
                 fibs[i, 256 * j + 240:256 * j + 256] = crc16(body)

@@ -155,6 +155,56 @@ class Oracle:
         self.lib.orc_fig01_scan(_p(bits, C.c_uint8), _p(crc, C.c_uint8), bits.shape[0], _p(table, C.c_int32))
         return table
 
+    # ---- the reference's OWN handler classes (oracle/ref_shim/ref_tierc.cpp; in libdabref.so only) ----
+    def ref_fic_frames(self, mode, sym):
+        """ficHandler::process_ficBlock (compiled unmodified, its own thread) over the FIC symbols of sym [nframes][L-1][2K]"""
+        p = self.mode_params(mode)
+        sym = np.ascontiguousarray(np.asarray(sym, np.int16)[:, :3, :])
+        nframes = sym.shape[0]
+        bits = np.zeros((nframes * p.ficGroups, 768), np.uint8)
+        crc = np.zeros((nframes * p.ficGroups, 3), np.uint8)
+        n = self.lib.ref_fic_frames(2 * p.K, _p(sym, C.c_int16), nframes, _p(bits, C.c_uint8), _p(crc, C.c_uint8))
+        assert n == bits.shape[0], n
+        return bits, crc
+
+    def ref_fig01_scan(self, bits, crc, table=None):
+        """fib_processor::process_FIB (compiled unmodified) for every CRC-clean FIB, then ficList's FIG 0/1 fields;
+        column 0 (`valid`) is not a reference field and is left alone"""
+        bits = np.ascontiguousarray(bits, np.uint8).reshape(-1, 768)
+        crc = np.ascontiguousarray(crc, np.uint8).reshape(-1, 3)
+        table = np.zeros((64, 6), np.int32) if table is None else table
+        self.lib.ref_fig01_scan(_p(bits, C.c_uint8), _p(crc, C.c_uint8), bits.shape[0], _p(table, C.c_int32))
+        return table
+
+    def ref_msc_run(self, mode, sym, startAddr, Length, bitRate, uepFlag, protLevel):
+        """mscHandler::process_mscBlock symbol by symbol with the reference's dabConcurrent behind it (both compiled unmodified)"""
+        p = self.mode_params(mode)
+        sym = np.ascontiguousarray(sym, np.int16)
+        nframes = sym.shape[0]
+        cap = max(nframes * p.cifsPerFrame - 16, 0)
+        out = np.zeros((cap, 24 * bitRate), np.uint8)
+        n = self.lib.ref_msc_run(mode, p.L, p.K, _p(sym, C.c_int16), nframes, startAddr, Length, bitRate, uepFlag, protLevel, _p(out, C.c_uint8), cap)
+        assert n == cap, n
+        return out
+
+    def ref_receive(self, mode, iq, sub, threshold=3, method=1, max_frames=64):
+        """the reference's whole receive chain (ofdmProcessor -> ofdmDecoder -> ficHandler / mscHandler -> dabConcurrent, all
+        compiled unmodified) over raw u8 IQ with one audio sub-channel sub = (startAddr, Length, bitRate, uepFlag, protLevel)
+        -> (fic_bits, fic_crc, msc_blocks, state = [coarse, fine, f2Correction, localPhase, samples taken])"""
+        p = self.mode_params(mode)
+        iq = np.ascontiguousarray(iq, np.uint8)
+        startAddr, Length, bitRate, uepFlag, protLevel = sub
+        mg, mb = max_frames * p.ficGroups, max_frames * p.cifsPerFrame
+        fic = np.zeros((mg, 768), np.uint8); crc = np.zeros((mg, 3), np.uint8); msc = np.zeros((mb, 24 * bitRate), np.uint8)
+        ng, nb = C.c_int(0), C.c_int(0)
+        state = np.zeros(6, np.int64)
+        self.lib.ref_receive.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        rc = self.lib.ref_receive(mode, iq.ctypes.data, iq.size // 2, threshold, method, startAddr, Length, bitRate, uepFlag, protLevel,
+                                  fic.ctypes.data, crc.ctypes.data, mg, C.addressof(ng), msc.ctypes.data, mb, C.addressof(nb), state.ctypes.data)
+        assert rc == 0, rc
+        return fic[:ng.value], crc[:ng.value], msc[:nb.value], state
+
     def resample_i16(self, iq, rate):
         iq = np.ascontiguousarray(iq, np.int16)
         n = iq.size // 2

