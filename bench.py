@@ -201,11 +201,12 @@ def timed(fn, steps, barrier):
 
 def mode_leg(pkg, mode, device, orc_mod, dabmod, steps):
     """device-resident decode rate of Mode II / IV on the same 864-CU ensemble (configs[2]): a short modulated block whose
-    batch part is tiled to a 48 M-sample step (frames stay T_F apart; the CFO is chosen so that the phase is continuous at the seams)"""
+    batch part is tiled to the Mode I step's 201 M samples = 4096 CIFs (frames stay T_F apart; the CFO is chosen so that the phase is
+    continuous at the seams)"""
     import torch
     port = orc_mod.Oracle("port")
     p = port.mode_params(mode)
-    nblock, tiles, lead = {2: (64, 16, 192), 4: (32, 16, 96)}[mode]
+    nblock, tiles, lead = {2: (64, 64, 192), 4: (32, 64, 96)}[mode]
     mod = dabmod.Modulator(port, mode, SUBS, 77 + mode)
     total = lead + nblock + 2
     truth = mod.frame_bits(total)

@@ -292,5 +292,4 @@ def test_engine_equals_the_references_own_chain(ref, mode, cfo, snr, sub):
     m = min(res.msc[0].shape[0], r_msc.shape[0])
     assert m >= (res.nframes - 1) * mod.p.cifsPerFrame - 17 and m > 0
     assert np.array_equal(res.msc[0][:m], r_msc[:m])
-    assert (res.msc[0][:m] == tr["payloads"][0][:m]).all(axis=1).mean() > 0.5 or True
     eng.close()
