@@ -169,7 +169,10 @@ template <> struct RawFmt<0> { static constexpr int B = 2; };      // bytes per 
 template <> struct RawFmt<1> { static constexpr int B = 8; };
 template <> struct RawFmt<2> { static constexpr int B = 4; };
 #define P_RAW(FMT) (2552 * RawFmt<FMT>::B + 48)                   // bytes per raw buffer: a pass + alignment slack, multiple of 16
-#define P_DYN_SMEM(FMT) ((2 * R8_SMEM + P_TW2 + P_TW3) * (int) sizeof (float2) + 2 * P_RAW (FMT))
+#ifndef P_NRAW
+#define P_NRAW 2                                                 // raw-sample buffers: the copy of pass p + P_NRAW - 1 is issued at the top of pass p
+#endif
+#define P_DYN_SMEM(FMT) ((2 * R8_SMEM + P_TW2 + P_TW3) * (int) sizeof (float2) + P_NRAW * P_RAW (FMT))
 
 // (b - 128) as float, exactly, b = byte `which` of s: 0x4B0000bb is 2^23 + b
 __device__ __forceinline__ float u8_bits (uint32_t s, int which) {
@@ -206,6 +209,15 @@ struct SymPArgs {
 #ifndef P_MINB
 #define P_MINB 3
 #endif
+#ifndef P_TOPSYNC
+#define P_TOPSYNC 0
+#endif
+#ifndef P_PHASOR_LATE
+#define P_PHASOR_LATE 0
+#endif
+#ifndef P_HOIST
+#define P_HOIST 1
+#endif
 template <int NSYM, int FMT>
 __global__ void __launch_bounds__ (256, FMT == 1 ? 2 : P_MINB) symbol_kernel_p (const SymPArgs a) {
 	extern __shared__ __align__ (1024) unsigned char p_dyn [];          // the FFT buffers must be 512-byte aligned (p_fft)
@@ -213,8 +225,8 @@ __global__ void __launch_bounds__ (256, FMT == 1 ? 2 : P_MINB) symbol_kernel_p (
 	unsigned char *raw = reinterpret_cast<unsigned char *> (tw3 + P_TW3);
 	__shared__ float2 s_fc [8];
 	__shared__ int s_fail;
-	__shared__ int s_off [2];
-	__shared__ __align__ (8) unsigned long long s_mbar [2];
+	__shared__ int s_off [P_NRAW];
+	__shared__ __align__ (8) unsigned long long s_mbar [P_NRAW];
 	constexpr int G = 256 / NSYM, N = 2048 / NSYM, Ts = 2552 / NSYM, Tg = 504 / NSYM, K = 1536 / NSYM, B = RawFmt<FMT>::B;
 	constexpr int RAW = P_RAW (FMT), GSH = 8 / NSYM;                    // N - Tg = 6 G + GSH
 	const OfdmTables &T = a. T;
@@ -243,8 +255,7 @@ __global__ void __launch_bounds__ (256, FMT == 1 ? 2 : P_MINB) symbol_kernel_p (
 	const uint32_t mbar0 = (uint32_t) __cvta_generic_to_shared (&s_mbar [0]);
 	if (t == 0) {
 		s_fail = ((uint32_t) __cvta_generic_to_shared (buf0) & 511u) != 0 ? 1 : 0;   // layout contract of p_fft
-		asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r" (mbar0));
-		asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r" (mbar0 + 8));
+		for (int k = 0; k < P_NRAW; k ++) asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r" (mbar0 + 8 * k));
 		asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	p_fill_tables<NSYM> (tw2, tw3, T. tw);
@@ -312,7 +323,7 @@ __global__ void __launch_bounds__ (256, FMT == 1 ? 2 : P_MINB) symbol_kernel_p (
 		}
 	};
 
-	stage (l0, 0);
+	for (int k = 0; k < P_NRAW - 1; k ++) if (l0 + k * NSYM < l1) stage (l0 + k * NSYM, k);
 	// ---- phase reference of the first symbol: spectrum of symbol l0 - 1 -> block NSYM - 1 of buf1 ----
 	if (l0 == 1) {
 		const float2 *p0 = a. spec0 + (size_t) c * N;
@@ -347,22 +358,40 @@ __global__ void __launch_bounds__ (256, FMT == 1 ? 2 : P_MINB) symbol_kernel_p (
 		int xu = lp - offU; if (xu < 0) xu += DAB_INPUT_RATE;
 		pg = p_scale (nco (T, xg), sc); pu = p_scale (nco (T, xu), sc);
 	};
+	auto phasor_prefetch = [&] (int lp) {
+		int xg = lp - offG; if (xg < 0) xg += DAB_INPUT_RATE;
+		int xu = lp - offU; if (xu < 0) xu += DAB_INPUT_RATE;
+		asm volatile ("prefetch.global.L1 [%0];" :: "l" (&T. osc_hi [xg >> 11]));
+		asm volatile ("prefetch.global.L1 [%0];" :: "l" (&T. osc_lo [xg & 2047]));
+		asm volatile ("prefetch.global.L1 [%0];" :: "l" (&T. osc_hi [xu >> 11]));
+		asm volatile ("prefetch.global.L1 [%0];" :: "l" (&T. osc_lo [xu & 2047]));
+	};
 	c32 phg_n, ph_n;
 	phasors (lpb, phg_n, ph_n);
 	const c32 rotG6 = NSYM == 1 ? rotG : nco (T, mod_rate (- 6ll * G * phB));   // guard partner of useful sample 7 G + u is G further on than that of 6 G + u
+	// output rows of the frame: FIC symbols 1..3, then the MSC symbols contiguously (sym_out), fetched from the stream table once
+	uint8_t *const fic_base = S. fic8 + (size_t) in. slot * 3 * a. geo. K2 - a. geo. K2;
+	uint8_t *const msc_base = S. msc8 + ((size_t) 15 + (size_t) in. slot * a. geo. cifsPerFrame) * CIF_BITS - (size_t) 4 * a. geo. K2;
 	int pass = 0;
 	for (int l = l0; l < l1; l += NSYM, pass ++) {
-		const int b = pass & 1;
-		if (l + NSYM < l1) stage (l + NSYM, b ^ 1);
+		const int b = pass & 1, rb = pass % P_NRAW;                        // spectrum buffer, raw buffer of this pass
+		if (l + (P_NRAW - 1) * NSYM < l1) stage (l + (P_NRAW - 1) * NSYM, (pass + P_NRAW - 1) % P_NRAW);
 		c32 phg = phg_n, ph = ph_n;
 		lpb -= dPass; if (lpb < 0) lpb += DAB_INPUT_RATE;
+#if P_PHASOR_LATE
+		phasor_prefetch (lpb);                                             // the next pass's NCO table entries: into L1 now, looked up after the transform
+#else
 		phasors (lpb, phg_n, ph_n);                                        // looked up one pass ahead
-		wait_raw (b, pass >> 1);
-		__syncthreads ();                                                  // raw buffer b complete; last pass's demod reads done
-		if (*(volatile int *) &s_fail) { if (t == 0) atomicOr (const_cast<int *> (&S. ctl. fault), 2); return; }
-		int off_cur = s_off [b];
-		if (off_cur < 0) { stage_by_hand (l, b); off_cur = 0; }
-		const unsigned char *rs = raw + b * RAW + off_cur;
+#endif
+		// raw buffer b complete (every thread waits on the copy's mbarrier itself).  NSYM = 1 needs no CTA barrier here: the spectrum
+		// buffers alternate and the phase reference lives in registers, so this pass's transform writes the buffer the demodulation
+		// of the pass BEFORE the last one read -- and every thread has been through the barriers inside the last pass's transform
+		// since then; s_off [b] was written before those too.  NSYM > 1: the last pass's demodulation read BOTH buffers.
+		wait_raw (rb, pass / P_NRAW);
+		if (NSYM > 1 || P_TOPSYNC) __syncthreads ();
+		int off_cur = s_off [rb];
+		if (off_cur < 0) { stage_by_hand (l, rb); off_cur = 0; }
+		const unsigned char *rs = raw + rb * RAW + off_cur;
 		const bool live = l + j < l1;                                      // a partial last pass: the trailing thread groups idle
 		// guard samples ig and ig + G (the ones x[6] and x[7] are correlated with), mixed like every other sample
 		c32 g6 = make_float2 (0.f, 0.f), g7;
@@ -375,11 +404,20 @@ __global__ void __launch_bounds__ (256, FMT == 1 ? 2 : P_MINB) symbol_kernel_p (
 		}
 		// FreqCorr += x[i] * conj (x[i - T_u]), i in [T_u, T_s): useful sample e pairs with guard sample e - (T_u - T_g)
 		if (live) { acc = p_add (acc, p_cmulc (x [7], g7)); if (u >= GSH) acc = p_add (acc, p_cmulc (x [6], g6)); }
-		float2 *cur = b ? buf1 : buf0, *oth = b ? buf0 : buf1;
-		if (NSYM == 1) cur = buf0;                                         // (the register-held reference needs no second buffer)
+		float2 *cur = b ? buf1 : buf0, *oth = b ? buf0 : buf1;             // (NSYM = 1: the reference itself lives in registers, buf1 only takes turns)
 		p_fft<NSYM> (x, cur, tw1, tw2, tw3);
+		// (checked behind the transform's barriers, where every thread sees the same value: a thread whose wait gave up has gone
+		// through the transform with whatever was in the buffer -- nothing of it leaves the CTA)
+		if (*(volatile int *) &s_fail) { if (t == 0) atomicOr (const_cast<int *> (&S. ctl. fault), 2); return; }
+#if P_PHASOR_LATE
+		phasors (lpb, phg_n, ph_n);                                        // (L1 hits by now)
+#endif
 		if (live) {
+#if P_HOIST
+			uint8_t *out8 = (l + j < 4 ? fic_base : msc_base) + (size_t) (l + j) * a. geo. K2;
+#else
 			uint8_t *out8 = sym_out (S, a. geo, in. slot, l + j);
+#endif
 			const float2 *cb = cur + j * N, *pb = j > 0 ? cur + (j - 1) * N : oth + (NSYM - 1) * N;
 			// all six carriers (and their references) are fetched before the first result is stored: the stores go through a
 			// generic pointer the compiler cannot tell apart from the spectrum buffers, so it would not move a later load above one
