@@ -60,7 +60,7 @@ __device__ __forceinline__ float2 sy_conv (const SampleWin &w, uint2 r) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// acquisition: notSynced -> SyncOnNull -> SyncOnEndNull (ofdm-processor.cpp:275-338), one CTA of four warps per stream.
+// acquisition: notSynced -> SyncOnNull -> SyncOnEndNull (ofdm-processor.cpp:275-338), one CTA of eight warps per stream.
 // The reference walks the samples one by one through two recurrences -- the signal level IIR
 // (sLevel = 0.00001 * jan_abs (v) + (1 - 0.00001) * sLevel, in double, rounded to float, :168) and the running sum of a
 // 50-sample envelope window -- and tests a threshold before every sample.  Only the two recurrences are serial.  Per chunk:
@@ -84,7 +84,7 @@ __device__ __forceinline__ float2 sy_conv (const SampleWin &w, uint2 r) {
 #else
 #define ACQ_T(k)
 #endif
-#define ACQ_THREADS 128
+#define ACQ_THREADS 256
 __device__ __forceinline__ float acq_level_exact (float a, float ja) {          // ofdm-processor.cpp:168, operation by operation
 	return __double2float_rn (__dadd_rn (__dmul_rn (0.00001, (double) ja), __dmul_rn (1 - 0.00001, (double) a)));
 }
@@ -160,8 +160,10 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 		// surrogate, warp 1 (concurrently) the window sum.  The inputs of 32 steps come in with eight 128-bit broadcast loads,
 		// requested a block ahead, so only the dependent arithmetic is on the chain -- ONE FFMA / FADD a step; all lanes of the
 		// warp compute the same chain and lane 0 records it (a predicated store per step, nothing waits for it).
-		// Surrogate: a' = fma (a, c_hi, u), u = fma (a_prev, c_lo, k |v|) with c_hi + c_lo = 1 - 1e-5 to 48 bits; u takes the level
-		// of one step EARLIER (it differs by 1e-5 a, times c_lo ~ 1e-8: invisible), which keeps it off the chain.
+		// Surrogate: a' = fma (a, c_hi, u), u = fma (a_before, c_lo, k |v|) with c_hi + c_lo = 1 - 1e-5 to 48 bits; u takes the level
+		// of TWO steps earlier (it differs by 2e-5 a, times c_lo ~ 1e-8: invisible), which keeps it off the chain.  (Measured: the
+		// chain costs ~7.5 cycles a step with two FFMAs or with one -- a fully prepared additive term -- so it is the dependent-issue
+		// latency of this loop, not the instruction count, that bounds it.)
 		const int lane = tid & 31;
 		if (tid >= 32 && tid < 64) {
 			float c = cs;
@@ -191,9 +193,9 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 			if (tid < 32) {                                          // surrogate chain from `from` on
 				const float c_hi = 0.99999f, c_lo = (float) ((1 - 0.00001) - (double) 0.99999f);
 				int i0 = from;
-				float a = s_sl [from], ap = a;
+				float a = s_sl [from], ap = a, app = a;                  // the level now, one and two steps ago
 				for (; (i0 & 31) != 0 && i0 < n; i0 ++) {                // (after a repair: up to the next block boundary one by one)
-					const float u = __fmaf_rn (ap, c_lo, s_t [i0]); ap = a; a = __fmaf_rn (a, c_hi, u);
+					const float u = __fmaf_rn (app, c_lo, s_t [i0]); app = ap; ap = a; a = __fmaf_rn (a, c_hi, u);
 					if (lane == 0) s_sl [i0 + 1] = a;
 				}
 				float4 tn [8];
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__ (ACQ_THREADS) acquire_kernel (StreamDev *sd, O
 					for (int k = 0; k < 32; k += 4) {
 						float r [4];
 #pragma unroll
-						for (int j = 0; j < 4; j ++) { const float u = __fmaf_rn (ap, c_lo, tc [k + j]); ap = a; a = __fmaf_rn (a, c_hi, u); r [j] = a; }
+						for (int j = 0; j < 4; j ++) { const float u = __fmaf_rn (app, c_lo, tc [k + j]); app = ap; ap = a; a = __fmaf_rn (a, c_hi, u); r [j] = a; }
 						if (lane == 0) *reinterpret_cast<float4 *> (&s_sl [i0 + 1 + k]) = make_float4 (r [0], r [1], r [2], r [3]);
 					}
 				}
