@@ -229,11 +229,15 @@ int dabgpu_decode_i16_dev (dabgpu_t *h, const int16_t *d_iq, size_t nsamples, da
 /* Many independent streams in one call (BASELINE configs[3]: short recordings of different ensembles).  The reference
  * runs one ofdmProcessor / ficHandler / mscHandler chain per stream (gui.cpp:160-179); its sample-serial acquisition
  * (ofdm-processor.cpp:275-338) and the frame-by-frame AFC convergence (:390-405, 445-466) are independent across streams,
- * so the engine walks all streams in lockstep through the same kernel launches: n acquisitions cost the time of one.
+ * so the engine runs the streams side by side: the null-symbol searches asynchronously (every stream joins the decoding
+ * rounds the moment ITS search ends), the streams in sync through the same kernel launches round by round.
  * Stream i is decoded exactly as a FRESH handle with this handle's configuration and sub-channels would decode it with
  * one dabgpu_decode call (acquisition from the first sample, coarse search on, empty de-interleaver): jobs[i].out is
  * filled like dabgpu_decode fills it (out->consumed = samples of the stream consumed).  The handle's own stream state
  * is not touched.  sample_format: 0 = u8 I,Q (rawfiles.cpp:113-116), 1 = complex float, 2 = int16 I,Q.
+ * Host input is uploaded in interleaved pieces and decoded as it arrives.  Result buffers in PINNED host memory (all of a
+ * stream's fic_bits / fic_crc / msc_bits pointers, soft == NULL) are filled by asynchronous copies while later rounds run;
+ * pageable ones are filled from a staging buffer at the end of the call.
  * _dev: jobs[i].iq are device pointers on the handle's device (result pointers stay host pointers). */
 typedef struct {
 	const void *iq;            /* nsamples complex samples of the given format                                     */

@@ -625,9 +625,9 @@ extern "C" int dabgpu_decode_cf32 (dabgpu_t *h, const float *iq, size_t nsamples
 // The input of a host call goes up in pieces on its own stream, into one of two device buffers; every chunk of frames waits only
 // for the pieces it reads, so the host-to-device copy overlaps the decode of the frames already there.  dabgpu_prefetch starts
 // the upload of the NEXT block while the current call is still busy with its last frames (the link never idles between calls).
-static long long upload_piece_init () {                      // samples per piece: 8 M (16 MB of u8 IQ); DABGPU_PIECE_MSAMPLES overrides (A/B runs)
+static long long upload_piece_init () {                      // samples per piece: 16 M (32 MB of u8 IQ; measured 4 / 8 / 16 / 32 / 64 M: 8.08 / 7.86 / 7.75 / 7.77 / 7.80 ms per 1024-frame step); DABGPU_PIECE_MSAMPLES overrides (A/B runs)
 	if (const char *e = getenv ("DABGPU_PIECE_MSAMPLES")) { const long long v = atoll (e); if (v >= 1 && v <= 1024) return v << 20; }
-	return 8ll << 20;
+	return 16ll << 20;
 }
 static const long long UPLOAD_PIECE = upload_piece_init ();
 
