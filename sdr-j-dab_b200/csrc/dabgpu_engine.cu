@@ -800,14 +800,20 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 	int rc = ensure_round_bufs (h, nstreams, MULTI_SLOT_CAP, &cb);
 	if (rc) return rc;
 	// inputs: one copy per stream on the copy stream (pinned or pageable, as the caller has them); history rows = erasures
-	// Host input goes up on the copy stream in NPIECE pieces per stream, piece k of every stream before piece k + 1 of any: the first
-	// piece covers what an acquisition normally reads (6.6 frames), so the null search starts after a fraction of the upload and the
-	// rounds follow the arriving samples (StreamDev::limit; the scan cuts a chunk at the first frame whose window is not resident)
-	const int NPIECE = 4;
-	const long long first_piece = (long long) (6.6 * p. T_F);
-	auto piece_end = [&] (const MultiStream &m, int k) -> long long {      // samples of the stream resident once piece k has arrived
-		if (m. nsamples <= first_piece || k >= NPIECE - 1) return m. nsamples;
-		return first_piece + (m. nsamples - first_piece) * k / (NPIECE - 1);
+	// Host input goes up on the copy stream in two steps: first the head of EVERY stream (what a null search normally reads: 6.6
+	// frames, so the searches start after a fraction of the upload), then the rest of the streams one after the other in GROUPS
+	// (large copies: many small ones did not reach the link rate).  An event follows the heads and every group; the rounds follow
+	// the arriving samples (StreamDev::limit; the scan cuts a chunk at the first frame whose window is not resident).
+	static const int NGROUP = [] { const char *e = getenv ("DABGPU_MULTI_PIECES"); const int v = e ? atoi (e) : 0; return v >= 1 && v <= 64 ? v : 4; } ();     // (A/B knobs)
+	static const double first_frames = [] { const char *e = getenv ("DABGPU_MULTI_FIRST"); const double v = e ? atof (e) : 0; return v > 0 ? v : 6.6; } ();
+	const long long first_piece = ((long long) (first_frames * p. T_F) + 4095) / 4096 * 4096;       // (copies start on 8 KB boundaries of the stream)
+	const int ngroups = nstreams < NGROUP ? nstreams : NGROUP;
+	const int NPIECE = 1 + ngroups;                          // events: heads, then group 0 .. ngroups - 1
+	auto group_of = [&] (int i) { return (int) ((long long) i * ngroups / nstreams); };
+	auto piece_end = [&] (int i, int k) -> long long {       // samples of stream i resident once events 0 .. k have been seen
+		const MultiStream &m = ms [i];
+		if (m. nsamples <= first_piece || k >= 1 + group_of (i)) return m. nsamples;
+		return first_piece;
 	};
 	std::vector<cudaEvent_t> &pev = E -> copy_events [0];
 	int pieces_waited = dev_input ? NPIECE : 0;
@@ -817,19 +823,19 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 		for (int k = 0; k < NPIECE; k ++) {
 			for (int i = 0; i < nstreams; i ++) {
 				const MultiStream &m = ms [i];
-				const long long a = k ? piece_end (m, k - 1) : 0, b = piece_end (m, k);
+				const long long a = k ? piece_end (i, k - 1) : 0, b = piece_end (i, k);
 				if (b > a)
 					CUDA_TRY (h, cudaMemcpyAsync ((char *) E -> m_in. p + m. in_off + (size_t) a * sb, (const char *) jobs [i]. iq + (size_t) a * sb, (size_t) (b - a) * sb, cudaMemcpyHostToDevice, E -> copy_st));
 			}
 			CUDA_TRY (h, cudaEventRecord (pev [k], E -> copy_st));
 		}
 	}
-	// pieces [0, upto) must have arrived before the main stream goes on (the host does not wait)
+	// events [0, upto) must have been passed before the main stream goes on (the host does not wait)
 	auto wait_pieces = [&] (int upto) -> cudaError_t {
 		cudaError_t e = cudaSuccess;
 		if (upto > NPIECE) upto = NPIECE;
 		if (upto > pieces_waited) { e = cudaStreamWaitEvent (h -> stream, pev [upto - 1], 0); pieces_waited = upto; }
-		for (auto &m : ms) m. limit = piece_end (m, pieces_waited - 1);
+		for (int i = 0; i < nstreams; i ++) ms [i]. limit = piece_end (i, pieces_waited - 1);
 		return e;
 	};
 	for (int i = 0; i < nstreams; i ++) {
