@@ -51,7 +51,10 @@ struct DevBuf {
 	void *p = nullptr; size_t cap = 0; int dev = 0;
 	cudaError_t ensure (size_t bytes) {
 		if (bytes <= cap) return cudaSuccess;
-		if (p) cudaFree (p);
+		// growing: the old buffer goes to the cache, not back to the driver (cudaFree costs about a millisecond each, and a handle
+		// that starts small -- a lead-in call -- grows some twenty buffers at its first big call).  Work that may still read it is
+		// waited for first, as cudaFree would have done implicitly.
+		if (p) { cudaDeviceSynchronize (); release (); }
 		p = nullptr; cap = 0;
 		size_t want = bytes + bytes / 4 + 256;
 		cudaGetDevice (&dev);
@@ -72,7 +75,7 @@ struct PinBuf {
 	void *p = nullptr; size_t cap = 0;
 	cudaError_t ensure (size_t bytes) {
 		if (bytes <= cap) return cudaSuccess;
-		if (p) cudaFreeHost (p);
+		if (p) { cudaDeviceSynchronize (); release (); }
 		p = nullptr; cap = 0;
 		size_t want = bytes + bytes / 4 + 256;
 		BufCache &c = buf_cache ();

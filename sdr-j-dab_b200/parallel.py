@@ -90,15 +90,25 @@ def _state_words(s):
     return [int(s.abs_pos), int(s.coarse), int(s.fine), int(s.localPhase), int(s.f2Correction), int(s.synced)]
 
 
-def decode_sharded(engine, iq, alloc, rank, world, dist=None, device="cpu", lead_frames=24):
+def decode_sharded(engine, iq, alloc, rank, world, dist=None, device="cpu", lead_frames=24, timing=None):
     """Decode ONE recording `iq` (interleaved u8 I,Q; every rank can address all of it but touches only its own sample
     range) on `world` ranks in parallel.  `engine` is a fresh handle of this rank, `alloc(max_frames)` returns a result
     buffer.  Returns (result, first_frame, mode): `result` holds this rank's frames (overlap already removed), and
-    mode is "parallel" or "chain" (the fallback).  Rank 0's result starts with the lead-in frames."""
-    import torch
+    mode is "parallel" or "chain" (the fallback).  Rank 0's result starts with the lead-in frames.
+    timing (optional dict): timing["decoded"] = time.perf_counter() when this rank's frames are decoded, delivered and the
+    boundaries verified -- before the host-side assembly of the returned arrays (trimming the overlap / prepending the lead-in)."""
+    import os, sys, time, torch
     T_F, cpf, need = engine.frame_len, engine.cifs_per_frame, engine.frame_need
     overlap = -(-16 // cpf)                                   # frames that hold the 16 warm-up CIFs
     nsamp = len(iq) // 2
+    trace = os.environ.get("DAB_SHARD_TRACE")
+    t_last = [time.perf_counter()]
+
+    def mark(what):
+        if trace:
+            now = time.perf_counter()
+            sys.stderr.write("[shard %d] %-28s %8.2f ms  (launches so far %s)\n" % (rank, what, (now - t_last[0]) * 1e3, engine.launch_count() if hasattr(engine, "launch_count") else "?"))
+            t_last[0] = now
 
     def bcast(words):
         t = torch.tensor(words, dtype=torch.int64, device=device)
@@ -120,7 +130,9 @@ def decode_sharded(engine, iq, alloc, rank, world, dist=None, device="cpu", lead
         lead = engine.decode(iq[:2 * lead_samples], alloc(lead_frames + 2))
         s0 = engine.state_get()
         words = _state_words(s0) + [int(s0.previous_1), int(s0.previous_2), int(s0.frames), int(s0.cifs)]
+    mark("lead-in")
     words = bcast(words)
+    mark("state broadcast")
     s0 = engine.make_state(abs_pos=words[0], coarse=words[1], fine=words[2], localPhase=words[3], f2Correction=words[4],
                            synced=words[5], previous_1=words[6], previous_2=words[7], frames=words[8], cifs=words[9])
     locked = s0.synced == 1 and s0.f2Correction == 0
@@ -142,6 +154,7 @@ def decode_sharded(engine, iq, alloc, rank, world, dist=None, device="cpu", lead
             res = engine.decode(iq[2 * sp.abs_pos:2 * end_abs], alloc(b - a + overlap + 2))
             first_state = res.info[overlap] if res.nframes > overlap else None
         fin = _state_words(engine.state_get())
+        mark("decode of my range")
         # ---- 3. verify every boundary: my assumed state at frame a == the left neighbour's true final state
         if world > 1:
             t = torch.tensor(fin, dtype=torch.int64, device=device)
@@ -159,7 +172,11 @@ def decode_sharded(engine, iq, alloc, rank, world, dist=None, device="cpu", lead
                 ok = 1 if (mine == g and fin[4] == 0 and fin[5] == 1 and res.nframes == b - a + overlap) or (a == b and first_state is None) else 0
             else:
                 ok = 1 if (fin[4] == 0 and fin[5] == 1) else 0
+        mark("boundary exchange")
         if all_min(ok):
+            mark("agreement")
+            if timing is not None:
+                timing["decoded"] = time.perf_counter()
             if rank > 0:
                 res = engine.drop_frames(res, overlap)
             elif lead is not None:
