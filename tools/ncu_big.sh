@@ -4,7 +4,7 @@
 # pass 1 lists every launch of the kernel with its grid size and duration, pass 2 captures the first launch of the largest grid
 cd "$(dirname "$0")/.."
 K=$1; NAME=$2
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
+CMD=${NCU_CMD:-"python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras"}      # NCU_CMD: another workload (e.g. "python tools/mode_perf.py 2")
 $CMD > gpurun_out/plain_$NAME.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$NAME.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:$K --csv --log-file gpurun_out/${NAME}_list.csv $CMD > /dev/null 2>&1
 SKIP=$(python - gpurun_out/${NAME}_list.csv <<'PY'
