@@ -40,6 +40,7 @@
 #include "msc-handler.h"
 #undef private
 #include "dab-concurrent.h"
+#include "dab-serial.h"
 #include "charsets.h"
 #include "gui.h"
 #include "../dab_oracle.h"
@@ -172,6 +173,25 @@ int ref_msc_run (int mode, int L, int K, const int16_t *sym, int nframes, int st
 	return rc;
 }
 
+}
+
+extern "C" {
+/* dabSerial::process (dab-serial.cpp:110-147, the backend without a thread: warm-up of 15 CIFs where dabConcurrent has 16) over
+ * ncif CIF fragments frags [ncif][fragmentSize]; out receives the blocks handed to addtoFrame; returns their number */
+int ref_serial_run (const int16_t *frags, int ncif, int fragmentSize, int bitRate, int uepFlag, int protLevel, uint8_t *out, int out_cap_blocks) {
+	RadioInterface mr;
+	audioSink sink;
+	dabSerial *b = new dabSerial (DAB /* plain DAB: the mp2Processor stand-in records */, (int16_t) fragmentSize, (int16_t) bitRate, (int16_t) uepFlag, (int16_t) protLevel, &mr, NULL, NULL, &sink);
+	std::vector<int16_t> frag (fragmentSize);
+	for (int c = 0; c < ncif; c ++) {                        /* process () de-interleaves IN PLACE: work on a copy */
+		memcpy (frag. data (), frags + (size_t) c * fragmentSize, (size_t) fragmentSize * sizeof (int16_t));
+		b -> process (frag. data (), (int16_t) fragmentSize);
+	}
+	const int nb = sink. blocks < out_cap_blocks ? sink. blocks : out_cap_blocks;
+	memcpy (out, sink. bits. data (), (size_t) nb * 24 * bitRate);
+	delete b;
+	return sink. blocks;
+}
 }
 
 /* ---------------------------------------------------------------------------------------------------------------------

@@ -187,6 +187,15 @@ class Oracle:
         assert n == cap, n
         return out
 
+    def ref_serial_run(self, frags, bitRate, uepFlag, protLevel):
+        """dabSerial::process (compiled unmodified) over CIF fragments [ncif][fragmentSize] -> blocks [ncif - 15][24 bitRate]"""
+        frags = np.ascontiguousarray(frags, np.int16)
+        ncif, fragmentSize = frags.shape
+        out = np.zeros((max(ncif - 15, 0), 24 * bitRate), np.uint8)
+        n = self.lib.ref_serial_run(_p(frags, C.c_int16), ncif, fragmentSize, bitRate, uepFlag, protLevel, _p(out, C.c_uint8), out.shape[0])
+        assert n == out.shape[0], n
+        return out
+
     def ref_receive(self, mode, iq, sub, threshold=3, method=1, max_frames=64):
         """the reference's whole receive chain (ofdmProcessor -> ofdmDecoder -> ficHandler / mscHandler -> dabConcurrent, all
         compiled unmodified) over raw u8 IQ with one audio sub-channel sub = (startAddr, Length, bitRate, uepFlag, protLevel)

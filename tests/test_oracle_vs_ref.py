@@ -171,3 +171,21 @@ def test_whole_receive_chain_classes(port, ref, mode, cfo, snr, lead, sub):
     assert np.array_equal(a_msc[:m], b_msc[:m])
     last = info[min(len(info), b_fic.shape[0] // g) - 1]
     assert state[0] == last.coarse or abs(state[0] - last.coarse) % p.carrierDiff == 0
+
+
+@pytest.mark.parametrize("sub", [(96, 128, 1, 0o103), (84, 128, 1, 0o202), (96, 128, 0, 3)])
+def test_dab_serial_class(port, ref, sub):
+    """dabSerial (the backend without a thread) starts decoding one CIF EARLIER than dabConcurrent (15 against 16 CIFs of warm-up,
+    dab-serial.cpp:126-129 / dab-concurrent.cpp:172-175): from its second block on its output is the concurrent backend's, the
+    first is the decode of the de-interleaver's 16th output row -- which is how host/dab_adapters.h models it"""
+    Length, bitRate, uepFlag, protLevel = sub
+    rng = np.random.default_rng(Length + protLevel)
+    ncif = 40
+    frags = rng.integers(-127, 128, (ncif, Length * 64)).astype(np.int16)
+    serial = ref.ref_serial_run(frags, bitRate, uepFlag, protLevel)
+    conc = port.msc_backend(frags, bitRate, uepFlag, protLevel)
+    assert serial.shape[0] == ncif - 15 and conc.shape[0] == ncif - 16
+    assert np.array_equal(serial[1:], conc)
+    row = port.time_deinterleave(frags)[15]
+    first = (port.uep_deconvolve(bitRate, protLevel, row) if uepFlag == 0 else port.eep_deconvolve(bitRate, protLevel, row)) ^ port.prbs(24 * bitRate)
+    assert np.array_equal(serial[0], first)
