@@ -12,6 +12,8 @@ public:
 	void stop () {}
 	void take (const uint8_t *v, int n) { std::lock_guard<std::mutex> l (m); bits. insert (bits. end (), v, v + n); blocks ++; }
 	int nblocks () { std::lock_guard<std::mutex> l (m); return blocks; }
+	void take_au (const uint8_t *v, int n) { std::lock_guard<std::mutex> l (m); aus. emplace_back (v, v + n); }
+	std::vector<std::vector<uint8_t> > aus;                 /* access units the DAB+ front handed to the AAC decoder stand-in */
 	std::mutex m;
 	std::vector<uint8_t> bits;
 	int blocks = 0;

@@ -38,6 +38,7 @@
 #include "fic-handler.h"
 #include "fib-processor.h"
 #include "msc-handler.h"
+#include "mp4processor.h"
 #undef private
 #include "dab-concurrent.h"
 #include "dab-serial.h"
@@ -63,6 +64,7 @@ void ficHandler::show_ficCRC (bool ok) {
 	r. crc. push_back (ok ? 1 : 0);
 	r. calls ++;
 }
+void mp4Processor::show_successRate (int) {}
 void fib_processor::addEnsembleChar (char, int) {}
 void fib_processor::addtoEnsemble (const QString &) {}
 void fib_processor::nameofEnsemble (int, const QString &) {}
@@ -191,6 +193,47 @@ int ref_serial_run (const int16_t *frags, int ncif, int fragmentSize, int bitRat
 	memcpy (out, sink. bits. data (), (size_t) nb * 24 * bitRate);
 	delete b;
 	return sink. blocks;
+}
+}
+
+extern "C" {
+/* mp4Processor::addtoFrame (mp4processor.cpp:107-150, compiled unmodified: five-block window, Fire code, RS (120, 110) per column,
+ * access-unit table, AU CRCs) CIF by CIF over bits [ncif][24 bitRate]; for every super frame it accepts: the corrected bytes
+ * sf [n][110 bitRate / 8] and info [n] = { first_cif, -1 (the count of corrected symbols is a local of the reference), num_aus,
+ * au_start [7], au_crc mask }.  Returns n. */
+int ref_dabplus_run (const uint8_t *bits, int ncif, int bitRate, uint8_t *sf, orc_superframe_info *info, int max_sf) {
+	RadioInterface mr;
+	audioSink sink;
+	mp4Processor *p = new mp4Processor (&mr, &sink, (int16_t) bitRate);
+	const int nb = 24 * bitRate, sfb = 110 * (bitRate / 8);
+	std::vector<uint8_t> row (nb);
+	int n = 0;
+	for (int c = 0; c < ncif; c ++) {
+		memcpy (row. data (), bits + (size_t) c * nb, nb);
+		const int before = p -> blocksInBuffer;
+		const size_t aus_before = sink. aus. size ();
+		p -> addtoFrame (row. data (), (int16_t) nb);
+		if (before >= 4 && p -> blocksInBuffer == 0) {           /* accepted: Fire code held and processSuperframe returned true */
+			if (n < max_sf) {
+				memcpy (sf + (size_t) n * sfb, p -> outVector, sfb);
+				orc_superframe_info &I = info [n];
+				memset (&I, 0, sizeof (I));
+				I. first_cif = c - 4; I. corrected = -1;
+				const uint8_t *o = p -> outVector;
+				const int kind = 2 * ((o [2] >> 6) & 1) + ((o [2] >> 5) & 1);
+				I. num_aus = kind == 0 ? 4 : kind == 1 ? 2 : kind == 2 ? 6 : 3;
+				for (int i = 0; i <= I. num_aus; i ++) I. au_start [i] = p -> au_start [i];
+				size_t k = aus_before;                               /* the access units that passed their CRC, in order */
+				for (int i = 0; i < I. num_aus && k < sink. aus. size (); i ++) {
+					const int len = p -> au_start [i + 1] - p -> au_start [i] - 2;
+					if (len >= 0 && (int) sink. aus [k]. size () == len && memcmp (sink. aus [k]. data (), o + p -> au_start [i], len) == 0) { I. au_crc |= 1 << i; k ++; }
+				}
+			}
+			n ++;
+		}
+	}
+	delete p;
+	return n;
 }
 }
 

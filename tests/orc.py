@@ -187,6 +187,17 @@ class Oracle:
         assert n == cap, n
         return out
 
+    def ref_dabplus_run(self, bits, bitRate):
+        """mp4Processor::addtoFrame (compiled unmodified) CIF by CIF -> (superframes, [(first_cif, num_aus, au_start, au_crc)])"""
+        bits = np.ascontiguousarray(bits, np.uint8).reshape(-1, 24 * bitRate)
+        cap = bits.shape[0] // 5 + 2
+        sf = np.zeros((cap, 110 * (bitRate // 8)), np.uint8)
+        info = (SuperframeInfo * cap)()
+        self.lib.ref_dabplus_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        n = self.lib.ref_dabplus_run(bits.ctypes.data, bits.shape[0], bitRate, sf.ctypes.data, C.addressof(info), cap)
+        assert n <= cap
+        return sf[:n], [(info[i].first_cif, info[i].num_aus, tuple(info[i].au_start), info[i].au_crc) for i in range(n)]
+
     def ref_serial_run(self, frags, bitRate, uepFlag, protLevel):
         """dabSerial::process (compiled unmodified) over CIF fragments [ncif][fragmentSize] -> blocks [ncif - 15][24 bitRate]"""
         frags = np.ascontiguousarray(frags, np.int16)

@@ -95,3 +95,25 @@ def test_superframe_sync_and_repair(bitRate):
             assert (corrected > 0) == (i % 3 == 1)
     if len(res) == 2:
         assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
+
+
+@pytest.mark.parametrize("bitRate", [32, 72, 128])
+def test_superframe_layer_equals_the_references_mp4processor(bitRate):
+    """the oracle's restated super-frame front against the reference's OWN mp4Processor (mp4processor.cpp compiled unmodified,
+    AAC decoder and PAD handler replaced by recorders): the same super frames are accepted at the same CIFs, with the same
+    corrected bytes, access-unit tables and AU CRC verdicts -- on a damaged stream and on noise with planted frames"""
+    os_ = _oracles()
+    if len(os_) < 2:
+        pytest.skip("no compiled reference in this checkout")
+    port, ref = os_
+    rng = np.random.default_rng(100 + bitRate)
+    bits, sfs = _stream(bitRate, rng, 9)
+    more, _ = _stream(bitRate, rng, 4, junk_before=7, damage=False)
+    more[rng.integers(0, more.shape[0], 3)] ^= 1                          # three CIFs inverted: their super frames fail
+    stream = np.concatenate([bits, rng.integers(0, 2, (11, 24 * bitRate), dtype=np.uint8), more])
+    a_sf, a_info = port.dabplus(bitRate).process(stream)
+    b_sf, b_info = ref.ref_dabplus_run(stream, bitRate)
+    assert len(a_info) == len(b_info) >= 8
+    assert np.array_equal(a_sf, b_sf)
+    for (first, corrected, n, au, crc), (bfirst, bn, bau, bcrc) in zip(a_info, b_info):
+        assert (first, n, tuple(au[:n + 1]), crc) == (bfirst, bn, tuple(bau[:bn + 1]), bcrc)
