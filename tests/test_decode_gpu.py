@@ -293,3 +293,30 @@ def test_engine_equals_the_references_own_chain(ref, mode, cfo, snr, sub):
     assert m >= (res.nframes - 1) * mod.p.cifsPerFrame - 17 and m > 0
     assert np.array_equal(res.msc[0][:m], r_msc[:m])
     eng.close()
+
+
+def test_engine_equals_golden_of_the_references_own_chain():
+    """the committed outputs of the reference's own receive chain (tests/golden/golden_chain.npz) against dabgpu_decode on the
+    recordings regenerated from their seeds: needs neither /root/reference nor the compiled reference"""
+    import hashlib
+    import os
+    import sys
+    import orc
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden_chain as mg
+    pkg = engine_pkg()
+    O = orc.Oracle("port")                                   # (tables for the modulator only)
+    g = np.load(os.path.join(here, "golden", "golden_chain.npz"))
+    for k, case in enumerate(mg.CASES):
+        mod, tr = mg.recording(O, case)
+        assert np.array_equal(np.frombuffer(hashlib.sha256(tr["iq"].tobytes()).digest(), np.uint8), g["iq_sha_%d" % k])
+        s = mod.sub[0]
+        eng = pkg.DabGpu(mode=case[0])
+        eng.set_subchannels([(s.startAddr, s.length, s.bitRate, s.uepFlag, s.protLevel)])
+        res = eng.decode(tr["iq"], eng.alloc_result(case[2] + 4, want_soft=False))
+        gf, gc, gm = np.unpackbits(g["fic_%d" % k], axis=1), g["crc_%d" % k], np.unpackbits(g["msc_%d" % k], axis=1)
+        n, m = min(res.fic_bits.shape[0], gf.shape[0]), min(res.msc[0].shape[0], gm.shape[0])
+        assert n >= gf.shape[0] - 2 * mod.p.ficGroups and m >= gm.shape[0] - mod.p.cifsPerFrame - 1 and m > 0
+        assert np.array_equal(res.fic_bits[:n], gf[:n]) and np.array_equal(res.fic_crc[:n], gc[:n]) and np.array_equal(res.msc[0][:m], gm[:m])
+        eng.close()

@@ -85,3 +85,27 @@ def test_whole_chain(port):
     for i, m in enumerate(msc):
         assert np.array_equal(np.packbits(m, axis=1), G["chain_msc%d" % i])
     assert crc[-8:].all()
+
+
+def test_chain_equals_the_references_own_chain_golden(port):
+    """tests/golden/golden_chain.npz = what the reference's own classes, compiled unmodified and wired as the reference wires them,
+    delivered for three seeded recordings (make_golden_chain.py): the restated chain reproduces every FIC group, CRC flag and MSC
+    block -- with or without /root/reference at hand"""
+    import hashlib
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden_chain as mg
+    g = np.load(os.path.join(here, "golden", "golden_chain.npz"))
+    for k, case in enumerate(mg.CASES):
+        mod, tr = mg.recording(port, case)
+        assert np.array_equal(np.frombuffer(hashlib.sha256(tr["iq"].tobytes()).digest(), np.uint8), g["iq_sha_%d" % k]), "the recording is not the one the golden was made from"
+        s = mod.sub[0]
+        sym, info = port.ofdm_run(case[0], tr["iq"], case[2] + 4)
+        fic, crc = port.fic_frames(case[0], sym)
+        msc = port.msc_backend(port.msc_slice(case[0], sym, s.startAddr, s.length), s.bitRate, s.uepFlag, s.protLevel)
+        gf, gc, gm = np.unpackbits(g["fic_%d" % k], axis=1), g["crc_%d" % k], np.unpackbits(g["msc_%d" % k], axis=1)
+        n, m = min(fic.shape[0], gf.shape[0]), min(msc.shape[0], gm.shape[0])
+        assert n >= gf.shape[0] - 2 * mod.p.ficGroups and m >= gm.shape[0] - mod.p.cifsPerFrame - 1 and m > 0
+        assert np.array_equal(fic[:n], gf[:n]) and np.array_equal(crc[:n], gc[:n]) and np.array_equal(msc[:m], gm[:m])
