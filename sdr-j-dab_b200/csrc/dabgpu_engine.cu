@@ -969,7 +969,22 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 		if (!any) {
 			if (inflight > 0) {                                  // nothing but searches going on: decode what is pending, then wait for the next outcome
 				if ((rc = channel_all (true))) return rc;
-				while (collect () == 0) std::this_thread::yield ();
+				for (unsigned spin = 0; ; spin ++) {
+					if (collect () > 0) break;
+					std::this_thread::yield ();
+					if ((spin & 0xfff) != 0xfff) continue;
+					// no outcome for a while: are the searches still running?  (a launch that failed, or a fault, must not hang the caller)
+					bool busy = false;
+					for (int k = 0; k < 4; k ++) {
+						const cudaError_t q = cudaStreamQuery (E -> acq_st [k]);
+						if (q == cudaErrorNotReady) busy = true;
+						else if (q != cudaSuccess) return dab_fail (h, DABGPU_ERR_CUDA, "acquisition kernel: %s", cudaGetErrorString (q));
+					}
+					cudaGetLastError ();
+					if (busy) continue;
+					if (collect () > 0) break;                       // (finished between the two looks)
+					return dab_fail (h, DABGPU_ERR_CUDA, "acquisition kernel ended without publishing %d outcome(s)", inflight);
+				}
 				continue;
 			}
 			if (starved && !all_in) { CUDA_TRY (h, wait_pieces (pieces_waited + 1)); continue; }   // let the main stream wait for the next piece
