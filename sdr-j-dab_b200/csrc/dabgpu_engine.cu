@@ -21,6 +21,7 @@
 #include "dabgpu_engine.h"
 #include <atomic>
 #include <chrono>
+#include <functional>
 #include <thread>
 static double now_ms () { return std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now (). time_since_epoch ()). count (); }
 
@@ -254,7 +255,7 @@ static int ensure_round_bufs (dabgpu *h, int nstreams, int nslots, ChunkBufs *cb
 // [acquire] -> predict -> front, symbol, scan (derive) -> front, symbol, scan (verify).  On return every StreamDev::ctl holds
 // the committed state (ctl.n_valid frames accepted from the stream's chunk, ctl.n_redo of them after a recomputation) and
 // StreamDev::nframes the frames the round actually attempted.
-static int run_round (dabgpu *h, int nstreams, int nslots, int max_budget, bool any_acquire, int fmt, const ChunkBufs &cb) {
+static int run_round (dabgpu *h, int nstreams, int nslots, int max_budget, bool any_acquire, int fmt, const ChunkBufs &cb, const std::function<int ()> *while_running = nullptr) {
 	Engine *E = h -> engine;
 	cudaStream_t st = h -> stream;
 	StreamDev *hsd = (StreamDev *) E -> h_sd. p, *dsd = (StreamDev *) E -> d_sd. p;
@@ -279,6 +280,7 @@ static int run_round (dabgpu *h, int nstreams, int nslots, int max_budget, bool 
 	}
 	CUDA_TRY (h, cudaGetLastError ());
 	CUDA_TRY (h, cudaMemcpyAsync (hsd, dsd, (size_t) nstreams * sizeof (StreamDev), cudaMemcpyDeviceToHost, st));
+	if (while_running) { const int rc = (*while_running) (); if (rc) return rc; }      // host work that fits behind the round's kernels
 	CUDA_TRY (h, cudaStreamSynchronize (st));
 	for (int i = 0; i < nstreams; i ++)
 		if (hsd [i]. ctl. fault)
@@ -327,7 +329,11 @@ struct ChanPart {                                           // frames [f0, f0 + 
 // buffers on the same stream.  All parts go through ONE launch pair of the throughput kernels when that path is taken.
 // defer_crc: no CRC launch and no delivery of CRC flags here (dabgpu_decode_multi checks every group of the call in one launch at
 // its end, so that its channel-decoding batches are independent of each other and may run on different side streams)
-static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts, bool defer_crc = false) {
+// later: the device-to-host result copies of the parts are not issued here but appended to this list -- with hundreds of them per
+// batch (streams x sub-channels) issuing them costs the host half a millisecond, which dabgpu_decode_multi spends while a round's
+// kernels are running instead of between two rounds
+struct LaterCopy { void *dst; const void *src; size_t bytes; cudaStream_t st; };
+static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts, bool defer_crc = false, std::vector<LaterCopy> *later = nullptr) {
 	Engine *E = h -> engine;
 	const DabParams &p = h -> p;
 	const size_t nsub = E -> backends. size ();
@@ -396,13 +402,16 @@ static int channel_parts (dabgpu *h, std::vector<ChanPart> &parts, bool defer_cr
 			}
 			const int c0 = q. f0 > q. out_skip ? q. f0 : q. out_skip, cg = (q. f0 + q. nv - c0) * p. ficGroups;      // frames [c0, f0 + nv) are delivered
 			const size_t src_g = (size_t) c0 * p. ficGroups, dst_g = (size_t) (c0 - q. out_skip) * p. ficGroups;
-			if (cg > 0 && q. out -> fic_bits) e = cudaMemcpyAsync (q. out -> fic_bits + dst_g * 768, q. ficbits + src_g * 768, (size_t) cg * 768, cudaMemcpyDeviceToHost, st);
-			if (e == cudaSuccess && cg > 0 && q. out -> fic_crc && !defer_crc) e = cudaMemcpyAsync (q. out -> fic_crc + dst_g * 3, q. ficcrc + src_g * 3, (size_t) cg * 3, cudaMemcpyDeviceToHost, st);
+			auto d2h = [&] (void *dst, const void *src, size_t bytes) -> cudaError_t {
+				if (later) { later -> push_back (LaterCopy { dst, src, bytes, st }); return cudaSuccess; }
+				return cudaMemcpyAsync (dst, src, bytes, cudaMemcpyDeviceToHost, st);
+			};
+			if (cg > 0 && q. out -> fic_bits) e = d2h (q. out -> fic_bits + dst_g * 768, q. ficbits + src_g * 768, (size_t) cg * 768);
+			if (e == cudaSuccess && cg > 0 && q. out -> fic_crc && !defer_crc) e = d2h (q. out -> fic_crc + dst_g * 3, q. ficcrc + src_g * 3, (size_t) cg * 3);
 			for (size_t i = 0; i < nsub && e == cudaSuccess; i ++) {
 				const size_t fbytes = msc_block_bytes (E, E -> subch [i]);
 				if (q. out -> msc_bits && q. out -> msc_bits [i] && n_here [k] [i] > 0)
-					e = cudaMemcpyAsync (q. out -> msc_bits [i] + (size_t) q. nblk [i] * fbytes, q. mscbits [i] + (size_t) q. nblk [i] * fbytes,
-					                     (size_t) n_here [k] [i] * fbytes, cudaMemcpyDeviceToHost, st);
+					e = d2h (q. out -> msc_bits [i] + (size_t) q. nblk [i] * fbytes, q. mscbits [i] + (size_t) q. nblk [i] * fbytes, (size_t) n_here [k] [i] * fbytes);
 				q. nblk [i] += n_here [k] [i];
 			}
 		}
@@ -857,6 +866,7 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 	StreamDev *hsd = (StreamDev *) E -> h_sd. p;
 	// channel decoding of everything accepted since the last call, all streams in one launch pair
 	dabgpu_result no_copy {};
+	std::vector<LaterCopy> later;
 	auto channel_all = [&] (bool final) -> int {
 		std::vector<ChanPart> parts;
 		long long pending = 0;
@@ -876,7 +886,13 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 			parts. push_back (q);
 			m. decoded_upto = m. nframes;
 		}
-		return channel_parts (h, parts, true);      // (CRC flags: one launch over every group of the call at its end)
+		return channel_parts (h, parts, true, &later);      // (CRC flags: one launch over every group of the call at its end)
+	};
+	const std::function<int ()> flush_later = [&] () -> int {    // the result copies queued by the batches so far
+		for (const LaterCopy &c : later)
+			CUDA_TRY (h, cudaMemcpyAsync (c. dst, c. src, c. bytes, cudaMemcpyDeviceToHost, c. st));
+		later. clear ();
+		return DABGPU_OK;
 	};
 	const bool trace = getenv ("DABGPU_TRACE") != nullptr;
 	const double t_call0 = now_ms ();
@@ -968,7 +984,7 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 		}
 		if (!any) {
 			if (inflight > 0) {                                  // nothing but searches going on: decode what is pending, then wait for the next outcome
-				if ((rc = channel_all (true))) return rc;
+				if ((rc = channel_all (true)) || (rc = flush_later ())) return rc;
 				for (unsigned spin = 0; ; spin ++) {
 					if (collect () > 0) break;
 					std::this_thread::yield ();
@@ -991,7 +1007,7 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 			break;
 		}
 		const double t_r0 = trace ? now_ms () : 0;
-		if ((rc = run_round (h, nstreams, nslots, max_budget, false, fmt, cb))) return rc;
+		if ((rc = run_round (h, nstreams, nslots, max_budget, false, fmt, cb, &flush_later))) return rc;
 		if (trace) {
 			int acc = 0, redo = 0, att = 0;
 			for (int i = 0; i < nstreams; i ++) { acc += hsd [i]. ctl. n_valid * (hsd [i]. budget > 0); redo += hsd [i]. ctl. n_redo * (hsd [i]. budget > 0); att += hsd [i]. nframes; }
@@ -1010,7 +1026,7 @@ static int decode_multi_core (dabgpu *h, const dabgpu_stream_job *jobs, int nstr
 		if ((rc = channel_all (false))) return rc;
 	}
 	if (trace) fprintf (stderr, "[multi] rounds done at %.3f ms\n", now_ms () - t_call0);
-	if ((rc = channel_all (true))) return rc;
+	if ((rc = channel_all (true)) || (rc = flush_later ())) return rc;
 	for (int i = 1; i < 4; i ++) CUDA_TRY (h, cudaStreamSynchronize (h -> vctx [i]. st));
 	if (trace) fprintf (stderr, "[multi] channel decoding done at %.3f ms\n", now_ms () - t_call0);
 	if (ngroups_all > 0) {                                   // FIB CRCs of every group of every stream (groups never decoded give flags nobody reads)
